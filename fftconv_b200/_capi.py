@@ -1,0 +1,66 @@
+"""ctypes binding of libfftconv_cuda.so (include/fftconv_cuda.h).
+
+The product path: there is no CPU fallback.  If the shared library is missing this
+module raises at import of the first symbol; if no CUDA device is usable every call
+raises RuntimeError with the library's message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfftconv_cuda.so")
+
+FULL, SAME = 0, 1
+
+# every symbol include/fftconv_cuda.h declares
+SYMBOLS = [
+    "fftconv_cuda_version", "fftconv_cuda_last_error", "fftconv_cuda_optimal_fft_size",
+    "fftconv_cuda_clear_cache", "fftconv_cuda_launch_count",
+] + [
+    f"fftconv_cuda_{name}_{sfx}"
+    for sfx in ("f32", "f64")
+    for name in ("oaconvolve", "oaconvolve_batched", "convolve", "convolve_batched",
+                 "hilbert", "hilbert_batched", "add")
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m fftconv_b200.build` "
+            "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.fftconv_cuda_version.restype = C.c_char_p
+    L.fftconv_cuda_last_error.restype = C.c_char_p
+    L.fftconv_cuda_optimal_fft_size.restype = C.c_size_t
+    L.fftconv_cuda_optimal_fft_size.argtypes = [C.c_size_t]
+    L.fftconv_cuda_clear_cache.restype = C.c_int
+    L.fftconv_cuda_launch_count.restype = C.c_ulonglong
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    for sfx in ("f32", "f64"):
+        for name in ("oaconvolve", "convolve"):
+            f = getattr(L, f"fftconv_cuda_{name}_{sfx}")
+            f.restype, f.argtypes = i, [vp, sz, vp, sz, vp, sz, i]
+            f = getattr(L, f"fftconv_cuda_{name}_batched_{sfx}")
+            f.restype, f.argtypes = i, [vp, sz, sz, sz, vp, sz, vp, sz, sz, i, vp]
+        f = getattr(L, f"fftconv_cuda_hilbert_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz]
+        f = getattr(L, f"fftconv_cuda_hilbert_batched_{sfx}")
+        f.restype, f.argtypes = i, [vp, sz, sz, sz, vp, sz, vp]
+        f = getattr(L, f"fftconv_cuda_add_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().fftconv_cuda_last_error().decode("utf-8", "replace")
+        raise RuntimeError(msg or f"libfftconv_cuda error {rc}")

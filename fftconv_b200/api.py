@@ -1,0 +1,189 @@
+"""Python face of the hot path, mirroring the reference's `pyfftconv` module
+(/root/reference/py/main.cpp:147-174, stubs py/pyfftconv/_pyfftconv.pyi):
+
+    convolve(a, k, mode="full")      convolve_(a, k, out, mode="full")
+    oaconvolve(a, k, mode="full")    oaconvolve_(a, k, out, mode="full")
+    hilbert(a)                       hilbert_(a, out)
+
+Same names, argument meaning, defaults and error behaviour (RuntimeError for a
+kernel longer than the signal or an unknown mode).  Extensions over the reference:
+2-D inputs are batches of rows convolved with the same taps (the reference's
+binding rejects ndim != 1), and CUDA `torch.Tensor`s are accepted and processed in
+place on the device on torch's current stream (no host round trip).
+
+Everything goes through the C ABI of libfftconv_cuda.so; nothing here computes.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi
+
+try:  # torch is plumbing (device memory, streams); numpy-only callers do not need it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_SFX = {"float32": "f32", "float64": "f64"}
+
+
+def _mode(mode) -> int:
+    # py/main.cpp:21-27
+    if mode == "same":
+        return _capi.SAME
+    if mode == "full":
+        return _capi.FULL
+    raise RuntimeError(f"Unsupported convolution mode: {mode}")
+
+
+def _is_tensor(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class _Buf:
+    """pointer + shape view of a numpy array or a torch tensor (rows contiguous)."""
+
+    def __init__(self, x, name: str):
+        self.obj = x
+        if _is_tensor(x):
+            self.dtype = str(x.dtype).replace("torch.", "")
+            self.shape = tuple(x.shape)
+            if x.dim() >= 1 and x.stride(-1) != 1 and x.shape[-1] > 1:
+                raise RuntimeError(f"{name}: last dimension must be contiguous")
+            self.row_stride = x.stride(0) if x.dim() == 2 else (x.shape[-1] if x.dim() else 1)
+            self.ptr = x.data_ptr()
+            self.is_cuda = x.is_cuda
+        else:
+            x = np.asarray(x)
+            self.obj = x
+            self.dtype = str(x.dtype)
+            self.shape = x.shape
+            if x.ndim >= 1 and x.shape[-1] > 1 and x.strides[-1] != x.itemsize:
+                raise RuntimeError(f"{name}: last dimension must be contiguous")
+            self.row_stride = (x.strides[0] // x.itemsize) if x.ndim == 2 else (x.shape[-1] if x.ndim else 1)
+            self.ptr = x.ctypes.data
+            self.is_cuda = False
+        if self.dtype not in _SFX:
+            raise TypeError(f"{name}: float32 or float64 expected, got {self.dtype}")
+        self.ndim = len(self.shape)
+
+
+def _stream_of(buf: _Buf):
+    if buf.is_cuda:
+        return torch.cuda.current_stream(buf.obj.device).cuda_stream
+    return None
+
+
+def _empty_like_rows(a, out_len: int):
+    if _is_tensor(a):
+        shape = (out_len,) if a.dim() == 1 else (a.shape[0], out_len)
+        return torch.empty(shape, dtype=a.dtype, device=a.device)
+    a = np.asarray(a)
+    shape = (out_len,) if a.ndim == 1 else (a.shape[0], out_len)
+    return np.empty(shape, dtype=a.dtype)
+
+
+def _conv_(name: str, a, k, out, mode):
+    A, K, O = _Buf(a, "a"), _Buf(k, "k"), _Buf(out, "out")
+    # py/main.cpp:38-44 / :85-91
+    if K.ndim != 1 or A.ndim not in (1, 2) or O.ndim != A.ndim:
+        raise RuntimeError("Number of dimensions must be one")
+    if A.dtype != K.dtype or A.dtype != O.dtype:
+        raise TypeError("a, k and out must share one dtype")
+    n, klen = A.shape[-1], K.shape[0]
+    if n < klen:
+        raise RuntimeError("Kernel size must be smaller than input size")
+    m = _mode(mode)
+    out_len = O.shape[-1]
+    batch = 1 if A.ndim == 1 else A.shape[0]
+    if A.ndim == 2 and O.shape[0] != batch:
+        raise RuntimeError("out must have one row per input row")
+    if A.is_cuda != O.is_cuda:
+        raise RuntimeError("a and out must live on the same side (host or device)")
+    fn = getattr(_capi.lib(), f"fftconv_cuda_{name}_batched_{_SFX[A.dtype]}")
+    if A.is_cuda:
+        with torch.cuda.device(A.obj.device):
+            rc = fn(A.ptr, batch, n, A.row_stride, K.ptr, klen, O.ptr, out_len, O.row_stride, m,
+                    _stream_of(A))
+    else:
+        rc = fn(A.ptr, batch, n, A.row_stride, K.ptr, klen, O.ptr, out_len, O.row_stride, m, None)
+    _capi.check(rc)
+
+
+def _conv(name: str, a, k, mode):
+    m = _mode(mode)
+    n = a.shape[-1]
+    klen = k.shape[0] if hasattr(k, "shape") else len(k)
+    out = _empty_like_rows(a, n if m == _capi.SAME else n + klen - 1)  # py/main.cpp:62-71
+    _conv_(name, a, k, out, mode)
+    return out
+
+
+def convolve_(a, k, out, mode: str = "full") -> None:
+    """fftconv::convolve_fftw into `out` (py/main.cpp:29-55)."""
+    _conv_("convolve", a, k, out, mode)
+
+
+def convolve(a, k, mode: str = "full"):
+    """fftconv::convolve_fftw; API compatible with np.convolve (py/main.cpp:58-74)."""
+    return _conv("convolve", a, k, mode)
+
+
+def oaconvolve_(a, k, out, mode: str = "full") -> None:
+    """fftconv::oaconvolve_fftw into `out` (py/main.cpp:76-102)."""
+    _conv_("oaconvolve", a, k, out, mode)
+
+
+def oaconvolve(a, k, mode: str = "full"):
+    """fftconv::oaconvolve_fftw (py/main.cpp:105-121)."""
+    return _conv("oaconvolve", a, k, mode)
+
+
+def hilbert_(a, out) -> None:
+    """fftconv::hilbert into `out`: envelope |a + j H{a}| (py/main.cpp:123-126)."""
+    A, O = _Buf(a, "a"), _Buf(out, "out")
+    if A.ndim not in (1, 2) or O.ndim != A.ndim or A.shape != O.shape:
+        raise RuntimeError("hilbert: a and out must have the same 1-D or 2-D shape")
+    if A.dtype != O.dtype:
+        raise TypeError("a and out must share one dtype")
+    if A.is_cuda != O.is_cuda:
+        raise RuntimeError("a and out must live on the same side (host or device)")
+    n = A.shape[-1]
+    batch = 1 if A.ndim == 1 else A.shape[0]
+    fn = getattr(_capi.lib(), f"fftconv_cuda_hilbert_batched_{_SFX[A.dtype]}")
+    if A.is_cuda:
+        with torch.cuda.device(A.obj.device):
+            rc = fn(A.ptr, batch, n, A.row_stride, O.ptr, O.row_stride, _stream_of(A))
+    else:
+        rc = fn(A.ptr, batch, n, A.row_stride, O.ptr, O.row_stride, None)
+    _capi.check(rc)
+
+
+def hilbert(a):
+    """Equivalent to np.abs(scipy.signal.hilbert(a)) (py/main.cpp:128-132, :142-145)."""
+    out = _empty_like_rows(a, a.shape[-1])
+    hilbert_(a, out)
+    return out
+
+
+def optimal_fft_size(klen: int) -> int:
+    """Segment FFT size for `klen` taps (include/fftconv/fftconv.hpp:53-66)."""
+    return int(_capi.lib().fftconv_cuda_optimal_fft_size(int(klen)))
+
+
+def add_(dst, src) -> None:
+    """dst += src on the device (tail hand-over between chunks of a long signal)."""
+    D, S = _Buf(dst, "dst"), _Buf(src, "src")
+    if not (D.is_cuda and S.is_cuda) or D.dtype != S.dtype or D.shape != S.shape or D.ndim != 1:
+        raise RuntimeError("add_: two 1-D CUDA tensors of one dtype and length expected")
+    fn = getattr(_capi.lib(), f"fftconv_cuda_add_{_SFX[D.dtype]}")
+    with torch.cuda.device(D.obj.device):
+        _capi.check(fn(D.ptr, S.ptr, D.shape[0], _stream_of(D)))
+
+
+def launch_count() -> int:
+    return int(_capi.lib().fftconv_cuda_launch_count())
+
+
+def clear_cache() -> None:
+    _capi.check(_capi.lib().fftconv_cuda_clear_cache())

@@ -1,0 +1,68 @@
+"""Build recipe for libfftconv_cuda.so (sm_100a only, in-tree).
+
+`python -m fftconv_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles
+without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libfftconv_cuda.so")
+MICROBENCH = os.path.join(LIBDIR, "microbench")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources() -> list[str]:
+    out = [os.path.join(ROOT, "include", "fftconv_cuda.h")]
+    for f in sorted(os.listdir(CSRC)):
+        out.append(os.path.join(CSRC, f))
+    return out
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    if not force and _newer(LIB, _sources()):
+        return LIB
+    cmd = ["nvcc", *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "fftconv_cuda.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_microbench(force: bool = False) -> str:
+    src = os.path.join(CSRC, "microbench.cu")
+    if not os.path.exists(src):
+        return ""
+    if not force and _newer(MICROBENCH, [src]):
+        return MICROBENCH
+    subprocess.run(["nvcc", *NVCC_FLAGS, "-o", MICROBENCH, src], check=True)
+    return MICROBENCH
+
+
+def build_all(force: bool = False) -> None:
+    build_lib(force)
+    build_microbench(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)
+    print(LIB)

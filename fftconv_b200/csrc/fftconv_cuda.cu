@@ -1,0 +1,552 @@
+// fftconv_cuda.cu -- libfftconv_cuda: C ABI (include/fftconv_cuda.h), plan /
+// workspace cache and kernel dispatch for the B200 convolution hot path.
+//
+// What the cache replaces: the reference keeps one FFTW plan pair plus three
+// aligned buffers per FFT length in a thread_local map
+// (/root/reference/include/fftconv/fftw.hpp:443-461, fftconv.hpp:288-336).
+// Here a "plan" is keyed by (device, FFT length, dtype) and owns the twiddle
+// tables in device memory; per (device, stream) there is a small workspace for
+// the taps and their spectrum; per device there are staging buffers and three
+// streams for the host-pointer path.  The segment length comes from the same
+// table as the reference (fftconv.hpp:38-66).
+#include "../../include/fftconv_cuda.h"
+
+#include "generic_kernels.cuh"
+#include "oa_n2048_kernel.cuh"
+#include "oa_n2048_tables.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+namespace {
+
+using fc::generic::cx;
+
+thread_local std::string g_err;
+std::mutex g_mu;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(FFTCONV_CUDA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+// /root/reference/include/fftconv/fftconv.hpp:38-66
+constexpr size_t kOaTable[9][2] = {{7, 16},    {12, 32},    {21, 64},    {36, 128},  {65, 256},
+                                   {120, 512}, {221, 1024}, {411, 2048}, {769, 4096}};
+constexpr size_t kMaxOaFft = 8192;
+
+size_t optimal_fft_size(size_t klen) {
+  for (const auto &row : kOaTable)
+    if (klen < row[0]) return row[1];
+  size_t size = kMaxOaFft;
+  while (size < klen * 2) size *= 2;
+  return size;
+}
+
+int ilog2(size_t n) {
+  int l = 0;
+  while ((size_t(1) << l) < n) ++l;
+  return l;
+}
+
+struct Tables {           // per (FFT length, dtype)
+  void *W = nullptr;      // cx<T>[N]   exp(-2 pi i k / N)
+  double2 *Wd = nullptr;  // double2[N] same, double (spectrum kernel)
+  void *G = nullptr;      // cx<T>[N]   Hilbert multiplier, DIF order (lazy)
+};
+
+struct StreamWs {         // per stream
+  void *taps = nullptr;
+  size_t taps_bytes = 0;
+  void *H = nullptr;
+  size_t h_bytes = 0;
+};
+
+constexpr int kPipe = 3;
+
+struct DeviceCtx {
+  int device = -1;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  std::map<std::pair<size_t, int>, Tables> tables;
+  fc::n2048::cpair *tw1 = nullptr, *tw2 = nullptr;
+  std::map<cudaStream_t, StreamWs> ws;
+  cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
+  void *stage_in[kPipe] = {nullptr, nullptr, nullptr};
+  void *stage_out[kPipe] = {nullptr, nullptr, nullptr};
+  size_t cap_in[kPipe] = {0, 0, 0}, cap_out[kPipe] = {0, 0, 0};
+  std::map<const void *, size_t> smem_set; // kernel -> opted-in dynamic smem
+};
+
+std::map<int, DeviceCtx> g_ctx;
+
+int get_ctx(DeviceCtx **out) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  auto it = g_ctx.find(dev);
+  if (it == g_ctx.end()) {
+    DeviceCtx c;
+    c.device = dev;
+    int v = 0;
+    CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    c.sm_count = v;
+    CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    c.smem_optin = (size_t)v;
+    it = g_ctx.emplace(dev, c).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+void free_ctx(DeviceCtx &c) {
+  for (auto &kv : c.tables) {
+    cudaFree(kv.second.W);
+    cudaFree(kv.second.Wd);
+    cudaFree(kv.second.G);
+  }
+  c.tables.clear();
+  cudaFree(c.tw1);
+  cudaFree(c.tw2);
+  c.tw1 = c.tw2 = nullptr;
+  for (auto &kv : c.ws) {
+    cudaFree(kv.second.taps);
+    cudaFree(kv.second.H);
+  }
+  c.ws.clear();
+  for (int i = 0; i < kPipe; ++i) {
+    if (c.pipe[i]) cudaStreamDestroy(c.pipe[i]);
+    cudaFree(c.stage_in[i]);
+    cudaFree(c.stage_out[i]);
+    c.pipe[i] = nullptr;
+    c.stage_in[i] = c.stage_out[i] = nullptr;
+    c.cap_in[i] = c.cap_out[i] = 0;
+  }
+}
+
+template <typename T> constexpr int dtype_id() { return std::is_same<T, float>::value ? 0 : 1; }
+
+template <typename T> int get_tables(DeviceCtx &c, size_t N, Tables **out) {
+  auto key = std::make_pair(N, dtype_id<T>());
+  auto it = c.tables.find(key);
+  if (it == c.tables.end()) {
+    std::vector<cx<T>> w(N);
+    std::vector<double2> wd(N);
+    for (size_t k = 0; k < N; ++k) {
+      const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)N;
+      const long double cr = cosl(a), si = -sinl(a);
+      w[k].x = (T)cr;
+      w[k].y = (T)si;
+      wd[k].x = (double)cr;
+      wd[k].y = (double)si;
+    }
+    Tables t;
+    CU_TRY(cudaMalloc(&t.W, N * sizeof(cx<T>)));
+    CU_TRY(cudaMalloc((void **)&t.Wd, N * sizeof(double2)));
+    CU_TRY(cudaMemcpy(t.W, w.data(), N * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(t.Wd, wd.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
+    it = c.tables.emplace(key, t).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+template <typename T> int get_hilbert_table(DeviceCtx &c, size_t N, Tables &t) {
+  if (t.G) return 0;
+  // full-spectrum multiplier of the Hilbert transformer, 1/n folded in
+  // (/root/reference/include/fftconv/hilbert.hpp:39-51, :57)
+  std::vector<cx<T>> g(N);
+  for (size_t pos = 0; pos < N; ++pos) {
+    const size_t k = fc::generic::dif_freq_of_pos((unsigned)pos, (unsigned)N);
+    T im = 0;
+    if (k != 0 && 2 * k != N) im = (T)((2 * k < N ? -1.0 : 1.0) / (double)N);
+    g[pos].x = 0;
+    g[pos].y = im;
+  }
+  CU_TRY(cudaMalloc(&t.G, N * sizeof(cx<T>)));
+  CU_TRY(cudaMemcpy(t.G, g.data(), N * sizeof(cx<T>), cudaMemcpyHostToDevice));
+  (void)c;
+  return 0;
+}
+
+int get_n2048_tables(DeviceCtx &c) {
+  if (c.tw1) return 0;
+  std::vector<fc::n2048::cpair> t1(2048), t2(128);
+  fc::n2048::fill_tw1(t1.data());
+  fc::n2048::fill_tw2(t2.data());
+  CU_TRY(cudaMalloc((void **)&c.tw1, t1.size() * sizeof(fc::n2048::cpair)));
+  CU_TRY(cudaMalloc((void **)&c.tw2, t2.size() * sizeof(fc::n2048::cpair)));
+  CU_TRY(cudaMemcpy(c.tw1, t1.data(), t1.size() * sizeof(fc::n2048::cpair), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(c.tw2, t2.data(), t2.size() * sizeof(fc::n2048::cpair), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int grow(void **p, size_t *cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*p) CU_TRY(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  CU_TRY(cudaMalloc(p, bytes));
+  *cap = bytes;
+  return 0;
+}
+
+template <typename K> int ensure_smem(DeviceCtx &c, K kernel, size_t bytes) {
+  const void *key = (const void *)kernel;
+  auto it = c.smem_set.find(key);
+  if (it != c.smem_set.end() && it->second >= bytes) return 0;
+  if (bytes > c.smem_optin)
+    return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "needs " + std::to_string(bytes) +
+                                                 " B of shared memory per CTA, device allows " +
+                                                 std::to_string(c.smem_optin));
+  CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  c.smem_set[key] = bytes;
+  return 0;
+}
+
+bool is_device_ptr(const void *p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int env_int(const char *name, int dflt) {
+  const char *v = std::getenv(name);
+  return v && *v ? std::atoi(v) : dflt;
+}
+
+// taps -> device (per-stream buffer) -> spectrum H in the layout the kernel wants
+template <typename T>
+int prepare_spectrum(DeviceCtx &c, cudaStream_t st, const T *k, size_t klen, size_t N, int layout,
+                     Tables &tab, const cx<T> **H_out) {
+  StreamWs &ws = c.ws[st];
+  const T *taps_dev = k;
+  if (!is_device_ptr(k)) {
+    if (int r = grow(&ws.taps, &ws.taps_bytes, klen * sizeof(T))) return r;
+    CU_TRY(cudaMemcpyAsync(ws.taps, k, klen * sizeof(T), cudaMemcpyHostToDevice, st));
+    taps_dev = static_cast<const T *>(ws.taps);
+  }
+  if (int r = grow(&ws.H, &ws.h_bytes, N * sizeof(cx<T>))) return r;
+  const int threads = 128;
+  fc::generic::spectrum_kernel<T><<<(unsigned)((N + threads - 1) / threads), threads, 0, st>>>(
+      taps_dev, (int)klen, (int)N, tab.Wd, layout, 1.0 / (double)N, static_cast<cx<T> *>(ws.H));
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  *H_out = static_cast<const cx<T> *>(ws.H);
+  return 0;
+}
+
+// ---- overlap-add on device pointers -------------------------------------------------
+template <typename T>
+int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride,
+              const T *k, size_t klen, T *out, size_t out_len, size_t out_stride, int mode,
+              size_t N) {
+  Tables *tab = nullptr;
+  if (int r = get_tables<T>(c, N, &tab)) return r;
+  const size_t step = N - (klen - 1);
+  const long long segs = (long long)((n + step - 1) / step);
+
+  const bool use_n2048 = std::is_same<T, float>::value && N == 2048 &&
+                         !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0);
+  if (use_n2048) {
+    if constexpr (std::is_same<T, float>::value) {
+      if (int r = get_n2048_tables(c)) return r;
+      const cx<float> *H = nullptr;
+      if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_N2048, *tab, &H))
+        return r;
+      int G = env_int("FFTCONV_CUDA_N2048_GROUPS", 4);
+      if (G != 2 && G != 3 && G != 4) G = 4;
+      const long long slots = (long long)c.sm_count * G;
+      // streams per row: enough quads to fill every group, but never so many that
+      // the per-chunk warm-up segment costs more than ~6 %
+      long long chunks = 1;
+      if ((long long)batch < 4 * slots) {
+        chunks = (4 * slots + (long long)batch - 1) / (long long)batch;
+        const long long max_chunks = std::max<long long>(1, segs / 16);
+        chunks = std::min(chunks, max_chunks);
+      }
+      fc::n2048::OaParams p{};
+      fc::n2048::fill_params(p, a, out, (long long)batch, (long long)n, (long long)a_stride,
+                             (long long)out_stride, (long long)out_len, (int)klen, mode, chunks);
+      p.tw1 = c.tw1;
+      p.tw2 = c.tw2;
+      p.hs = reinterpret_cast<const fc::n2048::cpair *>(H);
+      const size_t smem = fc::n2048::smem_bytes(G, (int)klen);
+      const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
+      if (G == 4) {
+        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<4>, smem)) return r;
+        fc::n2048::oa_n2048_kernel<4><<<(unsigned)grid, 128 * 4, smem, st>>>(p);
+      } else if (G == 3) {
+        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<3>, smem)) return r;
+        fc::n2048::oa_n2048_kernel<3><<<(unsigned)grid, 128 * 3, smem, st>>>(p);
+      } else {
+        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<2>, smem)) return r;
+        fc::n2048::oa_n2048_kernel<2><<<(unsigned)grid, 128 * 2, smem, st>>>(p);
+      }
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+      return 0;
+    }
+  }
+
+  const cx<T> *H = nullptr;
+  if (int r = prepare_spectrum<T>(c, st, k, klen, N, fc::generic::LAYOUT_DIF, *tab, &H)) return r;
+  fc::generic::OaArgs<T> p{};
+  p.in = a;
+  p.out = out;
+  p.batch = (long long)batch;
+  p.n = (long long)n;
+  p.in_stride = (long long)a_stride;
+  p.out_stride = (long long)out_stride;
+  p.out_len = (long long)out_len;
+  p.klen = (int)klen;
+  p.log2n = ilog2(N);
+  p.step = (int)step;
+  p.pad = mode == FFTCONV_CUDA_SAME ? (int)(klen / 2) : 0;
+  p.segs = segs;
+  const long long target_streams = 8LL * c.sm_count;
+  long long chunks = 1;
+  if ((long long)batch < target_streams) {
+    chunks = (target_streams + (long long)batch - 1) / (long long)batch;
+    chunks = std::min(chunks, std::max<long long>(1, segs / 8));
+  }
+  p.segs_per_chunk = (segs + chunks - 1) / chunks;
+  p.chunks = (segs + p.segs_per_chunk - 1) / p.segs_per_chunk;
+  p.n_streams = (long long)batch * p.chunks;
+  p.W = static_cast<const cx<T> *>(tab->W);
+  p.H = H;
+  const size_t smem = (N + 2 * (klen - 1)) * sizeof(cx<T>);
+  if (int r = ensure_smem(c, fc::generic::oa_generic_kernel<T>, smem)) return r;
+  const long long grid = (p.n_streams + 1) / 2;
+  if (grid > 0x7fffffffLL) return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "batch too large for one launch");
+  const int threads = (int)std::min<size_t>(512, std::max<size_t>(32, N / 4));
+  fc::generic::oa_generic_kernel<T><<<(unsigned)grid, threads, smem, st>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+template <typename T> size_t max_generic_fft(const DeviceCtx &c, size_t klen) {
+  size_t N = 1;
+  while ((2 * N + 2 * (klen - 1)) * sizeof(cx<T>) <= c.smem_optin) N *= 2;
+  return N;
+}
+
+enum Op { OP_OA, OP_CONV, OP_HILBERT };
+
+template <typename T>
+int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, size_t n,
+                size_t a_stride, const T *k, size_t klen, T *out, size_t out_len,
+                size_t out_stride, int mode) {
+  size_t N;
+  if (op == OP_OA) {
+    N = optimal_fft_size(klen);
+  } else {
+    // single FFT of length >= n + K - 1 (any such length gives the same linear
+    // convolution as the reference's exact-length transform, fftconv.hpp:458)
+    N = 16;
+    while (N < n + klen - 1) N *= 2;
+    if (N > max_generic_fft<T>(c, klen)) {
+      // TODO(round 2): multi-kernel FFT for rows longer than one CTA's shared
+      // memory.  Until then long rows are convolved segment-wise; the result is
+      // the same linear convolution.
+      N = optimal_fft_size(klen);
+    }
+  }
+  if (N > max_generic_fft<T>(c, klen))
+    return fail(FFTCONV_CUDA_ERR_UNSUPPORTED,
+                "kernel of " + std::to_string(klen) + " taps needs FFT size " + std::to_string(N) +
+                    ", beyond the single-CTA shared-memory FFT");
+  return oa_device<T>(c, st, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode, N);
+}
+
+template <typename T>
+int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size_t n,
+                   size_t x_stride, T *env, size_t env_stride) {
+  if ((n & (n - 1)) != 0)
+    return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
+                                                 " is not a power of two (Bluestein path pending)");
+  const size_t smem = n * sizeof(cx<T>);
+  if (smem > c.smem_optin)
+    return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
+                                                 " exceeds the single-CTA shared-memory FFT");
+  Tables *tab = nullptr;
+  if (int r = get_tables<T>(c, n, &tab)) return r;
+  if (int r = get_hilbert_table<T>(c, n, *tab)) return r;
+  fc::generic::HilbertArgs<T> p{};
+  p.in = x;
+  p.out = env;
+  p.batch = (long long)batch;
+  p.n = (long long)n;
+  p.in_stride = (long long)x_stride;
+  p.out_stride = (long long)env_stride;
+  p.log2n = ilog2(n);
+  p.W = static_cast<const cx<T> *>(tab->W);
+  p.G = static_cast<const cx<T> *>(tab->G);
+  if (int r = ensure_smem(c, fc::generic::hilbert_pow2_kernel<T>, std::max<size_t>(smem, 16))) return r;
+  const long long grid = ((long long)batch + 1) / 2;
+  const int threads = (int)std::min<size_t>(512, std::max<size_t>(32, n / 4));
+  fc::generic::hilbert_pow2_kernel<T><<<(unsigned)grid, threads, std::max<size_t>(smem, 16), st>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+// ---- host-pointer path: pipelined row blocks over three streams ------------------------
+template <typename T>
+int run_host(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k,
+             size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
+  for (int i = 0; i < kPipe; ++i)
+    if (!c.pipe[i]) CU_TRY(cudaStreamCreateWithFlags(&c.pipe[i], cudaStreamNonBlocking));
+  const size_t row_bytes = std::max(n, out_len) * sizeof(T);
+  const size_t target = (size_t)env_int("FFTCONV_CUDA_HOST_BLOCK_MB", 32) << 20;
+  size_t rows_per_block = std::max<size_t>(1, target / std::max<size_t>(1, row_bytes));
+  rows_per_block = std::min(rows_per_block, batch);
+  const size_t nblocks = (batch + rows_per_block - 1) / rows_per_block;
+  for (size_t b = 0; b < nblocks; ++b) {
+    const int s = (int)(b % kPipe);
+    const size_t r0 = b * rows_per_block, rows = std::min(rows_per_block, batch - r0);
+    if (int r = grow(&c.stage_in[s], &c.cap_in[s], rows_per_block * n * sizeof(T))) return r;
+    if (int r = grow(&c.stage_out[s], &c.cap_out[s], rows_per_block * out_len * sizeof(T))) return r;
+    T *din = static_cast<T *>(c.stage_in[s]);
+    T *dout = static_cast<T *>(c.stage_out[s]);
+    CU_TRY(cudaMemcpy2DAsync(din, n * sizeof(T), a + r0 * a_stride, a_stride * sizeof(T),
+                             n * sizeof(T), rows, cudaMemcpyHostToDevice, c.pipe[s]));
+    int r;
+    if (op == OP_HILBERT) r = hilbert_device<T>(c, c.pipe[s], din, rows, n, n, dout, out_len);
+    else r = conv_device<T>(c, c.pipe[s], op, din, rows, n, n, k, klen, dout, out_len, out_len, mode);
+    if (r) return r;
+    CU_TRY(cudaMemcpy2DAsync(out + r0 * out_stride, out_stride * sizeof(T), dout,
+                             out_len * sizeof(T), out_len * sizeof(T), rows,
+                             cudaMemcpyDeviceToHost, c.pipe[s]));
+  }
+  for (int i = 0; i < kPipe; ++i) CU_TRY(cudaStreamSynchronize(c.pipe[i]));
+  return 0;
+}
+
+template <typename T>
+int entry(Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k, size_t klen,
+          T *out, size_t out_len, size_t out_stride, int mode, void *stream) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (!a || !out) return fail(FFTCONV_CUDA_ERR_ARG, "null data pointer");
+  if (batch == 0) return 0;
+  if (n == 0) return fail(FFTCONV_CUDA_ERR_ARG, "empty signal");
+  if (a_stride < n || out_stride < out_len) return fail(FFTCONV_CUDA_ERR_ARG, "row stride shorter than row");
+  if (op != OP_HILBERT) {
+    if (!k || klen == 0) return fail(FFTCONV_CUDA_ERR_ARG, "empty kernel");
+    if (mode != FFTCONV_CUDA_FULL && mode != FFTCONV_CUDA_SAME)
+      return fail(FFTCONV_CUDA_ERR_ARG, "Unsupported convolution mode: " + std::to_string(mode));
+    const size_t want = mode == FFTCONV_CUDA_FULL ? n + klen - 1 : n;
+    if (out_len != want)
+      return fail(FFTCONV_CUDA_ERR_ARG, "output length " + std::to_string(out_len) + ", expected " +
+                                            std::to_string(want));
+  } else if (out_len != n) {
+    return fail(FFTCONV_CUDA_ERR_ARG, "hilbert: output length must equal input length");
+  }
+  DeviceCtx *c = nullptr;
+  if (int r = get_ctx(&c)) return r;
+  const bool dev_in = is_device_ptr(a), dev_out = is_device_ptr(out);
+  if (dev_in != dev_out)
+    return fail(FFTCONV_CUDA_ERR_ARG, "input and output must both be host or both be device pointers");
+  if (dev_in) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (op == OP_HILBERT) return hilbert_device<T>(*c, st, a, batch, n, a_stride, out, out_stride);
+    return conv_device<T>(*c, st, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+  }
+  return run_host<T>(*c, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+}
+
+template <typename T> int add_entry(T *dst, const T *src, size_t n, void *stream) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (n == 0) return 0;
+  if (!dst || !src) return fail(FFTCONV_CUDA_ERR_ARG, "null pointer");
+  const int threads = 256;
+  fc::generic::add_inplace_kernel<T><<<(unsigned)((n + threads - 1) / threads), threads, 0,
+                                       static_cast<cudaStream_t>(stream)>>>(dst, src, (long long)n);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *fftconv_cuda_version(void) { return FFTCONV_CUDA_VERSION; }
+const char *fftconv_cuda_last_error(void) { return g_err.c_str(); }
+size_t fftconv_cuda_optimal_fft_size(size_t klen) { return optimal_fft_size(klen); }
+unsigned long long fftconv_cuda_launch_count(void) { return g_launches.load(); }
+
+int fftconv_cuda_clear_cache(void) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) {
+    cudaGetLastError();
+    g_ctx.clear();
+    return 0;
+  }
+  for (auto &kv : g_ctx) {
+    cudaSetDevice(kv.first);
+    cudaDeviceSynchronize();
+    free_ctx(kv.second);
+  }
+  g_ctx.clear();
+  cudaSetDevice(cur);
+  return 0;
+}
+
+#define FFTCONV_API(SFX, T)                                                                      \
+  int fftconv_cuda_oaconvolve_##SFX(const T *a, size_t n, const T *k, size_t klen, T *out,       \
+                                    size_t out_len, int mode) {                                  \
+    return entry<T>(OP_OA, a, 1, n, n, k, klen, out, out_len, out_len, mode, nullptr);           \
+  }                                                                                              \
+  int fftconv_cuda_oaconvolve_batched_##SFX(const T *a, size_t batch, size_t n, size_t a_stride, \
+                                            const T *k, size_t klen, T *out, size_t out_len,     \
+                                            size_t out_stride, int mode, void *stream) {         \
+    return entry<T>(OP_OA, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode, stream); \
+  }                                                                                              \
+  int fftconv_cuda_convolve_##SFX(const T *a, size_t n, const T *k, size_t klen, T *out,         \
+                                  size_t out_len, int mode) {                                    \
+    return entry<T>(OP_CONV, a, 1, n, n, k, klen, out, out_len, out_len, mode, nullptr);         \
+  }                                                                                              \
+  int fftconv_cuda_convolve_batched_##SFX(const T *a, size_t batch, size_t n, size_t a_stride,   \
+                                          const T *k, size_t klen, T *out, size_t out_len,       \
+                                          size_t out_stride, int mode, void *stream) {           \
+    return entry<T>(OP_CONV, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode, stream); \
+  }                                                                                              \
+  int fftconv_cuda_hilbert_##SFX(const T *x, T *env, size_t n) {                                 \
+    return entry<T>(OP_HILBERT, x, 1, n, n, nullptr, 0, env, n, n, 0, nullptr);                  \
+  }                                                                                              \
+  int fftconv_cuda_hilbert_batched_##SFX(const T *x, size_t batch, size_t n, size_t x_stride,    \
+                                         T *env, size_t env_stride, void *stream) {              \
+    return entry<T>(OP_HILBERT, x, batch, n, x_stride, nullptr, 0, env, n, env_stride, 0, stream); \
+  }                                                                                              \
+  int fftconv_cuda_add_##SFX(T *dst, const T *src, size_t n, void *stream) {                     \
+    return add_entry<T>(dst, src, n, stream);                                                    \
+  }
+
+FFTCONV_API(f32, float)
+FFTCONV_API(f64, double)
+
+} // extern "C"

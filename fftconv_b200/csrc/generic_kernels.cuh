@@ -1,0 +1,199 @@
+// generic_kernels.cuh -- fallback CUDA kernels (any power-of-two FFT size, float
+// or double) for the three reference entry points:
+//   oaconvolve_fftw  /root/reference/include/fftconv/fftconv.hpp:474-480, :382-437
+//   convolve_fftw    /root/reference/include/fftconv/fftconv.hpp:453-461, :338-380
+//   hilbert          /root/reference/include/fftconv/hilbert.hpp:16-66
+// The f32 / N = 2048 overlap-add case has its own kernel (oa_n2048_kernel.cuh).
+#pragma once
+
+#include "generic_fft.cuh"
+
+namespace fc {
+namespace generic {
+
+// ---------------------------------------------------------------------------
+// Spectrum of the taps, evaluated directly in double:
+//   H[pos] = scale * sum_j taps[j] exp(-2 pi i j k(pos) / N)
+// k(pos) follows the layout of the consuming kernel.  wd[e] = exp(-2 pi i e / N)
+// in double.  O(N K) work -- K <= a few thousand taps by construction.
+// ---------------------------------------------------------------------------
+enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1 };
+
+__device__ __forceinline__ unsigned n2048_freq_of_index(unsigned idx) {
+  // idx = slot * 128 + c0 (see fc::n2048::p2_freq)
+  const unsigned s = idx >> 7, c0 = idx & 127;
+  const unsigned h = s >> 3, k1b = s & 7, c = c0 + 128 * h;
+  return 16 * (c & 15) + 256 * k1b + (c >> 4);
+}
+
+template <typename T>
+__global__ void spectrum_kernel(const T *__restrict__ taps, int klen, int N,
+                                const double2 *__restrict__ wd, int layout, double scale,
+                                cx<T> *__restrict__ H) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= N) return;
+  const unsigned k = layout == LAYOUT_N2048 ? n2048_freq_of_index(pos) : dif_freq_of_pos(pos, N);
+  double re = 0.0, im = 0.0;
+  unsigned e = 0; // (j * k) mod N
+  for (int j = 0; j < klen; ++j) {
+    const double2 w = wd[e];
+    const double v = (double)taps[j];
+    re += v * w.x;
+    im += v * w.y;
+    e = (e + k) & (unsigned)(N - 1);
+  }
+  H[pos].x = (T)(re * scale);
+  H[pos].y = (T)(im * scale);
+}
+
+// ---------------------------------------------------------------------------
+// Overlap-add (and, with one segment covering the whole row, single-FFT
+// convolution).  CTA b walks streams 2b (real part) and 2b+1 (imaginary part).
+// ---------------------------------------------------------------------------
+template <typename T> struct OaArgs {
+  const T *in;
+  T *out;
+  long long batch, n, in_stride, out_stride, out_len;
+  int klen, log2n, step, pad;
+  long long segs, chunks, segs_per_chunk, n_streams;
+  const cx<T> *W; // N twiddles
+  const cx<T> *H; // N spectrum values, DIF order, 1/N folded in
+};
+
+template <typename T> __global__ void oa_generic_kernel(const OaArgs<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = 1 << p.log2n;
+  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
+  cx<T> *tails = buf + N; // 2 x (klen - 1)
+  const int tail_len = p.klen - 1;
+
+  const T *src[2];
+  T *dst[2];
+  long long seg0[2], cnt[2];
+  bool active[2];
+  long long max_cnt = 0;
+  bool warm_needed = false;
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    const long long sid = (long long)blockIdx.x * 2 + l;
+    active[l] = sid < p.n_streams;
+    const long long row = active[l] ? sid / p.chunks : 0;
+    const long long chunk = active[l] ? sid - row * p.chunks : 0;
+    seg0[l] = chunk * p.segs_per_chunk;
+    const long long rem = p.segs - seg0[l];
+    cnt[l] = active[l] ? (rem < p.segs_per_chunk ? rem : p.segs_per_chunk) : 0;
+    src[l] = p.in + row * p.in_stride;
+    dst[l] = p.out + row * p.out_stride;
+    if (cnt[l] > max_cnt) max_cnt = cnt[l];
+    warm_needed = warm_needed || (active[l] && seg0[l] > 0);
+  }
+
+  int parity = 0;
+  bool add_tail = false;
+  for (long long j = warm_needed ? -1 : 0; j < max_cnt; ++j) {
+    const bool warm = j < 0;
+    long long pos[2];
+    int len[2];
+    bool on[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      const long long seg = seg0[l] + j;
+      on[l] = active[l] && seg >= 0 && j < cnt[l];
+      pos[l] = seg * p.step;
+      long long ll = on[l] ? p.n - pos[l] : 0;
+      if (ll > p.step) ll = p.step;
+      len[l] = (int)ll;
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      cx<T> v;
+      v.x = i < len[0] ? src[0][pos[0] + i] : (T)0;
+      v.y = i < len[1] ? src[1][pos[1] + i] : (T)0;
+      buf[i] = v;
+    }
+    __syncthreads();
+    fft_dif(buf, p.W, p.log2n);
+    spectrum_mul(buf, p.H, N);
+    fft_dit_inv(buf, p.W, p.log2n);
+
+    cx<T> *tail_prev = tails + (parity ^ 1) * tail_len;
+    cx<T> *tail_next = tails + parity * tail_len;
+    int limit[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      long long lim = p.step;
+      if (seg0[l] + j == p.segs - 1) {
+        lim = p.out_len + p.pad - pos[l];
+        if (lim > N) lim = N;
+      }
+      limit[l] = (on[l] && !warm) ? (int)lim : 0;
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      cx<T> y = buf[i];
+      if (add_tail && i < tail_len) {
+        y.x += tail_prev[i].x;
+        y.y += tail_prev[i].y;
+      }
+      if (i >= p.step) tail_next[i - p.step] = y;
+      const long long o0 = pos[0] - p.pad + i, o1 = pos[1] - p.pad + i;
+      if (i < limit[0] && o0 >= 0) dst[0][o0] = y.x;
+      if (i < limit[1] && o1 >= 0) dst[1][o1] = y.y;
+    }
+    __syncthreads();
+    parity ^= 1;
+    add_tail = true;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Hilbert envelope, power-of-two length n = N: rows 2b and 2b+1 in one complex
+// FFT; G (DIF order) holds the Hilbert multiplier -j sgn(f) / n with DC and
+// Nyquist zeroed (hilbert.hpp:39-51), so buf becomes h0 + i h1; env = sqrt(x^2 + h^2).
+// ---------------------------------------------------------------------------
+template <typename T> struct HilbertArgs {
+  const T *in;
+  T *out;
+  long long batch, n, in_stride, out_stride;
+  int log2n;
+  const cx<T> *W;
+  const cx<T> *G;
+};
+
+template <typename T> __global__ void hilbert_pow2_kernel(const HilbertArgs<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = 1 << p.log2n;
+  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
+  const long long r0 = (long long)blockIdx.x * 2, r1 = r0 + 1;
+  const bool has1 = r1 < p.batch;
+  const T *x0 = p.in + r0 * p.in_stride;
+  const T *x1 = p.in + (has1 ? r1 : r0) * p.in_stride;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    cx<T> v;
+    v.x = x0[i];
+    v.y = has1 ? x1[i] : (T)0;
+    buf[i] = v;
+  }
+  __syncthreads();
+  fft_dif(buf, p.W, p.log2n);
+  spectrum_mul(buf, p.G, N);
+  fft_dit_inv(buf, p.W, p.log2n);
+  T *e0 = p.out + r0 * p.out_stride;
+  T *e1 = p.out + (has1 ? r1 : r0) * p.out_stride;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const cx<T> h = buf[i];
+    const T a = x0[i];
+    e0[i] = sqrt(a * a + h.x * h.x);
+    if (has1) {
+      const T b = x1[i];
+      e1[i] = sqrt(b * b + h.y * h.y);
+    }
+  }
+}
+
+// dst[i] += src[i]  (tail hand-over between neighbouring chunks of a long signal)
+template <typename T> __global__ void add_inplace_kernel(T *dst, const T *src, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+} // namespace generic
+} // namespace fc

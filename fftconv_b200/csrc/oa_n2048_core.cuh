@@ -1,0 +1,246 @@
+// oa_n2048_core.cuh -- the fused overlap-add segment engine for FFT size 2048
+// (the reference's segment size for 221 <= K < 411 taps, e.g. K = 245:
+// /root/reference/include/fftconv/fftconv.hpp:38-66), float32.
+//
+// One "group" of 128 threads transforms FOUR real segments at once:
+//   * two segments ride in the real and imaginary parts of one complex FFT --
+//     the taps are real, so IFFT(FFT(a + i b) * H) = (a conv h) + i (b conv h)
+//     and no r2c/c2r untangling pass exists at all;
+//   * two such complex FFTs ride in the two halves of every packed f32x2
+//     register (packed_f32x2.cuh), so each butterfly is ONE instruction.
+// This replaces, per segment, the reference's copy_to_padded_buffer + r2c +
+// multiply_cx + c2r + normalize_add (fftconv.hpp:400-410 / :417-432).
+//
+// 2048 = 16 x 16 x 8, 16 points per thread, decimation in frequency:
+//   n = t + 128 m            (thread t loads x[t + 128 m], m = 0..15, coalesced)
+//   t = 8 t1 + t0
+//   k = 16 k1a + 256 k1b + k2
+//   W_N^{nk} = W_16^{m k2} W_2048^{t k2}  W_16^{t1 k1a} W_128^{t0 k1a}  W_8^{t0 k1b}
+//   P0 (thread t):        radix-16 over m  -> k2,  twiddle W_2048^{t k2}
+//   P1 (thread t0 + 8k2): radix-16 over t1 -> k1a, twiddle W_128^{t0 k1a}
+//   P2 (thread c, c+128; c = 16 k2 + k1a): radix-8 over t0 -> k1b, times H[k],
+//                         inverse radix-8 back to t0
+//   P3 / P4 mirror P1 / P0 with conjugated twiddles; 1/N is folded into H.
+// The three exchanges go through ONE 32 KB shared buffer of 16-byte points
+// (reA, reB, imA, imB).  Its layouts are chosen so that every phase writes
+// exactly the addresses it has just read, so only four barriers per segment
+// quad are needed, and every 128-bit access is bank-conflict free:
+//   X1: point (t, k2)        at k2*128 + 8 t1 + ((t0 + t1) & 7)
+//   X2: point (c, t0)        at c*8 + ((t0 + c) & 7)
+//
+// Everything here is __host__ __device__ so tests can emulate the 128 threads
+// phase by phase on the CPU (tests/cpu/emulate_oa_n2048.cpp).
+#pragma once
+
+#include "packed_f32x2.cuh"
+
+namespace fc {
+namespace n2048 {
+
+constexpr int kN = 2048;
+constexpr int kThreads = 128; // per group
+constexpr int kPts = 16;      // points per thread
+
+struct pt4 {                  // one complex point of both packed FFTs (16 B)
+  float reA, reB, imA, imB;
+};
+
+struct Regs {
+  f2 re[kPts];
+  f2 im[kPts];
+};
+
+constexpr float kC8 = 0.70710678118654752440f;  // cos(pi/4)
+constexpr float kC16 = 0.92387953251128675613f; // cos(pi/8)
+constexpr float kS16 = 0.38268343236508977173f; // sin(pi/8)
+
+// 4-point DFT, sign S (-1 forward, +1 inverse), in place on 4 named slots.
+template <int S>
+FC_HD void bfly4(f2 &r0, f2 &i0, f2 &r1, f2 &i1, f2 &r2, f2 &i2, f2 &r3, f2 &i3) {
+  const f2 s0r = add2(r0, r2), s0i = add2(i0, i2);
+  const f2 d0r = sub2(r0, r2), d0i = sub2(i0, i2);
+  const f2 s1r = add2(r1, r3), s1i = add2(i1, i3);
+  const f2 d1r = sub2(r1, r3), d1i = sub2(i1, i3);
+  r0 = add2(s0r, s1r); i0 = add2(s0i, s1i);
+  r2 = sub2(s0r, s1r); i2 = sub2(s0i, s1i);
+  if (S < 0) { // X1 = d0 - j d1, X3 = d0 + j d1
+    r1 = add2(d0r, d1i); i1 = sub2(d0i, d1r);
+    r3 = sub2(d0r, d1i); i3 = add2(d0i, d1r);
+  } else {     // X1 = d0 + j d1, X3 = d0 - j d1
+    r1 = sub2(d0r, d1i); i1 = add2(d0i, d1r);
+    r3 = add2(d0r, d1i); i3 = sub2(d0i, d1r);
+  }
+}
+
+// multiply by -j (S<0) or +j (S>0)
+template <int S> FC_HD void rot90(f2 &r, f2 &i) {
+  const f2 t = r;
+  if (S < 0) { r = i; i = muls2(t, -1.0f); }
+  else       { r = muls2(i, -1.0f); i = t; }
+}
+
+// 16-point DFT of v.re/im[0..15], natural order in, natural order out.
+//   m = m0 + 4 m1, k = k1 + 4 k0:
+//   X[k1 + 4 k0] = sum_m0 W4^{m0 k0} W16^{m0 k1} sum_m1 x[m0 + 4 m1] W4^{m1 k1}
+template <int S> FC_HD void dft16(Regs &v) {
+  // step A: 4-point DFTs over m1 for each m0; result A[m0][k1] stays in slot m0 + 4 k1
+#pragma unroll
+  for (int m0 = 0; m0 < 4; ++m0)
+    bfly4<S>(v.re[m0], v.im[m0], v.re[m0 + 4], v.im[m0 + 4], v.re[m0 + 8], v.im[m0 + 8],
+             v.re[m0 + 12], v.im[m0 + 12]);
+  // step B: twiddles W16^{m0 k1} on slot m0 + 4 k1   (imag sign follows S)
+  const float s = (S < 0) ? -1.0f : 1.0f;
+  cmul2(v.re[1 + 4], v.im[1 + 4], kC16, s * kS16);    // e = 1
+  cmul2(v.re[2 + 4], v.im[2 + 4], kC8, s * kC8);      // e = 2
+  cmul2(v.re[3 + 4], v.im[3 + 4], kS16, s * kC16);    // e = 3
+  cmul2(v.re[1 + 8], v.im[1 + 8], kC8, s * kC8);      // e = 2
+  rot90<S>(v.re[2 + 8], v.im[2 + 8]);                 // e = 4
+  cmul2(v.re[3 + 8], v.im[3 + 8], -kC8, s * kC8);     // e = 6
+  cmul2(v.re[1 + 12], v.im[1 + 12], kS16, s * kC16);  // e = 3
+  cmul2(v.re[2 + 12], v.im[2 + 12], -kC8, s * kC8);   // e = 6
+  cmul2(v.re[3 + 12], v.im[3 + 12], -kC16, -s * kS16); // e = 9
+  // step C: 4-point DFTs over m0 for each k1; X[k1 + 4 k0] lands in slot 4 k1 + k0
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+    bfly4<S>(v.re[4 * k1], v.im[4 * k1], v.re[4 * k1 + 1], v.im[4 * k1 + 1], v.re[4 * k1 + 2],
+             v.im[4 * k1 + 2], v.re[4 * k1 + 3], v.im[4 * k1 + 3]);
+}
+// slot that holds output k of dft16 (k = k1 + 4 k0 sits in slot 4 k1 + k0)
+FC_HD constexpr int slot16(int k) { return 4 * (k & 3) + (k >> 2); }
+
+// 8-point DFT on slots base..base+7, natural in, output k in slot base + slot8(k).
+//   m = m0 + 2 m1, k = k1 + 4 k0:
+//   X[k1 + 4 k0] = sum_m0 W2^{m0 k0} W8^{m0 k1} sum_m1 x[m0 + 2 m1] W4^{m1 k1}
+template <int S> FC_HD void dft8(f2 *re, f2 *im) {
+  bfly4<S>(re[0], im[0], re[2], im[2], re[4], im[4], re[6], im[6]); // m0 = 0: A[0][k1] in slot 2 k1
+  bfly4<S>(re[1], im[1], re[3], im[3], re[5], im[5], re[7], im[7]); // m0 = 1: A[1][k1] in slot 2 k1 + 1
+  const float s = (S < 0) ? -1.0f : 1.0f;
+  cmul2(re[3], im[3], kC8, s * kC8);    // W8^1
+  rot90<S>(re[5], im[5]);               // W8^2
+  cmul2(re[7], im[7], -kC8, s * kC8);   // W8^3
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {      // X[k1] -> slot 2 k1, X[k1 + 4] -> slot 2 k1 + 1
+    const f2 ar = re[2 * k1], ai = im[2 * k1], br = re[2 * k1 + 1], bi = im[2 * k1 + 1];
+    re[2 * k1] = add2(ar, br); im[2 * k1] = add2(ai, bi);
+    re[2 * k1 + 1] = sub2(ar, br); im[2 * k1 + 1] = sub2(ai, bi);
+  }
+}
+FC_HD constexpr int slot8(int k) { return 2 * (k & 3) + (k >> 2); }
+
+// shared-memory layouts ------------------------------------------------------
+FC_HD int x1_addr(int t, int k2) { // t = 8 t1 + t0
+  const int t1 = t >> 3, t0 = t & 7;
+  return k2 * 128 + 8 * t1 + ((t0 + t1) & 7);
+}
+FC_HD int x2_addr(int c, int t0) { return c * 8 + ((t0 + c) & 7); }
+
+FC_HD void put(pt4 *buf, int addr, f2 re, f2 im) {
+  pt4 p;
+  p.reA = re.x; p.reB = re.y; p.imA = im.x; p.imB = im.y;
+  buf[addr] = p;
+}
+FC_HD void get(const pt4 *buf, int addr, f2 &re, f2 &im) {
+  const pt4 p = buf[addr];
+  re = make_f2(p.reA, p.reB);
+  im = make_f2(p.imA, p.imB);
+}
+
+// Twiddle / spectrum tables (float2-like pairs), shared by all groups of a CTA:
+//   tw1[k2 * 128 + t]   = W_2048^{t k2}       k2 = 0..15
+//   tw2[k1a * 8 + t0]   = W_128^{t0 k1a}      k1a = 0..15
+//   hs[slot * 128 + c0] = H[k] / 2048, slot = 8 h + k1b, c = c0 + 128 h,
+//                         k = 16 (c & 15) + 256 k1b + (c >> 4)
+struct cpair { float re, im; };
+
+// frequency handled by thread c0 in register slot s of phase P2
+FC_HD int p2_freq(int c0, int s) {
+  const int h = s >> 3, k1b = s & 7, c = c0 + 128 * h;
+  return 16 * (c & 15) + 256 * k1b + (c >> 4);
+}
+
+// ---- phases (called between group barriers) ---------------------------------
+// P0: v holds x[t + 128 m] in slot m.
+FC_HD void phase0(int t, Regs &v, pt4 *xb, const cpair *tw1) {
+  dft16<-1>(v);
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const int s = slot16(k2);
+    if (k2 > 0) {
+      const cpair w = tw1[k2 * 128 + t];
+      cmul2(v.re[s], v.im[s], w.re, w.im);
+    }
+    put(xb, x1_addr(t, k2), v.re[s], v.im[s]);
+  }
+}
+
+FC_HD void phase1(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
+  const int t0 = tau & 7, k2 = tau >> 3;
+#pragma unroll
+  for (int t1 = 0; t1 < 16; ++t1) get(xb, x1_addr(8 * t1 + t0, k2), v.re[t1], v.im[t1]);
+  dft16<-1>(v);
+#pragma unroll
+  for (int k1a = 0; k1a < 16; ++k1a) {
+    const int s = slot16(k1a);
+    if (k1a > 0) {
+      const cpair w = tw2[k1a * 8 + t0];
+      cmul2(v.re[s], v.im[s], w.re, w.im);
+    }
+    // same address set as the reads above: k2*128 + 8 j + ((t0 + j) & 7)
+    put(xb, x2_addr(k2 * 16 + k1a, t0), v.re[s], v.im[s]);
+  }
+}
+
+FC_HD void phase2(int c0, Regs &v, pt4 *xb, const cpair *hs) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = c0 + 128 * h;
+#pragma unroll
+    for (int t0 = 0; t0 < 8; ++t0) get(xb, x2_addr(c, t0), v.re[8 * h + t0], v.im[8 * h + t0]);
+    dft8<-1>(&v.re[8 * h], &v.im[8 * h]);
+    // spectrum multiply; dft8 output k1b sits in slot slot8(k1b).  The inverse
+    // dft8 wants natural order in, so gather while multiplying.
+    f2 yr[8], yi[8];
+#pragma unroll
+    for (int k1b = 0; k1b < 8; ++k1b) {
+      const cpair w = hs[(8 * h + k1b) * 128 + c0];
+      yr[k1b] = v.re[8 * h + slot8(k1b)];
+      yi[k1b] = v.im[8 * h + slot8(k1b)];
+      cmul2(yr[k1b], yi[k1b], w.re, w.im);
+    }
+    dft8<+1>(yr, yi);
+#pragma unroll
+    for (int t0 = 0; t0 < 8; ++t0) put(xb, x2_addr(c, t0), yr[slot8(t0)], yi[slot8(t0)]);
+  }
+}
+
+FC_HD void phase3(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
+  const int t0 = tau & 7, k2 = tau >> 3;
+#pragma unroll
+  for (int k1a = 0; k1a < 16; ++k1a) {
+    get(xb, x2_addr(k2 * 16 + k1a, t0), v.re[k1a], v.im[k1a]);
+    if (k1a > 0) {
+      const cpair w = tw2[k1a * 8 + t0];
+      cmul2(v.re[k1a], v.im[k1a], w.re, -w.im);
+    }
+  }
+  dft16<+1>(v);
+#pragma unroll
+  for (int t1 = 0; t1 < 16; ++t1)
+    put(xb, x1_addr(8 * t1 + t0, k2), v.re[slot16(t1)], v.im[slot16(t1)]);
+}
+
+// P4: leaves y[t + 128 m] in slot slot16(m).
+FC_HD void phase4(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    get(xb, x1_addr(t, k2), v.re[k2], v.im[k2]);
+    if (k2 > 0) {
+      const cpair w = tw1[k2 * 128 + t];
+      cmul2(v.re[k2], v.im[k2], w.re, -w.im);
+    }
+  }
+  dft16<+1>(v);
+}
+
+} // namespace n2048
+} // namespace fc

@@ -1,0 +1,111 @@
+// packed_f32x2.cuh -- two-lane FP32 arithmetic for sm_100a.
+//
+// Blackwell has packed FP32 instructions (PTX add/sub/mul/fma .f32x2 -> SASS
+// FADD2 / FMUL2 / FFMA2) that process a 64-bit register pair per lane in one
+// issue slot, and FMUL2/FFMA2 accept a 32-bit scalar operand broadcast to both
+// halves.  The overlap-add kernels run TWO independent FFTs per thread, one in
+// each half of every register pair, so every butterfly is one packed
+// instruction for both FFTs and every twiddle is a broadcast scalar.
+//
+// The same functions compile for the host (plain float math) so that the whole
+// kernel can be emulated thread-by-thread on the CPU in tests.
+#pragma once
+
+#if defined(__CUDACC__)
+#define FC_HD __host__ __device__ __forceinline__
+#else
+#define FC_HD inline
+#endif
+
+namespace fc {
+
+struct f2 {
+  float x, y; // lane A, lane B
+};
+
+FC_HD f2 make_f2(float a, float b) {
+  f2 r;
+  r.x = a;
+  r.y = b;
+  return r;
+}
+
+#if defined(__CUDA_ARCH__)
+#define FC_PK2(a, b)                                                           \
+  "{.reg .b64 pa, pb, pc;\n\t"                                                 \
+  "mov.b64 pa, {%2, %3};\n\t"                                                  \
+  "mov.b64 pb, {%4, %5};\n\t"
+FC_HD f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm(FC_PK2(a, b) "add.rn.f32x2 pc, pa, pb;\n\t"
+                   "mov.b64 {%0, %1}, pc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+FC_HD f2 sub2(f2 a, f2 b) {
+  f2 r;
+  asm(FC_PK2(a, b) "sub.rn.f32x2 pc, pa, pb;\n\t"
+                   "mov.b64 {%0, %1}, pc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+// a * s (scalar broadcast to both lanes)
+FC_HD f2 muls2(f2 a, float s) {
+  f2 r;
+  asm("{.reg .b64 pa, pb, pc;\n\t"
+      "mov.b64 pa, {%2, %3};\n\t"
+      "mov.b64 pb, {%4, %4};\n\t"
+      "mul.rn.f32x2 pc, pa, pb;\n\t"
+      "mov.b64 {%0, %1}, pc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(s));
+  return r;
+}
+// a * s + c
+FC_HD f2 fmas2(f2 a, float s, f2 c) {
+  f2 r;
+  asm("{.reg .b64 pa, pb, pc, pd;\n\t"
+      "mov.b64 pa, {%2, %3};\n\t"
+      "mov.b64 pb, {%4, %4};\n\t"
+      "mov.b64 pc, {%5, %6};\n\t"
+      "fma.rn.f32x2 pd, pa, pb, pc;\n\t"
+      "mov.b64 {%0, %1}, pd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
+  return r;
+}
+// a * s - c
+FC_HD f2 fmss2(f2 a, float s, f2 c) {
+  f2 r;
+  asm("{.reg .b64 pa, pb, pc, pd;\n\t"
+      "mov.b64 pa, {%2, %3};\n\t"
+      "mov.b64 pb, {%4, %4};\n\t"
+      "mov.b64 pc, {%5, %6};\n\t"
+      "mul.rn.f32x2 pd, pa, pb;\n\t"
+      "sub.rn.f32x2 pd, pd, pc;\n\t"
+      "mov.b64 {%0, %1}, pd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
+  return r;
+}
+#undef FC_PK2
+#else
+FC_HD f2 add2(f2 a, f2 b) { return make_f2(a.x + b.x, a.y + b.y); }
+FC_HD f2 sub2(f2 a, f2 b) { return make_f2(a.x - b.x, a.y - b.y); }
+FC_HD f2 muls2(f2 a, float s) { return make_f2(a.x * s, a.y * s); }
+FC_HD f2 fmas2(f2 a, float s, f2 c) { return make_f2(a.x * s + c.x, a.y * s + c.y); }
+FC_HD f2 fmss2(f2 a, float s, f2 c) { return make_f2(a.x * s - c.x, a.y * s - c.y); }
+#endif
+
+// (re + i im) *= (wr + i wi), both lanes, scalar twiddle.
+FC_HD void cmul2(f2 &re, f2 &im, float wr, float wi) {
+  const f2 t = muls2(im, wi);
+  const f2 u = muls2(im, wr);
+  const f2 nre = fmss2(re, wr, t); // re*wr - im*wi
+  im = fmas2(re, wi, u);           // re*wi + im*wr
+  re = nre;
+}
+
+} // namespace fc

@@ -1,0 +1,93 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares; the
+host-side argument checks mirror the reference binding; the kernel's index logic is
+emulated on the CPU.  No compute call needs a GPU here."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from fftconv_b200 import _capi
+
+    header = open(os.path.join(ROOT, "include", "fftconv_cuda.h")).read()
+    declared = sorted(set(re.findall(r"\b(fftconv_cuda_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 19
+    lib = _capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(declared) == sorted(_capi.SYMBOLS)
+    assert lib.fftconv_cuda_version() == b"0.1.0"
+
+
+def test_segment_size_rule_matches_reference_table(built):
+    import fftconv_b200 as fc
+    from oracle import fftconv_oracle as O
+
+    for k in list(range(1, 1200)) + [4095, 4096, 4097, 8192, 8193, 20000]:
+        assert fc.optimal_fft_size(k) == O.get_optimal_fft_size(k), k
+
+
+def test_argument_errors_mirror_the_reference_binding(built):
+    """py/main.cpp:21-27,38-44: RuntimeError for bad mode / kernel longer than signal."""
+    import fftconv_b200 as fc
+
+    a, k = np.ones(5), np.ones(3)
+    with pytest.raises(RuntimeError, match="Unsupported convolution mode"):
+        fc.convolve(a, k, mode="valid")
+    with pytest.raises(RuntimeError, match="Kernel size must be smaller than input size"):
+        fc.oaconvolve(k, a)
+    with pytest.raises(RuntimeError, match="Number of dimensions must be one"):
+        fc.convolve(np.ones((2, 2, 2)), k)
+    with pytest.raises(TypeError):
+        fc.convolve(a.astype(np.int32), k.astype(np.int32))
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device the product path must fail loudly, never compute."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="(?i)cuda"):
+        fc.oaconvolve(np.ones(100, np.float32), np.ones(5, np.float32))
+    with pytest.raises(RuntimeError, match="(?i)cuda"):
+        fc.hilbert(np.ones(64))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fftconv_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "oracle/" not in src.replace("tests/cpu", ""), f
+
+
+EMU_CASES = [
+    # batch n K mode chunks slots
+    (4, 65536, 245, 0, 1, 7),    # BASELINE config 2 rows, work split mid-row (warm-up path)
+    (5, 10000, 245, 1, 1, 3),    # Same mode, batch not a multiple of 4
+    (1, 100000, 245, 0, 6, 5),   # one long row cut into chunks (config 5 shape)
+    (3, 5000, 300, 1, 2, 4),
+    (2, 1804, 245, 0, 1, 1),     # exactly one full segment
+    (1, 300, 245, 1, 1, 1),      # shorter than one segment
+    (6, 7000, 410, 0, 3, 2),     # largest K served by N = 2048
+    (2, 4000, 221, 1, 1, 1),     # smallest K served by N = 2048
+]
+
+
+@pytest.mark.parametrize("case", EMU_CASES)
+def test_n2048_kernel_logic_emulated_on_cpu(built, case):
+    """Runs the kernel's own __host__ __device__ phase functions thread by thread on
+    the CPU (tests/cpu/emulate_oa_n2048.cpp) against direct convolution in double."""
+    exe = os.path.join(ROOT, "tests", "cpu", "emulate_oa_n2048")
+    r = subprocess.run([exe, *map(str, case)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (case, r.stdout, r.stderr)
+    assert float(r.stdout.strip()) < 1e-6

@@ -1,0 +1,303 @@
+"""GPU: parity of the CUDA path (through the C ABI of libfftconv_cuda.so) with the
+oracle, the reference's golden fixtures and the mathematical definition.
+Tolerances are BASELINE.json's: relative L2 <= 1e-5 (float32), <= 1e-12 (float64)."""
+import numpy as np
+import pytest
+
+from oracle import fftconv_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(x, dev):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def _check(y, a, k, mode, tag):
+    tol = H.TOL[a.dtype]
+    y = np.asarray(y)
+    assert np.all(np.isfinite(y)), tag
+    e_def = O.rel_l2(y, O.conv_exact(a, k, mode))
+    e_orc = O.rel_l2(y, O.oaconvolve(a, k, mode))
+    assert e_def < tol and e_orc < tol, (tag, e_def, e_orc)
+
+
+def test_golden_reference_vectors_host_pointers(cuda):
+    """Every committed reference output (tests/golden) through the host-pointer API."""
+    import fftconv_b200 as fc
+
+    g, names = H.golden_conv_cases()
+    for name in names:
+        a, k = g[f"{name}__a"], g[f"{name}__k"]
+        fn = fc.oaconvolve if name.startswith("oa_") else fc.convolve
+        for mode in ("full", "same"):
+            got = fn(a, k, mode)
+            want = g[f"{name}__{mode}"]
+            assert got.shape == want.shape and got.dtype == want.dtype
+            assert O.rel_l2(got, want) < H.TOL[a.dtype], (name, mode, O.rel_l2(got, want))
+
+
+def test_golden_hilbert_vectors(cuda):
+    import fftconv_b200 as fc
+
+    g, names = H.golden_hilbert_cases()
+    for name in names:
+        x = g[f"{name}__x"]
+        n = x.size
+        if n & (n - 1):
+            continue  # non power of two: covered by test_hilbert_any_length when that path lands
+        assert O.rel_l2(fc.hilbert(x), g[f"{name}__env"]) < H.TOL[x.dtype], name
+
+
+def test_python_binding_cases(cuda):
+    """py/test/test_fftconv.py:9-70, same arrays and tolerances."""
+    import fftconv_b200 as fc
+
+    a = np.array([1, 2, 3, 4, 5], dtype=np.float64)
+    k = np.array([0.2, 0.5, 0.2], dtype=np.float64)
+    for fn, fn_ in ((fc.convolve, fc.convolve_), (fc.oaconvolve, fc.oaconvolve_)):
+        for mode in ("full", "same"):
+            expected = np.convolve(a, k, mode=mode)
+            np.testing.assert_allclose(fn(a, k, mode=mode), expected, rtol=1e-5, atol=1e-8)
+            out = np.empty(expected.size)
+            fn_(a, k, out, mode=mode)
+            np.testing.assert_allclose(out, expected, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_reference_gtest_shapes(cuda, dt):
+    """test/test_fftconv.cpp:127-218: n = k in 4..94 step 9 (convolve + oaconvolve, Full and
+    Same, even K included) and k = 95 with n in {200, 350, 500, 1000, 2000, 3000}; abs
+    tolerance 1e-9 / 1e-5 (test_common.hpp:9-18) against direct convolution."""
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(11)
+    atol = 1e-9 if dt == np.float64 else 1e-5
+    for size in range(4, 100, 9):
+        a, k = rng.standard_normal(size).astype(dt), rng.standard_normal(size).astype(dt)
+        for mode in ("full", "same"):
+            want = O.conv_exact(a, k, mode)
+            for fn in (fc.convolve, fc.oaconvolve):
+                got = fn(a, k, mode)
+                assert np.max(np.abs(got - want)) < atol * max(1.0, np.max(np.abs(want))), (size, mode, fn.__name__)
+    k = rng.standard_normal(95).astype(dt)
+    for n in (200, 350, 500, 1000, 2000, 3000):
+        a = rng.standard_normal(n).astype(dt)
+        for mode in ("full", "same"):
+            _check(fc.oaconvolve(a, k, mode), a, k, mode, (n, mode))
+
+
+def test_test_script_shapes(cuda):
+    """test/test_script.cpp:29-34: (1664|2816|2304|4352, 65), Same, both precisions."""
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(12)
+    for dt in (np.float64, np.float32):
+        for n in (1664, 2816, 2304, 4352):
+            a, k = rng.standard_normal(n).astype(dt), rng.standard_normal(65).astype(dt)
+            _check(fc.oaconvolve(a, k, "same"), a, k, "same", (n, dt))
+            _check(fc.convolve(a, k, "full"), a, k, "full", (n, dt))
+
+
+N2048_CASES = [
+    # batch, n, K
+    (4, 65536, 245), (5, 10000, 245), (1, 100000, 245), (3, 5000, 300), (2, 1804, 245),
+    (1, 300, 245), (6, 7000, 410), (2, 4000, 221), (7, 1805, 245), (9, 3607, 256), (64, 65536, 245),
+]
+
+
+@pytest.mark.parametrize("batch,n,klen", N2048_CASES)
+@pytest.mark.parametrize("mode", ["full", "same"])
+def test_n2048_kernel_device_pointers(cuda, batch, n, klen, mode):
+    """The headline kernel (float32, 221 <= K < 411): ragged last segments, batches that
+    are not multiples of four, rows cut into chunks, one-segment rows."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(batch * 1000 + n + klen)
+    a = rng.standard_normal((batch, n)).astype(np.float32)
+    k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(np.float32)
+    y = fc.oaconvolve(_t(a, cuda), _t(k, cuda), mode)
+    torch.cuda.synchronize()
+    _check(y.cpu().numpy(), a, k, mode, (batch, n, klen, mode))
+
+
+@pytest.mark.parametrize("groups", [2, 3, 4])
+def test_n2048_kernel_group_variants(cuda, groups, monkeypatch):
+    import torch
+
+    import fftconv_b200 as fc
+
+    monkeypatch.setenv("FFTCONV_CUDA_N2048_GROUPS", str(groups))
+    rng = np.random.default_rng(groups)
+    a = rng.standard_normal((37, 30000)).astype(np.float32)
+    k = (rng.standard_normal(245) / np.sqrt(245)).astype(np.float32)
+    y = fc.oaconvolve(_t(a, cuda), _t(k, cuda), "full")
+    torch.cuda.synchronize()
+    _check(y.cpu().numpy(), a, k, "full", groups)
+
+
+def test_n2048_matches_generic_kernel(cuda, monkeypatch):
+    """Two independent CUDA implementations of the same segments agree."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((6, 20000)).astype(np.float32)
+    k = (rng.standard_normal(245) / np.sqrt(245)).astype(np.float32)
+    y_fast = fc.oaconvolve(_t(a, cuda), _t(k, cuda), "full").cpu().numpy()
+    monkeypatch.setenv("FFTCONV_CUDA_FORCE_GENERIC", "1")
+    y_gen = fc.oaconvolve(_t(a, cuda), _t(k, cuda), "full").cpu().numpy()
+    torch.cuda.synchronize()
+    assert O.rel_l2(y_fast, y_gen) < 1e-6
+    _check(y_gen, a, k, "full", "generic")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("klen", [3, 6, 7, 20, 35, 64, 65, 119, 165, 220, 411, 768, 769, 1500])
+def test_generic_overlap_add_every_table_row(cuda, dt, klen):
+    """Every row of the segment-size table (fftconv.hpp:38-49) plus the doubling rule."""
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(klen)
+    n = max(3 * fc.optimal_fft_size(klen) + 17, klen)
+    a = rng.standard_normal((3, n)).astype(dt)
+    k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(dt)
+    for mode in ("full", "same"):
+        _check(fc.oaconvolve(a, k, mode), a, k, mode, (klen, dt, mode))
+
+
+def test_strided_rows_and_in_place_outputs(cuda):
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(8)
+    big = rng.standard_normal((5, 9000)).astype(np.float32)
+    a = big[:, :8000]                       # row stride 9000, row length 8000
+    k = (rng.standard_normal(245) / 16).astype(np.float32)
+    ta = _t(big, cuda)[:, :8000]
+    out = torch.full((5, 8300), float("nan"), device=cuda)[:, :8244]
+    fc.oaconvolve_(ta, _t(k, cuda), out, "full")
+    torch.cuda.synchronize()
+    _check(out.cpu().numpy(), np.ascontiguousarray(a), k, "full", "strided")
+    out_h = np.full((5, 8300), np.nan, dtype=np.float32)
+    fc.oaconvolve_(a, k, out_h[:, :8244], "full")
+    _check(out_h[:, :8244], np.ascontiguousarray(a), k, "full", "strided-host")
+    assert np.all(np.isnan(out_h[:, 8244:]))
+
+
+def test_linearity_and_shift_properties_at_full_size(cuda):
+    """BASELINE config 2 at full size (4096 x 65536, K = 245): dense CPU comparison of a
+    row sample plus size-independent properties -- linearity in the signal and the
+    response to a unit impulse (= the taps themselves, exactly placed)."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    g = torch.Generator(device=cuda).manual_seed(1)
+    a = torch.randn((4096, 65536), device=cuda, generator=g)
+    k = torch.randn(245, device=cuda, generator=g) / 245 ** 0.5
+    y = fc.oaconvolve(a, k, "full")
+    rows = [0, 1, 2, 3, 1023, 2048, 4093, 4094, 4095]
+    _check(y[rows].cpu().numpy(), a[rows].cpu().numpy(), k.cpu().numpy(), "full", "c2 rows")
+    # linearity: conv(2a + b) = 2 conv(a) + conv(b) with b = a rolled by one row
+    b = torch.roll(a, 1, 0)
+    y2 = fc.oaconvolve(2 * a[:256] + b[:256], k, "full")
+    lin = 2 * y[:256] + torch.roll(y, 1, 0)[:256]
+    assert float(torch.linalg.norm(y2 - lin) / torch.linalg.norm(lin)) < 1e-5
+    # impulse response: a unit impulse at position p reproduces the taps at p..p+K-1
+    imp = torch.zeros((4, 65536), device=cuda)
+    pos = [0, 1803, 1804, 65535]
+    for r, p in enumerate(pos):
+        imp[r, p] = 1.0
+    yi = fc.oaconvolve(imp, k, "full").cpu().numpy()
+    kk = k.cpu().numpy()
+    for r, p in enumerate(pos):
+        want = np.zeros(65536 + 244, dtype=np.float32)
+        want[p:p + 245] = kk
+        assert np.max(np.abs(yi[r] - want)) < 2e-6, (r, p)
+
+
+def test_batched_convolve_config3_sample(cuda):
+    """BASELINE config 3 shape (float64, n = 16384, K = 165, Full), 16 rows densely."""
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((16, 16384))
+    k = rng.standard_normal(165) / np.sqrt(165)
+    for mode in ("full", "same"):
+        got = fc.convolve(a, k, mode)
+        assert O.rel_l2(got, O.conv_exact(a, k, mode)) < 1e-12
+        assert O.rel_l2(got, O.convolve(a, k, mode)) < 1e-12
+
+
+def test_hilbert_config4_sample(cuda):
+    """BASELINE config 4 shape (float32, 8192-sample A-lines): dense check of 33 lines
+    (odd count: exercises the unpaired last row) for noise and an RF-like pulse."""
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(22)
+    t = np.arange(8192)
+    x = rng.standard_normal((33, 8192)).astype(np.float32)
+    x[1] = (np.exp(-0.5 * ((t - 4000) / 60.0) ** 2) * np.cos(2 * np.pi * 0.11 * t)).astype(np.float32)
+    x[2] = np.cos(4 * np.pi * t / 8191).astype(np.float32)   # benchmark/bench_hilbert.cpp:15-17
+    env = fc.hilbert(x)
+    assert O.rel_l2(env, O.hilbert_exact(x)) < 1e-5
+    assert O.rel_l2(env, O.hilbert(x)) < 1e-5
+    x64 = x[:5].astype(np.float64)
+    assert O.rel_l2(fc.hilbert(x64), O.hilbert_exact(x64)) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 64, 1024, 4096])
+def test_hilbert_power_of_two_lengths(cuda, n):
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(n)
+    for dt in (np.float32, np.float64):
+        x = rng.standard_normal((3, n)).astype(dt)
+        got = fc.hilbert(x)
+        want = O.hilbert_exact(x)
+        assert np.linalg.norm(got - want) <= H.TOL[np.dtype(dt)] * max(np.linalg.norm(want), 1.0), (n, dt)
+
+
+def test_long_signal_chunked_by_linearity(cuda):
+    """Config 5 in miniature: one long row cut into contiguous chunks, each convolved
+    in Full mode, K-1 tails added into the neighbour (fftconv_cuda_add_*)."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(31)
+    n, klen, parts = 1_000_003, 245, 4
+    a = rng.standard_normal(n).astype(np.float32)
+    k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(np.float32)
+    ta, tk = _t(a, cuda), _t(k, cuda)
+    whole = fc.oaconvolve(ta, tk, "full")
+    out = torch.zeros(n + klen - 1, device=cuda)
+    bounds = [n * i // parts for i in range(parts + 1)]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        y = fc.oaconvolve(ta[lo:hi], tk, "full")
+        fc.add_(out[lo:hi + klen - 1], y)
+    torch.cuda.synchronize()
+    assert float(torch.linalg.norm(out - whole) / torch.linalg.norm(whole)) < 1e-6
+    idx = np.concatenate([np.arange(0, 600), np.array(bounds[1:-1])[:, None].repeat(600, 1).ravel()
+                          + np.tile(np.arange(-300, 300), parts - 1), np.arange(n + klen - 601, n + klen - 1)])
+    want = O.conv_exact_at(a, k, idx)
+    got = whole.cpu().numpy()[idx]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-5
+
+
+def test_launch_counter_and_errors(cuda):
+    import fftconv_b200 as fc
+
+    before = fc.launch_count()
+    fc.oaconvolve(np.ones(100, np.float32), np.ones(5, np.float32))
+    assert fc.launch_count() >= before + 2   # spectrum + segment kernel
+    with pytest.raises(RuntimeError, match="expected"):
+        fc.oaconvolve_(np.ones(100), np.ones(5), np.empty(100), "full")
