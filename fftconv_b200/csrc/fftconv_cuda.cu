@@ -248,8 +248,8 @@ int prepare_spectrum(DeviceCtx &c, cudaStream_t st, const T *k, size_t klen, siz
     taps_dev = static_cast<const T *>(ws.taps);
   }
   if (int r = grow(&ws.H, &ws.h_bytes, N * sizeof(cx<T>))) return r;
-  const int threads = 128;
-  fc::generic::spectrum_kernel<T><<<(unsigned)((N + threads - 1) / threads), threads, 0, st>>>(
+  const int warps = fc::generic::kSpectrumWarps;
+  fc::generic::spectrum_kernel<T><<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(
       taps_dev, (int)klen, (int)N, tab.Wd, layout, 1.0 / (double)N, static_cast<cx<T> *>(ws.H));
   CU_TRY(cudaGetLastError());
   ++g_launches;
@@ -275,8 +275,8 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
       const cx<float> *H = nullptr;
       if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_N2048, *tab, &H))
         return r;
-      int G = env_int("FFTCONV_CUDA_N2048_GROUPS", 4);
-      if (G != 2 && G != 3 && G != 4) G = 4;
+      int G = env_int("FFTCONV_CUDA_N2048_GROUPS", 2);
+      if (G != 1 && G != 2) G = 2;
       const long long slots = (long long)c.sm_count * G;
       // streams per row: enough quads to fill every group, but never so many that
       // the per-chunk warm-up segment costs more than ~6 %
@@ -294,15 +294,12 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
       p.hs = reinterpret_cast<const fc::n2048::cpair *>(H);
       const size_t smem = fc::n2048::smem_bytes(G, (int)klen);
       const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
-      if (G == 4) {
-        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<4>, smem)) return r;
-        fc::n2048::oa_n2048_kernel<4><<<(unsigned)grid, 128 * 4, smem, st>>>(p);
-      } else if (G == 3) {
-        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<3>, smem)) return r;
-        fc::n2048::oa_n2048_kernel<3><<<(unsigned)grid, 128 * 3, smem, st>>>(p);
-      } else {
+      if (G == 2) {
         if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<2>, smem)) return r;
         fc::n2048::oa_n2048_kernel<2><<<(unsigned)grid, 128 * 2, smem, st>>>(p);
+      } else {
+        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<1>, smem)) return r;
+        fc::n2048::oa_n2048_kernel<1><<<(unsigned)grid, 128 * 1, smem, st>>>(p);
       }
       CU_TRY(cudaGetLastError());
       ++g_launches;

@@ -15,7 +15,8 @@ namespace generic {
 // Spectrum of the taps, evaluated directly in double:
 //   H[pos] = scale * sum_j taps[j] exp(-2 pi i j k(pos) / N)
 // k(pos) follows the layout of the consuming kernel.  wd[e] = exp(-2 pi i e / N)
-// in double.  O(N K) work -- K <= a few thousand taps by construction.
+// in double.  O(N K) work -- K <= a few thousand taps by construction.  (j k fits
+// 32 bits: j < K <= N / 2, k < N <= 2^15.)
 // ---------------------------------------------------------------------------
 enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1 };
 
@@ -26,24 +27,33 @@ __device__ __forceinline__ unsigned n2048_freq_of_index(unsigned idx) {
   return 16 * (c & 15) + 256 * k1b + (c >> 4);
 }
 
+// One warp per spectrum bin; the lanes split the taps and reduce with shuffles.
+constexpr int kSpectrumWarps = 8;
 template <typename T>
 __global__ void spectrum_kernel(const T *__restrict__ taps, int klen, int N,
                                 const double2 *__restrict__ wd, int layout, double scale,
                                 cx<T> *__restrict__ H) {
-  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int pos = blockIdx.x * kSpectrumWarps + (threadIdx.x >> 5);
   if (pos >= N) return;
   const unsigned k = layout == LAYOUT_N2048 ? n2048_freq_of_index(pos) : dif_freq_of_pos(pos, N);
+  const unsigned mask = (unsigned)(N - 1);
   double re = 0.0, im = 0.0;
-  unsigned e = 0; // (j * k) mod N
-  for (int j = 0; j < klen; ++j) {
-    const double2 w = wd[e];
+  for (int j = lane; j < klen; j += 32) {
+    const double2 w = wd[((unsigned)j * k) & mask]; // (j k) mod N, N a power of two
     const double v = (double)taps[j];
     re += v * w.x;
     im += v * w.y;
-    e = (e + k) & (unsigned)(N - 1);
   }
-  H[pos].x = (T)(re * scale);
-  H[pos].y = (T)(im * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if (lane == 0) {
+    H[pos].x = (T)(re * scale);
+    H[pos].y = (T)(im * scale);
+  }
 }
 
 // ---------------------------------------------------------------------------

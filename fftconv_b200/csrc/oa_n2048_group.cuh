@@ -14,9 +14,21 @@
 // addends -> deterministic, no atomics.  A stream that starts in the middle of
 // a row first runs its predecessor segment with stores disabled ("warm-up") to
 // obtain the incoming tail.
+//
+// Global memory is touched in two ways:
+//   * fast path (all four lanes hold a full interior segment): the segment is
+//     staged through shared memory by bulk asynchronous copies (TMA, 16-byte
+//     granularity, issued by one thread, prefetched one segment ahead); threads
+//     only do 4-byte shared-memory accesses with immediate offsets.  Misaligned
+//     rows are handled by copying the enclosing 16-byte-aligned span and
+//     indexing it with a per-lane shift.
+//   * slow path (first / last / ragged segments, partly filled quads): plain
+//     predicated 4-byte global loads and stores.
 #pragma once
 
 #include "oa_n2048_core.cuh"
+
+#include <cstddef>
 
 namespace fc {
 namespace n2048 {
@@ -72,6 +84,7 @@ FC_HD bool needs_warmup(const Lane (&ln)[4], long long j) {
   return w;
 }
 
+// ---- slow path: direct global access -------------------------------------------
 // Load x[t + 128 m] of the four lanes' segments (chunk-local index j, may be -1
 // for a warm-up) into the packed registers, zero padded.
 //   lane 0 -> re, half A    lane 1 -> im, half A
@@ -145,35 +158,257 @@ FC_HD void io_store(int t, const Regs &v, const OaParams &p, const Lane (&ln)[4]
   }
 }
 
-// Uniform (per group) control flow.  Exec::iteration(lanes, j, warm, add_tail,
-// parity) runs load -> P0..P4 -> store for all 128 threads of the group.
-template <class Exec>
-FC_HD void run_group(const OaParams &p, long long w0, long long w1, Exec &ex) {
-  int parity = 0;
-  long long w = w0;
-  while (w < w1) {
-    const long long quad = w / p.segs_per_chunk;
-    long long j = w - quad * p.segs_per_chunk;
-    long long jend = j + (w1 - w);
-    if (jend > p.segs_per_chunk) jend = p.segs_per_chunk;
-    Lane ln[4];
-    make_lanes(p, quad, ln);
-    // one call site (keeps a single copy of the ~1600-instruction body in the
-    // instruction cache): a warm-up is simply iteration j - 1 with stores off.
-    const long long jfirst = j;
-    long long jj = needs_warmup(ln, j) ? j - 1 : j;
-    bool add_tail = false;
-    w += jend - j;
-    for (; jj < jend; ++jj) {
-      ex.iteration(ln, jj, /*warm=*/jj < jfirst, add_tail, parity);
-      parity ^= 1;
-      add_tail = true;
+// ---- fast path: staged through shared memory ------------------------------------
+// staging buffers hold 4 lanes of `ls` floats each, ls = (3 + step + 3) & ~3 (oa_n2048_kernel.cuh)
+
+struct InPlan {            // where the bulk loads of one segment quad come from
+  bool fast;
+  const float *src[4];     // 16-byte aligned global address
+  int bytes[4];            // multiple of 16
+  int shift[4];            // element i of the segment sits at staging index shift + i
+};
+struct OutPlan {           // where the staged outputs of one segment quad go
+  bool fast;
+  float *dst[4];           // global address of y[0] (any 4-byte alignment)
+  int shift[4];            // y[i] sits at staging index shift + i  (shift = (dst / 4) & 3)
+};
+
+FC_HD int align_shift(const void *ptr) { return (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ULL); }
+
+FC_HD void plan_in(const OaParams &p, const Lane (&ln)[4], long long j, InPlan &ip) {
+  ip.fast = true;
+  // the aligned span may reach up to 3 samples past the segment: never past the tensor
+  const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const long long seg = ln[l].seg0 + j;
+    const bool on = ln[l].active && seg >= 0 && j < ln[l].cnt;
+    const long long pos = seg * p.step;
+    const bool full = on && (p.n - pos >= p.step);
+    ip.fast = ip.fast && full;
+    const float *a = ln[l].in + (full ? pos : 0);
+    const int sh = align_shift(a);
+    ip.shift[l] = sh;
+    ip.src[l] = a - sh;
+    ip.bytes[l] = ((sh + p.step) * 4 + 15) & ~15;
+    ip.fast = ip.fast && (ip.src[l] + ip.bytes[l] / 4 <= tensor_end);
+  }
+}
+
+FC_HD void plan_out(const OaParams &p, const Lane (&ln)[4], long long j, bool warm, OutPlan &op) {
+  op.fast = !warm;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const long long seg = ln[l].seg0 + j;
+    const bool on = ln[l].active && seg >= 0 && j < ln[l].cnt;
+    const long long o0 = seg * p.step - p.pad;
+    // interior segment: owns exactly y[0..step), all of it inside the row
+    const bool interior = on && seg < p.segs - 1 && o0 >= 0;
+    op.fast = op.fast && interior;
+    float *d = ln[l].out + (interior ? o0 : 0);
+    op.dst[l] = d;
+    op.shift[l] = align_shift(d);
+  }
+}
+
+// Per-thread constants of the fast path (depend on t, K only).
+struct ThreadMasks {
+  unsigned in_zero;   // bit m: t + 128 m >= step  (padding region: value is 0, no load)
+  unsigned tail_add;  // bit m: t + 128 m <  K - 1 (incoming tail is added)
+};
+FC_HD ThreadMasks make_masks(int t, const OaParams &p) {
+  ThreadMasks k;
+  k.in_zero = 0;
+  k.tail_add = 0;
+#pragma unroll
+  for (int m = 0; m < kPts; ++m) {
+    const int i = t + 128 * m;
+    if (i >= p.step) k.in_zero |= 1u << m;
+    if (i < p.klen - 1) k.tail_add |= 1u << m;
+  }
+  return k;
+}
+
+// staged input -> registers.  `in` is the group's input staging buffer.
+FC_HD void fast_load(int t, Regs &v, const float *in, int ls, const int (&shift)[4], unsigned in_zero) {
+  const float *b0 = in + 0 * ls + shift[0] + t;
+  const float *b1 = in + 1 * ls + shift[1] + t;
+  const float *b2 = in + 2 * ls + shift[2] + t;
+  const float *b3 = in + 3 * ls + shift[3] + t;
+#pragma unroll
+  for (int m = 0; m < kPts; ++m) {
+    // step >= 2048 - 409: only m >= 12 can fall into the padding region
+    const bool z = (m >= 12) && ((in_zero >> m) & 1u);
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+    if (!z) {
+      x0 = b0[128 * m];
+      x1 = b1[128 * m];
+      x2 = b2[128 * m];
+      x3 = b3[128 * m];
+    }
+    v.re[m] = make_f2(x0, x2);
+    v.im[m] = make_f2(x1, x3);
+  }
+}
+
+// registers -> staged output (+ tail hand-over).  `out` is the output staging buffer.
+FC_HD void fast_store(int t, const Regs &v, float *out, int ls, const int (&shift)[4], const ThreadMasks &k,
+                      const pt4 *tail_prev, pt4 *tail_next, bool add_tail, bool stage, int step) {
+  float *b0 = out + 0 * ls + shift[0] + t;
+  float *b1 = out + 1 * ls + shift[1] + t;
+  float *b2 = out + 2 * ls + shift[2] + t;
+  float *b3 = out + 3 * ls + shift[3] + t;
+#pragma unroll
+  for (int m = 0; m < kPts; ++m) {
+    const int i = t + 128 * m;
+    const int s = slot16(m);
+    f2 yr = v.re[s], yi = v.im[s];
+    if (m < 4) { // K - 1 <= 409 < 512
+      if (add_tail && ((k.tail_add >> m) & 1u)) {
+        f2 tr, ti;
+        get(tail_prev, i, tr, ti);
+        yr = add2(yr, tr);
+        yi = add2(yi, ti);
+      }
+    }
+    const bool in_tail = (m >= 12) && ((k.in_zero >> m) & 1u); // i >= step
+    if (in_tail) {
+      put(tail_next, i - step, yr, yi);
+    } else if (stage) {
+      b0[128 * m] = yr.x;
+      b1[128 * m] = yi.x;
+      b2[128 * m] = yr.y;
+      b3[128 * m] = yi.y;
     }
   }
 }
 
+// ---- uniform (per group) control flow ---------------------------------------------
+struct IterDesc {
+  long long quad;
+  long long j;    // chunk-local segment index (jfirst - 1 for a warm-up)
+  bool warm;
+  bool first;     // first iteration of a quad visit: no incoming tail
+};
+
+// Enumerates the iterations of the work slice [w0, w1): for every quad visit an
+// optional warm-up iteration, then the visit's segments in order.
+struct WorkIter {
+  long long w, w1;
+  long long quad, j, jend, jfirst;
+  bool in_visit;
+
+  FC_HD void init(long long w0_, long long w1_) {
+    w = w0_;
+    w1 = w1_;
+    in_visit = false;
+    quad = j = jend = jfirst = 0;
+  }
+  // returns false when the slice is exhausted; `ln` is refreshed on a new quad
+  FC_HD bool next(const OaParams &p, Lane (&ln)[4], IterDesc &d) {
+    if (!in_visit) {
+      if (w >= w1) return false;
+      quad = w / p.segs_per_chunk;
+      jfirst = w - quad * p.segs_per_chunk;
+      jend = jfirst + (w1 - w);
+      if (jend > p.segs_per_chunk) jend = p.segs_per_chunk;
+      make_lanes(p, quad, ln);
+      w += jend - jfirst;
+      j = needs_warmup(ln, jfirst) ? jfirst - 1 : jfirst;
+      in_visit = true;
+      d.first = true;
+    } else {
+      d.first = false;
+    }
+    d.quad = quad;
+    d.j = j;
+    d.warm = j < jfirst;
+    ++j;
+    if (j >= jend) in_visit = false;
+    return true;
+  }
+};
+
 // tail buffers: two (ping-pong) arrays of tail_pts(K) points per group
 FC_HD int tail_pts(int klen) { return ((klen - 1) + 7) & ~7; }
+
+struct Packet {        // one iteration of one group, produced by thread 0
+  int valid;           // 0: the slice is exhausted
+  int warm;
+  int first;           // no incoming tail
+  int in_fast;
+  int out_fast;
+  int in_shift[4];
+  int out_shift[4];
+  float *out_dst[4];
+  Lane ln[4];          // slow path only
+  long long j;
+};
+
+struct GroupLayout {   // byte offsets inside a group's shared-memory block
+  int lane_stride;     // floats
+  int xb, in, out, tails, packets, sched, mbar, total;
+};
+FC_HD GroupLayout group_layout(int klen) {
+  GroupLayout g;
+  const int step = kN - (klen - 1);
+  g.lane_stride = (3 + step + 3) & ~3;
+  int off = 0;
+  g.xb = off;      off += kN * (int)sizeof(pt4);
+  g.in = off;      off += 4 * g.lane_stride * 4;
+  g.out = off;     off += 4 * g.lane_stride * 4;
+  g.tails = off;   off += 2 * tail_pts(klen) * (int)sizeof(pt4);
+  g.packets = off; off += 2 * (((int)sizeof(Packet) + 15) & ~15);
+  g.sched = off;   off += ((int)sizeof(WorkIter) + 15) & ~15;
+  g.mbar = off;    off += 16;
+  g.total = off;
+  return g;
+}
+inline size_t smem_bytes(int groups, int klen) {
+  return (size_t)(2048 + 2048 + 128) * sizeof(cpair) + (size_t)groups * group_layout(klen).total;
+}
+
+
+// Thread 0 (or the host emulator): describe the next iteration in `pk`; `prev` is
+// the packet of the iteration before it.  Returns false when the slice is done.
+FC_HD bool fill_packet(const OaParams &p, WorkIter &it, const Packet *prev, Packet *pk, InPlan &ip) {
+  IterDesc d;
+  if (it.in_visit) { // same quad as before: the lanes carry over
+#pragma unroll
+    for (int l = 0; l < 4; ++l) pk->ln[l] = prev->ln[l];
+  }
+  if (!it.next(p, pk->ln, d)) {
+    pk->valid = 0;
+    ip.fast = false;
+    return false;
+  }
+  OutPlan op;
+  plan_in(p, pk->ln, d.j, ip);
+  plan_out(p, pk->ln, d.j, d.warm, op);
+  pk->valid = 1;
+  pk->warm = d.warm;
+  pk->first = d.first;
+  pk->in_fast = ip.fast;
+  pk->out_fast = op.fast;
+  pk->j = d.j;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    pk->in_shift[l] = ip.shift[l];
+    pk->out_shift[l] = op.shift[l];
+    pk->out_dst[l] = op.dst[l];
+  }
+  return true;
+}
+
+// How a staged output lane [0, step) splits into a 16-byte aligned bulk part and
+// up to 3 + 3 boundary samples.
+struct FlushSplit { int head, nb; };
+FC_HD FlushSplit flush_split(int shift, int step) {
+  FlushSplit f;
+  f.head = (4 - shift) & 3;
+  f.nb = (step - f.head) & ~3;
+  return f;
+}
 
 } // namespace n2048
 } // namespace fc

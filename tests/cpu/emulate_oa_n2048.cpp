@@ -1,41 +1,109 @@
 // CPU emulation of the N = 2048 overlap-add kernel: the very same
-// __host__ __device__ phase functions the CUDA kernel runs, executed thread by
-// thread with the barriers replaced by loop boundaries.  Checks the FFT
-// decomposition, shared-memory layouts, twiddle/spectrum table layouts and the
-// stream / warm-up / tail logic against direct convolution in double.
+// __host__ __device__ functions the CUDA kernel runs (FFT phases, shared-memory
+// layouts, packet scheduler, fast/slow I/O paths), executed thread by thread
+// with the barriers replaced by loop boundaries and the bulk (TMA) copies by
+// memcpy.  Checked against direct convolution in double.
 //
-// usage: emulate_oa_n2048 batch n K mode(0 full,1 same) chunks n_slots  -> prints rel-L2 error
+// usage: emulate_oa_n2048 batch n K mode(0 full,1 same) chunks n_slots [misalign]
+//   misalign: shifts the input/output base pointers by that many floats (0..3)
 #include "../../fftconv_b200/csrc/oa_n2048_group.cuh"
 #include "../../fftconv_b200/csrc/oa_n2048_tables.h"
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <vector>
 
 using namespace fc;
 using namespace fc::n2048;
 
-struct HostExec {
+static long long g_fast_in = 0, g_fast_out = 0, g_iters = 0;
+
+struct HostGroup {
   const OaParams &p;
+  GroupLayout L;
   std::vector<pt4> xb, tails;
+  std::vector<float> in_stage, out_stage;
   std::vector<Regs> regs;
+  Packet pk[2];
+  WorkIter it;
   int tpts;
-  explicit HostExec(const OaParams &pp)
-      : p(pp), xb(kN), tails(2 * tail_pts(pp.klen)), regs(kThreads), tpts(tail_pts(pp.klen)) {}
-  void iteration(const Lane (&ln)[4], long long j, bool warm, bool add_tail, int parity) {
-    for (int t = 0; t < kThreads; ++t) { io_load(t, regs[t], p, ln, j); phase0(t, regs[t], xb.data(), p.tw1); }
-    for (int t = 0; t < kThreads; ++t) phase1(t, regs[t], xb.data(), p.tw2);
-    for (int t = 0; t < kThreads; ++t) phase2(t, regs[t], xb.data(), p.hs);
-    for (int t = 0; t < kThreads; ++t) phase3(t, regs[t], xb.data(), p.tw2);
-    // tail reads of this iteration must all see the previous buffer: it is the
-    // other half of the ping-pong, so thread order does not matter.
-    for (int t = 0; t < kThreads; ++t) {
-      phase4(t, regs[t], xb.data(), p.tw1);
-      io_store(t, regs[t], p, ln, j, tails.data() + (parity ^ 1) * tpts, tails.data() + parity * tpts,
-               add_tail, warm);
+
+  explicit HostGroup(const OaParams &pp)
+      : p(pp), L(group_layout(pp.klen)), xb(kN), tails(2 * tail_pts(pp.klen)),
+        in_stage(4 * L.lane_stride, NAN), out_stage(4 * L.lane_stride, NAN), regs(kThreads),
+        tpts(tail_pts(pp.klen)) {
+    std::memset(pk, 0, sizeof(pk));
+  }
+
+  void schedule(const Packet *prev, Packet *next) {
+    InPlan ip;
+    fill_packet(p, it, prev, next, ip);
+    if (ip.fast)
+      for (int l = 0; l < 4; ++l)
+        std::memcpy(in_stage.data() + l * L.lane_stride, ip.src[l], ip.bytes[l]);
+  }
+  void flush(const Packet *q) {
+    for (int l = 0; l < 4; ++l) {
+      const int d = q->out_shift[l];
+      const FlushSplit f = flush_split(d, p.step);
+      float *dst = q->out_dst[l];
+      const float *src = out_stage.data() + l * L.lane_stride + d;
+      if ((reinterpret_cast<unsigned long long>(dst + f.head) & 15ULL) != 0) { std::printf("misaligned bulk store\n"); std::exit(3); }
+      std::memcpy(dst + f.head, src + f.head, (size_t)f.nb * 4);
+      for (int i = 0; i < f.head; ++i) dst[i] = src[i];
+      for (int i = f.head + f.nb; i < p.step; ++i) dst[i] = src[i];
     }
+  }
+
+  void run(long long w0, long long w1) {
+    it.init(w0, w1);
+    Packet *cur = &pk[0], *nxt = &pk[1];
+    schedule(nxt, cur);
+    int parity = 0;
+    bool out_pending = false;
+    std::vector<ThreadMasks> masks(kThreads);
+    for (int t = 0; t < kThreads; ++t) masks[t] = make_masks(t, p);
+    while (cur->valid) {
+      ++g_iters;
+      g_fast_in += cur->in_fast;
+      g_fast_out += cur->out_fast;
+      const bool warm = cur->warm != 0, add_tail = cur->first == 0;
+      for (int t = 0; t < kThreads; ++t) {
+        if (cur->in_fast) {
+          int sh[4] = {cur->in_shift[0], cur->in_shift[1], cur->in_shift[2], cur->in_shift[3]};
+          fast_load(t, regs[t], in_stage.data(), L.lane_stride, sh, masks[t].in_zero);
+        } else {
+          io_load(t, regs[t], p, cur->ln, cur->j);
+        }
+        phase0(t, regs[t], xb.data(), p.tw1);
+      }
+      // --- barrier B1; thread 0: flush previous outputs, schedule next ---
+      if (out_pending) flush(nxt);
+      std::fill(in_stage.begin(), in_stage.end(), NAN); // stale data must never be consumed
+      schedule(cur, nxt);
+      for (int t = 0; t < kThreads; ++t) phase1(t, regs[t], xb.data(), p.tw2);
+      for (int t = 0; t < kThreads; ++t) phase2(t, regs[t], xb.data(), p.hs);
+      for (int t = 0; t < kThreads; ++t) phase3(t, regs[t], xb.data(), p.tw2);
+      if (out_pending) std::fill(out_stage.begin(), out_stage.end(), NAN);
+      pt4 *tail_prev = tails.data() + (parity ^ 1) * tpts, *tail_next = tails.data() + parity * tpts;
+      for (int t = 0; t < kThreads; ++t) {
+        phase4(t, regs[t], xb.data(), p.tw1);
+        if (cur->out_fast || warm) {
+          int sh[4] = {cur->out_shift[0], cur->out_shift[1], cur->out_shift[2], cur->out_shift[3]};
+          fast_store(t, regs[t], out_stage.data(), L.lane_stride, sh, masks[t], tail_prev, tail_next,
+                     add_tail, cur->out_fast != 0, p.step);
+        } else {
+          io_store(t, regs[t], p, cur->ln, cur->j, tail_prev, tail_next, add_tail, warm);
+        }
+      }
+      out_pending = cur->out_fast != 0;
+      parity ^= 1;
+      std::swap(cur, nxt);
+    }
+    if (out_pending) flush(nxt);
   }
 };
 
@@ -44,27 +112,33 @@ int main(int argc, char **argv) {
   const long long batch = atoll(argv[1]), n = atoll(argv[2]);
   const int K = atoi(argv[3]), mode = atoi(argv[4]);
   const long long chunks = atoll(argv[5]), n_slots = atoll(argv[6]);
+  const int mis = argc > 7 ? atoi(argv[7]) : 0;
 
   std::mt19937 rng(1234);
   std::normal_distribution<float> nd(0.f, 1.f);
-  std::vector<float> a(batch * n), k(K);
-  for (auto &v : a) v = nd(rng);
+  const long long out_len = mode ? n : n + K - 1;
+  // 16-byte aligned backing stores, then an optional misalignment of the views
+  std::vector<float> a_store(batch * n + 8), out_store(batch * out_len + 8, NAN), k(K);
+  float *a = a_store.data(), *out = out_store.data();
+  while (reinterpret_cast<unsigned long long>(a) & 15ULL) ++a;
+  while (reinterpret_cast<unsigned long long>(out) & 15ULL) ++out;
+  a += mis;
+  out += mis;
+  for (long long i = 0; i < batch * n; ++i) a[i] = nd(rng);
   for (auto &v : k) v = nd(rng);
 
   OaParams p{};
-  const long long out_len = mode ? n : n + K - 1;
-  std::vector<float> out(batch * out_len, NAN);
   std::vector<cpair> tw1(2048), tw2(128), hs(2048);
   fill_tw1(tw1.data());
   fill_tw2(tw2.data());
   fill_hs_host(k.data(), K, hs.data());
-  fill_params(p, a.data(), out.data(), batch, n, n, out_len, out_len, K, mode, chunks);
+  fill_params(p, a, out, batch, n, n, out_len, out_len, K, mode, chunks);
   p.tw1 = tw1.data(); p.tw2 = tw2.data(); p.hs = hs.data();
 
   for (long long s = 0; s < n_slots; ++s) {
     const long long w0 = p.total_work * s / n_slots, w1 = p.total_work * (s + 1) / n_slots;
-    HostExec ex(p);
-    run_group(p, w0, w1, ex);
+    HostGroup grp(p);
+    grp.run(w0, w1);
   }
 
   double num = 0, den = 0;
@@ -81,6 +155,6 @@ int main(int argc, char **argv) {
       num += d * d; den += acc * acc;
     }
   const double err = std::sqrt(num / (den > 0 ? den : 1));
-  std::printf("%.3e\n", err);
+  std::printf("%.3e iters %lld fast_in %lld fast_out %lld\n", err, g_iters, g_fast_in, g_fast_out);
   return (err < 2e-6 && std::isfinite(err)) ? 0 : 1;
 }
