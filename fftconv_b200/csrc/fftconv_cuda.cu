@@ -275,8 +275,8 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
       const cx<float> *H = nullptr;
       if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_N2048, *tab, &H))
         return r;
-      int G = env_int("FFTCONV_CUDA_N2048_GROUPS", 2);
-      if (G != 1 && G != 2) G = 2;
+      int G = env_int("FFTCONV_CUDA_N2048_GROUPS", 4);
+      if (G < 1 || G > 4) G = 4;
       const long long slots = (long long)c.sm_count * G;
       // streams per row: enough quads to fill every group, but never so many that
       // the per-chunk warm-up segment costs more than ~6 %
@@ -294,7 +294,13 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
       p.hs = reinterpret_cast<const fc::n2048::cpair *>(H);
       const size_t smem = fc::n2048::smem_bytes(G, (int)klen);
       const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
-      if (G == 2) {
+      if (G == 4) {
+        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<4>, smem)) return r;
+        fc::n2048::oa_n2048_kernel<4><<<(unsigned)grid, 128 * 4, smem, st>>>(p);
+      } else if (G == 3) {
+        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<3>, smem)) return r;
+        fc::n2048::oa_n2048_kernel<3><<<(unsigned)grid, 128 * 3, smem, st>>>(p);
+      } else if (G == 2) {
         if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<2>, smem)) return r;
         fc::n2048::oa_n2048_kernel<2><<<(unsigned)grid, 128 * 2, smem, st>>>(p);
       } else {

@@ -159,18 +159,25 @@ FC_HD int p2_freq(int c0, int s) {
 }
 
 // ---- phases (called between group barriers) ---------------------------------
-// P0: v holds x[t + 128 m] in slot m.
-FC_HD void phase0(int t, Regs &v, pt4 *xb, const cpair *tw1) {
+// P0: v holds x[t + 128 m] in slot m.  Split in two so that a barrier can sit
+// between the last read of the (aliased) input staging area and the first write
+// of the exchange buffer.
+FC_HD void phase0_compute(int t, Regs &v, const cpair *tw1) {
   dft16<-1>(v);
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) {
+  for (int k2 = 1; k2 < 16; ++k2) {
     const int s = slot16(k2);
-    if (k2 > 0) {
-      const cpair w = tw1[k2 * 128 + t];
-      cmul2(v.re[s], v.im[s], w.re, w.im);
-    }
-    put(xb, x1_addr(t, k2), v.re[s], v.im[s]);
+    const cpair w = tw1[k2 * 128 + t];
+    cmul2(v.re[s], v.im[s], w.re, w.im);
   }
+}
+FC_HD void phase0_put(int t, const Regs &v, pt4 *xb) {
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) put(xb, x1_addr(t, k2), v.re[slot16(k2)], v.im[slot16(k2)]);
+}
+FC_HD void phase0(int t, Regs &v, pt4 *xb, const cpair *tw1) {
+  phase0_compute(t, v, tw1);
+  phase0_put(t, v, xb);
 }
 
 FC_HD void phase1(int tau, Regs &v, pt4 *xb, const cpair *tw2) {

@@ -346,17 +346,17 @@ struct Packet {        // one iteration of one group, produced by thread 0
 };
 
 struct GroupLayout {   // byte offsets inside a group's shared-memory block
-  int lane_stride;     // floats
-  int xb, in, out, tails, packets, sched, mbar, total;
+  int lane_stride;     // floats per lane of the staging area (which aliases xb)
+  int xb, tails, packets, sched, mbar, total;
 };
+// The input and output staging areas alias the exchange buffer: 4 lanes x
+// lane_stride floats <= 4 * 1832 * 4 B = 29312 B <= 32768 B.
 FC_HD GroupLayout group_layout(int klen) {
   GroupLayout g;
   const int step = kN - (klen - 1);
   g.lane_stride = (3 + step + 3) & ~3;
   int off = 0;
   g.xb = off;      off += kN * (int)sizeof(pt4);
-  g.in = off;      off += 4 * g.lane_stride * 4;
-  g.out = off;     off += 4 * g.lane_stride * 4;
   g.tails = off;   off += 2 * tail_pts(klen) * (int)sizeof(pt4);
   g.packets = off; off += 2 * (((int)sizeof(Packet) + 15) & ~15);
   g.sched = off;   off += ((int)sizeof(WorkIter) + 15) & ~15;
@@ -367,7 +367,6 @@ FC_HD GroupLayout group_layout(int klen) {
 inline size_t smem_bytes(int groups, int klen) {
   return (size_t)(2048 + 2048 + 128) * sizeof(cpair) + (size_t)groups * group_layout(klen).total;
 }
-
 
 // Thread 0 (or the host emulator): describe the next iteration in `pk`; `prev` is
 // the packet of the iteration before it.  Returns false when the slice is done.

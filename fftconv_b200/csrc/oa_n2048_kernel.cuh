@@ -1,23 +1,30 @@
 // oa_n2048_kernel.cuh -- the sm_100a overlap-add kernel for float32, FFT size 2048.
 //
-// Persistent grid: one CTA per SM, G groups of 128 threads per CTA.  Every group
-// owns an equal, contiguous slice of the (stream-quad, segment) work list.
+// Persistent grid: one CTA per SM, G groups of 128 threads per CTA (G = 4: 16
+// warps per SM, 128 registers per thread).  Every group owns an equal,
+// contiguous slice of the (stream-quad, segment) work list.
 //
-// Per segment quad a group
-//   * waits on an mbarrier for the four input segments that thread 0 requested
-//     one iteration earlier with cp.async.bulk (TMA, global -> shared), and reads
-//     them with 4-byte shared loads at immediate offsets;
-//   * runs phases P0..P4 of oa_n2048_core.cuh (~1100 packed-FP32 instructions per
-//     thread) across four 128-thread named barriers;
-//   * writes the 4 x step results into a shared staging buffer that thread 0
-//     drains with cp.async.bulk (shared -> global) during the next iteration.
-// Thread 0 of each group is also the group's scheduler: it walks the work slice
-// one iteration ahead and publishes a small descriptor ("packet") in shared
-// memory, so the other 127 threads execute no 64-bit control arithmetic at all.
+// Shared memory is the scarce resource (the 32 KB exchange buffer per group is
+// irreducible), so the global <-> shared staging areas ALIAS the exchange
+// buffer and the group's time line per segment quad is
+//   mbarrier wait      four input segments have landed in xb (cp.async.bulk,
+//                      TMA, issued by thread 0 at the end of the previous
+//                      iteration)
+//   LDS.32 x 64        x[t + 128 m] of the four lanes -> packed registers
+//   P0 compute | bar | P0 put | bar | P1 | bar | P2 | bar | P3 | bar | P4
+//   tail hand-over     (K-1 samples, separate small ping-pong buffers)
+//   bar | STS.32 x 64 into xb (natural order) | fence.proxy.async | bar
+//   thread 0           cp.async.bulk shared -> global of the 4 x step results,
+//                      builds the next iteration's packet while they drain,
+//                      waits until xb has been read, requests the next inputs
+//   bar
+// While one group waits for its copies the other three groups keep the FP32
+// pipe busy.  Thread 0 of each group is the group's scheduler: the other 127
+// threads execute no 64-bit control arithmetic at all.
 //
-// Shared memory per CTA: hs 16 KB + tw1 16 KB + tw2 1 KB, then per group a 32 KB
-// exchange buffer, input and output staging (4 lanes each), two tail buffers,
-// two packets and one mbarrier.
+// Shared memory per CTA: hs 16 KB + tw1 16 KB + tw2 1 KB, then per group the
+// 32 KB exchange buffer, two (K-1)-point tail buffers, two packets, the
+// scheduler state and one mbarrier (~40.6 KB for K = 245).
 #pragma once
 
 #include "oa_n2048_group.cuh"
@@ -71,32 +78,33 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 
 } // namespace dev
 
-// Thread 0: describe the next iteration and, if it is a fast-path load, start the bulk copies.
+// Thread 0: describe the next iteration and, if it is a fast-path load, start the
+// bulk copies into the staging area (= the exchange buffer, which must be idle).
 __device__ __forceinline__ void schedule_next(const OaParams &p, WorkIter &it, const Packet *prev, Packet *pk,
-                                              float *in_stage, int lane_stride, uint32_t mbar) {
+                                              float *stage, int lane_stride, uint32_t mbar, bool drain_first) {
   InPlan ip;
   fill_packet(p, it, prev, pk, ip);
+  if (drain_first) dev::bulk_wait_read0(); // the bulk stores have finished reading the staging area
   if (ip.fast) {
-    dev::fence_proxy_async(); // the staging buffer was read through the generic proxy
+    dev::fence_proxy_async(); // the area was last touched through the generic proxy
     dev::mbar_expect_tx(mbar, (uint32_t)(ip.bytes[0] + ip.bytes[1] + ip.bytes[2] + ip.bytes[3]));
 #pragma unroll
     for (int l = 0; l < 4; ++l)
-      dev::bulk_load(dev::smem_u32(in_stage + l * lane_stride), ip.src[l], (uint32_t)ip.bytes[l], mbar);
+      dev::bulk_load(dev::smem_u32(stage + l * lane_stride), ip.src[l], (uint32_t)ip.bytes[l], mbar);
   }
 }
 
-// Thread 0: drain the staged outputs of the previous iteration to global memory.
-__device__ __forceinline__ void flush_out(const Packet *pk, const float *out_stage, int lane_stride, int step) {
+// Thread 0: send the staged outputs of this iteration to global memory.
+__device__ __forceinline__ void flush_out(const Packet *pk, const float *stage, int lane_stride, int step) {
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const int d = pk->out_shift[l];
     const FlushSplit f = flush_split(d, step);
-    const int head = f.head, nb = f.nb;
     float *dst = pk->out_dst[l];
-    const float *src = out_stage + l * lane_stride + d;
-    dev::bulk_store(dst + head, dev::smem_u32(src + head), (uint32_t)nb * 4u);
-    for (int i = 0; i < head; ++i) dst[i] = src[i];
-    for (int i = head + nb; i < step; ++i) dst[i] = src[i];
+    const float *src = stage + l * lane_stride + d;
+    dev::bulk_store(dst + f.head, dev::smem_u32(src + f.head), (uint32_t)f.nb * 4u);
+    for (int i = 0; i < f.head; ++i) dst[i] = src[i];
+    for (int i = f.head + f.nb; i < step; ++i) dst[i] = src[i];
   }
   dev::bulk_commit();
 }
@@ -113,8 +121,7 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   const int g = threadIdx.x >> 7, t = threadIdx.x & 127;
   unsigned char *base = grp0 + (size_t)g * L.total;
   pt4 *xb = reinterpret_cast<pt4 *>(base + L.xb);
-  float *in_stage = reinterpret_cast<float *>(base + L.in);
-  float *out_stage = reinterpret_cast<float *>(base + L.out);
+  float *stage = reinterpret_cast<float *>(base + L.xb); // aliases xb
   pt4 *tails = reinterpret_cast<pt4 *>(base + L.tails);
   const int pk_stride = ((int)sizeof(Packet) + 15) & ~15;
   Packet *pk0 = reinterpret_cast<Packet *>(base + L.packets);
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     dev::mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     it.init(w0, w1);
-    schedule_next(p, it, pk1, pk0, in_stage, LS, mbar);
+    schedule_next(p, it, pk1, pk0, stage, LS, mbar, false);
   }
   __syncthreads();
 
@@ -147,7 +154,6 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   const int bar_id = g + 1;
   uint32_t in_phase = 0;
   int parity = 0;
-  bool out_pending = false; // a staged output quad waits to be flushed (uniform)
   Packet *cur = pk0, *nxt = pk1;
 
   while (cur->valid) {
@@ -160,45 +166,44 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
       while (!dev::mbar_try_wait(mbar, in_phase)) {
       }
       in_phase ^= 1;
-      fast_load(t, v, in_stage, LS, sh, masks.in_zero);
+      fast_load(t, v, stage, LS, sh, masks.in_zero);
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_load(t, v, p, ln, cur->j);
     }
-    phase0(t, v, xb, tw1);
+    phase0_compute(t, v, tw1);
+    dev::bar_sync(bar_id); // every thread has read its inputs out of the staging area
+    phase0_put(t, v, xb);
     dev::bar_sync(bar_id);
-    if (t == 0) {
-      if (out_pending) flush_out(nxt, out_stage, LS, p.step); // nxt still holds the previous packet
-      schedule_next(p, it, cur, nxt, in_stage, LS, mbar);
-    }
     phase1(t, v, xb, tw2);
     dev::bar_sync(bar_id);
     phase2(t, v, xb, hs);
     dev::bar_sync(bar_id);
     phase3(t, v, xb, tw2);
-    if (t == 0 && out_pending) dev::bulk_wait_read0(); // staging buffer is free again
     dev::bar_sync(bar_id);
     phase4(t, v, xb, tw1);
     pt4 *tail_prev = tails + (parity ^ 1) * tpts, *tail_next = tails + parity * tpts;
+    dev::bar_sync(bar_id); // every thread has read its points: xb becomes the output staging area
     if (out_fast || warm) {
       int sh[4] = {cur->out_shift[0], cur->out_shift[1], cur->out_shift[2], cur->out_shift[3]};
-      fast_store(t, v, out_stage, LS, sh, masks, tail_prev, tail_next, add_tail, out_fast, p.step);
-      if (out_fast) dev::fence_proxy_async(); // make the staged values visible to the bulk-copy engine
+      fast_store(t, v, stage, LS, sh, masks, tail_prev, tail_next, add_tail, out_fast, p.step);
+      if (out_fast) dev::fence_proxy_async(); // staged values -> visible to the bulk-copy engine
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_store(t, v, p, ln, cur->j, tail_prev, tail_next, add_tail, warm);
     }
-    out_pending = out_fast;
+    dev::bar_sync(bar_id);
+    if (t == 0) {
+      if (out_fast) flush_out(cur, stage, LS, p.step);
+      schedule_next(p, it, cur, nxt, stage, LS, mbar, out_fast);
+    }
+    dev::bar_sync(bar_id); // the next packet is published
     parity ^= 1;
     Packet *tmp = cur;
     cur = nxt;
     nxt = tmp;
   }
-  dev::bar_sync(bar_id);
-  if (t == 0) {
-    if (out_pending) flush_out(nxt, out_stage, LS, p.step);
-    dev::bulk_wait0();
-  }
+  if (t == 0) dev::bulk_wait0();
 }
 #endif // __CUDACC__
 

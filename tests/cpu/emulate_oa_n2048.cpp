@@ -25,33 +25,41 @@ struct HostGroup {
   const OaParams &p;
   GroupLayout L;
   std::vector<pt4> xb, tails;
-  std::vector<float> in_stage, out_stage;
+  float *stage; // aliases xb, exactly as in the kernel
   std::vector<Regs> regs;
   Packet pk[2];
   WorkIter it;
   int tpts;
 
   explicit HostGroup(const OaParams &pp)
-      : p(pp), L(group_layout(pp.klen)), xb(kN), tails(2 * tail_pts(pp.klen)),
-        in_stage(4 * L.lane_stride, NAN), out_stage(4 * L.lane_stride, NAN), regs(kThreads),
+      : p(pp), L(group_layout(pp.klen)), xb(kN), tails(2 * tail_pts(pp.klen)), regs(kThreads),
         tpts(tail_pts(pp.klen)) {
     std::memset(pk, 0, sizeof(pk));
+    stage = reinterpret_cast<float *>(xb.data());
+    if (4 * L.lane_stride * 4 > kN * (int)sizeof(pt4)) { std::printf("staging does not fit xb\n"); std::exit(4); }
   }
 
+  void poison() { // whatever was in the exchange buffer must never be consumed as data
+    for (int i = 0; i < kN * 4; ++i) stage[i] = NAN;
+  }
   void schedule(const Packet *prev, Packet *next) {
     InPlan ip;
     fill_packet(p, it, prev, next, ip);
     if (ip.fast)
       for (int l = 0; l < 4; ++l)
-        std::memcpy(in_stage.data() + l * L.lane_stride, ip.src[l], ip.bytes[l]);
+        std::memcpy(stage + l * L.lane_stride, ip.src[l], ip.bytes[l]);
   }
   void flush(const Packet *q) {
     for (int l = 0; l < 4; ++l) {
       const int d = q->out_shift[l];
       const FlushSplit f = flush_split(d, p.step);
       float *dst = q->out_dst[l];
-      const float *src = out_stage.data() + l * L.lane_stride + d;
-      if ((reinterpret_cast<unsigned long long>(dst + f.head) & 15ULL) != 0) { std::printf("misaligned bulk store\n"); std::exit(3); }
+      const float *src = stage + l * L.lane_stride + d;
+      if ((reinterpret_cast<unsigned long long>(dst + f.head) & 15ULL) != 0 ||
+          (reinterpret_cast<unsigned long long>(src + f.head) & 15ULL) != 0) {
+        std::printf("misaligned bulk store\n");
+        std::exit(3);
+      }
       std::memcpy(dst + f.head, src + f.head, (size_t)f.nb * 4);
       for (int i = 0; i < f.head; ++i) dst[i] = src[i];
       for (int i = f.head + f.nb; i < p.step; ++i) dst[i] = src[i];
@@ -61,9 +69,9 @@ struct HostGroup {
   void run(long long w0, long long w1) {
     it.init(w0, w1);
     Packet *cur = &pk[0], *nxt = &pk[1];
+    poison();
     schedule(nxt, cur);
     int parity = 0;
-    bool out_pending = false;
     std::vector<ThreadMasks> masks(kThreads);
     for (int t = 0; t < kThreads; ++t) masks[t] = make_masks(t, p);
     while (cur->valid) {
@@ -74,36 +82,35 @@ struct HostGroup {
       for (int t = 0; t < kThreads; ++t) {
         if (cur->in_fast) {
           int sh[4] = {cur->in_shift[0], cur->in_shift[1], cur->in_shift[2], cur->in_shift[3]};
-          fast_load(t, regs[t], in_stage.data(), L.lane_stride, sh, masks[t].in_zero);
+          fast_load(t, regs[t], stage, L.lane_stride, sh, masks[t].in_zero);
         } else {
           io_load(t, regs[t], p, cur->ln, cur->j);
         }
-        phase0(t, regs[t], xb.data(), p.tw1);
+        phase0_compute(t, regs[t], p.tw1);
       }
-      // --- barrier B1; thread 0: flush previous outputs, schedule next ---
-      if (out_pending) flush(nxt);
-      std::fill(in_stage.begin(), in_stage.end(), NAN); // stale data must never be consumed
-      schedule(cur, nxt);
+      poison();
+      for (int t = 0; t < kThreads; ++t) phase0_put(t, regs[t], xb.data());
       for (int t = 0; t < kThreads; ++t) phase1(t, regs[t], xb.data(), p.tw2);
       for (int t = 0; t < kThreads; ++t) phase2(t, regs[t], xb.data(), p.hs);
       for (int t = 0; t < kThreads; ++t) phase3(t, regs[t], xb.data(), p.tw2);
-      if (out_pending) std::fill(out_stage.begin(), out_stage.end(), NAN);
+      for (int t = 0; t < kThreads; ++t) phase4(t, regs[t], xb.data(), p.tw1);
+      poison();
       pt4 *tail_prev = tails.data() + (parity ^ 1) * tpts, *tail_next = tails.data() + parity * tpts;
       for (int t = 0; t < kThreads; ++t) {
-        phase4(t, regs[t], xb.data(), p.tw1);
         if (cur->out_fast || warm) {
           int sh[4] = {cur->out_shift[0], cur->out_shift[1], cur->out_shift[2], cur->out_shift[3]};
-          fast_store(t, regs[t], out_stage.data(), L.lane_stride, sh, masks[t], tail_prev, tail_next,
-                     add_tail, cur->out_fast != 0, p.step);
+          fast_store(t, regs[t], stage, L.lane_stride, sh, masks[t], tail_prev, tail_next, add_tail,
+                     cur->out_fast != 0, p.step);
         } else {
           io_store(t, regs[t], p, cur->ln, cur->j, tail_prev, tail_next, add_tail, warm);
         }
       }
-      out_pending = cur->out_fast != 0;
+      if (cur->out_fast) flush(cur);
+      poison();
+      schedule(cur, nxt);
       parity ^= 1;
       std::swap(cur, nxt);
     }
-    if (out_pending) flush(nxt);
   }
 };
 

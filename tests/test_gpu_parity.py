@@ -126,7 +126,7 @@ def test_n2048_kernel_device_pointers(cuda, batch, n, klen, mode):
     _check(y.cpu().numpy(), a, k, mode, (batch, n, klen, mode))
 
 
-@pytest.mark.parametrize("groups", [1, 2])
+@pytest.mark.parametrize("groups", [1, 2, 3, 4])
 def test_n2048_kernel_group_variants(cuda, groups, monkeypatch):
     import torch
 
