@@ -340,6 +340,8 @@ struct Packet {        // one iteration of one group, produced by thread 0
   int out_fast;
   int in_shift[4];
   int out_shift[4];
+  int in_bytes[4];     // bulk-load size per lane (fast path)
+  const float *in_src[4];
   float *out_dst[4];
   Lane ln[4];          // slow path only
   long long j;
@@ -393,6 +395,8 @@ FC_HD bool fill_packet(const OaParams &p, WorkIter &it, const Packet *prev, Pack
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     pk->in_shift[l] = ip.shift[l];
+    pk->in_bytes[l] = ip.bytes[l];
+    pk->in_src[l] = ip.src[l];
     pk->out_shift[l] = op.shift[l];
     pk->out_dst[l] = op.dst[l];
   }

@@ -15,9 +15,8 @@
 //   tail hand-over     (K-1 samples, separate small ping-pong buffers)
 //   bar | STS.32 x 64 into xb (natural order) | fence.proxy.async | bar
 //   thread 0           cp.async.bulk shared -> global of the 4 x step results,
-//                      builds the next iteration's packet while they drain,
 //                      waits until xb has been read, requests the next inputs
-//   bar
+//                      (whose packet it built at the start of this iteration)
 // While one group waits for its copies the other three groups keep the FP32
 // pipe busy.  Thread 0 of each group is the group's scheduler: the other 127
 // threads execute no 64-bit control arithmetic at all.
@@ -78,19 +77,15 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 
 } // namespace dev
 
-// Thread 0: describe the next iteration and, if it is a fast-path load, start the
-// bulk copies into the staging area (= the exchange buffer, which must be idle).
-__device__ __forceinline__ void schedule_next(const OaParams &p, WorkIter &it, const Packet *prev, Packet *pk,
-                                              float *stage, int lane_stride, uint32_t mbar, bool drain_first) {
-  InPlan ip;
-  fill_packet(p, it, prev, pk, ip);
-  if (drain_first) dev::bulk_wait_read0(); // the bulk stores have finished reading the staging area
-  if (ip.fast) {
+// Thread 0: start the bulk copies of a fast-path packet into the staging area
+// (= the exchange buffer, which must be idle).
+__device__ __forceinline__ void issue_loads(const Packet *pk, float *stage, int lane_stride, uint32_t mbar) {
+  if (pk->valid && pk->in_fast) {
     dev::fence_proxy_async(); // the area was last touched through the generic proxy
-    dev::mbar_expect_tx(mbar, (uint32_t)(ip.bytes[0] + ip.bytes[1] + ip.bytes[2] + ip.bytes[3]));
+    dev::mbar_expect_tx(mbar, (uint32_t)(pk->in_bytes[0] + pk->in_bytes[1] + pk->in_bytes[2] + pk->in_bytes[3]));
 #pragma unroll
     for (int l = 0; l < 4; ++l)
-      dev::bulk_load(dev::smem_u32(stage + l * lane_stride), ip.src[l], (uint32_t)ip.bytes[l], mbar);
+      dev::bulk_load(dev::smem_u32(stage + l * lane_stride), pk->in_src[l], (uint32_t)pk->in_bytes[l], mbar);
   }
 }
 
@@ -146,7 +141,9 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     dev::mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     it.init(w0, w1);
-    schedule_next(p, it, pk1, pk0, stage, LS, mbar, false);
+    InPlan ip;
+    fill_packet(p, it, pk1, pk0, ip);
+    issue_loads(pk0, stage, LS, mbar);
   }
   __syncthreads();
 
@@ -161,6 +158,10 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     const bool add_tail = cur->first == 0;
     const bool in_fast = cur->in_fast != 0, out_fast = cur->out_fast != 0;
     Regs v;
+    if (t == 0) { // describe the next iteration now: it becomes visible at the next barrier
+      InPlan ip;
+      fill_packet(p, it, cur, nxt, ip);
+    }
     if (in_fast) {
       int sh[4] = {cur->in_shift[0], cur->in_shift[1], cur->in_shift[2], cur->in_shift[3]};
       while (!dev::mbar_try_wait(mbar, in_phase)) {
@@ -194,10 +195,14 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     }
     dev::bar_sync(bar_id);
     if (t == 0) {
-      if (out_fast) flush_out(cur, stage, LS, p.step);
-      schedule_next(p, it, cur, nxt, stage, LS, mbar, out_fast);
+      if (out_fast) {
+        flush_out(cur, stage, LS, p.step);
+        dev::bulk_wait_read0(); // the bulk stores have finished reading the staging area
+      }
+      issue_loads(nxt, stage, LS, mbar);
     }
-    dev::bar_sync(bar_id); // the next packet is published
+    // no barrier here: the next iteration touches xb only after its own first
+    // barrier, which thread 0 reaches after the drain above
     parity ^= 1;
     Packet *tmp = cur;
     cur = nxt;
