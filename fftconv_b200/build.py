@@ -58,9 +58,52 @@ def build_microbench(force: bool = False) -> str:
     return MICROBENCH
 
 
+REF_MAIN = "/root/reference/py/main.cpp"
+REF_BINDING_DIR = os.path.join(HERE, "refbinding", "pyfftconv")
+CPP_TEST = os.path.join(ROOT, "tests", "cpp", "test_headers")
+
+
+def _headers() -> list[str]:
+    inc = os.path.join(ROOT, "include")
+    return [os.path.join(inc, "fftconv_cuda.h")] + [
+        os.path.join(inc, "fftconv", f) for f in sorted(os.listdir(os.path.join(inc, "fftconv")))]
+
+
+def build_ref_binding(force: bool = False) -> str:
+    """Compile the REFERENCE's pybind11 module, unchanged and where it lies, against
+    this repo's headers.  Only possible where /root/reference exists."""
+    import sysconfig
+
+    if not os.path.exists(REF_MAIN):
+        return ""
+    import pybind11
+
+    target = os.path.join(REF_BINDING_DIR, "_pyfftconv" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not force and _newer(target, [REF_MAIN, LIB] + _headers()):
+        return target
+    cmd = ["g++", "-O2", "-std=c++20", "-shared", "-fPIC",
+           f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}",
+           f"-I{os.path.join(ROOT, 'include')}", REF_MAIN,
+           f"-L{LIBDIR}", "-lfftconv_cuda", "-Wl,-rpath,$ORIGIN/../../lib", "-o", target]
+    subprocess.run(cmd, check=True)
+    return target
+
+
+def build_cpp_test(force: bool = False) -> str:
+    src = CPP_TEST + ".cpp"
+    if not force and _newer(CPP_TEST, [src, LIB] + _headers()):
+        return CPP_TEST
+    cmd = ["g++", "-O2", "-std=c++20", f"-I{os.path.join(ROOT, 'include')}", src,
+           f"-L{LIBDIR}", "-lfftconv_cuda", "-Wl,-rpath,$ORIGIN/../../fftconv_b200/lib", "-o", CPP_TEST]
+    subprocess.run(cmd, check=True)
+    return CPP_TEST
+
+
 def build_all(force: bool = False) -> None:
     build_lib(force)
     build_microbench(force)
+    build_cpp_test(force)
+    build_ref_binding(force)
 
 
 if __name__ == "__main__":

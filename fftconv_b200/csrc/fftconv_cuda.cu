@@ -74,6 +74,12 @@ struct Tables {           // per (FFT length, dtype)
   void *G = nullptr;      // cx<T>[N]   Hilbert multiplier, DIF order (lazy)
 };
 
+struct BluesteinTables {  // per (n, dtype): Hilbert of a non-power-of-two length
+  size_t M = 0;
+  void *chirp = nullptr;  // cx<T>[n]
+  void *B = nullptr;      // cx<T>[M], DIF order, 1/M folded in
+};
+
 struct StreamWs {         // per stream
   void *taps = nullptr;
   size_t taps_bytes = 0;
@@ -88,6 +94,7 @@ struct DeviceCtx {
   int sm_count = 0;
   size_t smem_optin = 0;
   std::map<std::pair<size_t, int>, Tables> tables;
+  std::map<std::pair<size_t, int>, BluesteinTables> bluestein;
   fc::n2048::cpair *tw1 = nullptr, *tw2 = nullptr;
   std::map<cudaStream_t, StreamWs> ws;
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
@@ -124,6 +131,11 @@ void free_ctx(DeviceCtx &c) {
     cudaFree(kv.second.G);
   }
   c.tables.clear();
+  for (auto &kv : c.bluestein) {
+    cudaFree(kv.second.chirp);
+    cudaFree(kv.second.B);
+  }
+  c.bluestein.clear();
   cudaFree(c.tw1);
   cudaFree(c.tw2);
   c.tw1 = c.tw2 = nullptr;
@@ -184,6 +196,77 @@ template <typename T> int get_hilbert_table(DeviceCtx &c, size_t N, Tables &t) {
   CU_TRY(cudaMalloc(&t.G, N * sizeof(cx<T>)));
   CU_TRY(cudaMemcpy(t.G, g.data(), N * sizeof(cx<T>), cudaMemcpyHostToDevice));
   (void)c;
+  return 0;
+}
+
+// in-place radix-2 FFT in long double (host, table construction only)
+void host_fft_ld(std::vector<long double> &re, std::vector<long double> &im) {
+  const size_t n = re.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) {
+      std::swap(re[i], re[j]);
+      std::swap(im[i], im[j]);
+    }
+  }
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (size_t len = 2; len <= n; len <<= 1) {
+    for (size_t i = 0; i < n; i += len)
+      for (size_t k = 0; k < len / 2; ++k) {
+        const long double a = -2.0L * pi * (long double)k / (long double)len;
+        const long double wr = cosl(a), wi = sinl(a);
+        const size_t u = i + k, v = i + k + len / 2;
+        const long double tr = re[v] * wr - im[v] * wi, ti = re[v] * wi + im[v] * wr;
+        re[v] = re[u] - tr;
+        im[v] = im[u] - ti;
+        re[u] += tr;
+        im[u] += ti;
+      }
+  }
+}
+
+template <typename T> int get_bluestein(DeviceCtx &c, size_t n, BluesteinTables **out) {
+  auto key = std::make_pair(n, dtype_id<T>());
+  auto it = c.bluestein.find(key);
+  if (it == c.bluestein.end()) {
+    size_t M = 1;
+    while (M < 2 * n - 1) M *= 2;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    std::vector<long double> cr(n), ci(n);
+    std::vector<cx<T>> chirp(n);
+    for (size_t j = 0; j < n; ++j) {
+      const unsigned long long j2 = (unsigned long long)j * j % (2ULL * n); // angle reduced exactly
+      const long double a = pi * (long double)j2 / (long double)n;
+      cr[j] = cosl(a);
+      ci[j] = -sinl(a);
+      chirp[j].x = (T)cr[j];
+      chirp[j].y = (T)ci[j];
+    }
+    std::vector<long double> br(M, 0.0L), bi(M, 0.0L);
+    br[0] = cr[0];
+    bi[0] = -ci[0];
+    for (size_t j = 1; j < n; ++j) {
+      br[j] = br[M - j] = cr[j];
+      bi[j] = bi[M - j] = -ci[j];
+    }
+    host_fft_ld(br, bi);
+    std::vector<cx<T>> B(M);
+    for (size_t pos = 0; pos < M; ++pos) {
+      const size_t k = fc::generic::dif_freq_of_pos((unsigned)pos, (unsigned)M);
+      B[pos].x = (T)(br[k] / (long double)M);
+      B[pos].y = (T)(bi[k] / (long double)M);
+    }
+    BluesteinTables t;
+    t.M = M;
+    CU_TRY(cudaMalloc(&t.chirp, n * sizeof(cx<T>)));
+    CU_TRY(cudaMalloc(&t.B, M * sizeof(cx<T>)));
+    CU_TRY(cudaMemcpy(t.chirp, chirp.data(), n * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(t.B, B.data(), M * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    it = c.bluestein.emplace(key, t).first;
+  }
+  *out = &it->second;
   return 0;
 }
 
@@ -387,9 +470,37 @@ int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, 
 template <typename T>
 int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size_t n,
                    size_t x_stride, T *env, size_t env_stride) {
-  if ((n & (n - 1)) != 0)
-    return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
-                                                 " is not a power of two (Bluestein path pending)");
+  if ((n & (n - 1)) != 0) {
+    size_t M = 1;
+    while (M < 2 * n - 1) M *= 2;
+    const size_t smem_b = M * sizeof(cx<T>);
+    if (smem_b > c.smem_optin)
+      return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
+                                                   " needs a chirp-z FFT of " + std::to_string(M) +
+                                                   " points, beyond the single-CTA shared-memory FFT");
+    BluesteinTables *bt = nullptr;
+    if (int r = get_bluestein<T>(c, n, &bt)) return r;
+    Tables *tabm = nullptr;
+    if (int r = get_tables<T>(c, M, &tabm)) return r;
+    fc::generic::HilbertBluesteinArgs<T> p{};
+    p.in = x;
+    p.out = env;
+    p.batch = (long long)batch;
+    p.n = (long long)n;
+    p.in_stride = (long long)x_stride;
+    p.out_stride = (long long)env_stride;
+    p.log2m = ilog2(M);
+    p.W = static_cast<const cx<T> *>(tabm->W);
+    p.B = static_cast<const cx<T> *>(bt->B);
+    p.chirp = static_cast<const cx<T> *>(bt->chirp);
+    if (int r = ensure_smem(c, fc::generic::hilbert_bluestein_kernel<T>, std::max<size_t>(smem_b, 16))) return r;
+    const long long gridb = ((long long)batch + 1) / 2;
+    const int threadsb = (int)std::min<size_t>(512, std::max<size_t>(32, M / 4));
+    fc::generic::hilbert_bluestein_kernel<T><<<(unsigned)gridb, threadsb, std::max<size_t>(smem_b, 16), st>>>(p);
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+    return 0;
+  }
   const size_t smem = n * sizeof(cx<T>);
   if (smem > c.smem_optin)
     return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +

@@ -199,6 +199,81 @@ template <typename T> __global__ void hilbert_pow2_kernel(const HilbertArgs<T> p
   }
 }
 
+// ---------------------------------------------------------------------------
+// Hilbert envelope, any length n, by Bluestein's chirp-z identity on top of the
+// power-of-two engine (M >= 2 n - 1):
+//   DFT_n(x)[k] = c[k] * ((x c) (*)_M conj-chirp)[k],   c[j] = exp(-pi i j^2 / n)
+// Rows 2b and 2b+1 again ride in the real and imaginary parts (the Hilbert
+// transformer is a real filter).  Tables: chirp[n]; B[M] = FFT_M(wrapped
+// conj(chirp)) / M in DIF order.  The inverse DFT is conj(DFT(conj(.))) / n.
+// (/root/reference/include/fftconv/hilbert.hpp:16-66 accepts any n > 0.)
+// ---------------------------------------------------------------------------
+template <typename T> struct HilbertBluesteinArgs {
+  const T *in;
+  T *out;
+  long long batch, n, in_stride, out_stride;
+  int log2m;
+  const cx<T> *W;     // M twiddles
+  const cx<T> *B;     // M, DIF order, 1/M folded in
+  const cx<T> *chirp; // n
+};
+
+template <typename T> __global__ void hilbert_bluestein_kernel(const HilbertBluesteinArgs<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = 1 << p.log2m;
+  const int n = (int)p.n;
+  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
+  const long long r0 = (long long)blockIdx.x * 2, r1 = r0 + 1;
+  const bool has1 = r1 < p.batch;
+  const T *x0 = p.in + r0 * p.in_stride;
+  const T *x1 = p.in + (has1 ? r1 : r0) * p.in_stride;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    cx<T> v = {(T)0, (T)0};
+    if (i < n) {
+      v.x = x0[i];
+      v.y = has1 ? x1[i] : (T)0;
+      v = cmul(v, p.chirp[i]);
+    }
+    buf[i] = v;
+  }
+  __syncthreads();
+  fft_dif(buf, p.W, p.log2m);
+  spectrum_mul(buf, p.B, M);
+  fft_dit_inv(buf, p.W, p.log2m);
+  // X[k] = c[k] buf[k]; Hilbert multiplier (hilbert.hpp:39-51); set up the inverse
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    cx<T> u = {(T)0, (T)0};
+    if (k < n && k != 0 && 2 * k != n) {
+      const cx<T> c = p.chirp[k];
+      const cx<T> X = cmul(buf[k], c);
+      // Z = -j X for 0 < k < n/2, +j X for k > n/2
+      cx<T> Z;
+      if (2 * k < n) { Z.x = X.y; Z.y = -X.x; }
+      else           { Z.x = -X.y; Z.y = X.x; }
+      const cx<T> Zc = {Z.x, -Z.y};
+      u = cmul(Zc, c);
+    }
+    buf[k] = u;
+  }
+  __syncthreads();
+  fft_dif(buf, p.W, p.log2m);
+  spectrum_mul(buf, p.B, M);
+  fft_dit_inv(buf, p.W, p.log2m);
+  T *e0 = p.out + r0 * p.out_stride;
+  T *e1 = p.out + (has1 ? r1 : r0) * p.out_stride;
+  const T inv_n = (T)(1.0 / (double)n);
+  for (int m = threadIdx.x; m < n; m += blockDim.x) {
+    const cx<T> w = cmul(buf[m], p.chirp[m]); // conj(h) * n
+    const T h0 = w.x * inv_n, h1 = -w.y * inv_n;
+    const T a = x0[m];
+    e0[m] = sqrt(a * a + h0 * h0);
+    if (has1) {
+      const T b = x1[m];
+      e1[m] = sqrt(b * b + h1 * h1);
+    }
+  }
+}
+
 // dst[i] += src[i]  (tail hand-over between neighbouring chunks of a long signal)
 template <typename T> __global__ void add_inplace_kernel(T *dst, const T *src, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

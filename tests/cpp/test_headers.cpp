@@ -1,0 +1,151 @@
+// C++ drop-in test: the reference's GTest cases for the hot path, restated without
+// GTest/Armadillo, compiled against include/fftconv/*.hpp of THIS repo.
+//   test/test_fftconv.cpp:19-43   copy_to_padded_buffer
+//   test/test_fftconv.cpp:93-124  FFTConvEngine<double>::get_for_ksize(95).oaconvolve<Mode>
+//   test/test_fftconv.cpp:127-218 convolve_fftw / oaconvolve_fftw, f32 + f64, Full + Same,
+//                                 planner flags accepted
+//   test/test_hilbert.cpp:6-24    Hilbert known-answer vector
+// Oracle = direct convolution in double (what arma::conv computes); tolerances from
+// test/test_common.hpp:9-18 (1e-9 double, 1e-5 float).  Needs a GPU.
+#include <fftconv/fftconv.hpp>
+#include <fftconv/hilbert.hpp>
+
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+using fftconv::ConvMode;
+
+static int g_fail = 0;
+#define EXPECT(c)                                                     \
+  do {                                                                \
+    if (!(c)) {                                                       \
+      std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c);         \
+      ++g_fail;                                                       \
+    }                                                                 \
+  } while (0)
+
+template <class T> std::vector<T> randn(size_t n, unsigned seed) {
+  std::mt19937 g(seed);
+  std::normal_distribution<double> d(0, 1);
+  std::vector<T> v(n);
+  for (auto &x : v) x = (T)d(g);
+  return v;
+}
+template <class T> std::vector<double> direct(const std::vector<T> &a, const std::vector<T> &k, ConvMode m) {
+  const size_t n = a.size(), K = k.size();
+  std::vector<double> full(n + K - 1, 0.0);
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = 0; j < K; ++j) full[i + j] += (double)a[i] * (double)k[j];
+  if (m == ConvMode::Full) return full;
+  return std::vector<double>(full.begin() + K / 2, full.begin() + K / 2 + n);
+}
+template <class T> constexpr double tol() { return std::is_same_v<T, float> ? 1e-5 : 1e-9; }
+template <class T> void near(const std::vector<T> &got, const std::vector<double> &want, double scale = 1.0) {
+  EXPECT(got.size() == want.size());
+  double worst = 0;
+  for (size_t i = 0; i < want.size() && i < got.size(); ++i) worst = std::max(worst, std::abs((double)got[i] - want[i]));
+  if (!(worst < tol<T>() * scale)) {
+    std::printf("  worst abs error %.3e (tol %.1e)\n", worst, tol<T>() * scale);
+    ++g_fail;
+  }
+}
+
+template <class T, ConvMode Mode, class F> void test_conv(F f) {
+  for (int size = 4; size < 100; size += 9) {
+    auto a = randn<T>(size, 100 + size), k = randn<T>(size, 200 + size);
+    std::vector<T> out(Mode == ConvMode::Full ? 2 * size - 1 : size, T(0));
+    f(std::span<const T>(a), std::span<const T>(k), std::span<T>(out));
+    near<T>(out, direct(a, k, Mode), std::is_same_v<T, float> ? 10.0 : 1.0);
+  }
+}
+template <class T, ConvMode Mode, class F> void test_oaconv(F f) {
+  auto k = randn<T>(95, 7);
+  for (int size = 200; size < 501; size += 150) {
+    auto a = randn<T>(size, 300 + size);
+    std::vector<T> out(Mode == ConvMode::Full ? size + 94 : size, T(0));
+    f(std::span<const T>(a), std::span<const T>(k), std::span<T>(out));
+    near<T>(out, direct(a, k, Mode), std::is_same_v<T, float> ? 10.0 : 1.0);
+  }
+}
+
+int main() {
+  fftw::WisdomSetup wisdom(false);
+  { // copy_to_padded_buffer
+    const std::vector<int> src = {1, 2, 3};
+    std::vector<int> dst(5, -1);
+    fftconv::internal::copy_to_padded_buffer<int>(std::span<const int>(src), std::span<int>(dst));
+    EXPECT(dst[0] == 1 && dst[1] == 2 && dst[2] == 3 && dst[3] == 0 && dst[4] == 0);
+  }
+  EXPECT(fftconv::internal::get_optimal_fft_size(95) == 512);
+  EXPECT(fftconv::internal::get_optimal_fft_size(245) == 2048);
+  { // engine interface
+    using T = double;
+    auto k = randn<T>(95, 1);
+    auto &plans = fftconv::FFTConvEngine<T>::get_for_ksize(k.size());
+    for (int n : {1000, 2000, 3000}) {
+      auto a = randn<T>(n, n);
+      std::vector<T> full(n + 94), same(n);
+      plans.oaconvolve<ConvMode::Full>(a, k, full);
+      plans.oaconvolve<ConvMode::Same>(a, k, same);
+      near<T>(full, direct(a, k, ConvMode::Full));
+      near<T>(same, direct(a, k, ConvMode::Same));
+    }
+  }
+  test_conv<double, ConvMode::Full>(fftconv::convolve_fftw<double, ConvMode::Full>);
+  test_conv<float, ConvMode::Full>(fftconv::convolve_fftw<float, ConvMode::Full>);
+  test_conv<double, ConvMode::Same>(fftconv::convolve_fftw<double, ConvMode::Same>);
+  test_conv<float, ConvMode::Same>(fftconv::convolve_fftw<float, ConvMode::Same>);
+  test_conv<double, ConvMode::Full>(fftconv::convolve_fftw<double, ConvMode::Full, FFTW_PATIENT>);
+  test_conv<double, ConvMode::Full>(fftconv::convolve_fftw<double, ConvMode::Full, FFTW_EXHAUSTIVE>);
+  test_conv<double, ConvMode::Full>(fftconv::oaconvolve_fftw<double, ConvMode::Full>);
+  test_conv<float, ConvMode::Full>(fftconv::oaconvolve_fftw<float, ConvMode::Full>);
+  test_oaconv<double, ConvMode::Same>(fftconv::oaconvolve_fftw<double, ConvMode::Same>);
+  test_oaconv<float, ConvMode::Same>(fftconv::oaconvolve_fftw<float, ConvMode::Same>);
+  test_oaconv<double, ConvMode::Same>(fftconv::oaconvolve_fftw<double, ConvMode::Same, FFTW_MEASURE>);
+  test_oaconv<double, ConvMode::Same>(fftconv::oaconvolve<double, ConvMode::Same>);
+  { // default Mode is Same
+    auto a = randn<double>(300, 5), k = randn<double>(31, 6);
+    std::vector<double> out(300);
+    fftconv::oaconvolve_fftw<double>(std::span<const double>(a), std::span<const double>(k), std::span<double>(out));
+    near<double>(out, direct(a, k, ConvMode::Same));
+  }
+  { // batched forms
+    const size_t batch = 5, n = 3000;
+    auto a = randn<float>(batch * n, 9), k = randn<float>(245, 10);
+    std::vector<float> out(batch * (n + 244));
+    fftconv::oaconvolve_batched<float, ConvMode::Full>(std::span<const float>(a), n, std::span<const float>(k),
+                                                       std::span<float>(out));
+    for (size_t b = 0; b < batch; ++b) {
+      std::vector<float> row(a.begin() + b * n, a.begin() + (b + 1) * n);
+      std::vector<float> got(out.begin() + b * (n + 244), out.begin() + (b + 1) * (n + 244));
+      near<float>(got, direct(row, k, ConvMode::Full), 100.0);
+    }
+  }
+  { // Hilbert known-answer vector, double and float, abs 1e-6
+    const std::array<double, 10> inp = {-0.999984, -0.736924, 0.511211, -0.0826997, 0.0655345,
+                                        -0.562082, -0.905911, 0.357729, 0.358593,   0.869386};
+    const std::array<double, 10> expect = {1.45197493, 1.15365169, 0.54703078, 0.27346519, 0.15097965,
+                                           0.83696245, 1.1476185,  0.71885109, 0.46089151, 1.07384968};
+    std::array<double, 10> out{};
+    fftconv::hilbert<double>(inp, out);
+    for (int i = 0; i < 10; ++i) EXPECT(std::abs(out[i] - expect[i]) < 1e-6);
+    std::array<float, 10> inf{}, outf{};
+    for (int i = 0; i < 10; ++i) inf[i] = (float)inp[i];
+    fftconv::hilbert<float>(inf, outf);
+    for (int i = 0; i < 10; ++i) EXPECT(std::abs(outf[i] - expect[i]) < 1e-6 * 5);
+  }
+  { // errors surface as exceptions (the reference only asserts)
+    bool threw = false;
+    std::vector<double> a(10), k(3), out(10);
+    try {
+      fftconv::convolve_fftw<double, ConvMode::Full>(std::span<const double>(a), std::span<const double>(k),
+                                                     std::span<double>(out));
+    } catch (const std::runtime_error &) { threw = true; }
+    EXPECT(threw);
+  }
+  std::printf(g_fail ? "FAILED %d\n" : "ALL PASSED\n", g_fail);
+  return g_fail ? 1 : 0;
+}
