@@ -1,0 +1,80 @@
+"""Multi-GPU partitioning of the hot path: one process per GPU, `torch.distributed`
+(NCCL over NVLink on the box, gloo in CPU tests) for plumbing.
+
+* Batches: rows are independent (the reference handles one signal per call,
+  /root/reference/include/fftconv/fftconv.hpp:474-480) -> `shard_rows`, no collective.
+* One long signal: overlap-add blocks are independent except for the K-1 sample
+  output tail that block s adds into block s+1 (fftconv.hpp:387-410).  Cut the
+  signal into one contiguous chunk per rank, convolve each chunk in Full mode, and
+  hand the chunk's last K-1 outputs to the right neighbour, which adds them to its
+  first K-1 outputs (<= 2 addends per sample: deterministic).  Message size
+  4 (K-1) bytes -> latency bound; send and receive are posted together.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+
+def shard_rows(batch: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range [lo, hi) of `rank`; sizes differ by at most one."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def chunk_bounds(n: int, world: int, rank: int, align: int = 4) -> Tuple[int, int]:
+    """Contiguous sample range [lo, hi) of `rank` in a signal of n samples.  Interior
+    cuts are multiples of `align` samples so every chunk starts 16-byte aligned
+    (float32) when the whole signal does."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+
+    def cut(r: int) -> int:
+        if r <= 0:
+            return 0
+        if r >= world:
+            return n
+        return min(n, (n * r // world) // align * align)
+
+    return cut(rank), cut(rank + 1)
+
+
+def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
+                    conv: Optional[Callable] = None, add: Optional[Callable] = None):
+    """Full-mode overlap-add convolution of one long signal split across ranks.
+
+    `a_chunk` is this rank's contiguous chunk (torch tensor, 1-D), `k` the taps
+    (replicated).  Returns this rank's slice of the full result: chunk length
+    samples, plus the final K-1 samples on the last rank.  `conv(a, k)` defaults to
+    the CUDA `oaconvolve(..., "full")`, `add(dst, src)` to the CUDA in-place add;
+    tests inject CPU stand-ins to exercise the exchange on gloo.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if conv is None or add is None:
+        from . import api
+
+        conv = conv or (lambda a, kk: api.oaconvolve(a, kk, "full"))
+        add = add or api.add_
+    klen = int(k.shape[0])
+    m = int(a_chunk.shape[0])
+    tail_len = klen - 1
+    if world > 1 and m < tail_len:
+        raise RuntimeError(f"chunk of {m} samples is shorter than the K-1 = {tail_len} tail")
+    y = conv(a_chunk, k)                      # m + K - 1 samples
+    if world == 1 or tail_len == 0:
+        return y
+    recv_buf = torch.empty(tail_len, dtype=y.dtype, device=y.device) if rank > 0 else None
+    ops = []
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, y[m:].contiguous(), rank + 1, group))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.irecv, recv_buf, rank - 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    if rank > 0:
+        add(y[:tail_len], recv_buf)
+    return y if rank == world - 1 else y[:m]
