@@ -1,0 +1,266 @@
+// fast_fft.cuh -- register-blocked shared-memory FFT engine for power-of-two
+// lengths 512 .. 16384, float and double.  Host+device (tests emulate it on the CPU).
+//
+// One complex FFT of length N = 2^LOG2N is owned by N/16 threads, 16 points per
+// thread per pass.  The transform is a sequence of in-place decimation-in-frequency
+// passes: first a radix-2^R0 pass (R0 = LOG2N mod 4, or 4), then radix-16 passes.
+// Every pass reads 16 points into registers, runs 16-point (or smaller) DFTs there,
+// multiplies by twiddles and writes the SAME shared-memory addresses back, so one
+// barrier per pass suffices and no reordering pass exists: the spectrum table is
+// stored in the resulting digit-reversed position order, and the inverse is the
+// exact mirror (conjugate twiddles first, then the inverse small DFT).
+//
+// First pass inputs come straight from global memory into registers and the last
+// inverse pass leaves the outputs in registers at the same (thread, slot) places, so
+// the signal itself never round-trips through shared memory for I/O.  The last
+// forward pass, the spectrum multiply and the first inverse pass are fused in
+// registers.
+//
+// Shared-memory layout: element i at i + (i >> 4) (one pad element per 16), which
+// makes every pass bank-conflict free for 8- and 16-byte elements.
+#pragma once
+
+#if defined(__CUDACC__)
+#define FCF_HD __host__ __device__ __forceinline__
+#else
+#define FCF_HD inline
+#endif
+
+namespace fc {
+namespace fast {
+
+template <typename T> struct cx {
+  T x, y;
+};
+
+template <typename T> FCF_HD cx<T> operator+(cx<T> a, cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> FCF_HD cx<T> operator-(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> FCF_HD cx<T> cmul(cx<T> a, cx<T> w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
+template <typename T> FCF_HD cx<T> cmulc(cx<T> a, cx<T> w) { return {a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y}; }
+// multiply by -j (S < 0) or +j (S > 0)
+template <int S, typename T> FCF_HD cx<T> rot90(cx<T> a) {
+  return S < 0 ? cx<T>{a.y, -a.x} : cx<T>{-a.y, a.x};
+}
+
+template <int LOG2N> struct Plan {
+  static_assert(LOG2N >= 9 && LOG2N <= 14, "fast engine covers N = 512 .. 16384");
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int R0 = (LOG2N % 4 == 0) ? 4 : (LOG2N % 4); // log2 of the first radix
+  static constexpr int P = (LOG2N - R0) / 4 + 1;                // passes
+  static constexpr int THREADS = N / 16;                        // per FFT
+  static constexpr int SMEM_ELEMS = N + N / 16;                 // padded
+};
+
+FCF_HD constexpr int phys(int i) { return i + (i >> 4); }
+
+// position (after all forward passes) -> frequency index
+FCF_HD constexpr unsigned freq_of_pos(unsigned pos, int log2n) {
+  const int r0 = (log2n % 4 == 0) ? 4 : (log2n % 4);
+  unsigned k = 0, mult = 1;
+  int lm = log2n; // log2 of the current sub-transform length
+  int r = r0;
+  while (lm > 0) {
+    const unsigned stride = 1u << (lm - r);
+    const unsigned digit = pos / stride;
+    pos -= digit * stride;
+    k += mult * digit;
+    mult <<= r;
+    lm -= r;
+    r = 4;
+  }
+  return k;
+}
+
+// ---- small DFTs in registers: natural order in, natural order out -----------------
+template <int S, typename T> FCF_HD void dft2(cx<T> *v) {
+  const cx<T> a = v[0], b = v[1];
+  v[0] = a + b;
+  v[1] = a - b;
+}
+template <int S, typename T> FCF_HD void dft4(cx<T> *v) {
+  const cx<T> s0 = v[0] + v[2], d0 = v[0] - v[2], s1 = v[1] + v[3], d1 = v[1] - v[3];
+  const cx<T> jd1 = rot90<S>(d1); // -j d1 (forward) / +j d1 (inverse)
+  v[0] = s0 + s1;
+  v[1] = d0 + jd1;
+  v[2] = s0 - s1;
+  v[3] = d0 - jd1;
+}
+template <int S, typename T> FCF_HD void dft8(cx<T> *v) {
+  // m = m0 + 2 m1, k = k1 + 4 k0
+  cx<T> e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+  dft4<S>(e);
+  dft4<S>(o);
+  const T h = (T)0.70710678118654752440084436210485L;
+  const T s = S < 0 ? (T)-1 : (T)1;
+  o[1] = cmul(o[1], cx<T>{h, s * h});
+  o[2] = rot90<S>(o[2]);
+  o[3] = cmul(o[3], cx<T>{-h, s * h});
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    v[k1] = e[k1] + o[k1];
+    v[k1 + 4] = e[k1] - o[k1];
+  }
+}
+template <int S, typename T> FCF_HD void dft16(cx<T> *v) {
+  // m = m0 + 4 m1, k = k1 + 4 k0
+  const T c8 = (T)0.70710678118654752440084436210485L;
+  const T c16 = (T)0.92387953251128675612818318939679L;
+  const T s16 = (T)0.38268343236508977172845998403040L;
+  const T s = S < 0 ? (T)-1 : (T)1;
+  cx<T> a[4][4]; // a[m0][k1]
+#pragma unroll
+  for (int m0 = 0; m0 < 4; ++m0) {
+    cx<T> t[4] = {v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]};
+    dft4<S>(t);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) a[m0][k1] = t[k1];
+  }
+  a[1][1] = cmul(a[1][1], cx<T>{c16, s * s16});
+  a[2][1] = cmul(a[2][1], cx<T>{c8, s * c8});
+  a[3][1] = cmul(a[3][1], cx<T>{s16, s * c16});
+  a[1][2] = cmul(a[1][2], cx<T>{c8, s * c8});
+  a[2][2] = rot90<S>(a[2][2]);
+  a[3][2] = cmul(a[3][2], cx<T>{-c8, s * c8});
+  a[1][3] = cmul(a[1][3], cx<T>{s16, s * c16});
+  a[2][3] = cmul(a[2][3], cx<T>{-c8, s * c8});
+  a[3][3] = cmul(a[3][3], cx<T>{-c16, -s * s16});
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    cx<T> t[4] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1]};
+    dft4<S>(t);
+#pragma unroll
+    for (int k0 = 0; k0 < 4; ++k0) v[k1 + 4 * k0] = t[k0];
+  }
+}
+template <int S, int LOGR, typename T> FCF_HD void dft_small(cx<T> *v) {
+  if (LOGR == 1) dft2<S>(v);
+  else if (LOGR == 2) dft4<S>(v);
+  else if (LOGR == 3) dft8<S>(v);
+  else dft16<S>(v);
+}
+
+// ---- passes --------------------------------------------------------------------
+// Register slot convention: pass 0 holds butterfly u (of U = 16 >> R0) in slots
+// [u R, u R + R), element q = logical index p_u + q (N >> R0), p_u = tid + u THREADS.
+template <int LOG2N> FCF_HD int pass0_index(int tid, int slot) {
+  using P = Plan<LOG2N>;
+  constexpr int R = 1 << P::R0;
+  const int u = slot / R, q = slot % R;
+  return tid + u * P::THREADS + q * (P::N >> P::R0);
+}
+
+// forward pass 0: v = inputs (slot convention above) -> shared memory
+template <int LOG2N, typename T> FCF_HD void fwd_pass0(int tid, cx<T> *v, cx<T> *buf, const cx<T> *W) {
+  using P = Plan<LOG2N>;
+  constexpr int R = 1 << P::R0, U = 16 / R, S0 = P::N >> P::R0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int p = tid + u * P::THREADS;
+    dft_small<-1, P::R0>(v + u * R);
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      cx<T> y = v[u * R + s];
+      if (s > 0) y = cmul(y, W[p * s]); // W_N^{p s}
+      buf[phys(p + s * S0)] = y;
+    }
+  }
+}
+// inverse pass 0: shared memory -> v = outputs (same slot convention)
+template <int LOG2N, typename T> FCF_HD void inv_pass0(int tid, cx<T> *v, const cx<T> *buf, const cx<T> *W) {
+  using P = Plan<LOG2N>;
+  constexpr int R = 1 << P::R0, U = 16 / R, S0 = P::N >> P::R0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int p = tid + u * P::THREADS;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      cx<T> y = buf[phys(p + s * S0)];
+      if (s > 0) y = cmulc(y, W[p * s]);
+      v[u * R + s] = y;
+    }
+    dft_small<+1, P::R0>(v + u * R);
+  }
+}
+
+// middle radix-16 pass J (1 <= J <= P - 2): sub-transform length m = N >> (R0 + 4 (J - 1))
+template <int LOG2N, int J, typename T> FCF_HD void fwd_mid(int tid, cx<T> *buf, const cx<T> *W) {
+  using P = Plan<LOG2N>;
+  constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4, SHIFT = LOG2N - LM;
+  const int p = tid & ((1 << LS) - 1), base = ((tid >> LS) << LM) + p;
+  cx<T> v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = buf[phys(base + (q << LS))];
+  dft16<-1>(v);
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    cx<T> y = v[s];
+    if (s > 0) y = cmul(y, W[(p * s) << SHIFT]); // W_m^{p s}
+    buf[phys(base + (s << LS))] = y;
+  }
+}
+template <int LOG2N, int J, typename T> FCF_HD void inv_mid(int tid, cx<T> *buf, const cx<T> *W) {
+  using P = Plan<LOG2N>;
+  constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4, SHIFT = LOG2N - LM;
+  const int p = tid & ((1 << LS) - 1), base = ((tid >> LS) << LM) + p;
+  cx<T> v[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    cx<T> y = buf[phys(base + (s << LS))];
+    if (s > 0) y = cmulc(y, W[(p * s) << SHIFT]);
+    v[s] = y;
+  }
+  dft16<+1>(v);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) buf[phys(base + (q << LS))] = v[q];
+}
+
+// last forward pass (m = 16) + spectrum multiply + first inverse pass, in registers.
+// H is in position order: H[16 tid + s].
+template <int LOG2N, typename T> FCF_HD void last_fused(int tid, cx<T> *buf, const cx<T> *H) {
+  cx<T> v[16];
+  const int base = 16 * tid;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = buf[phys(base + q)];
+  dft16<-1>(v);
+#pragma unroll
+  for (int s = 0; s < 16; ++s) v[s] = cmul(v[s], H[base + s]);
+  dft16<+1>(v);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) buf[phys(base + q)] = v[q];
+}
+
+// compile-time loops over the middle passes
+template <int LOG2N, int J, typename T> struct FwdMids {
+  template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<T> *W, Sync &sync) {
+    if constexpr (J <= Plan<LOG2N>::P - 2) {
+      fwd_mid<LOG2N, J>(tid, buf, W);
+      sync();
+      FwdMids<LOG2N, J + 1, T>::run(tid, buf, W, sync);
+    }
+  }
+};
+template <int LOG2N, int J, typename T> struct InvMids {
+  template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<T> *W, Sync &sync) {
+    if constexpr (J >= 1) {
+      inv_mid<LOG2N, J>(tid, buf, W);
+      sync();
+      InvMids<LOG2N, J - 1, T>::run(tid, buf, W, sync);
+    }
+  }
+};
+
+// Whole circular convolution with the spectrum H: v (inputs, pass-0 slot convention)
+// -> v (outputs, same convention).  `sync` is the barrier among the FFT's threads.
+template <int LOG2N, typename T, class Sync>
+FCF_HD void conv_core(int tid, cx<T> *v, cx<T> *buf, const cx<T> *W, const cx<T> *H, Sync &sync) {
+  fwd_pass0<LOG2N>(tid, v, buf, W);
+  sync();
+  FwdMids<LOG2N, 1, T>::run(tid, buf, W, sync);
+  last_fused<LOG2N>(tid, buf, H);
+  sync();
+  InvMids<LOG2N, Plan<LOG2N>::P - 2, T>::run(tid, buf, W, sync);
+  inv_pass0<LOG2N>(tid, v, buf, W);
+}
+
+} // namespace fast
+} // namespace fc

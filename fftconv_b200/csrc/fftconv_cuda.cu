@@ -11,6 +11,7 @@
 // table as the reference (fftconv.hpp:38-66).
 #include "../../include/fftconv_cuda.h"
 
+#include "fast_kernels.cuh"
 #include "generic_kernels.cuh"
 #include "oa_n2048_kernel.cuh"
 #include "oa_n2048_tables.h"
@@ -72,6 +73,7 @@ struct Tables {           // per (FFT length, dtype)
   void *W = nullptr;      // cx<T>[N]   exp(-2 pi i k / N)
   double2 *Wd = nullptr;  // double2[N] same, double (spectrum kernel)
   void *G = nullptr;      // cx<T>[N]   Hilbert multiplier, DIF order (lazy)
+  void *Gfast = nullptr;  // cx<T>[N]   Hilbert multiplier, fast-engine position order (lazy)
 };
 
 struct BluesteinTables {  // per (n, dtype): Hilbert of a non-power-of-two length
@@ -129,6 +131,7 @@ void free_ctx(DeviceCtx &c) {
     cudaFree(kv.second.W);
     cudaFree(kv.second.Wd);
     cudaFree(kv.second.G);
+    cudaFree(kv.second.Gfast);
   }
   c.tables.clear();
   for (auto &kv : c.bluestein) {
@@ -181,20 +184,22 @@ template <typename T> int get_tables(DeviceCtx &c, size_t N, Tables **out) {
   return 0;
 }
 
-template <typename T> int get_hilbert_table(DeviceCtx &c, size_t N, Tables &t) {
-  if (t.G) return 0;
+template <typename T> int get_hilbert_table(DeviceCtx &c, size_t N, Tables &t, bool fast_layout = false) {
+  void *&slot = fast_layout ? t.Gfast : t.G;
+  if (slot) return 0;
   // full-spectrum multiplier of the Hilbert transformer, 1/n folded in
   // (/root/reference/include/fftconv/hilbert.hpp:39-51, :57)
   std::vector<cx<T>> g(N);
   for (size_t pos = 0; pos < N; ++pos) {
-    const size_t k = fc::generic::dif_freq_of_pos((unsigned)pos, (unsigned)N);
+    const size_t k = fast_layout ? fc::fast::freq_of_pos((unsigned)pos, ilog2(N))
+                                 : fc::generic::dif_freq_of_pos((unsigned)pos, (unsigned)N);
     T im = 0;
     if (k != 0 && 2 * k != N) im = (T)((2 * k < N ? -1.0 : 1.0) / (double)N);
     g[pos].x = 0;
     g[pos].y = im;
   }
-  CU_TRY(cudaMalloc(&t.G, N * sizeof(cx<T>)));
-  CU_TRY(cudaMemcpy(t.G, g.data(), N * sizeof(cx<T>), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMalloc(&slot, N * sizeof(cx<T>)));
+  CU_TRY(cudaMemcpy(slot, g.data(), N * sizeof(cx<T>), cudaMemcpyHostToDevice));
   (void)c;
   return 0;
 }
@@ -340,6 +345,59 @@ int prepare_spectrum(DeviceCtx &c, cudaStream_t st, const T *k, size_t klen, siz
   return 0;
 }
 
+// ---- fast engine (fast_fft.cuh): N = 512 .. 16384 ------------------------------------
+template <typename T> constexpr int fast_fpc(int log2n) {
+  // FFTs per CTA: 256 threads (float) / 128 threads (double) where one FFT has fewer
+  const int target = sizeof(T) == 4 ? 256 : 128;
+  const int threads = (1 << log2n) / 16;
+  return threads >= target ? 1 : target / threads;
+}
+template <typename T> size_t fast_smem(int log2n, size_t klen) {
+  const size_t n = size_t(1) << log2n;
+  return (size_t)fast_fpc<T>(log2n) * (n + n / 16 + 2 * (klen ? klen - 1 : 0)) * sizeof(cx<T>);
+}
+template <typename T> bool fast_ok(const DeviceCtx &c, size_t N, size_t klen) {
+  if (N < 512 || N > 16384 || env_int("FFTCONV_CUDA_FORCE_GENERIC", 0)) return false;
+  if (sizeof(T) == 8 && N > 8192) return false; // 1024 threads x complex double does not fit the register file
+  return fast_smem<T>(ilog2(N), klen) <= c.smem_optin;
+}
+
+template <typename T, int LOG2N>
+int launch_oa_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::OaArgs<T> &p, size_t klen) {
+  constexpr int FPC = fast_fpc<T>(LOG2N);
+  const size_t smem = fast_smem<T>(LOG2N, klen);
+  auto kern = fc::fast::oa_fast_kernel<T, LOG2N, FPC>;
+  if (int r = ensure_smem(c, kern, smem)) return r;
+  const long long grid = (p.n_streams + 2 * FPC - 1) / (2 * FPC);
+  if (grid > 0x7fffffffLL) return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "batch too large for one launch");
+  kern<<<(unsigned)grid, fc::fast::Plan<LOG2N>::THREADS * FPC, smem, st>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+template <typename T, int LOG2N>
+int launch_hilbert_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::HilbertArgs<T> &p) {
+  constexpr int FPC = fast_fpc<T>(LOG2N);
+  const size_t smem = fast_smem<T>(LOG2N, 0);
+  auto kern = fc::fast::hilbert_fast_kernel<T, LOG2N, FPC>;
+  if (int r = ensure_smem(c, kern, smem)) return r;
+  const long long grid = (p.batch + 2 * FPC - 1) / (2 * FPC);
+  kern<<<(unsigned)grid, fc::fast::Plan<LOG2N>::THREADS * FPC, smem, st>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+#define FAST_SWITCH(FN, log2n, ...)                                        \
+  switch (log2n) {                                                         \
+  case 9: return FN<T, 9>(__VA_ARGS__);                                    \
+  case 10: return FN<T, 10>(__VA_ARGS__);                                  \
+  case 11: return FN<T, 11>(__VA_ARGS__);                                  \
+  case 12: return FN<T, 12>(__VA_ARGS__);                                  \
+  case 13: return FN<T, 13>(__VA_ARGS__);                                  \
+  case 14: return FN<T, 14>(__VA_ARGS__);                                  \
+  default: return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "fast engine: bad size"); \
+  }
+
 // ---- overlap-add on device pointers -------------------------------------------------
 template <typename T>
 int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride,
@@ -396,8 +454,11 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
     }
   }
 
+  const bool use_fast = fast_ok<T>(c, N, klen);
   const cx<T> *H = nullptr;
-  if (int r = prepare_spectrum<T>(c, st, k, klen, N, fc::generic::LAYOUT_DIF, *tab, &H)) return r;
+  if (int r = prepare_spectrum<T>(c, st, k, klen, N,
+                                  use_fast ? fc::generic::LAYOUT_FAST : fc::generic::LAYOUT_DIF, *tab, &H))
+    return r;
   fc::generic::OaArgs<T> p{};
   p.in = a;
   p.out = out;
@@ -415,13 +476,20 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
   long long chunks = 1;
   if ((long long)batch < target_streams) {
     chunks = (target_streams + (long long)batch - 1) / (long long)batch;
-    chunks = std::min(chunks, std::max<long long>(1, segs / 8));
+    // >= 8 segments per chunk keeps the warm-up segment under ~12 %; when even that
+    // cannot fill a quarter of the SMs (single short signals) go down to 2
+    long long min_segs = 8;
+    if ((long long)batch * std::max<long long>(1, segs / 8) < c.sm_count / 4) min_segs = 2;
+    chunks = std::min(chunks, std::max<long long>(1, segs / min_segs));
   }
   p.segs_per_chunk = (segs + chunks - 1) / chunks;
   p.chunks = (segs + p.segs_per_chunk - 1) / p.segs_per_chunk;
   p.n_streams = (long long)batch * p.chunks;
   p.W = static_cast<const cx<T> *>(tab->W);
   p.H = H;
+  if (use_fast) {
+    FAST_SWITCH(launch_oa_fast, p.log2n, c, st, p, klen)
+  }
   const size_t smem = (N + 2 * (klen - 1)) * sizeof(cx<T>);
   if (int r = ensure_smem(c, fc::generic::oa_generic_kernel<T>, smem)) return r;
   const long long grid = (p.n_streams + 1) / 2;
@@ -507,7 +575,8 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
                                                  " exceeds the single-CTA shared-memory FFT");
   Tables *tab = nullptr;
   if (int r = get_tables<T>(c, n, &tab)) return r;
-  if (int r = get_hilbert_table<T>(c, n, *tab)) return r;
+  const bool use_fast = fast_ok<T>(c, n, 0);
+  if (int r = get_hilbert_table<T>(c, n, *tab, use_fast)) return r;
   fc::generic::HilbertArgs<T> p{};
   p.in = x;
   p.out = env;
@@ -517,7 +586,10 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
   p.out_stride = (long long)env_stride;
   p.log2n = ilog2(n);
   p.W = static_cast<const cx<T> *>(tab->W);
-  p.G = static_cast<const cx<T> *>(tab->G);
+  p.G = static_cast<const cx<T> *>(use_fast ? tab->Gfast : tab->G);
+  if (use_fast) {
+    FAST_SWITCH(launch_hilbert_fast, p.log2n, c, st, p)
+  }
   if (int r = ensure_smem(c, fc::generic::hilbert_pow2_kernel<T>, std::max<size_t>(smem, 16))) return r;
   const long long grid = ((long long)batch + 1) / 2;
   const int threads = (int)std::min<size_t>(512, std::max<size_t>(32, n / 4));

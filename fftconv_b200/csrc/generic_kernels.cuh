@@ -6,6 +6,7 @@
 // The f32 / N = 2048 overlap-add case has its own kernel (oa_n2048_kernel.cuh).
 #pragma once
 
+#include "fast_fft.cuh"
 #include "generic_fft.cuh"
 
 namespace fc {
@@ -18,7 +19,7 @@ namespace generic {
 // in double.  O(N K) work -- K <= a few thousand taps by construction.  (j k fits
 // 32 bits: j < K <= N / 2, k < N <= 2^15.)
 // ---------------------------------------------------------------------------
-enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1 };
+enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1, LAYOUT_FAST = 2 };
 
 __device__ __forceinline__ unsigned n2048_freq_of_index(unsigned idx) {
   // idx = slot * 128 + c0 (see fc::n2048::p2_freq)
@@ -36,7 +37,10 @@ __global__ void spectrum_kernel(const T *__restrict__ taps, int klen, int N,
   const int lane = threadIdx.x & 31;
   const int pos = blockIdx.x * kSpectrumWarps + (threadIdx.x >> 5);
   if (pos >= N) return;
-  const unsigned k = layout == LAYOUT_N2048 ? n2048_freq_of_index(pos) : dif_freq_of_pos(pos, N);
+  unsigned k;
+  if (layout == LAYOUT_N2048) k = n2048_freq_of_index(pos);
+  else if (layout == LAYOUT_FAST) k = fc::fast::freq_of_pos(pos, 31 - __clz(N));
+  else k = dif_freq_of_pos(pos, N);
   const unsigned mask = (unsigned)(N - 1);
   double re = 0.0, im = 0.0;
   for (int j = lane; j < klen; j += 32) {

@@ -95,3 +95,11 @@ def test_n2048_kernel_logic_emulated_on_cpu(built, case):
     r = subprocess.run([exe, *map(str, case)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (case, r.stdout, r.stderr)
     assert float(r.stdout.split()[0]) < 1e-6
+
+
+def test_fast_fft_engine_emulated_on_cpu(built):
+    """fast_fft.cuh (N = 512 .. 16384, float and double): the kernel's own pass functions
+    run for all threads pass by pass on the CPU against direct circular convolution."""
+    exe = os.path.join(ROOT, "tests", "cpu", "emulate_fast_fft")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL PASSED" in r.stdout, r.stdout + r.stderr
