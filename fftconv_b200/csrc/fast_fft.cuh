@@ -49,9 +49,26 @@ template <int LOG2N> struct Plan {
   static constexpr int P = (LOG2N - R0) / 4 + 1;                // passes
   static constexpr int THREADS = N / 16;                        // per FFT
   static constexpr int SMEM_ELEMS = N + N / 16;                 // padded
+  // Per-pass twiddle tables, s-major so that the threads of a warp read consecutive
+  // entries: pass 0 holds (R-1) rows of N/R entries, TW0[(s-1) (N/R) + p] = W_N^{p s};
+  // middle pass J holds 15 rows of m/16 entries, TWJ[(s-1) (m/16) + p] = W_m^{p s}.
+  static constexpr int tw_offset(int pass) { // first entry of pass `pass` (0 .. P-2)
+    int off = 0;
+    if (pass == 0) return 0;
+    off += ((1 << R0) - 1) * (N >> R0);
+    for (int j = 1; j < pass; ++j) off += 15 * ((N >> (R0 + 4 * (j - 1))) >> 4);
+    return off;
+  }
+  static constexpr int TW_ELEMS = tw_offset(P - 1);
 };
 
 FCF_HD constexpr int phys(int i) { return i + (i >> 4); }
+
+// spectrum-table index (s-major, see last_fused) -> position after the forward passes
+FCF_HD constexpr unsigned pos_of_table_index(unsigned idx, int log2n) {
+  const unsigned threads = (1u << log2n) / 16;
+  return 16 * (idx % threads) + idx / threads;
+}
 
 // position (after all forward passes) -> frequency index
 FCF_HD constexpr unsigned freq_of_pos(unsigned pos, int log2n) {
@@ -150,7 +167,7 @@ template <int LOG2N> FCF_HD int pass0_index(int tid, int slot) {
 }
 
 // forward pass 0: v = inputs (slot convention above) -> shared memory
-template <int LOG2N, typename T> FCF_HD void fwd_pass0(int tid, cx<T> *v, cx<T> *buf, const cx<T> *W) {
+template <int LOG2N, typename T> FCF_HD void fwd_pass0(int tid, cx<T> *v, cx<T> *buf, const cx<T> *TW) {
   using P = Plan<LOG2N>;
   constexpr int R = 1 << P::R0, U = 16 / R, S0 = P::N >> P::R0;
 #pragma unroll
@@ -160,13 +177,13 @@ template <int LOG2N, typename T> FCF_HD void fwd_pass0(int tid, cx<T> *v, cx<T> 
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       cx<T> y = v[u * R + s];
-      if (s > 0) y = cmul(y, W[p * s]); // W_N^{p s}
+      if (s > 0) y = cmul(y, TW[(s - 1) * S0 + p]); // W_N^{p s}
       buf[phys(p + s * S0)] = y;
     }
   }
 }
 // inverse pass 0: shared memory -> v = outputs (same slot convention)
-template <int LOG2N, typename T> FCF_HD void inv_pass0(int tid, cx<T> *v, const cx<T> *buf, const cx<T> *W) {
+template <int LOG2N, typename T> FCF_HD void inv_pass0(int tid, cx<T> *v, const cx<T> *buf, const cx<T> *TW) {
   using P = Plan<LOG2N>;
   constexpr int R = 1 << P::R0, U = 16 / R, S0 = P::N >> P::R0;
 #pragma unroll
@@ -175,7 +192,7 @@ template <int LOG2N, typename T> FCF_HD void inv_pass0(int tid, cx<T> *v, const 
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       cx<T> y = buf[phys(p + s * S0)];
-      if (s > 0) y = cmulc(y, W[p * s]);
+      if (s > 0) y = cmulc(y, TW[(s - 1) * S0 + p]);
       v[u * R + s] = y;
     }
     dft_small<+1, P::R0>(v + u * R);
@@ -183,9 +200,10 @@ template <int LOG2N, typename T> FCF_HD void inv_pass0(int tid, cx<T> *v, const 
 }
 
 // middle radix-16 pass J (1 <= J <= P - 2): sub-transform length m = N >> (R0 + 4 (J - 1))
-template <int LOG2N, int J, typename T> FCF_HD void fwd_mid(int tid, cx<T> *buf, const cx<T> *W) {
+template <int LOG2N, int J, typename T> FCF_HD void fwd_mid(int tid, cx<T> *buf, const cx<T> *TWALL) {
   using P = Plan<LOG2N>;
-  constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4, SHIFT = LOG2N - LM;
+  constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4;
+  const cx<T> *TW = TWALL + P::tw_offset(J);
   const int p = tid & ((1 << LS) - 1), base = ((tid >> LS) << LM) + p;
   cx<T> v[16];
 #pragma unroll
@@ -194,19 +212,20 @@ template <int LOG2N, int J, typename T> FCF_HD void fwd_mid(int tid, cx<T> *buf,
 #pragma unroll
   for (int s = 0; s < 16; ++s) {
     cx<T> y = v[s];
-    if (s > 0) y = cmul(y, W[(p * s) << SHIFT]); // W_m^{p s}
+    if (s > 0) y = cmul(y, TW[((s - 1) << LS) + p]); // W_m^{p s}
     buf[phys(base + (s << LS))] = y;
   }
 }
-template <int LOG2N, int J, typename T> FCF_HD void inv_mid(int tid, cx<T> *buf, const cx<T> *W) {
+template <int LOG2N, int J, typename T> FCF_HD void inv_mid(int tid, cx<T> *buf, const cx<T> *TWALL) {
   using P = Plan<LOG2N>;
-  constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4, SHIFT = LOG2N - LM;
+  constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4;
+  const cx<T> *TW = TWALL + P::tw_offset(J);
   const int p = tid & ((1 << LS) - 1), base = ((tid >> LS) << LM) + p;
   cx<T> v[16];
 #pragma unroll
   for (int s = 0; s < 16; ++s) {
     cx<T> y = buf[phys(base + (s << LS))];
-    if (s > 0) y = cmulc(y, W[(p * s) << SHIFT]);
+    if (s > 0) y = cmulc(y, TW[((s - 1) << LS) + p]);
     v[s] = y;
   }
   dft16<+1>(v);
@@ -215,7 +234,7 @@ template <int LOG2N, int J, typename T> FCF_HD void inv_mid(int tid, cx<T> *buf,
 }
 
 // last forward pass (m = 16) + spectrum multiply + first inverse pass, in registers.
-// H is in position order: H[16 tid + s].
+// H is s-major: H[s THREADS + tid] belongs to position 16 tid + s (coalesced reads).
 template <int LOG2N, typename T> FCF_HD void last_fused(int tid, cx<T> *buf, const cx<T> *H) {
   cx<T> v[16];
   const int base = 16 * tid;
@@ -223,7 +242,7 @@ template <int LOG2N, typename T> FCF_HD void last_fused(int tid, cx<T> *buf, con
   for (int q = 0; q < 16; ++q) v[q] = buf[phys(base + q)];
   dft16<-1>(v);
 #pragma unroll
-  for (int s = 0; s < 16; ++s) v[s] = cmul(v[s], H[base + s]);
+  for (int s = 0; s < 16; ++s) v[s] = cmul(v[s], H[s * Plan<LOG2N>::THREADS + tid]);
   dft16<+1>(v);
 #pragma unroll
   for (int q = 0; q < 16; ++q) buf[phys(base + q)] = v[q];
@@ -252,7 +271,8 @@ template <int LOG2N, int J, typename T> struct InvMids {
 // Whole circular convolution with the spectrum H: v (inputs, pass-0 slot convention)
 // -> v (outputs, same convention).  `sync` is the barrier among the FFT's threads.
 template <int LOG2N, typename T, class Sync>
-FCF_HD void conv_core(int tid, cx<T> *v, cx<T> *buf, const cx<T> *W, const cx<T> *H, Sync &sync) {
+FCF_HD void conv_core(int tid, cx<T> *v, cx<T> *buf, const cx<T> *W /* pass twiddle tables */, const cx<T> *H,
+                      Sync &sync) {
   fwd_pass0<LOG2N>(tid, v, buf, W);
   sync();
   FwdMids<LOG2N, 1, T>::run(tid, buf, W, sync);
@@ -260,6 +280,21 @@ FCF_HD void conv_core(int tid, cx<T> *v, cx<T> *buf, const cx<T> *W, const cx<T>
   sync();
   InvMids<LOG2N, Plan<LOG2N>::P - 2, T>::run(tid, buf, W, sync);
   inv_pass0<LOG2N>(tid, v, buf, W);
+}
+
+// Host: fill the per-pass twiddle tables (TW_ELEMS entries) in long double.
+template <int LOG2N, typename T, class RootFn> void fill_pass_twiddles(cx<T> *tw, RootFn root /* (num, den) -> exp(-2 pi i num/den) */) {
+  using P = Plan<LOG2N>;
+  constexpr int R = 1 << P::R0, S0 = P::N >> P::R0;
+  for (int s = 1; s < R; ++s)
+    for (int p = 0; p < S0; ++p) tw[(s - 1) * S0 + p] = root((long long)p * s, (long long)P::N);
+  int lm = LOG2N - P::R0;
+  for (int j = 1; j <= P::P - 2; ++j, lm -= 4) {
+    cx<T> *t = tw + P::tw_offset(j);
+    const int ls = lm - 4;
+    for (int s = 1; s < 16; ++s)
+      for (int p = 0; p < (1 << ls); ++p) t[((s - 1) << ls) + p] = root((long long)p * s, 1LL << lm);
+  }
 }
 
 } // namespace fast

@@ -73,7 +73,8 @@ struct Tables {           // per (FFT length, dtype)
   void *W = nullptr;      // cx<T>[N]   exp(-2 pi i k / N)
   double2 *Wd = nullptr;  // double2[N] same, double (spectrum kernel)
   void *G = nullptr;      // cx<T>[N]   Hilbert multiplier, DIF order (lazy)
-  void *Gfast = nullptr;  // cx<T>[N]   Hilbert multiplier, fast-engine position order (lazy)
+  void *Gfast = nullptr;  // cx<T>[N]   Hilbert multiplier, fast-engine table order (lazy)
+  void *TWfast = nullptr; // cx<T>[..]  fast-engine per-pass twiddle tables (lazy)
 };
 
 struct BluesteinTables {  // per (n, dtype): Hilbert of a non-power-of-two length
@@ -132,6 +133,7 @@ void free_ctx(DeviceCtx &c) {
     cudaFree(kv.second.Wd);
     cudaFree(kv.second.G);
     cudaFree(kv.second.Gfast);
+    cudaFree(kv.second.TWfast);
   }
   c.tables.clear();
   for (auto &kv : c.bluestein) {
@@ -191,8 +193,9 @@ template <typename T> int get_hilbert_table(DeviceCtx &c, size_t N, Tables &t, b
   // (/root/reference/include/fftconv/hilbert.hpp:39-51, :57)
   std::vector<cx<T>> g(N);
   for (size_t pos = 0; pos < N; ++pos) {
-    const size_t k = fast_layout ? fc::fast::freq_of_pos((unsigned)pos, ilog2(N))
-                                 : fc::generic::dif_freq_of_pos((unsigned)pos, (unsigned)N);
+    const size_t k = fast_layout
+                         ? fc::fast::freq_of_pos(fc::fast::pos_of_table_index((unsigned)pos, ilog2(N)), ilog2(N))
+                         : fc::generic::dif_freq_of_pos((unsigned)pos, (unsigned)N);
     T im = 0;
     if (k != 0 && 2 * k != N) im = (T)((2 * k < N ? -1.0 : 1.0) / (double)N);
     g[pos].x = 0;
@@ -387,6 +390,18 @@ int launch_hilbert_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::Hilber
   ++g_launches;
   return 0;
 }
+template <typename T, int LOG2N> int build_fast_twiddles(Tables &t) {
+  using P = fc::fast::Plan<LOG2N>;
+  std::vector<fc::fast::cx<T>> tw(P::TW_ELEMS);
+  fc::fast::fill_pass_twiddles<LOG2N, T>(tw.data(), [](long long num, long long den) {
+    const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)(num % den) / (long double)den;
+    return fc::fast::cx<T>{(T)cosl(a), (T)(-sinl(a))};
+  });
+  CU_TRY(cudaMalloc(&t.TWfast, tw.size() * sizeof(fc::fast::cx<T>)));
+  CU_TRY(cudaMemcpy(t.TWfast, tw.data(), tw.size() * sizeof(fc::fast::cx<T>), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 #define FAST_SWITCH(FN, log2n, ...)                                        \
   switch (log2n) {                                                         \
   case 9: return FN<T, 9>(__VA_ARGS__);                                    \
@@ -488,6 +503,11 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
   p.W = static_cast<const cx<T> *>(tab->W);
   p.H = H;
   if (use_fast) {
+    if (!tab->TWfast) {
+      auto build = [&]() -> int { FAST_SWITCH(build_fast_twiddles, p.log2n, *tab) };
+      if (int r = build()) return r;
+    }
+    p.W = static_cast<const cx<T> *>(tab->TWfast);
     FAST_SWITCH(launch_oa_fast, p.log2n, c, st, p, klen)
   }
   const size_t smem = (N + 2 * (klen - 1)) * sizeof(cx<T>);
@@ -588,6 +608,11 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
   p.W = static_cast<const cx<T> *>(tab->W);
   p.G = static_cast<const cx<T> *>(use_fast ? tab->Gfast : tab->G);
   if (use_fast) {
+    if (!tab->TWfast) {
+      auto build = [&]() -> int { FAST_SWITCH(build_fast_twiddles, p.log2n, *tab) };
+      if (int r = build()) return r;
+    }
+    p.W = static_cast<const cx<T> *>(tab->TWfast);
     FAST_SWITCH(launch_hilbert_fast, p.log2n, c, st, p)
   }
   if (int r = ensure_smem(c, fc::generic::hilbert_pow2_kernel<T>, std::max<size_t>(smem, 16))) return r;

@@ -39,7 +39,7 @@ __global__ void spectrum_kernel(const T *__restrict__ taps, int klen, int N,
   if (pos >= N) return;
   unsigned k;
   if (layout == LAYOUT_N2048) k = n2048_freq_of_index(pos);
-  else if (layout == LAYOUT_FAST) k = fc::fast::freq_of_pos(pos, 31 - __clz(N));
+  else if (layout == LAYOUT_FAST) k = fc::fast::freq_of_pos(fc::fast::pos_of_table_index(pos, 31 - __clz(N)), 31 - __clz(N));
   else k = dif_freq_of_pos(pos, N);
   const unsigned mask = (unsigned)(N - 1);
   double re = 0.0, im = 0.0;

@@ -41,13 +41,14 @@ template <int LOG2N, typename T> double run_case() {
   std::vector<double> h(K);
   for (auto &v : x) v = {nd(rng), nd(rng)};
   for (auto &v : h) v = nd(rng);
-  std::vector<cx<T>> W(N), H(N);
-  for (int k = 0; k < N; ++k) {
-    const long double a = 2 * pi * k / N;
-    W[k] = {(T)cosl(a), (T)-sinl(a)};
-  }
-  for (int pos = 0; pos < N; ++pos) {
-    const unsigned k = freq_of_pos(pos, LOG2N);
+  std::vector<cx<T>> W(P::TW_ELEMS), H(N);
+  fill_pass_twiddles<LOG2N, T>(W.data(), [&](long long num, long long den) {
+    const long double a = 2 * pi * (long double)(num % den) / (long double)den;
+    return cx<T>{(T)cosl(a), (T)-sinl(a)};
+  });
+  for (int idx = 0; idx < N; ++idx) {
+    const int pos = idx;
+    const unsigned k = freq_of_pos(pos_of_table_index(idx, LOG2N), LOG2N);
     long double re = 0, im = 0;
     for (int j = 0; j < K; ++j) {
       const long double a = 2 * pi * ((long long)j * k % N) / N;
