@@ -52,7 +52,7 @@ template <int LOG2N> struct Plan {
   // Per-pass twiddle tables, s-major so that the threads of a warp read consecutive
   // entries: pass 0 holds (R-1) rows of N/R entries, TW0[(s-1) (N/R) + p] = W_N^{p s};
   // middle pass J holds 15 rows of m/16 entries, TWJ[(s-1) (m/16) + p] = W_m^{p s}.
-  static constexpr int tw_offset(int pass) { // first entry of pass `pass` (0 .. P-2)
+  FCF_HD static constexpr int tw_offset(int pass) { // first entry of pass `pass` (0 .. P-2)
     int off = 0;
     if (pass == 0) return 0;
     off += ((1 << R0) - 1) * (N >> R0);
@@ -203,7 +203,8 @@ template <int LOG2N, typename T> FCF_HD void inv_pass0(int tid, cx<T> *v, const 
 template <int LOG2N, int J, typename T> FCF_HD void fwd_mid(int tid, cx<T> *buf, const cx<T> *TWALL) {
   using P = Plan<LOG2N>;
   constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4;
-  const cx<T> *TW = TWALL + P::tw_offset(J);
+  constexpr int OFF = P::tw_offset(J);
+  const cx<T> *TW = TWALL + OFF;
   const int p = tid & ((1 << LS) - 1), base = ((tid >> LS) << LM) + p;
   cx<T> v[16];
 #pragma unroll
@@ -219,7 +220,8 @@ template <int LOG2N, int J, typename T> FCF_HD void fwd_mid(int tid, cx<T> *buf,
 template <int LOG2N, int J, typename T> FCF_HD void inv_mid(int tid, cx<T> *buf, const cx<T> *TWALL) {
   using P = Plan<LOG2N>;
   constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4;
-  const cx<T> *TW = TWALL + P::tw_offset(J);
+  constexpr int OFF = P::tw_offset(J);
+  const cx<T> *TW = TWALL + OFF;
   const int p = tid & ((1 << LS) - 1), base = ((tid >> LS) << LM) + p;
   cx<T> v[16];
 #pragma unroll

@@ -424,7 +424,7 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
   const long long segs = (long long)((n + step - 1) / step);
 
   const bool use_n2048 = std::is_same<T, float>::value && N == 2048 &&
-                         !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0);
+                         !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) && !env_int("FFTCONV_CUDA_NO_N2048", 0);
   if (use_n2048) {
     if constexpr (std::is_same<T, float>::value) {
       if (int r = get_n2048_tables(c)) return r;
