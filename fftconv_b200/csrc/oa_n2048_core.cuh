@@ -236,8 +236,10 @@ FC_HD void phase3(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
     put(xb, x1_addr(8 * t1 + t0, k2), v.re[slot16(t1)], v.im[slot16(t1)]);
 }
 
-// P4: leaves y[t + 128 m] in slot slot16(m).
-FC_HD void phase4(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
+// P4: leaves y[t + 128 m] in slot slot16(m).  Split so that a barrier (and the
+// request for the next inputs, which land in the exchange buffer) can follow the
+// last read of the buffer.
+FC_HD void phase4_read(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
     get(xb, x1_addr(t, k2), v.re[k2], v.im[k2]);
@@ -246,7 +248,11 @@ FC_HD void phase4(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
       cmul2(v.re[k2], v.im[k2], w.re, -w.im);
     }
   }
-  dft16<+1>(v);
+}
+FC_HD void phase4_compute(Regs &v) { dft16<+1>(v); }
+FC_HD void phase4(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
+  phase4_read(t, v, xb, tw1);
+  phase4_compute(v);
 }
 
 } // namespace n2048

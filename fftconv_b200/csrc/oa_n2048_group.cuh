@@ -251,13 +251,21 @@ FC_HD void fast_load(int t, Regs &v, const float *in, int ls, const int (&shift)
   }
 }
 
+// registers -> the four lanes' outputs (+ tail hand-over).  b_l points at y[t] of
+// lane l -- in a shared staging buffer or directly in global memory (one coalesced
+// 128-byte line per warp instruction); element y[t + 128 m] goes to b_l[128 m].
+FC_HD void fast_store_to(int t, const Regs &v, float *b0, float *b1, float *b2, float *b3, const ThreadMasks &k,
+                         const pt4 *tail_prev, pt4 *tail_next, bool add_tail, bool stage, int step);
+
 // registers -> staged output (+ tail hand-over).  `out` is the output staging buffer.
 FC_HD void fast_store(int t, const Regs &v, float *out, int ls, const int (&shift)[4], const ThreadMasks &k,
                       const pt4 *tail_prev, pt4 *tail_next, bool add_tail, bool stage, int step) {
-  float *b0 = out + 0 * ls + shift[0] + t;
-  float *b1 = out + 1 * ls + shift[1] + t;
-  float *b2 = out + 2 * ls + shift[2] + t;
-  float *b3 = out + 3 * ls + shift[3] + t;
+  fast_store_to(t, v, out + 0 * ls + shift[0] + t, out + 1 * ls + shift[1] + t, out + 2 * ls + shift[2] + t,
+                out + 3 * ls + shift[3] + t, k, tail_prev, tail_next, add_tail, stage, step);
+}
+
+FC_HD void fast_store_to(int t, const Regs &v, float *b0, float *b1, float *b2, float *b3, const ThreadMasks &k,
+                         const pt4 *tail_prev, pt4 *tail_next, bool add_tail, bool stage, int step) {
 #pragma unroll
   for (int m = 0; m < kPts; ++m) {
     const int i = t + 128 * m;
@@ -360,7 +368,7 @@ FC_HD GroupLayout group_layout(int klen) {
   int off = 0;
   g.xb = off;      off += kN * (int)sizeof(pt4);
   g.tails = off;   off += 2 * tail_pts(klen) * (int)sizeof(pt4);
-  g.packets = off; off += 2 * (((int)sizeof(Packet) + 15) & ~15);
+  g.packets = off; off += 3 * (((int)sizeof(Packet) + 15) & ~15);
   g.sched = off;   off += ((int)sizeof(WorkIter) + 15) & ~15;
   g.mbar = off;    off += 16;
   g.total = off;

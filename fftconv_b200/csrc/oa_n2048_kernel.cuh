@@ -11,12 +11,11 @@
 //                      TMA, issued by thread 0 at the end of the previous
 //                      iteration)
 //   LDS.32 x 64        x[t + 128 m] of the four lanes -> packed registers
-//   P0 compute | bar | P0 put | bar | P1 | bar | P2 | bar | P3 | bar | P4
-//   tail hand-over     (K-1 samples, separate small ping-pong buffers)
-//   bar | STS.32 x 64 into xb (natural order) | fence.proxy.async | bar
-//   thread 0           cp.async.bulk shared -> global of the 4 x step results,
-//                      waits until xb has been read, requests the next inputs
-//                      (whose packet it built at the start of this iteration)
+//   P0 compute | bar | P0 put | bar | P1 | bar | P2 | bar | P3 | bar | P4 reads | bar
+//   thread 0           requests the NEXT inputs (the buffer is idle from here on)
+//                      and then builds the packet of the iteration after next
+//   P4 DFT, tail hand-over (K-1 samples, separate small ping-pong buffers),
+//   64 coalesced 4-byte stores per thread straight from registers
 // While one group waits for its copies the other three groups keep the FP32
 // pipe busy.  Thread 0 of each group is the group's scheduler: the other 127
 // threads execute no 64-bit control arithmetic at all.
@@ -116,11 +115,12 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   const int g = threadIdx.x >> 7, t = threadIdx.x & 127;
   unsigned char *base = grp0 + (size_t)g * L.total;
   pt4 *xb = reinterpret_cast<pt4 *>(base + L.xb);
-  float *stage = reinterpret_cast<float *>(base + L.xb); // aliases xb
+  float *stage = reinterpret_cast<float *>(base + L.xb); // input staging aliases xb
   pt4 *tails = reinterpret_cast<pt4 *>(base + L.tails);
   const int pk_stride = ((int)sizeof(Packet) + 15) & ~15;
-  Packet *pk0 = reinterpret_cast<Packet *>(base + L.packets);
-  Packet *pk1 = reinterpret_cast<Packet *>(base + L.packets + pk_stride);
+  Packet *pk[3] = {reinterpret_cast<Packet *>(base + L.packets),
+                   reinterpret_cast<Packet *>(base + L.packets + pk_stride),
+                   reinterpret_cast<Packet *>(base + L.packets + 2 * pk_stride)};
   const uint32_t mbar = dev::smem_u32(base + L.mbar);
   const int tpts = tail_pts(p.klen);
   const int LS = L.lane_stride;
@@ -142,8 +142,9 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     it.init(w0, w1);
     InPlan ip;
-    fill_packet(p, it, pk1, pk0, ip);
-    issue_loads(pk0, stage, LS, mbar);
+    fill_packet(p, it, pk[2], pk[0], ip); // iteration 0
+    fill_packet(p, it, pk[0], pk[1], ip); // iteration 1
+    issue_loads(pk[0], stage, LS, mbar);
   }
   __syncthreads();
 
@@ -151,17 +152,14 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   const int bar_id = g + 1;
   uint32_t in_phase = 0;
   int parity = 0;
-  Packet *cur = pk0, *nxt = pk1;
+  int ci = 0; // ring index of the current packet
 
-  while (cur->valid) {
+  while (pk[ci]->valid) {
+    const Packet *cur = pk[ci];
     const bool warm = cur->warm != 0;
     const bool add_tail = cur->first == 0;
     const bool in_fast = cur->in_fast != 0, out_fast = cur->out_fast != 0;
     Regs v;
-    if (t == 0) { // describe the next iteration now: it becomes visible at the next barrier
-      InPlan ip;
-      fill_packet(p, it, cur, nxt, ip);
-    }
     if (in_fast) {
       int sh[4] = {cur->in_shift[0], cur->in_shift[1], cur->in_shift[2], cur->in_shift[3]};
       while (!dev::mbar_try_wait(mbar, in_phase)) {
@@ -182,33 +180,31 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     dev::bar_sync(bar_id);
     phase3(t, v, xb, tw2);
     dev::bar_sync(bar_id);
-    phase4(t, v, xb, tw1);
+    phase4_read(t, v, xb, tw1);
+    dev::bar_sync(bar_id); // every thread has read its points: the exchange buffer is idle
+    const int ni = ci == 2 ? 0 : ci + 1, nni = ni == 2 ? 0 : ni + 1;
+    if (t == 0) {
+      // request the next inputs now: they land while this iteration's last DFT and
+      // stores run; then describe the iteration after next (hidden behind the copies)
+      issue_loads(pk[ni], stage, LS, mbar);
+      if (pk[ni]->valid) {
+        InPlan ip;
+        fill_packet(p, it, pk[ni], pk[nni], ip);
+      }
+    }
+    phase4_compute(v);
     pt4 *tail_prev = tails + (parity ^ 1) * tpts, *tail_next = tails + parity * tpts;
-    dev::bar_sync(bar_id); // every thread has read its points: xb becomes the output staging area
     if (out_fast || warm) {
-      int sh[4] = {cur->out_shift[0], cur->out_shift[1], cur->out_shift[2], cur->out_shift[3]};
-      fast_store(t, v, stage, LS, sh, masks, tail_prev, tail_next, add_tail, out_fast, p.step);
-      if (out_fast) dev::fence_proxy_async(); // staged values -> visible to the bulk-copy engine
+      // 4-byte coalesced stores straight from registers (one 128-byte line per warp instruction)
+      fast_store_to(t, v, cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t, cur->out_dst[3] + t,
+                    masks, tail_prev, tail_next, add_tail, out_fast, p.step);
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_store(t, v, p, ln, cur->j, tail_prev, tail_next, add_tail, warm);
     }
-    dev::bar_sync(bar_id);
-    if (t == 0) {
-      if (out_fast) {
-        flush_out(cur, stage, LS, p.step);
-        dev::bulk_wait_read0(); // the bulk stores have finished reading the staging area
-      }
-      issue_loads(nxt, stage, LS, mbar);
-    }
-    // no barrier here: the next iteration touches xb only after its own first
-    // barrier, which thread 0 reaches after the drain above
     parity ^= 1;
-    Packet *tmp = cur;
-    cur = nxt;
-    nxt = tmp;
+    ci = ni;
   }
-  if (t == 0) dev::bulk_wait0();
 }
 #endif // __CUDACC__
 

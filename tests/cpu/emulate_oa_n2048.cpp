@@ -42,39 +42,25 @@ struct HostGroup {
   void poison() { // whatever was in the exchange buffer must never be consumed as data
     for (int i = 0; i < kN * 4; ++i) stage[i] = NAN;
   }
-  void schedule(const Packet *prev, Packet *next) {
-    InPlan ip;
-    fill_packet(p, it, prev, next, ip);
-    if (ip.fast)
-      for (int l = 0; l < 4; ++l)
-        std::memcpy(stage + l * L.lane_stride, ip.src[l], ip.bytes[l]);
-  }
-  void flush(const Packet *q) {
-    for (int l = 0; l < 4; ++l) {
-      const int d = q->out_shift[l];
-      const FlushSplit f = flush_split(d, p.step);
-      float *dst = q->out_dst[l];
-      const float *src = stage + l * L.lane_stride + d;
-      if ((reinterpret_cast<unsigned long long>(dst + f.head) & 15ULL) != 0 ||
-          (reinterpret_cast<unsigned long long>(src + f.head) & 15ULL) != 0) {
-        std::printf("misaligned bulk store\n");
-        std::exit(3);
-      }
-      std::memcpy(dst + f.head, src + f.head, (size_t)f.nb * 4);
-      for (int i = 0; i < f.head; ++i) dst[i] = src[i];
-      for (int i = f.head + f.nb; i < p.step; ++i) dst[i] = src[i];
-    }
+  void issue(const Packet *q) { // the bulk (TMA) loads of a fast-path packet
+    if (q->valid && q->in_fast)
+      for (int l = 0; l < 4; ++l) std::memcpy(stage + l * L.lane_stride, q->in_src[l], q->in_bytes[l]);
   }
 
   void run(long long w0, long long w1) {
     it.init(w0, w1);
-    Packet *cur = &pk[0], *nxt = &pk[1];
+    Packet ring[3];
+    std::memset(ring, 0, sizeof(ring));
+    InPlan ip;
+    fill_packet(p, it, &ring[2], &ring[0], ip);
+    fill_packet(p, it, &ring[0], &ring[1], ip);
     poison();
-    schedule(nxt, cur);
-    int parity = 0;
+    issue(&ring[0]);
+    int parity = 0, ci = 0;
     std::vector<ThreadMasks> masks(kThreads);
     for (int t = 0; t < kThreads; ++t) masks[t] = make_masks(t, p);
-    while (cur->valid) {
+    while (ring[ci].valid) {
+      const Packet *cur = &ring[ci];
       ++g_iters;
       g_fast_in += cur->in_fast;
       g_fast_out += cur->out_fast;
@@ -93,23 +79,24 @@ struct HostGroup {
       for (int t = 0; t < kThreads; ++t) phase1(t, regs[t], xb.data(), p.tw2);
       for (int t = 0; t < kThreads; ++t) phase2(t, regs[t], xb.data(), p.hs);
       for (int t = 0; t < kThreads; ++t) phase3(t, regs[t], xb.data(), p.tw2);
-      for (int t = 0; t < kThreads; ++t) phase4(t, regs[t], xb.data(), p.tw1);
+      for (int t = 0; t < kThreads; ++t) phase4_read(t, regs[t], xb.data(), p.tw1);
+      // --- barrier; thread 0: request the next inputs, describe the iteration after next ---
+      const int ni = ci == 2 ? 0 : ci + 1, nni = ni == 2 ? 0 : ni + 1;
       poison();
+      issue(&ring[ni]);
+      if (ring[ni].valid) fill_packet(p, it, &ring[ni], &ring[nni], ip);
       pt4 *tail_prev = tails.data() + (parity ^ 1) * tpts, *tail_next = tails.data() + parity * tpts;
       for (int t = 0; t < kThreads; ++t) {
+        phase4_compute(regs[t]);
         if (cur->out_fast || warm) {
-          int sh[4] = {cur->out_shift[0], cur->out_shift[1], cur->out_shift[2], cur->out_shift[3]};
-          fast_store(t, regs[t], stage, L.lane_stride, sh, masks[t], tail_prev, tail_next, add_tail,
-                     cur->out_fast != 0, p.step);
+          fast_store_to(t, regs[t], cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t,
+                        cur->out_dst[3] + t, masks[t], tail_prev, tail_next, add_tail, cur->out_fast != 0, p.step);
         } else {
           io_store(t, regs[t], p, cur->ln, cur->j, tail_prev, tail_next, add_tail, warm);
         }
       }
-      if (cur->out_fast) flush(cur);
-      poison();
-      schedule(cur, nxt);
       parity ^= 1;
-      std::swap(cur, nxt);
+      ci = ni;
     }
   }
 };
