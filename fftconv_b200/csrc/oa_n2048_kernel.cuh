@@ -118,9 +118,10 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   float *stage = reinterpret_cast<float *>(base + L.xb); // input staging aliases xb
   pt4 *tails = reinterpret_cast<pt4 *>(base + L.tails);
   const int pk_stride = ((int)sizeof(Packet) + 15) & ~15;
-  Packet *pk[3] = {reinterpret_cast<Packet *>(base + L.packets),
-                   reinterpret_cast<Packet *>(base + L.packets + pk_stride),
-                   reinterpret_cast<Packet *>(base + L.packets + 2 * pk_stride)};
+  // ring of three packets, addressed arithmetically so that every access stays a
+  // shared-memory access (an array of pointers would live in local memory)
+  unsigned char *pk_base = base + L.packets;
+  auto PK = [&](int i) -> Packet * { return reinterpret_cast<Packet *>(pk_base + i * pk_stride); };
   const uint32_t mbar = dev::smem_u32(base + L.mbar);
   const int tpts = tail_pts(p.klen);
   const int LS = L.lane_stride;
@@ -142,9 +143,9 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     it.init(w0, w1);
     InPlan ip;
-    fill_packet(p, it, pk[2], pk[0], ip); // iteration 0
-    fill_packet(p, it, pk[0], pk[1], ip); // iteration 1
-    issue_loads(pk[0], stage, LS, mbar);
+    fill_packet(p, it, PK(2), PK(0), ip); // iteration 0
+    fill_packet(p, it, PK(0), PK(1), ip); // iteration 1
+    issue_loads(PK(0), stage, LS, mbar);
   }
   __syncthreads();
 
@@ -154,8 +155,8 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   int parity = 0;
   int ci = 0; // ring index of the current packet
 
-  while (pk[ci]->valid) {
-    const Packet *cur = pk[ci];
+  while (PK(ci)->valid) {
+    const Packet *cur = PK(ci);
     const bool warm = cur->warm != 0;
     const bool add_tail = cur->first == 0;
     const bool in_fast = cur->in_fast != 0, out_fast = cur->out_fast != 0;
@@ -183,15 +184,8 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     phase4_read(t, v, xb, tw1);
     dev::bar_sync(bar_id); // every thread has read its points: the exchange buffer is idle
     const int ni = ci == 2 ? 0 : ci + 1, nni = ni == 2 ? 0 : ni + 1;
-    if (t == 0) {
-      // request the next inputs now: they land while this iteration's last DFT and
-      // stores run; then describe the iteration after next (hidden behind the copies)
-      issue_loads(pk[ni], stage, LS, mbar);
-      if (pk[ni]->valid) {
-        InPlan ip;
-        fill_packet(p, it, pk[ni], pk[nni], ip);
-      }
-    }
+    // request the next inputs now: they land while this iteration's last DFT and stores run
+    if (t == 0) issue_loads(PK(ni), stage, LS, mbar);
     phase4_compute(v);
     pt4 *tail_prev = tails + (parity ^ 1) * tpts, *tail_next = tails + parity * tpts;
     if (out_fast || warm) {
@@ -201,6 +195,12 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_store(t, v, p, ln, cur->j, tail_prev, tail_next, add_tail, warm);
+    }
+    // describe the iteration after next; thread 0 is late by this much at the next
+    // mbarrier wait, where everybody waits for the copies anyway
+    if (t == 0 && PK(ni)->valid) {
+      InPlan ip;
+      fill_packet(p, it, PK(ni), PK(nni), ip);
     }
     parity ^= 1;
     ci = ni;
