@@ -161,55 +161,7 @@ FC_HD void io_store(int t, const Regs &v, const OaParams &p, const Lane (&ln)[4]
 // ---- fast path: staged through shared memory ------------------------------------
 // staging buffers hold 4 lanes of `ls` floats each, ls = (3 + step + 3) & ~3 (oa_n2048_kernel.cuh)
 
-struct InPlan {            // where the bulk loads of one segment quad come from
-  bool fast;
-  const float *src[4];     // 16-byte aligned global address
-  int bytes[4];            // multiple of 16
-  int shift[4];            // element i of the segment sits at staging index shift + i
-};
-struct OutPlan {           // where the staged outputs of one segment quad go
-  bool fast;
-  float *dst[4];           // global address of y[0] (any 4-byte alignment)
-  int shift[4];            // y[i] sits at staging index shift + i  (shift = (dst / 4) & 3)
-};
-
 FC_HD int align_shift(const void *ptr) { return (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ULL); }
-
-FC_HD void plan_in(const OaParams &p, const Lane (&ln)[4], long long j, InPlan &ip) {
-  ip.fast = true;
-  // the aligned span may reach up to 3 samples past the segment: never past the tensor
-  const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
-#pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    const long long seg = ln[l].seg0 + j;
-    const bool on = ln[l].active && seg >= 0 && j < ln[l].cnt;
-    const long long pos = seg * p.step;
-    const bool full = on && (p.n - pos >= p.step);
-    ip.fast = ip.fast && full;
-    const float *a = ln[l].in + (full ? pos : 0);
-    const int sh = align_shift(a);
-    ip.shift[l] = sh;
-    ip.src[l] = a - sh;
-    ip.bytes[l] = ((sh + p.step) * 4 + 15) & ~15;
-    ip.fast = ip.fast && (ip.src[l] + ip.bytes[l] / 4 <= tensor_end);
-  }
-}
-
-FC_HD void plan_out(const OaParams &p, const Lane (&ln)[4], long long j, bool warm, OutPlan &op) {
-  op.fast = !warm;
-#pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    const long long seg = ln[l].seg0 + j;
-    const bool on = ln[l].active && seg >= 0 && j < ln[l].cnt;
-    const long long o0 = seg * p.step - p.pad;
-    // interior segment: owns exactly y[0..step), all of it inside the row
-    const bool interior = on && seg < p.segs - 1 && o0 >= 0;
-    op.fast = op.fast && interior;
-    float *d = ln[l].out + (interior ? o0 : 0);
-    op.dst[l] = d;
-    op.shift[l] = align_shift(d);
-  }
-}
 
 // Per-thread constants of the fast path (depend on t, K only).
 struct ThreadMasks {
@@ -337,6 +289,12 @@ struct WorkIter {
   }
 };
 
+struct SchedSlot {      // private scheduler state of one warp leader
+  WorkIter it;
+  Lane ln[4];
+  long long pad_;
+};
+
 // tail buffers: two (ping-pong) arrays of tail_pts(K) points per group
 FC_HD int tail_pts(int klen) { return ((klen - 1) + 7) & ~7; }
 
@@ -344,8 +302,8 @@ struct Packet {        // one iteration of one group, produced by thread 0
   int valid;           // 0: the slice is exhausted
   int warm;
   int first;           // no incoming tail
-  int in_fast;
-  int out_fast;
+  int in_fast[4];      // per lane; the quad takes the fast path when all four are set
+  int out_fast[4];
   int in_shift[4];
   int out_shift[4];
   int in_bytes[4];     // bulk-load size per lane (fast path)
@@ -369,7 +327,7 @@ FC_HD GroupLayout group_layout(int klen) {
   g.xb = off;      off += kN * (int)sizeof(pt4);
   g.tails = off;   off += 2 * tail_pts(klen) * (int)sizeof(pt4);
   g.packets = off; off += 3 * (((int)sizeof(Packet) + 15) & ~15);
-  g.sched = off;   off += ((int)sizeof(WorkIter) + 15) & ~15;
+  g.sched = off;   off += 4 * (int)sizeof(SchedSlot);
   g.mbar = off;    off += 16;
   g.total = off;
   return g;
@@ -378,38 +336,46 @@ inline size_t smem_bytes(int groups, int klen) {
   return (size_t)(2048 + 2048 + 128) * sizeof(cpair) + (size_t)groups * group_layout(klen).total;
 }
 
-// Thread 0 (or the host emulator): describe the next iteration in `pk`; `prev` is
-// the packet of the iteration before it.  Returns false when the slice is done.
-FC_HD bool fill_packet(const OaParams &p, WorkIter &it, const Packet *prev, Packet *pk, InPlan &ip) {
+// One lane of the description of the next iteration.  The group's four warp
+// leaders each own one lane (`slot` holds that leader's private copy of the work
+// iterator and of the quad's lanes, so the leaders never wait for one another);
+// lane 0 also writes the fields shared by the quad.
+FC_HD void fill_packet_lane(const OaParams &p, SchedSlot &slot, Packet *pk, int lane) {
   IterDesc d;
-  if (it.in_visit) { // same quad as before: the lanes carry over
-#pragma unroll
-    for (int l = 0; l < 4; ++l) pk->ln[l] = prev->ln[l];
+  if (!slot.it.next(p, slot.ln, d)) {
+    if (lane == 0) pk->valid = 0;
+    return;
   }
-  if (!it.next(p, pk->ln, d)) {
-    pk->valid = 0;
-    ip.fast = false;
-    return false;
+  const Lane ln = slot.ln[lane];
+  const long long seg = ln.seg0 + d.j;
+  const bool on = ln.active && seg >= 0 && d.j < ln.cnt;
+  const long long pos = seg * p.step;
+  // input: a full segment whose 16-byte aligned span stays inside the tensor
+  const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
+  const bool full = on && (p.n - pos >= p.step);
+  const float *a = ln.in + (full ? pos : 0);
+  const int ish = align_shift(a);
+  const int bytes = ((ish + p.step) * 4 + 15) & ~15;
+  pk->in_shift[lane] = ish;
+  pk->in_src[lane] = a - ish;
+  pk->in_bytes[lane] = bytes;
+  pk->in_fast[lane] = full && (a - ish + bytes / 4 <= tensor_end);
+  // output: an interior segment owns exactly y[0..step), all of it inside the row
+  const long long o0 = pos - p.pad;
+  const bool interior = on && seg < p.segs - 1 && o0 >= 0;
+  float *dst = ln.out + (interior ? o0 : 0);
+  pk->out_dst[lane] = dst;
+  pk->out_shift[lane] = align_shift(dst);
+  pk->out_fast[lane] = interior && !d.warm;
+  pk->ln[lane] = ln;
+  if (lane == 0) {
+    pk->valid = 1;
+    pk->warm = d.warm;
+    pk->first = d.first;
+    pk->j = d.j;
   }
-  OutPlan op;
-  plan_in(p, pk->ln, d.j, ip);
-  plan_out(p, pk->ln, d.j, d.warm, op);
-  pk->valid = 1;
-  pk->warm = d.warm;
-  pk->first = d.first;
-  pk->in_fast = ip.fast;
-  pk->out_fast = op.fast;
-  pk->j = d.j;
-#pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    pk->in_shift[l] = ip.shift[l];
-    pk->in_bytes[l] = ip.bytes[l];
-    pk->in_src[l] = ip.src[l];
-    pk->out_shift[l] = op.shift[l];
-    pk->out_dst[l] = op.dst[l];
-  }
-  return true;
 }
+FC_HD bool all4(const int (&f)[4]) { return (f[0] & f[1] & f[2] & f[3]) != 0; }
 
 // How a staged output lane [0, step) splits into a 16-byte aligned bulk part and
 // up to 3 + 3 boundary samples.

@@ -79,7 +79,7 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // Thread 0: start the bulk copies of a fast-path packet into the staging area
 // (= the exchange buffer, which must be idle).
 __device__ __forceinline__ void issue_loads(const Packet *pk, float *stage, int lane_stride, uint32_t mbar) {
-  if (pk->valid && pk->in_fast) {
+  if (pk->valid && all4(pk->in_fast)) {
     dev::fence_proxy_async(); // the area was last touched through the generic proxy
     dev::mbar_expect_tx(mbar, (uint32_t)(pk->in_bytes[0] + pk->in_bytes[1] + pk->in_bytes[2] + pk->in_bytes[3]));
 #pragma unroll
@@ -137,17 +137,21 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   const long long w0 = p.total_work / n_slots * slot + min(p.total_work % n_slots, slot);
   const long long w1 = w0 + p.total_work / n_slots + (slot < p.total_work % n_slots ? 1 : 0);
 
-  WorkIter &it = *reinterpret_cast<WorkIter *>(base + L.sched); // used by thread 0 only
+  // the four warp leaders of a group are its scheduler: leader w describes lane w
+  const bool leader = (t & 31) == 0;
+  const int my_lane = t >> 5;
+  SchedSlot &sslot = reinterpret_cast<SchedSlot *>(base + L.sched)[my_lane];
+  if (leader) {
+    sslot.it.init(w0, w1);
+    fill_packet_lane(p, sslot, PK(0), my_lane); // iteration 0
+    fill_packet_lane(p, sslot, PK(1), my_lane); // iteration 1
+  }
   if (t == 0) {
     dev::mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    it.init(w0, w1);
-    InPlan ip;
-    fill_packet(p, it, PK(2), PK(0), ip); // iteration 0
-    fill_packet(p, it, PK(0), PK(1), ip); // iteration 1
-    issue_loads(PK(0), stage, LS, mbar);
   }
   __syncthreads();
+  if (t == 0) issue_loads(PK(0), stage, LS, mbar);
 
   const ThreadMasks masks = make_masks(t, p);
   const int bar_id = g + 1;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     const Packet *cur = PK(ci);
     const bool warm = cur->warm != 0;
     const bool add_tail = cur->first == 0;
-    const bool in_fast = cur->in_fast != 0, out_fast = cur->out_fast != 0;
+    const bool in_fast = all4(cur->in_fast), out_fast = all4(cur->out_fast);
     Regs v;
     if (in_fast) {
       int sh[4] = {cur->in_shift[0], cur->in_shift[1], cur->in_shift[2], cur->in_shift[3]};
@@ -196,12 +200,9 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_store(t, v, p, ln, cur->j, tail_prev, tail_next, add_tail, warm);
     }
-    // describe the iteration after next; thread 0 is late by this much at the next
-    // mbarrier wait, where everybody waits for the copies anyway
-    if (t == 0 && PK(ni)->valid) {
-      InPlan ip;
-      fill_packet(p, it, PK(ni), PK(nni), ip);
-    }
+    // describe the iteration after next, one lane per warp leader (no warp is later
+    // than the others, and the copies requested above are still in flight)
+    if (leader && PK(ni)->valid) fill_packet_lane(p, sslot, PK(nni), my_lane);
     parity ^= 1;
     ci = ni;
   }

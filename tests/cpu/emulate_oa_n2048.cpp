@@ -28,7 +28,6 @@ struct HostGroup {
   float *stage; // aliases xb, exactly as in the kernel
   std::vector<Regs> regs;
   Packet pk[2];
-  WorkIter it;
   int tpts;
 
   explicit HostGroup(const OaParams &pp)
@@ -43,17 +42,20 @@ struct HostGroup {
     for (int i = 0; i < kN * 4; ++i) stage[i] = NAN;
   }
   void issue(const Packet *q) { // the bulk (TMA) loads of a fast-path packet
-    if (q->valid && q->in_fast)
+    if (q->valid && all4(q->in_fast))
       for (int l = 0; l < 4; ++l) std::memcpy(stage + l * L.lane_stride, q->in_src[l], q->in_bytes[l]);
   }
 
   void run(long long w0, long long w1) {
-    it.init(w0, w1);
+    SchedSlot slots[4];
     Packet ring[3];
     std::memset(ring, 0, sizeof(ring));
-    InPlan ip;
-    fill_packet(p, it, &ring[2], &ring[0], ip);
-    fill_packet(p, it, &ring[0], &ring[1], ip);
+    std::memset(slots, 0, sizeof(slots));
+    for (int l = 0; l < 4; ++l) {
+      slots[l].it.init(w0, w1);
+      fill_packet_lane(p, slots[l], &ring[0], l);
+      fill_packet_lane(p, slots[l], &ring[1], l);
+    }
     poison();
     issue(&ring[0]);
     int parity = 0, ci = 0;
@@ -62,11 +64,12 @@ struct HostGroup {
     while (ring[ci].valid) {
       const Packet *cur = &ring[ci];
       ++g_iters;
-      g_fast_in += cur->in_fast;
-      g_fast_out += cur->out_fast;
+      const bool in_fast = all4(cur->in_fast), out_fast = all4(cur->out_fast);
+      g_fast_in += in_fast;
+      g_fast_out += out_fast;
       const bool warm = cur->warm != 0, add_tail = cur->first == 0;
       for (int t = 0; t < kThreads; ++t) {
-        if (cur->in_fast) {
+        if (in_fast) {
           int sh[4] = {cur->in_shift[0], cur->in_shift[1], cur->in_shift[2], cur->in_shift[3]};
           fast_load(t, regs[t], stage, L.lane_stride, sh, masks[t].in_zero);
         } else {
@@ -84,17 +87,19 @@ struct HostGroup {
       const int ni = ci == 2 ? 0 : ci + 1, nni = ni == 2 ? 0 : ni + 1;
       poison();
       issue(&ring[ni]);
-      if (ring[ni].valid) fill_packet(p, it, &ring[ni], &ring[nni], ip);
+
       pt4 *tail_prev = tails.data() + (parity ^ 1) * tpts, *tail_next = tails.data() + parity * tpts;
       for (int t = 0; t < kThreads; ++t) {
         phase4_compute(regs[t]);
-        if (cur->out_fast || warm) {
+        if (out_fast || warm) {
           fast_store_to(t, regs[t], cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t,
-                        cur->out_dst[3] + t, masks[t], tail_prev, tail_next, add_tail, cur->out_fast != 0, p.step);
+                        cur->out_dst[3] + t, masks[t], tail_prev, tail_next, add_tail, out_fast, p.step);
         } else {
           io_store(t, regs[t], p, cur->ln, cur->j, tail_prev, tail_next, add_tail, warm);
         }
       }
+      if (ring[ni].valid)
+        for (int l = 0; l < 4; ++l) fill_packet_lane(p, slots[l], &ring[nni], l);
       parity ^= 1;
       ci = ni;
     }
