@@ -450,19 +450,18 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
       p.hs = reinterpret_cast<const fc::n2048::cpair *>(H);
       const size_t smem = fc::n2048::smem_bytes(G, (int)klen);
       const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
-      if (G == 4) {
-        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<4>, smem)) return r;
-        fc::n2048::oa_n2048_kernel<4><<<(unsigned)grid, 128 * 4, smem, st>>>(p);
-      } else if (G == 3) {
-        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<3>, smem)) return r;
-        fc::n2048::oa_n2048_kernel<3><<<(unsigned)grid, 128 * 3, smem, st>>>(p);
-      } else if (G == 2) {
-        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<2>, smem)) return r;
-        fc::n2048::oa_n2048_kernel<2><<<(unsigned)grid, 128 * 2, smem, st>>>(p);
-      } else {
-        if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<1>, smem)) return r;
-        fc::n2048::oa_n2048_kernel<1><<<(unsigned)grid, 128 * 1, smem, st>>>(p);
-      }
+      const bool recomp = env_int("FFTCONV_CUDA_TW_RECOMPUTE", 1) != 0;
+#define FC_LAUNCH_N2048(GG, RR)                                                         \
+  {                                                                                     \
+    if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<GG, RR>, smem)) return r;     \
+    fc::n2048::oa_n2048_kernel<GG, RR><<<(unsigned)grid, 128 * GG, smem, st>>>(p);      \
+  }
+      if (G == 4 && recomp) FC_LAUNCH_N2048(4, true)
+      else if (G == 4) FC_LAUNCH_N2048(4, false)
+      else if (G == 3) FC_LAUNCH_N2048(3, false)
+      else if (G == 2) FC_LAUNCH_N2048(2, false)
+      else FC_LAUNCH_N2048(1, false)
+#undef FC_LAUNCH_N2048
       CU_TRY(cudaGetLastError());
       ++g_launches;
       return 0;

@@ -158,42 +158,72 @@ FC_HD int p2_freq(int c0, int s) {
   return 16 * (c & 15) + 256 * k1b + (c >> 4);
 }
 
+// Twiddles w[k], k = 1..15, of one thread: either all 15 read from the table, or
+// (RECOMP) only k = 1, 2, 4, 8 read and the rest formed as products in registers --
+// the shared-memory crossbar is this kernel's bottleneck and the FP32 pipe has
+// slack, so 11 fewer 8-byte loads are worth 44 scalar multiply-adds.  Products are
+// at most three deep (k = 15 = 8 * (4 * (1 * 2))): relative twiddle error <= ~2e-7.
+FC_HD cpair cpair_mul(cpair a, cpair b) {
+  cpair r;
+  r.re = a.re * b.re - a.im * b.im;
+  r.im = a.re * b.im + a.im * b.re;
+  return r;
+}
+template <bool RECOMP, class Use>
+FC_HD void for_each_twiddle(const cpair *col /* entry k = 0 */, int stride, Use &&use) {
+  if (!RECOMP) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) use(k, col[k * stride]);
+  } else {
+    const cpair w1 = col[1 * stride], w2 = col[2 * stride], w4 = col[4 * stride], w8 = col[8 * stride];
+    use(1, w1); use(2, w2); use(4, w4); use(8, w8);
+    const cpair w3 = cpair_mul(w1, w2); use(3, w3);
+    const cpair w5 = cpair_mul(w4, w1); use(5, w5);
+    const cpair w6 = cpair_mul(w4, w2); use(6, w6);
+    const cpair w7 = cpair_mul(w4, w3); use(7, w7);
+    use(9, cpair_mul(w8, w1));
+    use(10, cpair_mul(w8, w2));
+    use(11, cpair_mul(w8, w3));
+    use(12, cpair_mul(w8, w4));
+    use(13, cpair_mul(w8, w5));
+    use(14, cpair_mul(w8, w6));
+    use(15, cpair_mul(w8, w7));
+  }
+}
+
 // ---- phases (called between group barriers) ---------------------------------
 // P0: v holds x[t + 128 m] in slot m.  Split in two so that a barrier can sit
 // between the last read of the (aliased) input staging area and the first write
 // of the exchange buffer.
-FC_HD void phase0_compute(int t, Regs &v, const cpair *tw1) {
+template <bool RECOMP = false> FC_HD void phase0_compute(int t, Regs &v, const cpair *tw1) {
   dft16<-1>(v);
-#pragma unroll
-  for (int k2 = 1; k2 < 16; ++k2) {
+  for_each_twiddle<RECOMP>(tw1 + t, 128, [&](int k2, cpair w) {
     const int s = slot16(k2);
-    const cpair w = tw1[k2 * 128 + t];
     cmul2(v.re[s], v.im[s], w.re, w.im);
-  }
+  });
 }
 FC_HD void phase0_put(int t, const Regs &v, pt4 *xb) {
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) put(xb, x1_addr(t, k2), v.re[slot16(k2)], v.im[slot16(k2)]);
 }
 FC_HD void phase0(int t, Regs &v, pt4 *xb, const cpair *tw1) {
-  phase0_compute(t, v, tw1);
+  phase0_compute<false>(t, v, tw1);
   phase0_put(t, v, xb);
 }
 
-FC_HD void phase1(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
+template <bool RECOMP = false> FC_HD void phase1(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
   const int t0 = tau & 7, k2 = tau >> 3;
 #pragma unroll
   for (int t1 = 0; t1 < 16; ++t1) get(xb, x1_addr(8 * t1 + t0, k2), v.re[t1], v.im[t1]);
   dft16<-1>(v);
+  for_each_twiddle<RECOMP>(tw2 + t0, 8, [&](int k1a, cpair w) {
+    const int s = slot16(k1a);
+    cmul2(v.re[s], v.im[s], w.re, w.im);
+  });
 #pragma unroll
   for (int k1a = 0; k1a < 16; ++k1a) {
-    const int s = slot16(k1a);
-    if (k1a > 0) {
-      const cpair w = tw2[k1a * 8 + t0];
-      cmul2(v.re[s], v.im[s], w.re, w.im);
-    }
     // same address set as the reads above: k2*128 + 8 j + ((t0 + j) & 7)
-    put(xb, x2_addr(k2 * 16 + k1a, t0), v.re[s], v.im[s]);
+    put(xb, x2_addr(k2 * 16 + k1a, t0), v.re[slot16(k1a)], v.im[slot16(k1a)]);
   }
 }
 
@@ -220,16 +250,11 @@ FC_HD void phase2(int c0, Regs &v, pt4 *xb, const cpair *hs) {
   }
 }
 
-FC_HD void phase3(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
+template <bool RECOMP = false> FC_HD void phase3(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
   const int t0 = tau & 7, k2 = tau >> 3;
 #pragma unroll
-  for (int k1a = 0; k1a < 16; ++k1a) {
-    get(xb, x2_addr(k2 * 16 + k1a, t0), v.re[k1a], v.im[k1a]);
-    if (k1a > 0) {
-      const cpair w = tw2[k1a * 8 + t0];
-      cmul2(v.re[k1a], v.im[k1a], w.re, -w.im);
-    }
-  }
+  for (int k1a = 0; k1a < 16; ++k1a) get(xb, x2_addr(k2 * 16 + k1a, t0), v.re[k1a], v.im[k1a]);
+  for_each_twiddle<RECOMP>(tw2 + t0, 8, [&](int k1a, cpair w) { cmul2(v.re[k1a], v.im[k1a], w.re, -w.im); });
   dft16<+1>(v);
 #pragma unroll
   for (int t1 = 0; t1 < 16; ++t1)
@@ -239,19 +264,14 @@ FC_HD void phase3(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
 // P4: leaves y[t + 128 m] in slot slot16(m).  Split so that a barrier (and the
 // request for the next inputs, which land in the exchange buffer) can follow the
 // last read of the buffer.
-FC_HD void phase4_read(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
+template <bool RECOMP = false> FC_HD void phase4_read(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) {
-    get(xb, x1_addr(t, k2), v.re[k2], v.im[k2]);
-    if (k2 > 0) {
-      const cpair w = tw1[k2 * 128 + t];
-      cmul2(v.re[k2], v.im[k2], w.re, -w.im);
-    }
-  }
+  for (int k2 = 0; k2 < 16; ++k2) get(xb, x1_addr(t, k2), v.re[k2], v.im[k2]);
+  for_each_twiddle<RECOMP>(tw1 + t, 128, [&](int k2, cpair w) { cmul2(v.re[k2], v.im[k2], w.re, -w.im); });
 }
 FC_HD void phase4_compute(Regs &v) { dft16<+1>(v); }
 FC_HD void phase4(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
-  phase4_read(t, v, xb, tw1);
+  phase4_read<false>(t, v, xb, tw1);
   phase4_compute(v);
 }
 

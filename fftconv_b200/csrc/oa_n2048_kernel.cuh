@@ -103,7 +103,7 @@ __device__ __forceinline__ void flush_out(const Packet *pk, const float *stage, 
   dev::bulk_commit();
 }
 
-template <int G>
+template <int G, bool RECOMP>
 __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_constant__ OaParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cpair *hs = reinterpret_cast<cpair *>(smem_raw);
@@ -175,17 +175,17 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_load(t, v, p, ln, cur->j);
     }
-    phase0_compute(t, v, tw1);
+    phase0_compute<RECOMP>(t, v, tw1);
     dev::bar_sync(bar_id); // every thread has read its inputs out of the staging area
     phase0_put(t, v, xb);
     dev::bar_sync(bar_id);
-    phase1(t, v, xb, tw2);
+    phase1<RECOMP>(t, v, xb, tw2);
     dev::bar_sync(bar_id);
     phase2(t, v, xb, hs);
     dev::bar_sync(bar_id);
-    phase3(t, v, xb, tw2);
+    phase3<RECOMP>(t, v, xb, tw2);
     dev::bar_sync(bar_id);
-    phase4_read(t, v, xb, tw1);
+    phase4_read<RECOMP>(t, v, xb, tw1);
     dev::bar_sync(bar_id); // every thread has read its points: the exchange buffer is idle
     const int ni = ci == 2 ? 0 : ci + 1, nni = ni == 2 ? 0 : ni + 1;
     // request the next inputs now: they land while this iteration's last DFT and stores run

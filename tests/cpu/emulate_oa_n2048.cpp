@@ -6,6 +6,7 @@
 //
 // usage: emulate_oa_n2048 batch n K mode(0 full,1 same) chunks n_slots [misalign]
 //   misalign: shifts the input/output base pointers by that many floats (0..3)
+//   recomp:   1 (default) = twiddles k = 3, 5..7, 9..15 formed as products in registers
 #include "../../fftconv_b200/csrc/oa_n2048_group.cuh"
 #include "../../fftconv_b200/csrc/oa_n2048_tables.h"
 
@@ -46,7 +47,7 @@ struct HostGroup {
       for (int l = 0; l < 4; ++l) std::memcpy(stage + l * L.lane_stride, q->in_src[l], q->in_bytes[l]);
   }
 
-  void run(long long w0, long long w1) {
+  template <bool RECOMP> void run(long long w0, long long w1) {
     SchedSlot slots[4];
     Packet ring[3];
     std::memset(ring, 0, sizeof(ring));
@@ -75,14 +76,14 @@ struct HostGroup {
         } else {
           io_load(t, regs[t], p, cur->ln, cur->j);
         }
-        phase0_compute(t, regs[t], p.tw1);
+        phase0_compute<RECOMP>(t, regs[t], p.tw1);
       }
       poison();
       for (int t = 0; t < kThreads; ++t) phase0_put(t, regs[t], xb.data());
-      for (int t = 0; t < kThreads; ++t) phase1(t, regs[t], xb.data(), p.tw2);
+      for (int t = 0; t < kThreads; ++t) phase1<RECOMP>(t, regs[t], xb.data(), p.tw2);
       for (int t = 0; t < kThreads; ++t) phase2(t, regs[t], xb.data(), p.hs);
-      for (int t = 0; t < kThreads; ++t) phase3(t, regs[t], xb.data(), p.tw2);
-      for (int t = 0; t < kThreads; ++t) phase4_read(t, regs[t], xb.data(), p.tw1);
+      for (int t = 0; t < kThreads; ++t) phase3<RECOMP>(t, regs[t], xb.data(), p.tw2);
+      for (int t = 0; t < kThreads; ++t) phase4_read<RECOMP>(t, regs[t], xb.data(), p.tw1);
       // --- barrier; thread 0: request the next inputs, describe the iteration after next ---
       const int ni = ci == 2 ? 0 : ci + 1, nni = ni == 2 ? 0 : ni + 1;
       poison();
@@ -112,6 +113,7 @@ int main(int argc, char **argv) {
   const int K = atoi(argv[3]), mode = atoi(argv[4]);
   const long long chunks = atoll(argv[5]), n_slots = atoll(argv[6]);
   const int mis = argc > 7 ? atoi(argv[7]) : 0;
+  const int recomp = argc > 8 ? atoi(argv[8]) : 1; // twiddle recomputation (the kernel's default)
 
   std::mt19937 rng(1234);
   std::normal_distribution<float> nd(0.f, 1.f);
@@ -137,7 +139,8 @@ int main(int argc, char **argv) {
   for (long long s = 0; s < n_slots; ++s) {
     const long long w0 = p.total_work * s / n_slots, w1 = p.total_work * (s + 1) / n_slots;
     HostGroup grp(p);
-    grp.run(w0, w1);
+    if (recomp) grp.run<true>(w0, w1);
+    else grp.run<false>(w0, w1);
   }
 
   double num = 0, den = 0;
