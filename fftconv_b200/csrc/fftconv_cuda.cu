@@ -13,6 +13,7 @@
 
 #include "fast_kernels.cuh"
 #include "generic_kernels.cuh"
+#include "long_fft_kernels.cuh"
 #include "oa_n2048_kernel.cuh"
 #include "oa_n2048_tables.h"
 
@@ -75,6 +76,8 @@ struct Tables {           // per (FFT length, dtype)
   void *G = nullptr;      // cx<T>[N]   Hilbert multiplier, DIF order (lazy)
   void *Gfast = nullptr;  // cx<T>[N]   Hilbert multiplier, fast-engine table order (lazy)
   void *TWfast = nullptr; // cx<T>[..]  fast-engine per-pass twiddle tables (lazy)
+  void *TWbig = nullptr;  // cx<T>[15 N/16] outer-pass twiddles of the long FFT, N = 16 N_sub (lazy)
+  void *Glong = nullptr;  // cx<T>[N]   Hilbert multiplier in the long-FFT table order (lazy)
 };
 
 struct BluesteinTables {  // per (n, dtype): Hilbert of a non-power-of-two length
@@ -105,6 +108,8 @@ struct DeviceCtx {
   void *stage_out[kPipe] = {nullptr, nullptr, nullptr};
   size_t cap_in[kPipe] = {0, 0, 0}, cap_out[kPipe] = {0, 0, 0};
   std::map<const void *, size_t> smem_set; // kernel -> opted-in dynamic smem
+  void *scratch = nullptr;                 // long-FFT intermediate (grow only)
+  size_t scratch_bytes = 0;
 };
 
 std::map<int, DeviceCtx> g_ctx;
@@ -134,6 +139,8 @@ void free_ctx(DeviceCtx &c) {
     cudaFree(kv.second.G);
     cudaFree(kv.second.Gfast);
     cudaFree(kv.second.TWfast);
+    cudaFree(kv.second.TWbig);
+    cudaFree(kv.second.Glong);
   }
   c.tables.clear();
   for (auto &kv : c.bluestein) {
@@ -141,6 +148,9 @@ void free_ctx(DeviceCtx &c) {
     cudaFree(kv.second.B);
   }
   c.bluestein.clear();
+  cudaFree(c.scratch);
+  c.scratch = nullptr;
+  c.scratch_bytes = 0;
   cudaFree(c.tw1);
   cudaFree(c.tw2);
   c.tw1 = c.tw2 = nullptr;
@@ -526,6 +536,93 @@ template <typename T> size_t max_generic_fft(const DeviceCtx &c, size_t klen) {
   return N;
 }
 
+// ---- one FFT longer than a CTA: N_big = 16 N_sub through a global scratch ----------------
+template <typename T> bool long_ok(const DeviceCtx &c, size_t Nbig) {
+  if (Nbig < 16 * 512 || env_int("FFTCONV_CUDA_FORCE_GENERIC", 0)) return false;
+  const size_t nsub = Nbig / 16;
+  if (nsub > 16384 || (sizeof(T) == 8 && nsub > 8192)) return false;
+  return fast_smem<T>(ilog2(nsub), 0) <= c.smem_optin;
+}
+
+template <typename T, int LOG2N>
+int launch_inner(DeviceCtx &c, cudaStream_t st, cx<T> *scratch, long long n_subs, const cx<T> *W, const cx<T> *Hbig) {
+  constexpr int FPC = fast_fpc<T>(LOG2N);
+  const size_t smem = fast_smem<T>(LOG2N, 0);
+  auto kern = fc::longfft::inner_kernel<T, LOG2N, FPC>;
+  if (int r = ensure_smem(c, kern, smem)) return r;
+  const long long grid = (n_subs + FPC - 1) / FPC;
+  kern<<<(unsigned)grid, fc::fast::Plan<LOG2N>::THREADS * FPC, smem, st>>>(
+      reinterpret_cast<fc::fast::cx<T> *>(scratch), n_subs, reinterpret_cast<const fc::fast::cx<T> *>(W),
+      reinterpret_cast<const fc::fast::cx<T> *>(Hbig));
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+// Hbig: spectrum table of N_big entries in LAYOUT_LONG order (1/N_big folded in)
+template <typename T>
+int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride, T *out,
+                size_t out_len, size_t out_stride, int pad, size_t Nbig, const cx<T> *Hbig, bool hilbert) {
+  const size_t nsub = Nbig / 16;
+  const int l2s = ilog2(nsub);
+  Tables *tbig = nullptr, *tsub = nullptr;
+  if (int r = get_tables<T>(c, Nbig, &tbig)) return r;
+  if (int r = get_tables<T>(c, nsub, &tsub)) return r;
+  if (!tsub->TWfast) {
+    auto build = [&]() -> int { FAST_SWITCH(build_fast_twiddles, l2s, *tsub) };
+    if (int r = build()) return r;
+  }
+  if (!tbig->TWbig) {
+    std::vector<cx<T>> tw(15 * nsub);
+    for (size_t s = 1; s < 16; ++s)
+      for (size_t p = 0; p < nsub; ++p) {
+        const long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)((p * s) % Nbig) / (long double)Nbig;
+        tw[(s - 1) * nsub + p].x = (T)cosl(ang);
+        tw[(s - 1) * nsub + p].y = (T)(-sinl(ang));
+      }
+    CU_TRY(cudaMalloc(&tbig->TWbig, tw.size() * sizeof(cx<T>)));
+    CU_TRY(cudaMemcpy(tbig->TWbig, tw.data(), tw.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
+  }
+  const size_t pairs_total = (batch + 1) / 2;
+  const size_t pair_bytes = Nbig * sizeof(cx<T>);
+  const size_t budget = (size_t)env_int("FFTCONV_CUDA_SCRATCH_MB", 512) << 20;
+  size_t pairs_per = std::max<size_t>(1, std::min<size_t>(pairs_total, budget / pair_bytes));
+  pairs_per = std::min<size_t>(pairs_per, 65535);
+  if (int r = grow(&c.scratch, &c.scratch_bytes, pairs_per * pair_bytes)) return r;
+  fc::longfft::LongArgs<T> la{};
+  la.in = a;
+  la.out = out;
+  la.batch = (long long)batch;
+  la.n = (long long)n;
+  la.in_stride = (long long)a_stride;
+  la.out_stride = (long long)out_stride;
+  la.out_len = (long long)out_len;
+  la.pad = pad;
+  la.log2sub = l2s;
+  la.scratch = reinterpret_cast<fc::fast::cx<T> *>(c.scratch);
+  la.TWbig = reinterpret_cast<const fc::fast::cx<T> *>(tbig->TWbig);
+  la.hilbert = hilbert ? 1 : 0;
+  const int threads = 256;
+  for (size_t p0 = 0; p0 < pairs_total; p0 += pairs_per) {
+    const size_t np = std::min(pairs_per, pairs_total - p0);
+    la.pair0 = (long long)p0;
+    la.pairs = (long long)np;
+    const dim3 grid((unsigned)((nsub + threads - 1) / threads), (unsigned)np);
+    fc::longfft::outer_fwd_kernel<T><<<grid, threads, 0, st>>>(la);
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+    auto inner = [&]() -> int {
+      FAST_SWITCH(launch_inner, l2s, c, st, static_cast<cx<T> *>(c.scratch), (long long)np * 16,
+                  static_cast<const cx<T> *>(tsub->TWfast), Hbig)
+    };
+    if (int r = inner()) return r;
+    fc::longfft::outer_inv_kernel<T><<<grid, threads, 0, st>>>(la);
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+  }
+  return 0;
+}
+
 enum Op { OP_OA, OP_CONV, OP_HILBERT };
 
 template <typename T>
@@ -541,9 +638,19 @@ int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, 
     N = 16;
     while (N < n + klen - 1) N *= 2;
     if (N > max_generic_fft<T>(c, klen)) {
-      // TODO(round 2): multi-kernel FFT for rows longer than one CTA's shared
-      // memory.  Until then long rows are convolved segment-wise; the result is
-      // the same linear convolution.
+      // one long FFT split over three kernels (long_fft_kernels.cuh) while the direct
+      // O(N K) spectrum evaluation stays cheap; otherwise segment FFTs of the table
+      // size -- the same linear convolution either way
+      const bool want_long = !env_int("FFTCONV_CUDA_CONV_LONG_AS_OA", 0) && long_ok<T>(c, N) &&
+                             (double)N * (double)klen <= 536870912.0;
+      if (want_long) {
+        Tables *tbig = nullptr;
+        if (int r = get_tables<T>(c, N, &tbig)) return r;
+        const cx<T> *H = nullptr;
+        if (int r = prepare_spectrum<T>(c, st, k, klen, N, fc::generic::LAYOUT_LONG, *tbig, &H)) return r;
+        return long_device<T>(c, st, a, batch, n, a_stride, out, out_len, out_stride,
+                              mode == FFTCONV_CUDA_SAME ? (int)(klen / 2) : 0, N, H, false);
+      }
       N = optimal_fft_size(klen);
     }
   }
@@ -588,10 +695,31 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
     ++g_launches;
     return 0;
   }
+  if (!fast_ok<T>(c, n, 0) && long_ok<T>(c, n)) {
+    Tables *tbig = nullptr;
+    if (int r = get_tables<T>(c, n, &tbig)) return r;
+    if (!tbig->Glong) {
+      const int l2s = ilog2(n) - 4;
+      const size_t nsub = n / 16;
+      std::vector<cx<T>> g(n);
+      for (size_t idx = 0; idx < n; ++idx) {
+        const size_t kf = idx / nsub + 16 * (size_t)fc::fast::freq_of_pos(
+                                               fc::fast::pos_of_table_index((unsigned)(idx % nsub), l2s), l2s);
+        T im = 0;
+        if (kf != 0 && 2 * kf != n) im = (T)((2 * kf < n ? -1.0 : 1.0) / (double)n);
+        g[idx].x = 0;
+        g[idx].y = im;
+      }
+      CU_TRY(cudaMalloc(&tbig->Glong, n * sizeof(cx<T>)));
+      CU_TRY(cudaMemcpy(tbig->Glong, g.data(), n * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    }
+    return long_device<T>(c, st, x, batch, n, x_stride, env, n, env_stride, 0, n,
+                          static_cast<const cx<T> *>(tbig->Glong), true);
+  }
   const size_t smem = n * sizeof(cx<T>);
   if (smem > c.smem_optin)
     return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
-                                                 " exceeds the single-CTA shared-memory FFT");
+                                                 " exceeds the single-CTA and the split (16 x 16384) FFT");
   Tables *tab = nullptr;
   if (int r = get_tables<T>(c, n, &tab)) return r;
   const bool use_fast = fast_ok<T>(c, n, 0);

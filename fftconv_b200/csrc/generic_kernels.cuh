@@ -19,7 +19,7 @@ namespace generic {
 // in double.  O(N K) work -- K <= a few thousand taps by construction.  (j k fits
 // 32 bits: j < K <= N / 2, k < N <= 2^15.)
 // ---------------------------------------------------------------------------
-enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1, LAYOUT_FAST = 2 };
+enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1, LAYOUT_FAST = 2, LAYOUT_LONG = 3 };
 
 __device__ __forceinline__ unsigned n2048_freq_of_index(unsigned idx) {
   // idx = slot * 128 + c0 (see fc::n2048::p2_freq)
@@ -40,7 +40,12 @@ __global__ void spectrum_kernel(const T *__restrict__ taps, int klen, int N,
   unsigned k;
   if (layout == LAYOUT_N2048) k = n2048_freq_of_index(pos);
   else if (layout == LAYOUT_FAST) k = fc::fast::freq_of_pos(fc::fast::pos_of_table_index(pos, 31 - __clz(N)), 31 - __clz(N));
-  else k = dif_freq_of_pos(pos, N);
+  else if (layout == LAYOUT_LONG) {
+    // N = 16 N_sub (long_fft_kernels.cuh): entry (s, idx_sub) holds frequency s + 16 freq_sub(idx_sub)
+    const int l2s = 31 - __clz(N) - 4;
+    const unsigned sub = (unsigned)pos & ((1u << l2s) - 1);
+    k = ((unsigned)pos >> l2s) + 16u * fc::fast::freq_of_pos(fc::fast::pos_of_table_index(sub, l2s), l2s);
+  } else k = dif_freq_of_pos(pos, N);
   const unsigned mask = (unsigned)(N - 1);
   double re = 0.0, im = 0.0;
   for (int j = lane; j < klen; j += 32) {

@@ -1,0 +1,139 @@
+// long_fft_kernels.cuh -- one FFT longer than a CTA's shared memory: N_big = 16 N_sub.
+//
+// convolve_fftw (/root/reference/include/fftconv/fftconv.hpp:453-461, :338-380) uses ONE
+// transform of length n + K - 1 however long the row is, and hilbert
+// (include/fftconv/hilbert.hpp:16-66) one of length n.  For rows beyond the
+// single-CTA engine (16384 float / 8192 double points) the transform is split once
+// more, decimation in frequency, through a scratch array in global memory:
+//   outer_fwd_kernel   16-point DFTs over the slowest index (stride N_sub) in
+//                      registers, twiddle W_Nbig^{p s}, scratch[pair][s][p]
+//   inner_kernel       the 16 sub-transforms of length N_sub per row pair on the
+//                      register-blocked engine (fast_fft.cuh): forward passes,
+//                      spectrum multiply, inverse passes, in place in scratch
+//   outer_inv_kernel   conjugate twiddle, inverse 16-point DFTs, outputs
+// Two real rows ride in the real and imaginary parts, as everywhere else.  The
+// spectrum table is laid out [s][fast-engine table order]; frequency of entry
+// (s, idx) is s + 16 * freq_sub(idx).
+#pragma once
+
+#include "fast_fft.cuh"
+
+namespace fc {
+namespace longfft {
+
+using fast::cx;
+
+template <typename T> struct LongArgs {
+  const T *in;
+  T *out;
+  long long batch, n, in_stride, out_stride, out_len;
+  int pad;            // Same-mode offset (0 for Full / Hilbert)
+  int log2sub;        // log2 N_sub
+  long long pair0;    // first row pair handled by this launch
+  long long pairs;    // row pairs in this launch
+  cx<T> *scratch;     // pairs * 16 * N_sub
+  const cx<T> *TWbig; // 15 * N_sub: [(s-1) N_sub + p] = W_Nbig^{p s}
+  int hilbert;        // outer_inv: write the envelope instead of the convolution
+};
+
+template <typename T> __global__ void outer_fwd_kernel(const LongArgs<T> a) {
+  const int nsub = 1 << a.log2sub;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nsub) return;
+  const long long pair = blockIdx.y;
+  const long long r0 = (a.pair0 + pair) * 2, r1 = r0 + 1;
+  const bool has1 = r1 < a.batch;
+  const T *x0 = a.in + r0 * a.in_stride;
+  const T *x1 = a.in + (has1 ? r1 : r0) * a.in_stride;
+  cx<T> v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const long long i = p + (long long)q * nsub;
+    v[q].x = i < a.n ? x0[i] : (T)0;
+    v[q].y = (has1 && i < a.n) ? x1[i] : (T)0;
+  }
+  fast::dft16<-1>(v);
+  cx<T> *dst = a.scratch + pair * 16 * nsub + p;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    cx<T> y = v[s];
+    if (s > 0) y = fast::cmul(y, a.TWbig[(long long)(s - 1) * nsub + p]);
+    dst[(long long)s * nsub] = y;
+  }
+}
+
+template <typename T> __global__ void outer_inv_kernel(const LongArgs<T> a) {
+  const int nsub = 1 << a.log2sub;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nsub) return;
+  const long long pair = blockIdx.y;
+  const long long r0 = (a.pair0 + pair) * 2, r1 = r0 + 1;
+  const bool has1 = r1 < a.batch;
+  const cx<T> *src = a.scratch + pair * 16 * nsub + p;
+  cx<T> v[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    cx<T> y = src[(long long)s * nsub];
+    if (s > 0) y = fast::cmulc(y, a.TWbig[(long long)(s - 1) * nsub + p]);
+    v[s] = y;
+  }
+  fast::dft16<+1>(v);
+  T *o0 = a.out + r0 * a.out_stride;
+  T *o1 = a.out + (has1 ? r1 : r0) * a.out_stride;
+  if (a.hilbert) {
+    const T *x0 = a.in + r0 * a.in_stride;
+    const T *x1 = a.in + (has1 ? r1 : r0) * a.in_stride;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const long long i = p + (long long)q * nsub;
+      if (i < a.n) {
+        const T u = x0[i];
+        o0[i] = sqrt(u * u + v[q].x * v[q].x);
+        if (has1) {
+          const T w = x1[i];
+          o1[i] = sqrt(w * w + v[q].y * v[q].y);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const long long o = p + (long long)q * nsub - a.pad;
+      if (o >= 0 && o < a.out_len) {
+        o0[o] = v[q].x;
+        if (has1) o1[o] = v[q].y;
+      }
+    }
+  }
+}
+
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// one sub-transform per FFT slot, FPC slots per CTA; H = Hbig + (sub index) * N_sub
+template <typename T, int LOG2N, int FPC>
+__global__ void __launch_bounds__(fast::Plan<LOG2N>::THREADS *FPC)
+    inner_kernel(cx<T> *scratch, long long n_subs, const cx<T> *W, const cx<T> *Hbig) {
+  using P = fast::Plan<LOG2N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int f = threadIdx.x / P::THREADS, tid = threadIdx.x % P::THREADS;
+  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
+  long long g = (long long)blockIdx.x * FPC + f;
+  const bool on = g < n_subs;
+  if (!on) g = n_subs - 1; // keep the barriers uniform; results of the duplicate are dropped
+  cx<T> *x = scratch + g * P::N;
+  const cx<T> *H = Hbig + (g & 15) * P::N;
+  cx<T> v[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) v[s] = x[fast::pass0_index<LOG2N>(tid, s)];
+  CtaSync sync;
+  fast::conv_core<LOG2N>(tid, v, buf, W, H, sync);
+  if (on) {
+#pragma unroll
+    for (int s = 0; s < 16; ++s) x[fast::pass0_index<LOG2N>(tid, s)] = v[s];
+  }
+}
+
+} // namespace longfft
+} // namespace fc

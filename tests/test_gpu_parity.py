@@ -370,3 +370,38 @@ def test_reference_pybind_module_dropin(cuda):
     with pytest.raises(RuntimeError, match="Kernel size must be smaller"):
         ref_mod.convolve(k, a)
     assert ref_mod.__version__ == "0.5.1"
+
+
+@pytest.mark.parametrize("dt,n,klen", [(np.float64, 16384, 165), (np.float32, 100_000, 1000), (np.float64, 60_000, 33),
+                                       (np.float32, 200_000, 245), (np.float32, 16400, 16000)])
+def test_convolve_one_long_fft(cuda, dt, n, klen, monkeypatch):
+    """convolve_fftw semantics for rows longer than one CTA's FFT: ONE transform of length
+    nextpow2(n + K - 1) = 16 x N_sub through global scratch (long_fft_kernels.cuh); checked
+    against the definition, the oracle, and the segment-FFT route (same linear convolution)."""
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(n + klen)
+    a = rng.standard_normal((3, n)).astype(dt)
+    k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(dt)
+    tol = H.TOL[np.dtype(dt)]
+    before = fc.launch_count()
+    for mode in ("full", "same"):
+        got = fc.convolve(a, k, mode)
+        assert O.rel_l2(got, O.conv_exact(a, k, mode)) < tol, (dt, n, klen, mode)
+        assert O.rel_l2(got, O.convolve(a, k, mode)) < tol
+    launches_long = fc.launch_count() - before
+    monkeypatch.setenv("FFTCONV_CUDA_CONV_LONG_AS_OA", "1")
+    if klen <= 4096:
+        alt = fc.convolve(a, k, "full")
+        assert O.rel_l2(alt, O.conv_exact(a, k, "full")) < tol
+    assert launches_long >= 2 * 4   # spectrum + outer fwd + inner + outer inv, per call
+
+
+@pytest.mark.parametrize("dt,n", [(np.float32, 32768), (np.float32, 262144), (np.float64, 16384), (np.float64, 131072)])
+def test_hilbert_long_lines(cuda, dt, n):
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((3, n)).astype(dt)
+    got = fc.hilbert(x)
+    assert O.rel_l2(got, O.hilbert_exact(x)) < H.TOL[np.dtype(dt)]
