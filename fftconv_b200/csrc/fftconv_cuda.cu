@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -412,6 +413,22 @@ template <typename T, int LOG2N> int build_fast_twiddles(Tables &t) {
   return 0;
 }
 
+template <typename T, int LOG2N>
+int launch_hilbert_stream(DeviceCtx &c, cudaStream_t st, const fc::generic::HilbertArgs<T> &p) {
+  using P = fc::fast::Plan<LOG2N>;
+  const size_t smem = (size_t)P::SMEM_ELEMS * sizeof(cx<T>) + 2 * (size_t)P::N * sizeof(T) + 16;
+  auto kern = fc::fast::hilbert_stream_kernel<T, LOG2N>;
+  if (int r = ensure_smem(c, kern, smem)) return r;
+  int per_sm = 1;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::THREADS, smem));
+  const long long pairs = (p.batch + 1) / 2;
+  const long long grid = std::max<long long>(1, std::min<long long>(pairs, (long long)c.sm_count * std::max(1, per_sm)));
+  kern<<<(unsigned)grid, P::THREADS, smem, st>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
 #define FAST_SWITCH(FN, log2n, ...)                                        \
   switch (log2n) {                                                         \
   case 9: return FN<T, 9>(__VA_ARGS__);                                    \
@@ -740,6 +757,13 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
       if (int r = build()) return r;
     }
     p.W = static_cast<const cx<T> *>(tab->TWfast);
+    // persistent + TMA-prefetching form: one FFT per CTA, 16-byte aligned rows, and it fits
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && ((x_stride * sizeof(T)) % 16 == 0);
+    const size_t stream_smem = (n + n / 16) * sizeof(cx<T>) + 2 * n * sizeof(T) + 16;
+    if (aligned && fast_fpc<T>(p.log2n) == 1 && stream_smem <= c.smem_optin &&
+        !env_int("FFTCONV_CUDA_NO_HILBERT_STREAM", 0)) {
+      FAST_SWITCH(launch_hilbert_stream, p.log2n, c, st, p)
+    }
     FAST_SWITCH(launch_hilbert_fast, p.log2n, c, st, p)
   }
   if (int r = ensure_smem(c, fc::generic::hilbert_pow2_kernel<T>, std::max<size_t>(smem, 16))) return r;
