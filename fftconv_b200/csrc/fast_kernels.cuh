@@ -157,103 +157,5 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<T, Plan<
   }
 }
 
-// Persistent form of the Hilbert kernel (one FFT per CTA): the CTA walks row pairs
-// blockIdx.x, blockIdx.x + gridDim.x, ...
-//   STAGE  the next pair is fetched into a shared staging area by bulk asynchronous
-//          copies (TMA) while the current pair is transformed (needs 16-byte aligned rows)
-//   TSMEM  the per-pass twiddle tables and the Hilbert multiplier are copied into
-//          shared memory once per CTA instead of being re-read through L1/L2 per pair
-template <typename T, int LOG2N, bool STAGE, bool TSMEM>
-__global__ void __launch_bounds__(Plan<LOG2N>::THREADS, min_blocks<T, Plan<LOG2N>::THREADS>())
-    hilbert_stream_kernel(const generic::HilbertArgs<T> p) {
-  using P = Plan<LOG2N>;
-  constexpr int N = P::N;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
-  cx<T> *tw_s = buf + P::SMEM_ELEMS;                          // TSMEM: TW_ELEMS + N entries
-  T *stage = reinterpret_cast<T *>(tw_s + (TSMEM ? P::TW_ELEMS + N : 0)); // STAGE: 2 rows of N
-  unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(stage + (STAGE ? 2 * N : 0));
-  const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_p);
-  const int tid = threadIdx.x;
-  const cx<T> *W = reinterpret_cast<const cx<T> *>(p.W);
-  const cx<T> *G = reinterpret_cast<const cx<T> *>(p.G);
-  const long long pairs = (p.batch + 1) / 2;
-  constexpr unsigned kRowBytes = (unsigned)(N * sizeof(T));
-
-  auto request = [&](long long pair) { // thread 0 only
-    const long long r0 = pair * 2, r1 = r0 + 1;
-    const bool has1 = r1 < p.batch;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(has1 ? 2 * kRowBytes : kRowBytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"((unsigned)__cvta_generic_to_shared(stage)), "l"(p.in + r0 * p.in_stride), "r"(kRowBytes), "r"(mbar) : "memory");
-    if (has1)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"((unsigned)__cvta_generic_to_shared(stage + N)), "l"(p.in + r1 * p.in_stride), "r"(kRowBytes), "r"(mbar) : "memory");
-  };
-
-  if (STAGE && tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if ((long long)blockIdx.x < pairs) request(blockIdx.x);
-  }
-  if (TSMEM) {
-    for (int i = tid; i < P::TW_ELEMS; i += P::THREADS) tw_s[i] = W[i];
-    for (int i = tid; i < N; i += P::THREADS) tw_s[P::TW_ELEMS + i] = G[i];
-    W = tw_s;
-    G = tw_s + P::TW_ELEMS;
-  }
-  __syncthreads();
-  CtaSync sync;
-  unsigned phase = 0;
-  constexpr bool kKeep = sizeof(T) == 4;
-  for (long long pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-    const long long r0 = pair * 2, r1 = r0 + 1;
-    const bool has1 = r1 < p.batch;
-    const T *x0 = p.in + r0 * p.in_stride;
-    const T *x1 = p.in + (has1 ? r1 : r0) * p.in_stride;
-    cx<T> v[16], x[kKeep ? 16 : 1];
-    if (STAGE) {
-      unsigned ok = 0;
-      while (!ok)
-        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
-                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
-      phase ^= 1;
-    }
-#pragma unroll
-    for (int s = 0; s < 16; ++s) {
-      const int i = pass0_index<LOG2N>(tid, s);
-      v[s].x = STAGE ? stage[i] : x0[i];
-      v[s].y = has1 ? (STAGE ? stage[N + i] : x1[i]) : (T)0;
-      if constexpr (kKeep) x[s] = v[s];
-    }
-    fwd_pass0<LOG2N>(tid, v, buf, W);
-    sync(); // every thread has consumed the staging area
-    if (STAGE && tid == 0 && pair + gridDim.x < pairs) request(pair + gridDim.x);
-    FwdMids<LOG2N, 1, T>::run(tid, buf, W, sync);
-    last_fused<LOG2N>(tid, buf, G);
-    sync();
-    InvMids<LOG2N, P::P - 2, T>::run(tid, buf, W, sync);
-    inv_pass0<LOG2N>(tid, v, buf, W);
-    T *e0 = p.out + r0 * p.out_stride;
-    T *e1 = p.out + (has1 ? r1 : r0) * p.out_stride;
-#pragma unroll
-    for (int s = 0; s < 16; ++s) {
-      const int i = pass0_index<LOG2N>(tid, s);
-      T a, b;
-      if constexpr (kKeep) {
-        a = x[s].x;
-        b = x[s].y;
-      } else {
-        a = x0[i];
-        b = has1 ? x1[i] : (T)0;
-      }
-      e0[i] = sqrt(a * a + v[s].x * v[s].x);
-      if (has1) e1[i] = sqrt(b * b + v[s].y * v[s].y);
-    }
-    sync(); // buf is reused by the next pair's first pass
-  }
-}
-
 } // namespace fast
 } // namespace fc

@@ -413,37 +413,6 @@ template <typename T, int LOG2N> int build_fast_twiddles(Tables &t) {
   return 0;
 }
 
-template <typename T, int LOG2N, bool STAGE, bool TSMEM>
-int launch_hilbert_stream_v(DeviceCtx &c, cudaStream_t st, const fc::generic::HilbertArgs<T> &p, size_t smem) {
-  using P = fc::fast::Plan<LOG2N>;
-  auto kern = fc::fast::hilbert_stream_kernel<T, LOG2N, STAGE, TSMEM>;
-  if (int r = ensure_smem(c, kern, smem)) return r;
-  int per_sm = 1;
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::THREADS, smem));
-  const long long pairs = (p.batch + 1) / 2;
-  const long long grid = std::max<long long>(1, std::min<long long>(pairs, (long long)c.sm_count * std::max(1, per_sm)));
-  kern<<<(unsigned)grid, P::THREADS, smem, st>>>(p);
-  CU_TRY(cudaGetLastError());
-  ++g_launches;
-  return 0;
-}
-template <typename T, int LOG2N> size_t hilbert_stream_smem(bool stage, bool tsmem) {
-  using P = fc::fast::Plan<LOG2N>;
-  return (size_t)P::SMEM_ELEMS * sizeof(cx<T>) + (tsmem ? (size_t)(P::TW_ELEMS + P::N) * sizeof(cx<T>) : 0) +
-         (stage ? 2 * (size_t)P::N * sizeof(T) : 0) + 16;
-}
-// mode bits: 1 = stage inputs by TMA, 2 = tables in shared memory
-template <typename T, int LOG2N>
-int launch_hilbert_stream(DeviceCtx &c, cudaStream_t st, const fc::generic::HilbertArgs<T> &p, int mode) {
-  const bool stage = mode & 1, tsmem = mode & 2;
-  const size_t smem = hilbert_stream_smem<T, LOG2N>(stage, tsmem);
-  if (smem > c.smem_optin) return 1; // caller falls back
-  if (stage && tsmem) return launch_hilbert_stream_v<T, LOG2N, true, true>(c, st, p, smem);
-  if (stage) return launch_hilbert_stream_v<T, LOG2N, true, false>(c, st, p, smem);
-  if (tsmem) return launch_hilbert_stream_v<T, LOG2N, false, true>(c, st, p, smem);
-  return launch_hilbert_stream_v<T, LOG2N, false, false>(c, st, p, smem);
-}
-
 #define FAST_SWITCH(FN, log2n, ...)                                        \
   switch (log2n) {                                                         \
   case 9: return FN<T, 9>(__VA_ARGS__);                                    \
@@ -772,16 +741,6 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
       if (int r = build()) return r;
     }
     p.W = static_cast<const cx<T> *>(tab->TWfast);
-    // persistent form (one FFT per CTA): tables in shared memory (mode 2) and / or inputs
-    // staged by TMA (mode 1, needs 16-byte aligned rows); falls back when it does not fit
-    const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && ((x_stride * sizeof(T)) % 16 == 0);
-    int smode = env_int("FFTCONV_CUDA_HILBERT_STREAM", 0); // measured: no gain on C4, off by default
-    if (!aligned) smode &= ~1;
-    if (smode > 0 && fast_fpc<T>(p.log2n) == 1) {
-      auto go = [&]() -> int { FAST_SWITCH(launch_hilbert_stream, p.log2n, c, st, p, smode) };
-      const int r = go();
-      if (r <= 0) return r;
-    }
     FAST_SWITCH(launch_hilbert_fast, p.log2n, c, st, p)
   }
   if (int r = ensure_smem(c, fc::generic::hilbert_pow2_kernel<T>, std::max<size_t>(smem, 16))) return r;
