@@ -8,8 +8,9 @@
 Same names, argument meaning, defaults and error behaviour (RuntimeError for a
 kernel longer than the signal or an unknown mode).  Extensions over the reference:
 2-D inputs are batches of rows convolved with the same taps (the reference's
-binding rejects ndim != 1), and CUDA `torch.Tensor`s are accepted and processed in
-place on the device on torch's current stream (no host round trip).
+binding rejects ndim != 1), and CUDA `torch.Tensor`s -- or any object with
+`__cuda_array_interface__` (CuPy, Numba) in the `_` forms -- are processed in place on
+the device on the caller's stream (no host round trip).
 
 Everything goes through the C ABI of libfftconv_cuda.so; nothing here computes.
 """
@@ -45,7 +46,22 @@ class _Buf:
 
     def __init__(self, x, name: str):
         self.obj = x
-        if _is_tensor(x):
+        if not _is_tensor(x) and hasattr(x, "__cuda_array_interface__"):
+            # CuPy / Numba / any CUDA array: taken in place, no torch needed
+            ci = x.__cuda_array_interface__
+            self.dtype = {"<f4": "float32", "<f8": "float64"}.get(ci["typestr"], ci["typestr"])
+            self.shape = tuple(ci["shape"])
+            item = 4 if self.dtype == "float32" else 8
+            strides = ci.get("strides")
+            if strides is None:
+                strides = tuple(item * int(np.prod(self.shape[i + 1:])) for i in range(len(self.shape)))
+            if len(self.shape) >= 1 and self.shape[-1] > 1 and strides[-1] != item:
+                raise RuntimeError(f"{name}: last dimension must be contiguous")
+            self.row_stride = strides[0] // item if len(self.shape) == 2 else (self.shape[-1] if self.shape else 1)
+            self.ptr = int(ci["data"][0])
+            self.is_cuda = True
+            self.cai_stream = ci.get("stream")
+        elif _is_tensor(x):
             self.dtype = str(x.dtype).replace("torch.", "")
             self.shape = tuple(x.shape)
             if x.dim() >= 1 and x.stride(-1) != 1 and x.shape[-1] > 1:
@@ -69,9 +85,28 @@ class _Buf:
 
 
 def _stream_of(buf: _Buf):
-    if buf.is_cuda:
+    if not buf.is_cuda:
+        return None
+    if _is_tensor(buf.obj):
         return torch.cuda.current_stream(buf.obj.device).cuda_stream
-    return None
+    s = getattr(buf, "cai_stream", None)     # __cuda_array_interface__ v3: None / 1 = default stream
+    return None if s in (None, 1, 2) else int(s)
+
+
+class _device_of:
+    """Context: make the array's device current (torch tensors know theirs; other CUDA
+    arrays are taken to live on the current device, as their own libraries assume)."""
+
+    def __init__(self, buf: _Buf):
+        self.ctx = torch.cuda.device(buf.obj.device) if _is_tensor(buf.obj) else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
 
 
 def _empty_like_rows(a, out_len: int):
@@ -102,7 +137,7 @@ def _conv_(name: str, a, k, out, mode):
         raise RuntimeError("a and out must live on the same side (host or device)")
     fn = getattr(_capi.lib(), f"fftconv_cuda_{name}_batched_{_SFX[A.dtype]}")
     if A.is_cuda:
-        with torch.cuda.device(A.obj.device):
+        with _device_of(A):
             rc = fn(A.ptr, batch, n, A.row_stride, K.ptr, klen, O.ptr, out_len, O.row_stride, m,
                     _stream_of(A))
     else:
@@ -152,7 +187,7 @@ def hilbert_(a, out) -> None:
     batch = 1 if A.ndim == 1 else A.shape[0]
     fn = getattr(_capi.lib(), f"fftconv_cuda_hilbert_batched_{_SFX[A.dtype]}")
     if A.is_cuda:
-        with torch.cuda.device(A.obj.device):
+        with _device_of(A):
             rc = fn(A.ptr, batch, n, A.row_stride, O.ptr, O.row_stride, _stream_of(A))
     else:
         rc = fn(A.ptr, batch, n, A.row_stride, O.ptr, O.row_stride, None)

@@ -8,7 +8,8 @@
   signal into one contiguous chunk per rank, convolve each chunk in Full mode, and
   hand the chunk's last K-1 outputs to the right neighbour, which adds them to its
   first K-1 outputs (<= 2 addends per sample: deterministic).  Message size
-  4 (K-1) bytes -> latency bound; send and receive are posted together.
+  4 (K-1) bytes -> latency bound: the tail is produced first by a tiny side-stream
+  convolution of the chunk's last K-1 samples and sent while the main kernel runs.
 """
 from __future__ import annotations
 
@@ -64,17 +65,40 @@ def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
     tail_len = klen - 1
     if world > 1 and m < tail_len:
         raise RuntimeError(f"chunk of {m} samples is shorter than the K-1 = {tail_len} tail")
-    y = conv(a_chunk, k)                      # m + K - 1 samples
     if world == 1 or tail_len == 0:
-        return y
-    recv_buf = torch.empty(tail_len, dtype=y.dtype, device=y.device) if rank > 0 else None
-    ops = []
-    if rank < world - 1:
-        ops.append(dist.P2POp(dist.isend, y[m:].contiguous(), rank + 1, group))
-    if rank > 0:
-        ops.append(dist.P2POp(dist.irecv, recv_buf, rank - 1, group))
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
+        return conv(a_chunk, k)
+
+    # The tail (outputs m .. m+K-2 of the chunk's full convolution) depends only on the
+    # chunk's last K-1 samples, so it is computed FIRST by a tiny convolution (taps and
+    # samples swap roles: conv is commutative and the API wants signal >= kernel) on a
+    # side stream and sent at once; the exchange then overlaps the main kernel.
+    on_cuda = bool(getattr(a_chunk, "is_cuda", False))
+    side = torch.cuda.Stream(device=a_chunk.device) if on_cuda else None
+    recv_buf = torch.empty(tail_len, dtype=a_chunk.dtype, device=a_chunk.device) if rank > 0 else None
+
+    def exchange():
+        ops = []
+        send_buf = None
+        if rank < world - 1:
+            send_buf = conv(k, a_chunk[m - tail_len:].contiguous())[tail_len:].contiguous()
+            ops.append(dist.P2POp(dist.isend, send_buf, rank + 1, group))
+        if rank > 0:
+            ops.append(dist.P2POp(dist.irecv, recv_buf, rank - 1, group))
+        return dist.batch_isend_irecv(ops), send_buf
+
+    if on_cuda:
+        side.wait_stream(torch.cuda.current_stream(a_chunk.device))
+        with torch.cuda.stream(side):
+            reqs, send_buf = exchange()
+    else:
+        reqs, send_buf = exchange()
+    y = conv(a_chunk, k)                      # m + K - 1 samples, main stream
+    for req in reqs:
+        req.wait()                            # the current stream waits for the exchange
+    if on_cuda:
+        torch.cuda.current_stream(a_chunk.device).wait_stream(side)
+        if send_buf is not None:
+            send_buf.record_stream(torch.cuda.current_stream(a_chunk.device))
     if rank > 0:
         add(y[:tail_len], recv_buf)
     return y if rank == world - 1 else y[:m]

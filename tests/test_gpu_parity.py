@@ -405,3 +405,32 @@ def test_hilbert_long_lines(cuda, dt, n):
     x = rng.standard_normal((3, n)).astype(dt)
     got = fc.hilbert(x)
     assert O.rel_l2(got, O.hilbert_exact(x)) < H.TOL[np.dtype(dt)]
+
+
+def test_cuda_array_interface_inputs(cuda):
+    """device arrays of other libraries are taken in place through
+    __cuda_array_interface__ (exercised with a minimal wrapper around torch storage)."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    class CAI:
+        def __init__(self, t):
+            self.t = t
+            self.__cuda_array_interface__ = {
+                "shape": tuple(t.shape), "typestr": "<f4" if t.dtype == torch.float32 else "<f8",
+                "data": (t.data_ptr(), False), "version": 3, "strides": None, "stream": 1}
+
+    rng = np.random.default_rng(77)
+    a = rng.standard_normal((6, 9000)).astype(np.float32)
+    k = (rng.standard_normal(245) / 16).astype(np.float32)
+    ta, tk = _t(a, cuda), _t(k, cuda)
+    out = torch.empty((6, 9244), device=cuda)
+    torch.cuda.synchronize()
+    fc.oaconvolve_(CAI(ta), CAI(tk), CAI(out), "full")
+    torch.cuda.synchronize()
+    _check(out.cpu().numpy(), a, k, "full", "cai")
+    env = torch.empty((6, 8192), device=cuda)
+    fc.hilbert_(CAI(ta[:, :8192].contiguous()), CAI(env))
+    torch.cuda.synchronize()
+    assert O.rel_l2(env.cpu().numpy(), O.hilbert_exact(a[:, :8192])) < 1e-5
