@@ -22,8 +22,10 @@ SYMBOLS = [
     f"fftconv_cuda_{name}_{sfx}"
     for sfx in ("f32", "f64")
     for name in ("oaconvolve", "oaconvolve_batched", "convolve", "convolve_batched",
-                 "hilbert", "hilbert_batched", "add")
-]
+                 "hilbert", "hilbert_batched", "add",
+                 "filter_create", "filter_oaconvolve", "stream_create", "stream_push",
+                 "stream_flush")
+] + ["fftconv_cuda_filter_destroy", "fftconv_cuda_stream_destroy"]
 
 _lib = None
 
@@ -56,6 +58,18 @@ def lib():
         f.restype, f.argtypes = i, [vp, sz, sz, sz, vp, sz, vp]
         f = getattr(L, f"fftconv_cuda_add_{sfx}")
         f.restype, f.argtypes = i, [vp, vp, sz, vp]
+        f = getattr(L, f"fftconv_cuda_filter_create_{sfx}")
+        f.restype, f.argtypes = i, [vp, sz, C.POINTER(vp)]
+        f = getattr(L, f"fftconv_cuda_filter_oaconvolve_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, sz, sz, vp, sz, sz, i, vp]
+        f = getattr(L, f"fftconv_cuda_stream_create_{sfx}")
+        f.restype, f.argtypes = i, [vp, sz, C.POINTER(vp)]
+        f = getattr(L, f"fftconv_cuda_stream_push_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, sz, vp, sz, vp]
+        f = getattr(L, f"fftconv_cuda_stream_flush_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, vp]
+    L.fftconv_cuda_filter_destroy.restype, L.fftconv_cuda_filter_destroy.argtypes = i, [vp]
+    L.fftconv_cuda_stream_destroy.restype, L.fftconv_cuda_stream_destroy.argtypes = i, [vp]
     _lib = L
     return L
 

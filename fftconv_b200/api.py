@@ -216,6 +216,115 @@ def add_(dst, src) -> None:
         _capi.check(fn(D.ptr, S.ptr, D.shape[0], _stream_of(D)))
 
 
+class Filter:
+    """Taps and their spectrum, resident on the current device.
+    The reference transforms the kernel on every call (include/fftconv/fftconv.hpp:391-392);
+    a Filter does it once.  `k` may be a numpy array or a CUDA tensor."""
+
+    def __init__(self, k):
+        K = _Buf(k, "k")
+        if K.ndim != 1 or K.shape[0] == 0:
+            raise RuntimeError("Number of dimensions must be one")
+        self.dtype, self.klen = K.dtype, K.shape[0]
+        self._sfx = _SFX[K.dtype]
+        self._h = _capi.C.c_void_p()
+        with _device_of(K):
+            _capi.check(getattr(_capi.lib(), f"fftconv_cuda_filter_create_{self._sfx}")(
+                K.ptr, self.klen, _capi.C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _capi.lib().fftconv_cuda_filter_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def oaconvolve_(self, a, out, mode: str = "full") -> None:
+        """oaconvolve_(a, k, out, mode) with this filter's taps; no spectrum kernel is launched."""
+        A, O = _Buf(a, "a"), _Buf(out, "out")
+        if A.ndim not in (1, 2) or O.ndim != A.ndim:
+            raise RuntimeError("Number of dimensions must be one")
+        if A.dtype != self.dtype or O.dtype != self.dtype:
+            raise TypeError("a, out and the filter must share one dtype")
+        n = A.shape[-1]
+        if n < self.klen:
+            raise RuntimeError("Kernel size must be smaller than input size")
+        batch = 1 if A.ndim == 1 else A.shape[0]
+        if A.ndim == 2 and O.shape[0] != batch:
+            raise RuntimeError("out must have one row per input row")
+        if A.is_cuda != O.is_cuda:
+            raise RuntimeError("a and out must live on the same side (host or device)")
+        fn = getattr(_capi.lib(), f"fftconv_cuda_filter_oaconvolve_{self._sfx}")
+        with _device_of(A):
+            _capi.check(fn(self._h, A.ptr, batch, n, A.row_stride, O.ptr, O.shape[-1], O.row_stride,
+                           _mode(mode), _stream_of(A)))
+
+    def oaconvolve(self, a, mode: str = "full"):
+        n = a.shape[-1]
+        out = _empty_like_rows(a, n if _mode(mode) == _capi.SAME else n + self.klen - 1)
+        self.oaconvolve_(a, out, mode)
+        return out
+
+    def stream(self, rows: int = 1) -> "Stream":
+        return Stream(self, rows)
+
+
+class Stream:
+    """Overlap-add carried ACROSS calls: `rows` signals that arrive in pieces.  push(chunk)
+    returns the next chunk.shape[-1] samples of the running Full convolution of each row,
+    flush() the last K-1 samples (and resets the state).  Concatenating every push and the
+    flush equals oaconvolve(whole signal, k, "full").  CUDA tensors only."""
+
+    def __init__(self, filt: Filter, rows: int = 1):
+        self.filter, self.rows = filt, int(rows)
+        self._h = _capi.C.c_void_p()
+        _capi.check(getattr(_capi.lib(), f"fftconv_cuda_stream_create_{filt._sfx}")(
+            filt._h, self.rows, _capi.C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _capi.lib().fftconv_cuda_stream_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _rows2d(self, x, name):
+        X = _Buf(x, name)
+        if not X.is_cuda or X.dtype != self.filter.dtype:
+            raise RuntimeError(f"{name}: CUDA array of the filter's dtype expected")
+        rows = 1 if X.ndim == 1 else X.shape[0]
+        if X.ndim not in (1, 2) or rows != self.rows:
+            raise RuntimeError(f"{name}: expected {self.rows} row(s)")
+        return X
+
+    def push_(self, chunk, out) -> None:
+        A, O = self._rows2d(chunk, "chunk"), self._rows2d(out, "out")
+        if A.shape[-1] != O.shape[-1]:
+            raise RuntimeError("out must have the chunk's length")
+        fn = getattr(_capi.lib(), f"fftconv_cuda_stream_push_{self.filter._sfx}")
+        with _device_of(A):
+            _capi.check(fn(self._h, A.ptr, A.shape[-1], A.row_stride, O.ptr, O.row_stride, _stream_of(A)))
+
+    def push(self, chunk):
+        out = _empty_like_rows(chunk, chunk.shape[-1])
+        self.push_(chunk, out)
+        return out
+
+    def flush_(self, tail_out) -> None:
+        O = self._rows2d(tail_out, "tail_out")
+        if O.shape[-1] != self.filter.klen - 1:
+            raise RuntimeError("tail_out must hold K-1 samples per row")
+        fn = getattr(_capi.lib(), f"fftconv_cuda_stream_flush_{self.filter._sfx}")
+        with _device_of(O):
+            _capi.check(fn(self._h, O.ptr, O.row_stride, _stream_of(O)))
+
+    def flush(self, like):
+        """`like`: any CUDA tensor of the stream's device/dtype (shape donor for the result)."""
+        out = _empty_like_rows(like, self.filter.klen - 1)
+        self.flush_(out)
+        return out
+
+
 def launch_count() -> int:
     return int(_capi.lib().fftconv_cuda_launch_count())
 

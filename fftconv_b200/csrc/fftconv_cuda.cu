@@ -339,9 +339,25 @@ int env_int(const char *name, int dflt) {
 }
 
 // taps -> device (per-stream buffer) -> spectrum H in the layout the kernel wants
+// A filter handle (fftconv_cuda_filter_*): taps + their spectrum, resident on one device.
+struct Filter {
+  int dtype = 0;
+  int device = 0;
+  size_t klen = 0, N = 0;
+  int layout = 0;
+  void *taps = nullptr;
+  void *H = nullptr;
+};
+thread_local const Filter *tl_filter = nullptr; // set around a call made through a handle
+
 template <typename T>
 int prepare_spectrum(DeviceCtx &c, cudaStream_t st, const T *k, size_t klen, size_t N, int layout,
                      Tables &tab, const cx<T> **H_out) {
+  if (tl_filter && tl_filter->dtype == dtype_id<T>() && tl_filter->N == N && tl_filter->layout == layout &&
+      tl_filter->klen == klen && tl_filter->device == c.device && tl_filter->taps == (const void *)k) {
+    *H_out = static_cast<const cx<T> *>(tl_filter->H); // spectrum reuse: no kernel
+    return 0;
+  }
   StreamWs &ws = c.ws[st];
   const T *taps_dev = k;
   if (!is_device_ptr(k)) {
@@ -828,6 +844,124 @@ template <typename T> int add_entry(T *dst, const T *src, size_t n, void *stream
   return 0;
 }
 
+template <typename T> int oa_layout_for(const DeviceCtx &c, size_t N, size_t klen) {
+  if (std::is_same<T, float>::value && N == 2048 && !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) &&
+      !env_int("FFTCONV_CUDA_NO_N2048", 0))
+    return fc::generic::LAYOUT_N2048;
+  return fast_ok<T>(c, N, klen) ? fc::generic::LAYOUT_FAST : fc::generic::LAYOUT_DIF;
+}
+
+template <typename T> int filter_create(const T *k, size_t klen, void **out) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (!k || klen == 0 || !out) return fail(FFTCONV_CUDA_ERR_ARG, "filter_create: empty kernel or null output");
+  DeviceCtx *c = nullptr;
+  if (int r = get_ctx(&c)) return r;
+  const size_t N = optimal_fft_size(klen);
+  if (N > max_generic_fft<T>(*c, klen))
+    return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "filter_create: " + std::to_string(klen) + " taps need FFT size " +
+                                                 std::to_string(N) + ", beyond the single-CTA FFT");
+  Tables *tab = nullptr;
+  if (int r = get_tables<T>(*c, N, &tab)) return r;
+  auto *f = new Filter();
+  f->dtype = dtype_id<T>();
+  f->device = c->device;
+  f->klen = klen;
+  f->N = N;
+  f->layout = oa_layout_for<T>(*c, N, klen);
+  if (cudaMalloc(&f->taps, klen * sizeof(T)) != cudaSuccess || cudaMalloc(&f->H, N * sizeof(cx<T>)) != cudaSuccess) {
+    cudaFree(f->taps);
+    delete f;
+    return fail(FFTCONV_CUDA_ERR_CUDA, "filter_create: cudaMalloc failed");
+  }
+  CU_TRY(cudaMemcpy(f->taps, k, klen * sizeof(T), cudaMemcpyDefault));
+  const int warps = fc::generic::kSpectrumWarps;
+  fc::generic::spectrum_kernel<T><<<(unsigned)((N + warps - 1) / warps), warps * 32>>>(
+      static_cast<const T *>(f->taps), (int)klen, (int)N, tab->Wd, f->layout, 1.0 / (double)N,
+      static_cast<cx<T> *>(f->H));
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  CU_TRY(cudaDeviceSynchronize());
+  *out = f;
+  return 0;
+}
+
+template <typename T>
+int filter_oaconvolve(const void *filter, const T *a, size_t batch, size_t n, size_t a_stride, T *out,
+                      size_t out_len, size_t out_stride, int mode, void *stream) {
+  const Filter *f = static_cast<const Filter *>(filter);
+  if (!f || f->dtype != dtype_id<T>()) return fail(FFTCONV_CUDA_ERR_ARG, "filter handle of the wrong precision");
+  tl_filter = f;
+  const int r = entry<T>(OP_OA, a, batch, n, a_stride, static_cast<const T *>(f->taps), f->klen, out, out_len,
+                         out_stride, mode, stream);
+  tl_filter = nullptr;
+  return r;
+}
+
+struct StreamState {
+  const Filter *f = nullptr;
+  size_t rows = 0;
+  void *carry[2] = {nullptr, nullptr};
+  int cur = 0;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+};
+
+template <typename T> int stream_create(const void *filter, size_t rows, void **out) {
+  const Filter *f = static_cast<const Filter *>(filter);
+  if (!f || f->dtype != dtype_id<T>() || rows == 0 || !out)
+    return fail(FFTCONV_CUDA_ERR_ARG, "stream_create: bad filter handle or zero rows");
+  auto *s = new StreamState();
+  s->f = f;
+  s->rows = rows;
+  const size_t bytes = std::max<size_t>(1, rows * (f->klen - 1)) * sizeof(T);
+  for (int i = 0; i < 2; ++i) {
+    CU_TRY(cudaMalloc(&s->carry[i], bytes));
+    CU_TRY(cudaMemset(s->carry[i], 0, bytes));
+  }
+  CU_TRY(cudaDeviceSynchronize());
+  *out = s;
+  return 0;
+}
+
+template <typename T>
+int stream_push(void *state, const T *chunk, size_t n, size_t chunk_stride, T *out, size_t out_stride, void *stream) {
+  auto *s = static_cast<StreamState *>(state);
+  if (!s || s->f->dtype != dtype_id<T>()) return fail(FFTCONV_CUDA_ERR_ARG, "stream state of the wrong precision");
+  if (n == 0) return 0;
+  if (!is_device_ptr(chunk) || !is_device_ptr(out))
+    return fail(FFTCONV_CUDA_ERR_ARG, "stream_push: device pointers only");
+  const size_t tail_len = s->f->klen - 1, w = n + tail_len;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int r = grow(&s->tmp, &s->tmp_bytes, s->rows * w * sizeof(T))) return r;
+  }
+  if (int r = filter_oaconvolve<T>(s->f, chunk, s->rows, n, chunk_stride, static_cast<T *>(s->tmp), w, w,
+                                   FFTCONV_CUDA_FULL, stream))
+    return r;
+  const long long total = (long long)(s->rows * w);
+  const int threads = 256;
+  fc::generic::stream_merge_kernel<T><<<(unsigned)((total + threads - 1) / threads), threads, 0,
+                                        static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const T *>(s->tmp), (long long)s->rows, (long long)n, (int)tail_len,
+      static_cast<const T *>(s->carry[s->cur]), static_cast<T *>(s->carry[s->cur ^ 1]), out, (long long)out_stride);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  s->cur ^= 1;
+  return 0;
+}
+
+template <typename T> int stream_flush(void *state, T *tail_out, size_t tail_stride, void *stream) {
+  auto *s = static_cast<StreamState *>(state);
+  if (!s || s->f->dtype != dtype_id<T>()) return fail(FFTCONV_CUDA_ERR_ARG, "stream state of the wrong precision");
+  const size_t tail_len = s->f->klen - 1;
+  if (tail_len == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU_TRY(cudaMemcpy2DAsync(tail_out, tail_stride * sizeof(T), s->carry[s->cur], tail_len * sizeof(T),
+                           tail_len * sizeof(T), s->rows, cudaMemcpyDefault, st));
+  CU_TRY(cudaMemsetAsync(s->carry[s->cur], 0, s->rows * tail_len * sizeof(T), st));
+  return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -887,5 +1021,45 @@ int fftconv_cuda_clear_cache(void) {
 
 FFTCONV_API(f32, float)
 FFTCONV_API(f64, double)
+
+#define FFTCONV_HANDLE_API(SFX, T)                                                                   \
+  int fftconv_cuda_filter_create_##SFX(const T *k, size_t klen, void **filter_out) {                \
+    return filter_create<T>(k, klen, filter_out);                                                   \
+  }                                                                                                  \
+  int fftconv_cuda_filter_oaconvolve_##SFX(const void *filter, const T *a, size_t batch, size_t n,  \
+                                           size_t a_stride, T *out, size_t out_len,                  \
+                                           size_t out_stride, int mode, void *stream) {              \
+    return filter_oaconvolve<T>(filter, a, batch, n, a_stride, out, out_len, out_stride, mode, stream); \
+  }                                                                                                  \
+  int fftconv_cuda_stream_create_##SFX(const void *filter, size_t rows, void **state_out) {         \
+    return stream_create<T>(filter, rows, state_out);                                               \
+  }                                                                                                  \
+  int fftconv_cuda_stream_push_##SFX(void *state, const T *chunk, size_t n, size_t chunk_stride,    \
+                                     T *out, size_t out_stride, void *stream) {                      \
+    return stream_push<T>(state, chunk, n, chunk_stride, out, out_stride, stream);                  \
+  }                                                                                                  \
+  int fftconv_cuda_stream_flush_##SFX(void *state, T *tail_out, size_t tail_stride, void *stream) { \
+    return stream_flush<T>(state, tail_out, tail_stride, stream);                                   \
+  }
+FFTCONV_HANDLE_API(f32, float)
+FFTCONV_HANDLE_API(f64, double)
+
+int fftconv_cuda_filter_destroy(void *filter) {
+  auto *f = static_cast<Filter *>(filter);
+  if (!f) return 0;
+  cudaFree(f->taps);
+  cudaFree(f->H);
+  delete f;
+  return 0;
+}
+int fftconv_cuda_stream_destroy(void *state) {
+  auto *s = static_cast<StreamState *>(state);
+  if (!s) return 0;
+  cudaFree(s->carry[0]);
+  cudaFree(s->carry[1]);
+  cudaFree(s->tmp);
+  delete s;
+  return 0;
+}
 
 } // extern "C"

@@ -289,5 +289,22 @@ template <typename T> __global__ void add_inplace_kernel(T *dst, const T *src, l
   if (i < n) dst[i] += src[i];
 }
 
+// Streaming overlap-add across calls: `full` holds rows of n + K - 1 samples (this
+// call's Full convolution).  out[r][i] = full[r][i] + carry[r][i] (i < K-1), and the new
+// carry is what sticks out past n (plus the part of the old carry not yet consumed).
+template <typename T>
+__global__ void stream_merge_kernel(const T *__restrict__ full, long long rows, long long n, int tail_len,
+                                    const T *__restrict__ carry, T *__restrict__ carry_next, T *__restrict__ out,
+                                    long long out_stride) {
+  const long long w = n + tail_len;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * w) return;
+  const long long r = idx / w, i = idx - r * w;
+  T v = full[idx];
+  if (i < tail_len) v += carry[r * tail_len + i];
+  if (i < n) out[r * out_stride + i] = v;
+  else carry_next[r * tail_len + (i - n)] = v;
+}
+
 } // namespace generic
 } // namespace fc
