@@ -16,6 +16,8 @@
 #include "long_fft_kernels.cuh"
 #include "oa_n2048_kernel.cuh"
 #include "oa_n2048_tables.h"
+#include "oa_w2_kernel.cuh"
+#include "oa_w2_tables.h"
 
 #include <cuda_runtime.h>
 
@@ -102,7 +104,7 @@ struct DeviceCtx {
   size_t smem_optin = 0;
   std::map<std::pair<size_t, int>, Tables> tables;
   std::map<std::pair<size_t, int>, BluesteinTables> bluestein;
-  fc::n2048::cpair *tw1 = nullptr, *tw2 = nullptr;
+  fc::n2048::cpair *tw1 = nullptr, *tw2 = nullptr, *tw_w2 = nullptr;
   std::map<cudaStream_t, StreamWs> ws;
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
   void *stage_in[kPipe] = {nullptr, nullptr, nullptr};
@@ -154,7 +156,8 @@ void free_ctx(DeviceCtx &c) {
   c.scratch_bytes = 0;
   cudaFree(c.tw1);
   cudaFree(c.tw2);
-  c.tw1 = c.tw2 = nullptr;
+  cudaFree(c.tw_w2);
+  c.tw1 = c.tw2 = c.tw_w2 = nullptr;
   for (auto &kv : c.ws) {
     cudaFree(kv.second.taps);
     cudaFree(kv.second.H);
@@ -301,6 +304,15 @@ int get_n2048_tables(DeviceCtx &c) {
   return 0;
 }
 
+int get_w2_tables(DeviceCtx &c) {
+  if (c.tw_w2) return 0;
+  std::vector<fc::n2048::cpair> t(fc::w2::kTwElems);
+  fc::w2::fill_tw(t.data());
+  CU_TRY(cudaMalloc((void **)&c.tw_w2, t.size() * sizeof(fc::n2048::cpair)));
+  CU_TRY(cudaMemcpy(c.tw_w2, t.data(), t.size() * sizeof(fc::n2048::cpair), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 int grow(void **p, size_t *cap, size_t bytes) {
   if (*cap >= bytes) return 0;
   if (*p) CU_TRY(cudaFree(*p));
@@ -440,6 +452,15 @@ template <typename T, int LOG2N> int build_fast_twiddles(Tables &t) {
   default: return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "fast engine: bad size"); \
   }
 
+// Which kernel serves float32 overlap-add at FFT size 2048: 0 = the register-blocked engine,
+// 1 = oa_n2048_kernel (16 points per thread, 128-thread groups), 2 = oa_w2_kernel (32 points
+// per thread, warp pairs).  FFTCONV_CUDA_OA2048_ENGINE overrides the default.
+int oa2048_engine() {
+  if (env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) || env_int("FFTCONV_CUDA_NO_N2048", 0)) return 0;
+  const int e = env_int("FFTCONV_CUDA_OA2048_ENGINE", 1);
+  return e == 2 ? 2 : 1;
+}
+
 // ---- overlap-add on device pointers -------------------------------------------------
 template <typename T>
 int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride,
@@ -450,9 +471,42 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
   const size_t step = N - (klen - 1);
   const long long segs = (long long)((n + step - 1) / step);
 
-  const bool use_n2048 = std::is_same<T, float>::value && N == 2048 &&
-                         !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) && !env_int("FFTCONV_CUDA_NO_N2048", 0);
-  if (use_n2048) {
+  const int engine2048 = (std::is_same<T, float>::value && N == 2048) ? oa2048_engine() : 0;
+  if (engine2048 == 2) {
+    if constexpr (std::is_same<T, float>::value) {
+      if (int r = get_w2_tables(c)) return r;
+      const cx<float> *H = nullptr;
+      if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_W2, *tab, &H)) return r;
+      int G = env_int("FFTCONV_CUDA_W2_PAIRS", 4);
+      if (G < 1 || G > 4) G = 4;
+      const long long slots = (long long)c.sm_count * G;
+      long long chunks = 1;
+      if ((long long)batch < 4 * slots) {
+        chunks = (4 * slots + (long long)batch - 1) / (long long)batch;
+        chunks = std::min(chunks, std::max<long long>(1, segs / 16));
+      }
+      fc::n2048::OaParams p{};
+      fc::n2048::fill_params(p, a, out, (long long)batch, (long long)n, (long long)a_stride,
+                             (long long)out_stride, (long long)out_len, (int)klen, mode, chunks);
+      const size_t smem = fc::w2::smem_bytes(G, (int)klen);
+      const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
+      const fc::n2048::cpair *hs = reinterpret_cast<const fc::n2048::cpair *>(H);
+#define FC_LAUNCH_W2(GG)                                                                  \
+  {                                                                                       \
+    if (int r = ensure_smem(c, fc::w2::oa_w2_kernel<GG>, smem)) return r;                 \
+    fc::w2::oa_w2_kernel<GG><<<(unsigned)grid, 64 * GG, smem, st>>>(p, c.tw_w2, hs);      \
+  }
+      if (G == 4) FC_LAUNCH_W2(4)
+      else if (G == 3) FC_LAUNCH_W2(3)
+      else if (G == 2) FC_LAUNCH_W2(2)
+      else FC_LAUNCH_W2(1)
+#undef FC_LAUNCH_W2
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+      return 0;
+    }
+  }
+  if (engine2048 == 1) {
     if constexpr (std::is_same<T, float>::value) {
       if (int r = get_n2048_tables(c)) return r;
       const cx<float> *H = nullptr;
@@ -845,9 +899,8 @@ template <typename T> int add_entry(T *dst, const T *src, size_t n, void *stream
 }
 
 template <typename T> int oa_layout_for(const DeviceCtx &c, size_t N, size_t klen) {
-  if (std::is_same<T, float>::value && N == 2048 && !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) &&
-      !env_int("FFTCONV_CUDA_NO_N2048", 0))
-    return fc::generic::LAYOUT_N2048;
+  if (std::is_same<T, float>::value && N == 2048 && oa2048_engine())
+    return oa2048_engine() == 2 ? fc::generic::LAYOUT_W2 : fc::generic::LAYOUT_N2048;
   return fast_ok<T>(c, N, klen) ? fc::generic::LAYOUT_FAST : fc::generic::LAYOUT_DIF;
 }
 

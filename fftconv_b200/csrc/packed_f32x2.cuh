@@ -101,9 +101,9 @@ FC_HD f2 fmss2(f2 a, float s, f2 c) { return make_f2(a.x * s - c.x, a.y * s - c.
 
 // (re + i im) *= (wr + i wi), both lanes, scalar twiddle.
 FC_HD void cmul2(f2 &re, f2 &im, float wr, float wi) {
-  const f2 t = muls2(im, wi);
+  const f2 t = muls2(im, -wi);     // the negation is on the scalar (free for constants)
   const f2 u = muls2(im, wr);
-  const f2 nre = fmss2(re, wr, t); // re*wr - im*wi
+  const f2 nre = fmas2(re, wr, t); // re*wr - im*wi
   im = fmas2(re, wi, u);           // re*wi + im*wr
   re = nre;
 }

@@ -97,6 +97,15 @@ def test_n2048_kernel_logic_emulated_on_cpu(built, case):
     assert float(r.stdout.split()[0]) < 1e-6
 
 
+@pytest.mark.parametrize("case", EMU_CASES + [(8, 20000, 410, 0, 1, 2), (8, 20000, 221, 1, 1, 3, 2)])
+def test_w2_kernel_logic_emulated_on_cpu(built, case):
+    """The warp-pair engine (oa_w2_*.cuh): same method, tests/cpu/emulate_oa_w2.cpp."""
+    exe = os.path.join(ROOT, "tests", "cpu", "emulate_oa_w2")
+    r = subprocess.run([exe, *map(str, case)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (case, r.stdout, r.stderr)
+    assert float(r.stdout.split()[0]) < 1e-6
+
+
 def test_fast_fft_engine_emulated_on_cpu(built):
     """fast_fft.cuh (N = 512 .. 16384, float and double): the kernel's own pass functions
     run for all threads pass by pass on the CPU against direct circular convolution."""
