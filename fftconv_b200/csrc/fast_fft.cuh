@@ -20,6 +20,8 @@
 // makes every pass bank-conflict free for 8- and 16-byte elements.
 #pragma once
 
+#include "packed_f32x2.cuh"
+
 #if defined(__CUDACC__)
 #define FCF_HD __host__ __device__ __forceinline__
 #else
@@ -29,17 +31,45 @@
 namespace fc {
 namespace fast {
 
-template <typename T> struct cx {
-  T x, y;
+// A complex number whose parts are of the DATA type D: float, double, or the packed pair f2
+// (two independent float transforms per thread, one in each half of every 64-bit register
+// pair: SASS FADD2 / FMUL2 / FFMA2).  Twiddles and spectra are always of the SCALAR type
+// scalar_t<D> and are broadcast to both halves.
+template <typename D> struct cx {
+  D x, y;
 };
+template <typename D> struct scalar_of { using type = D; };
+template <> struct scalar_of<f2> { using type = float; };
+template <typename D> using scalar_t = typename scalar_of<D>::type;
 
-template <typename T> FCF_HD cx<T> operator+(cx<T> a, cx<T> b) { return {a.x + b.x, a.y + b.y}; }
-template <typename T> FCF_HD cx<T> operator-(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+FCF_HD f2 operator+(f2 a, f2 b) { return add2(a, b); }
+FCF_HD f2 operator-(f2 a, f2 b) { return sub2(a, b); }
+FCF_HD f2 operator-(f2 a) { return muls2(a, -1.0f); }
+
+template <typename D> FCF_HD cx<D> operator+(cx<D> a, cx<D> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename D> FCF_HD cx<D> operator-(cx<D> a, cx<D> b) { return {a.x - b.x, a.y - b.y}; }
 template <typename T> FCF_HD cx<T> cmul(cx<T> a, cx<T> w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
 template <typename T> FCF_HD cx<T> cmulc(cx<T> a, cx<T> w) { return {a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y}; }
+// packed data, scalar twiddle: four packed instructions
+FCF_HD cx<f2> cmul(cx<f2> a, cx<float> w) {
+  return {fmas2(a.x, w.x, muls2(a.y, -w.y)), fmas2(a.x, w.y, muls2(a.y, w.x))};
+}
+FCF_HD cx<f2> cmulc(cx<f2> a, cx<float> w) {
+  return {fmas2(a.x, w.x, muls2(a.y, w.y)), fmas2(a.x, -w.y, muls2(a.y, w.x))};
+}
 // multiply by -j (S < 0) or +j (S > 0)
-template <int S, typename T> FCF_HD cx<T> rot90(cx<T> a) {
-  return S < 0 ? cx<T>{a.y, -a.x} : cx<T>{-a.y, a.x};
+template <int S, typename D> FCF_HD cx<D> rot90(cx<D> a) {
+  return S < 0 ? cx<D>{a.y, -a.x} : cx<D>{-a.y, a.x};
+}
+// j g v for a real scalar g
+template <typename T> FCF_HD cx<T> mul_j(cx<T> v, T g) { return {-g * v.y, g * v.x}; }
+FCF_HD cx<f2> mul_j(cx<f2> v, float g) { return {muls2(v.y, -g), muls2(v.x, g)}; }
+// a + (-j b) (S < 0) / a + (+j b) (S > 0), and a - (...): no explicit negation
+template <int S, typename D> FCF_HD cx<D> add_rot(cx<D> a, cx<D> b) {
+  return S < 0 ? cx<D>{a.x + b.y, a.y - b.x} : cx<D>{a.x - b.y, a.y + b.x};
+}
+template <int S, typename D> FCF_HD cx<D> sub_rot(cx<D> a, cx<D> b) {
+  return S < 0 ? cx<D>{a.x - b.y, a.y + b.x} : cx<D>{a.x + b.y, a.y - b.x};
 }
 
 template <int LOG2N> struct Plan {
@@ -89,45 +119,50 @@ FCF_HD constexpr unsigned freq_of_pos(unsigned pos, int log2n) {
 }
 
 // ---- small DFTs in registers: natural order in, natural order out -----------------
-template <int S, typename T> FCF_HD void dft2(cx<T> *v) {
-  const cx<T> a = v[0], b = v[1];
+template <int S, typename D> FCF_HD void dft2(cx<D> *v) {
+  const cx<D> a = v[0], b = v[1];
   v[0] = a + b;
   v[1] = a - b;
 }
-template <int S, typename T> FCF_HD void dft4(cx<T> *v) {
-  const cx<T> s0 = v[0] + v[2], d0 = v[0] - v[2], s1 = v[1] + v[3], d1 = v[1] - v[3];
-  const cx<T> jd1 = rot90<S>(d1); // -j d1 (forward) / +j d1 (inverse)
+template <int S, typename D> FCF_HD void dft4(cx<D> *v) {
+  const cx<D> s0 = v[0] + v[2], d0 = v[0] - v[2], s1 = v[1] + v[3], d1 = v[1] - v[3];
   v[0] = s0 + s1;
-  v[1] = d0 + jd1;
+  v[1] = add_rot<S>(d0, d1); // d0 - j d1 (forward) / d0 + j d1 (inverse)
   v[2] = s0 - s1;
-  v[3] = d0 - jd1;
+  v[3] = sub_rot<S>(d0, d1);
 }
-template <int S, typename T> FCF_HD void dft8(cx<T> *v) {
+template <int S, typename D> FCF_HD void dft8(cx<D> *v) {
+  using T = scalar_t<D>;
   // m = m0 + 2 m1, k = k1 + 4 k0
-  cx<T> e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+  cx<D> e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
   dft4<S>(e);
   dft4<S>(o);
   const T h = (T)0.70710678118654752440084436210485L;
   const T s = S < 0 ? (T)-1 : (T)1;
   o[1] = cmul(o[1], cx<T>{h, s * h});
-  o[2] = rot90<S>(o[2]);
   o[3] = cmul(o[3], cx<T>{-h, s * h});
 #pragma unroll
   for (int k1 = 0; k1 < 4; ++k1) {
-    v[k1] = e[k1] + o[k1];
-    v[k1 + 4] = e[k1] - o[k1];
+    if (k1 == 2) { // W8^2 = -+j
+      v[k1] = add_rot<S>(e[k1], o[k1]);
+      v[k1 + 4] = sub_rot<S>(e[k1], o[k1]);
+    } else {
+      v[k1] = e[k1] + o[k1];
+      v[k1 + 4] = e[k1] - o[k1];
+    }
   }
 }
-template <int S, typename T> FCF_HD void dft16(cx<T> *v) {
+template <int S, typename D> FCF_HD void dft16(cx<D> *v) {
+  using T = scalar_t<D>;
   // m = m0 + 4 m1, k = k1 + 4 k0
   const T c8 = (T)0.70710678118654752440084436210485L;
   const T c16 = (T)0.92387953251128675612818318939679L;
   const T s16 = (T)0.38268343236508977172845998403040L;
   const T s = S < 0 ? (T)-1 : (T)1;
-  cx<T> a[4][4]; // a[m0][k1]
+  cx<D> a[4][4]; // a[m0][k1]
 #pragma unroll
   for (int m0 = 0; m0 < 4; ++m0) {
-    cx<T> t[4] = {v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]};
+    cx<D> t[4] = {v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]};
     dft4<S>(t);
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) a[m0][k1] = t[k1];
@@ -143,18 +178,44 @@ template <int S, typename T> FCF_HD void dft16(cx<T> *v) {
   a[3][3] = cmul(a[3][3], cx<T>{-c16, -s * s16});
 #pragma unroll
   for (int k1 = 0; k1 < 4; ++k1) {
-    cx<T> t[4] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1]};
+    cx<D> t[4] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1]};
     dft4<S>(t);
 #pragma unroll
     for (int k0 = 0; k0 < 4; ++k0) v[k1 + 4 * k0] = t[k0];
   }
 }
-template <int S, int LOGR, typename T> FCF_HD void dft_small(cx<T> *v) {
+template <int S, int LOGR, typename D> FCF_HD void dft_small(cx<D> *v) {
   if (LOGR == 1) dft2<S>(v);
   else if (LOGR == 2) dft4<S>(v);
   else if (LOGR == 3) dft8<S>(v);
   else dft16<S>(v);
 }
+
+// ---- twiddles of one thread and pass ---------------------------------------------------
+// tw[s] = TW[(s - 1) * stride + p], s = 1 .. R-1.  For packed data (D = f2) only the powers of
+// two are loaded and the rest are formed as products in registers (at most three deep): the
+// loads come from global memory through L1 and their latency, not arithmetic, is what a pass
+// waits for (ncu: DESIGN.md section 4).  Scalar data types read every entry (exact to the last
+// bit, which float64's 1e-12 parity bound wants).
+template <typename T> FCF_HD cx<T> cxmul(cx<T> a, cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+template <int R, bool RECOMP, typename T> FCF_HD void load_twiddles(cx<T> *tw, const cx<T> *TW, int stride, int p) {
+  if (!RECOMP) {
+#pragma unroll
+    for (int s = 1; s < R; ++s) tw[s] = TW[(s - 1) * stride + p];
+  } else {
+#pragma unroll
+    for (int s = 1; s < R; s <<= 1) tw[s] = TW[(s - 1) * stride + p];
+#pragma unroll
+    for (int s = 3; s < R; ++s)
+      if (s & (s - 1)) { // not a power of two: highest bit times the rest
+        int hb = 1;
+        while (2 * hb <= s) hb <<= 1;
+        tw[s] = cxmul(tw[hb], tw[s - hb]);
+      }
+  }
+}
+template <typename D> struct recomp_twiddles { static constexpr bool value = false; };
+template <> struct recomp_twiddles<f2> { static constexpr bool value = true; };
 
 // ---- passes --------------------------------------------------------------------
 // Register slot convention: pass 0 holds butterfly u (of U = 16 >> R0) in slots
@@ -167,32 +228,36 @@ template <int LOG2N> FCF_HD int pass0_index(int tid, int slot) {
 }
 
 // forward pass 0: v = inputs (slot convention above) -> shared memory
-template <int LOG2N, typename T> FCF_HD void fwd_pass0(int tid, cx<T> *v, cx<T> *buf, const cx<T> *TW) {
+template <int LOG2N, typename D> FCF_HD void fwd_pass0(int tid, cx<D> *v, cx<D> *buf, const cx<scalar_t<D>> *TW) {
   using P = Plan<LOG2N>;
   constexpr int R = 1 << P::R0, U = 16 / R, S0 = P::N >> P::R0;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int p = tid + u * P::THREADS;
+    cx<scalar_t<D>> tw[R];
+    load_twiddles<R, recomp_twiddles<D>::value>(tw, TW, S0, p); // W_N^{p s}
     dft_small<-1, P::R0>(v + u * R);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-      cx<T> y = v[u * R + s];
-      if (s > 0) y = cmul(y, TW[(s - 1) * S0 + p]); // W_N^{p s}
+      cx<D> y = v[u * R + s];
+      if (s > 0) y = cmul(y, tw[s]);
       buf[phys(p + s * S0)] = y;
     }
   }
 }
 // inverse pass 0: shared memory -> v = outputs (same slot convention)
-template <int LOG2N, typename T> FCF_HD void inv_pass0(int tid, cx<T> *v, const cx<T> *buf, const cx<T> *TW) {
+template <int LOG2N, typename D> FCF_HD void inv_pass0(int tid, cx<D> *v, const cx<D> *buf, const cx<scalar_t<D>> *TW) {
   using P = Plan<LOG2N>;
   constexpr int R = 1 << P::R0, U = 16 / R, S0 = P::N >> P::R0;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int p = tid + u * P::THREADS;
+    cx<scalar_t<D>> tw[R];
+    load_twiddles<R, recomp_twiddles<D>::value>(tw, TW, S0, p);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-      cx<T> y = buf[phys(p + s * S0)];
-      if (s > 0) y = cmulc(y, TW[(s - 1) * S0 + p]);
+      cx<D> y = buf[phys(p + s * S0)];
+      if (s > 0) y = cmulc(y, tw[s]);
       v[u * R + s] = y;
     }
     dft_small<+1, P::R0>(v + u * R);
@@ -200,34 +265,38 @@ template <int LOG2N, typename T> FCF_HD void inv_pass0(int tid, cx<T> *v, const 
 }
 
 // middle radix-16 pass J (1 <= J <= P - 2): sub-transform length m = N >> (R0 + 4 (J - 1))
-template <int LOG2N, int J, typename T> FCF_HD void fwd_mid(int tid, cx<T> *buf, const cx<T> *TWALL) {
+template <int LOG2N, int J, typename D> FCF_HD void fwd_mid(int tid, cx<D> *buf, const cx<scalar_t<D>> *TWALL) {
   using P = Plan<LOG2N>;
   constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4;
   constexpr int OFF = P::tw_offset(J);
-  const cx<T> *TW = TWALL + OFF;
+  const cx<scalar_t<D>> *TW = TWALL + OFF;
   const int p = tid & ((1 << LS) - 1), base = ((tid >> LS) << LM) + p;
-  cx<T> v[16];
+  cx<D> v[16];
+  cx<scalar_t<D>> tw[16];
+  load_twiddles<16, recomp_twiddles<D>::value>(tw, TW, 1 << LS, p); // W_m^{p s}
 #pragma unroll
   for (int q = 0; q < 16; ++q) v[q] = buf[phys(base + (q << LS))];
   dft16<-1>(v);
 #pragma unroll
   for (int s = 0; s < 16; ++s) {
-    cx<T> y = v[s];
-    if (s > 0) y = cmul(y, TW[((s - 1) << LS) + p]); // W_m^{p s}
+    cx<D> y = v[s];
+    if (s > 0) y = cmul(y, tw[s]);
     buf[phys(base + (s << LS))] = y;
   }
 }
-template <int LOG2N, int J, typename T> FCF_HD void inv_mid(int tid, cx<T> *buf, const cx<T> *TWALL) {
+template <int LOG2N, int J, typename D> FCF_HD void inv_mid(int tid, cx<D> *buf, const cx<scalar_t<D>> *TWALL) {
   using P = Plan<LOG2N>;
   constexpr int LM = LOG2N - P::R0 - 4 * (J - 1), LS = LM - 4;
   constexpr int OFF = P::tw_offset(J);
-  const cx<T> *TW = TWALL + OFF;
+  const cx<scalar_t<D>> *TW = TWALL + OFF;
   const int p = tid & ((1 << LS) - 1), base = ((tid >> LS) << LM) + p;
-  cx<T> v[16];
+  cx<D> v[16];
+  cx<scalar_t<D>> tw[16];
+  load_twiddles<16, recomp_twiddles<D>::value>(tw, TW, 1 << LS, p);
 #pragma unroll
   for (int s = 0; s < 16; ++s) {
-    cx<T> y = buf[phys(base + (s << LS))];
-    if (s > 0) y = cmulc(y, TW[((s - 1) << LS) + p]);
+    cx<D> y = buf[phys(base + (s << LS))];
+    if (s > 0) y = cmulc(y, tw[s]);
     v[s] = y;
   }
   dft16<+1>(v);
@@ -237,22 +306,38 @@ template <int LOG2N, int J, typename T> FCF_HD void inv_mid(int tid, cx<T> *buf,
 
 // last forward pass (m = 16) + spectrum multiply + first inverse pass, in registers.
 // H is s-major: H[s THREADS + tid] belongs to position 16 tid + s (coalesced reads).
-template <int LOG2N, typename T> FCF_HD void last_fused(int tid, cx<T> *buf, const cx<T> *H) {
-  cx<T> v[16];
+// The spectrum multiplier applied between the transforms: a table (the filter's spectrum), or
+// the Hilbert transformer -j sgn(f) / N, which needs no table: position 16 tid + s holds
+// frequency (N / 16) s + (lower digits of tid), so s < 8 are the positive frequencies, and DC /
+// Nyquist are (tid, s) = (0, 0) / (0, 8)  (/root/reference/include/fftconv/hilbert.hpp:39-51, :57).
+template <typename T> struct TableSpectrum {
+  const cx<T> *H;
+  int threads;
+  template <typename D> FCF_HD cx<D> apply(cx<D> v, int tid, int s) const { return cmul(v, H[s * threads + tid]); }
+};
+template <typename T> struct HilbertSpectrum {
+  T inv_n;
+  template <typename D> FCF_HD cx<D> apply(cx<D> v, int tid, int s) const {
+    const T g = (tid == 0 && (s & 7) == 0) ? (T)0 : (s < 8 ? -inv_n : inv_n); // times j g
+    return mul_j(v, g);
+  }
+};
+template <int LOG2N, typename D, class Spectrum> FCF_HD void last_fused(int tid, cx<D> *buf, const Spectrum &H) {
+  cx<D> v[16];
   const int base = 16 * tid;
 #pragma unroll
   for (int q = 0; q < 16; ++q) v[q] = buf[phys(base + q)];
   dft16<-1>(v);
 #pragma unroll
-  for (int s = 0; s < 16; ++s) v[s] = cmul(v[s], H[s * Plan<LOG2N>::THREADS + tid]);
+  for (int s = 0; s < 16; ++s) v[s] = H.apply(v[s], tid, s);
   dft16<+1>(v);
 #pragma unroll
   for (int q = 0; q < 16; ++q) buf[phys(base + q)] = v[q];
 }
 
 // compile-time loops over the middle passes
-template <int LOG2N, int J, typename T> struct FwdMids {
-  template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<T> *W, Sync &sync) {
+template <int LOG2N, int J, typename T> struct FwdMids { // T = data type
+  template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<scalar_t<T>> *W, Sync &sync) {
     if constexpr (J <= Plan<LOG2N>::P - 2) {
       fwd_mid<LOG2N, J>(tid, buf, W);
       sync();
@@ -261,7 +346,7 @@ template <int LOG2N, int J, typename T> struct FwdMids {
   }
 };
 template <int LOG2N, int J, typename T> struct InvMids {
-  template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<T> *W, Sync &sync) {
+  template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<scalar_t<T>> *W, Sync &sync) {
     if constexpr (J >= 1) {
       inv_mid<LOG2N, J>(tid, buf, W);
       sync();
@@ -272,9 +357,21 @@ template <int LOG2N, int J, typename T> struct InvMids {
 
 // Whole circular convolution with the spectrum H: v (inputs, pass-0 slot convention)
 // -> v (outputs, same convention).  `sync` is the barrier among the FFT's threads.
+template <int LOG2N, typename T, class Spectrum, class Sync>
+FCF_HD void conv_core_with(int tid, cx<T> *v, cx<T> *buf, const cx<scalar_t<T>> *W /* pass twiddle tables */,
+                           const Spectrum &H, Sync &sync) {
+  fwd_pass0<LOG2N>(tid, v, buf, W);
+  sync();
+  FwdMids<LOG2N, 1, T>::run(tid, buf, W, sync);
+  last_fused<LOG2N>(tid, buf, H);
+  sync();
+  InvMids<LOG2N, Plan<LOG2N>::P - 2, T>::run(tid, buf, W, sync);
+  inv_pass0<LOG2N>(tid, v, buf, W);
+}
 template <int LOG2N, typename T, class Sync>
-FCF_HD void conv_core(int tid, cx<T> *v, cx<T> *buf, const cx<T> *W /* pass twiddle tables */, const cx<T> *H,
-                      Sync &sync) {
+FCF_HD void conv_core(int tid, cx<T> *v, cx<T> *buf, const cx<scalar_t<T>> *W /* pass twiddle tables */,
+                      const cx<scalar_t<T>> *Htab, Sync &sync) {
+  const TableSpectrum<scalar_t<T>> H{Htab, Plan<LOG2N>::THREADS};
   fwd_pass0<LOG2N>(tid, v, buf, W);
   sync();
   FwdMids<LOG2N, 1, T>::run(tid, buf, W, sync);

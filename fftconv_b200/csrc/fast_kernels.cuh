@@ -14,8 +14,9 @@ namespace fc {
 namespace fast {
 
 // occupancy target: ~768 threads per SM (<= 85 registers) for float, ~512 (<= 128) for double
-template <typename T, int CTA_THREADS> constexpr int min_blocks() {
-  constexpr int target = sizeof(T) == 4 ? 768 : 512;
+// and for the packed float kernels (D = f2: four real streams per FFT, 64 data registers)
+template <typename D, int CTA_THREADS> constexpr int min_blocks() {
+  constexpr int target = sizeof(D) == 4 ? 768 : 512;
   return CTA_THREADS >= target ? 1 : target / CTA_THREADS;
 }
 
@@ -23,30 +24,63 @@ struct CtaSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-template <typename T, int LOG2N, int FPC>
-__global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<T, Plan<LOG2N>::THREADS * FPC>())
-    oa_fast_kernel(const generic::OaArgs<T> p) {
+// The real streams ("lanes") that ride in one complex value of data type D:
+//   D = T:   lane 0 = real part, lane 1 = imaginary part
+//   D = f2:  lane 0 = re half A, lane 1 = im half A, lane 2 = re half B, lane 3 = im half B
+template <typename D> struct Lanes {
+  static constexpr int N = 2;
+  static __device__ __forceinline__ cx<D> make(const D (&a)[2]) { return {a[0], a[1]}; }
+  static __device__ __forceinline__ void split(cx<D> c, D (&a)[2]) {
+    a[0] = c.x;
+    a[1] = c.y;
+  }
+};
+template <> struct Lanes<f2> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ cx<f2> make(const float (&a)[4]) {
+    return {make_f2(a[0], a[2]), make_f2(a[1], a[3])};
+  }
+  static __device__ __forceinline__ void split(cx<f2> c, float (&a)[4]) {
+    a[0] = c.x.x;
+    a[1] = c.y.x;
+    a[2] = c.x.y;
+    a[3] = c.y.y;
+  }
+};
+
+// D = T (two streams per FFT) or D = f2 with T = float (four streams per FFT)
+template <typename D, int LOG2N, int FPC>
+__global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<LOG2N>::THREADS * FPC>())
+    oa_fast_kernel(const generic::OaArgs<scalar_t<D>> p) {
   using P = Plan<LOG2N>;
-  constexpr int N = P::N;
+  using T = scalar_t<D>;
+  using L = Lanes<D>;
+  constexpr int N = P::N, NL = L::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int f = threadIdx.x / P::THREADS, tid = threadIdx.x % P::THREADS;
   const int tail_len = p.klen - 1;
-  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
-  cx<T> *tails = reinterpret_cast<cx<T> *>(smem_raw) + (size_t)FPC * P::SMEM_ELEMS + (size_t)f * 2 * tail_len;
+  cx<D> *buf = reinterpret_cast<cx<D> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
+  cx<D> *tails = reinterpret_cast<cx<D> *>(smem_raw) + (size_t)FPC * P::SMEM_ELEMS + (size_t)f * 2 * tail_len;
   const cx<T> *W = reinterpret_cast<const cx<T> *>(p.W);
   const cx<T> *H = reinterpret_cast<const cx<T> *>(p.H);
 
   // CTA-uniform loop bounds over all FPC FFTs (barriers are CTA-wide)
   long long max_cnt = 0;
   bool warm_needed = false;
-  const T *src[2] = {p.in, p.in};
-  T *dst[2] = {p.out, p.out};
-  long long seg0[2] = {0, 0}, cnt[2] = {0, 0};
+  const T *src[NL];
+  T *dst[NL];
+  long long seg0[NL], cnt[NL];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    src[l] = p.in;
+    dst[l] = p.out;
+    seg0[l] = cnt[l] = 0;
+  }
 #pragma unroll
   for (int ff = 0; ff < FPC; ++ff)
 #pragma unroll
-    for (int l = 0; l < 2; ++l) {
-      const long long sid = ((long long)blockIdx.x * FPC + ff) * 2 + l;
+    for (int l = 0; l < NL; ++l) {
+      const long long sid = ((long long)blockIdx.x * FPC + ff) * NL + l;
       const bool active = sid < p.n_streams;
       const long long row = active ? sid / p.chunks : 0;
       const long long chunk = active ? sid - row * p.chunks : 0;
@@ -68,10 +102,10 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<T, Plan<
   bool add_tail = false;
   for (long long j = warm_needed ? -1 : 0; j < max_cnt; ++j) {
     const bool warm = j < 0;
-    long long pos[2];
-    int len[2], limit[2];
+    long long pos[NL];
+    int len[NL], limit[NL];
 #pragma unroll
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < NL; ++l) {
       const long long seg = seg0[l] + j;
       const bool on = seg >= 0 && j < cnt[l];
       pos[l] = seg * p.step;
@@ -85,25 +119,31 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<T, Plan<
       }
       limit[l] = (on && !warm) ? (int)lim : 0;
     }
-    cx<T> v[16];
+    cx<D> v[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
       const int i = pass0_index<LOG2N>(tid, s);
-      v[s].x = i < len[0] ? src[0][pos[0] + i] : (T)0;
-      v[s].y = i < len[1] ? src[1][pos[1] + i] : (T)0;
+      T x[NL];
+#pragma unroll
+      for (int l = 0; l < NL; ++l) x[l] = i < len[l] ? src[l][pos[l] + i] : (T)0;
+      v[s] = L::make(x);
     }
     conv_core<LOG2N>(tid, v, buf, W, H, sync);
-    cx<T> *tail_prev = tails + (parity ^ 1) * tail_len;
-    cx<T> *tail_next = tails + parity * tail_len;
+    cx<D> *tail_prev = tails + (parity ^ 1) * tail_len;
+    cx<D> *tail_next = tails + parity * tail_len;
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
       const int i = pass0_index<LOG2N>(tid, s);
-      cx<T> y = v[s];
+      cx<D> y = v[s];
       if (add_tail && i < tail_len) y = y + tail_prev[i];
       if (i >= p.step) tail_next[i - p.step] = y;
-      const long long o0 = pos[0] - p.pad + i, o1 = pos[1] - p.pad + i;
-      if (i < limit[0] && o0 >= 0) dst[0][o0] = y.x;
-      if (i < limit[1] && o1 >= 0) dst[1][o1] = y.y;
+      T ys[NL];
+      L::split(y, ys);
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const long long o = pos[l] - p.pad + i;
+        if (i < limit[l] && o >= 0) dst[l][o] = ys[l];
+      }
     }
     __syncthreads(); // tails and the exchange buffer are reused by the next segment
     parity ^= 1;
@@ -111,49 +151,69 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<T, Plan<
   }
 }
 
-// Hilbert envelope of rows of length N (power of two): rows 2b, 2b+1 per FFT.
+// Hilbert envelope of rows of length N (power of two): rows 2b, 2b+1 (or 4b .. 4b+3) per FFT.
 // G (position order) = -j sgn(f) / N with DC and Nyquist zeroed (hilbert.hpp:39-51).
-template <typename T, int LOG2N, int FPC>
-__global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<T, Plan<LOG2N>::THREADS * FPC>())
-    hilbert_fast_kernel(const generic::HilbertArgs<T> p) {
+template <typename D, int LOG2N, int FPC>
+__global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<LOG2N>::THREADS * FPC>())
+    hilbert_fast_kernel(const generic::HilbertArgs<scalar_t<D>> p) {
   using P = Plan<LOG2N>;
+  using T = scalar_t<D>;
+  using L = Lanes<D>;
+  constexpr int NL = L::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int f = threadIdx.x / P::THREADS, tid = threadIdx.x % P::THREADS;
-  cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
+  cx<D> *buf = reinterpret_cast<cx<D> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
   const cx<T> *W = reinterpret_cast<const cx<T> *>(p.W);
-  const cx<T> *G = reinterpret_cast<const cx<T> *>(p.G);
-  const long long r0 = ((long long)blockIdx.x * FPC + f) * 2, r1 = r0 + 1;
-  const bool has0 = r0 < p.batch, has1 = r1 < p.batch;
-  const T *x0 = p.in + (has0 ? r0 : 0) * p.in_stride;
-  const T *x1 = p.in + (has1 ? r1 : 0) * p.in_stride;
-  // float keeps the inputs in registers for the envelope; double re-reads them
-  // (16 more complex doubles would not fit 128 registers per thread)
-  constexpr bool kKeep = sizeof(T) == 4;
-  cx<T> v[16], x[kKeep ? 16 : 1];
+  bool has[NL];
+  const T *x[NL];
+  T *e[NL];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    const long long r = ((long long)blockIdx.x * FPC + f) * NL + l;
+    has[l] = r < p.batch;
+    x[l] = p.in + (has[l] ? r : 0) * p.in_stride;
+    e[l] = p.out + (has[l] ? r : 0) * p.out_stride;
+  }
+  // plain float keeps the inputs in registers for the envelope; double and packed float
+  // re-read them (16 more complex values would not fit 128 registers per thread)
+  constexpr bool kKeep = sizeof(D) == 4;
+  cx<D> v[16], keep[kKeep ? 16 : 1];
 #pragma unroll
   for (int s = 0; s < 16; ++s) {
     const int i = pass0_index<LOG2N>(tid, s);
-    v[s].x = has0 ? x0[i] : (T)0;
-    v[s].y = has1 ? x1[i] : (T)0;
-    if constexpr (kKeep) x[s] = v[s];
+    T a[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) a[l] = has[l] ? x[l][i] : (T)0;
+    v[s] = L::make(a);
+    if constexpr (kKeep) keep[s] = v[s];
   }
   CtaSync sync;
-  conv_core<LOG2N>(tid, v, buf, W, G, sync);
-  T *e0 = p.out + (has0 ? r0 : 0) * p.out_stride;
-  T *e1 = p.out + (has1 ? r1 : 0) * p.out_stride;
+  const HilbertSpectrum<T> G{(T)(1.0 / (double)P::N)};
+  conv_core_with<LOG2N>(tid, v, buf, W, G, sync);
+  // envelope; the inputs are re-read (L2) in batches so that their latencies overlap
+  constexpr int kBatch = kKeep ? 16 : (NL == 4 ? 4 : 8);
 #pragma unroll
-  for (int s = 0; s < 16; ++s) {
-    const int i = pass0_index<LOG2N>(tid, s);
-    T a, b;
-    if constexpr (kKeep) {
-      a = x[s].x;
-      b = x[s].y;
-    } else {
-      a = has0 ? x0[i] : (T)0;
-      b = has1 ? x1[i] : (T)0;
+  for (int s0 = 0; s0 < 16; s0 += kBatch) {
+    T a[kBatch][NL];
+#pragma unroll
+    for (int s = 0; s < kBatch; ++s) {
+      if constexpr (kKeep) {
+        L::split(keep[s0 + s], a[s]);
+      } else {
+        const int i = pass0_index<LOG2N>(tid, s0 + s);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) a[s][l] = has[l] ? __ldg(x[l] + i) : (T)0;
+      }
     }
-    if (has0) e0[i] = sqrt(a * a + v[s].x * v[s].x);
-    if (has1) e1[i] = sqrt(b * b + v[s].y * v[s].y);
+#pragma unroll
+    for (int s = 0; s < kBatch; ++s) {
+      const int i = pass0_index<LOG2N>(tid, s0 + s);
+      T h[NL];
+      L::split(v[s0 + s], h);
+#pragma unroll
+      for (int l = 0; l < NL; ++l)
+        if (has[l]) e[l][i] = sqrt(a[s][l] * a[s][l] + h[l] * h[l]);
+    }
   }
 }
 

@@ -404,8 +404,40 @@ template <typename T> bool fast_ok(const DeviceCtx &c, size_t N, size_t klen) {
   return fast_smem<T>(ilog2(N), klen) <= c.smem_optin;
 }
 
+// Packed float (D = f2: four real streams per FFT, 16-byte shared-memory points): 512 threads
+// per CTA where one FFT has fewer, one CTA per SM, for FFT sizes <= 8192.
+constexpr int packed_fpc(int log2n) {
+  const int threads = (1 << log2n) / 16;
+  return threads >= 512 ? 1 : 512 / threads;
+}
+size_t packed_smem(int log2n, size_t klen) {
+  const size_t n = size_t(1) << log2n;
+  return (size_t)packed_fpc(log2n) * (n + n / 16 + 2 * (klen ? klen - 1 : 0)) * sizeof(cx<fc::f2>);
+}
+template <typename T> bool packed_ok(const DeviceCtx &c, size_t N, size_t klen) {
+  if (!std::is_same<T, float>::value || N < 512 || N > 8192) return false;
+  if (env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) || env_int("FFTCONV_CUDA_NO_PACKED", 0)) return false;
+  return packed_smem(ilog2(N), klen) <= c.smem_optin;
+}
+
 template <typename T, int LOG2N>
 int launch_oa_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::OaArgs<T> &p, size_t klen) {
+  if constexpr (std::is_same<T, float>::value && LOG2N <= 13) {
+    // four streams per FFT pay off once the streams fill the machine; a few short signals are
+    // latency-bound and better spread over more, smaller CTAs
+    if (packed_ok<T>(c, size_t(1) << LOG2N, klen) && p.n_streams >= 2LL * packed_fpc(LOG2N) * c.sm_count) {
+      constexpr int FPC = packed_fpc(LOG2N);
+      const size_t smem = packed_smem(LOG2N, klen);
+      auto kern = fc::fast::oa_fast_kernel<fc::f2, LOG2N, FPC>;
+      if (int r = ensure_smem(c, kern, smem)) return r;
+      const long long grid = (p.n_streams + 4 * FPC - 1) / (4 * FPC);
+      if (grid > 0x7fffffffLL) return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "batch too large for one launch");
+      kern<<<(unsigned)grid, fc::fast::Plan<LOG2N>::THREADS * FPC, smem, st>>>(p);
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+      return 0;
+    }
+  }
   constexpr int FPC = fast_fpc<T>(LOG2N);
   const size_t smem = fast_smem<T>(LOG2N, klen);
   auto kern = fc::fast::oa_fast_kernel<T, LOG2N, FPC>;
@@ -419,6 +451,19 @@ int launch_oa_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::OaArgs<T> &
 }
 template <typename T, int LOG2N>
 int launch_hilbert_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::HilbertArgs<T> &p) {
+  if constexpr (std::is_same<T, float>::value && LOG2N <= 13) {
+    if (packed_ok<T>(c, size_t(1) << LOG2N, 0) && p.batch >= 2LL * packed_fpc(LOG2N) * c.sm_count) {
+      constexpr int FPC = packed_fpc(LOG2N);
+      const size_t smem = packed_smem(LOG2N, 0);
+      auto kern = fc::fast::hilbert_fast_kernel<fc::f2, LOG2N, FPC>;
+      if (int r = ensure_smem(c, kern, smem)) return r;
+      const long long grid = (p.batch + 4 * FPC - 1) / (4 * FPC);
+      kern<<<(unsigned)grid, fc::fast::Plan<LOG2N>::THREADS * FPC, smem, st>>>(p);
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+      return 0;
+    }
+  }
   constexpr int FPC = fast_fpc<T>(LOG2N);
   const size_t smem = fast_smem<T>(LOG2N, 0);
   auto kern = fc::fast::hilbert_fast_kernel<T, LOG2N, FPC>;
