@@ -455,6 +455,16 @@ int launch_hilbert_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::Hilber
     if (packed_ok<T>(c, size_t(1) << LOG2N, 0) && p.batch >= 2LL * packed_fpc(LOG2N) * c.sm_count) {
       constexpr int FPC = packed_fpc(LOG2N);
       const size_t smem = packed_smem(LOG2N, 0);
+      const bool aligned = (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (p.in_stride & 3) == 0;
+      if (aligned && !env_int("FFTCONV_CUDA_NO_PERSISTENT_HILBERT", 0)) {
+        auto pk = fc::fast::hilbert_pk_persistent_kernel<LOG2N, FPC>;
+        if (int r = ensure_smem(c, pk, smem + 16)) return r;
+        const long long units = (p.batch + 4 * FPC - 1) / (4 * FPC);
+        pk<<<(unsigned)std::min<long long>(units, c.sm_count), fc::fast::Plan<LOG2N>::THREADS * FPC, smem + 16, st>>>(p);
+        CU_TRY(cudaGetLastError());
+        ++g_launches;
+        return 0;
+      }
       auto kern = fc::fast::hilbert_fast_kernel<fc::f2, LOG2N, FPC>;
       if (int r = ensure_smem(c, kern, smem)) return r;
       const long long grid = (p.batch + 4 * FPC - 1) / (4 * FPC);

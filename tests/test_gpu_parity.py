@@ -257,6 +257,34 @@ def test_hilbert_config4_sample(cuda):
     assert O.rel_l2(fc.hilbert(x64), O.hilbert_exact(x64)) < 1e-12
 
 
+@pytest.mark.parametrize("rows,n", [(301, 8192), (2371, 1024), (1190, 2048), (600, 4096), (4737, 512)])
+def test_hilbert_packed_persistent_kernel(cuda, rows, n):
+    """Batches large enough for the packed (four rows per FFT) persistent TMA-fed kernel, with
+    row counts that are not multiples of four; also rows at a 4-byte offset and with a padded
+    stride (the one-shot packed kernel), checked densely on a subset of rows."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(rows + n)
+    x = rng.standard_normal((rows, n)).astype(np.float32)
+    tx = _t(x, cuda)
+    env = fc.hilbert(tx)
+    torch.cuda.synchronize()
+    pick = np.unique(np.concatenate([np.arange(0, rows, max(1, rows // 40)), np.arange(rows - 9, rows)]))
+    want = O.hilbert_exact(x[pick])
+    assert O.rel_l2(env[pick].cpu().numpy(), want) < 1e-5
+    assert torch.isfinite(env).all()
+    # misaligned view: rows start 4 bytes off a 16-byte boundary, stride n + 1
+    store = torch.zeros(rows * (n + 1) + 1, dtype=torch.float32, device=cuda)
+    view = store[1:].view(rows, n + 1)[:, :n]
+    view.copy_(tx)
+    env2 = torch.empty_like(tx)
+    fc.hilbert_(view, env2)
+    torch.cuda.synchronize()
+    assert O.rel_l2(env2[pick].cpu().numpy(), want) < 1e-5
+
+
 @pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 64, 1024, 4096])
 def test_hilbert_power_of_two_lengths(cuda, n):
     import fftconv_b200 as fc
