@@ -139,22 +139,22 @@ def main():
         a = torch.randn((1024, 16384), device=dev, generator=g, dtype=torch.float64)
         k = torch.randn(165, device=dev, generator=g, dtype=torch.float64)
         out = torch.empty((1024, 16384 + 164), device=dev, dtype=torch.float64)
-        os.environ.pop("FFTCONV_CUDA_CONV_LONG_AS_OA", None)
+        os.environ.pop("FFTCONV_CUDA_CONV_SINGLE_FFT", None)
         ms = time_cuda(lambda: fc.convolve_(a, k, out, "full"), args.steps, args.warmup, flush)
-        os.environ["FFTCONV_CUDA_CONV_LONG_AS_OA"] = "1"
-        ms_seg = time_cuda(lambda: fc.convolve_(a, k, out, "full"), args.steps, args.warmup, flush)
-        os.environ.pop("FFTCONV_CUDA_CONV_LONG_AS_OA", None)
+        os.environ["FFTCONV_CUDA_CONV_SINGLE_FFT"] = "1"
+        ms_one = time_cuda(lambda: fc.convolve_(a, k, out, "full"), args.steps, args.warmup, flush)
+        os.environ.pop("FFTCONV_CUDA_CONV_SINGLE_FFT", None)
         alg = 1024 * (16384 + 16548) * 8 + 165 * 8
         emit({"config": "c3", "workload": "batched convolve f64 1024 x 16384, k=165, full",
               "ms_per_step": ms, "value": out.numel() / (ms * 1e-3) / 1e9, "unit": "Gsamples/s",
               "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None},
               "algorithmic_bytes": alg, "l2": "flushed between iterations (256 MB write)",
-              "method": "one FFT of length 32768 per row pair (16 x 2048 through global scratch), as the reference "
-                        "convolve_fftw does (default)",
-              "alt_segment_ffts": {"ms_per_step": ms_seg, "value": out.numel() / (ms_seg * 1e-3) / 1e9,
-                                   "frac": alg / (ms_seg * 1e-3) / 1e9 / peak,
-                                   "note": "FFTCONV_CUDA_CONV_LONG_AS_OA=1: same linear convolution by segment FFTs"},
+              "method": "segment FFTs of 1024 points on chip (default beyond one CTA's FFT; same linear convolution)",
+              "alt_one_long_fft": {"ms_per_step": ms_one, "value": out.numel() / (ms_one * 1e-3) / 1e9,
+                                   "frac": alg / (ms_one * 1e-3) / 1e9 / peak,
+                                   "note": "FFTCONV_CUDA_CONV_SINGLE_FFT=1: one FFT of length 32768 per row pair "
+                                           "(16 x 2048 through global scratch), the reference convolve_fftw's method"},
               "cpu_baseline": None if args.no_cpu else cpu_leg("conv", np.float64, 1024, 16384, 165)})
 
     if "c4" in which and world == 1:

@@ -192,11 +192,10 @@ template <int S, int LOGR, typename D> FCF_HD void dft_small(cx<D> *v) {
 }
 
 // ---- twiddles of one thread and pass ---------------------------------------------------
-// tw[s] = TW[(s - 1) * stride + p], s = 1 .. R-1.  For packed data (D = f2) only the powers of
-// two are loaded and the rest are formed as products in registers (at most three deep): the
-// loads come from global memory through L1 and their latency, not arithmetic, is what a pass
-// waits for (ncu: DESIGN.md section 4).  Scalar data types read every entry (exact to the last
-// bit, which float64's 1e-12 parity bound wants).
+// tw[s] = W^{p s}, s = 1 .. R-1: only the powers of two are loaded (TW[(s - 1) * stride + p]) and
+// the rest are formed as products in registers (at most three deep, relative error <= 3 eps):
+// the loads come from global memory through L1 and their latency, not arithmetic, is what a
+// pass waits for (ncu: DESIGN.md section 4).
 template <typename T> FCF_HD cx<T> cxmul(cx<T> a, cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 template <int R, bool RECOMP, typename T> FCF_HD void load_twiddles(cx<T> *tw, const cx<T> *TW, int stride, int p) {
   if (!RECOMP) {
@@ -214,8 +213,7 @@ template <int R, bool RECOMP, typename T> FCF_HD void load_twiddles(cx<T> *tw, c
       }
   }
 }
-template <typename D> struct recomp_twiddles { static constexpr bool value = false; };
-template <> struct recomp_twiddles<f2> { static constexpr bool value = true; };
+template <typename D> struct recomp_twiddles { static constexpr bool value = true; };
 
 // ---- passes --------------------------------------------------------------------
 // Register slot convention: pass 0 holds butterfly u (of U = 16 >> R0) in slots

@@ -764,10 +764,15 @@ int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, 
     N = 16;
     while (N < n + klen - 1) N *= 2;
     if (N > max_generic_fft<T>(c, klen)) {
-      // one long FFT split over three kernels (long_fft_kernels.cuh) while the direct
-      // O(N K) spectrum evaluation stays cheap; otherwise segment FFTs of the table
-      // size -- the same linear convolution either way
-      const bool want_long = !env_int("FFTCONV_CUDA_CONV_LONG_AS_OA", 0) && long_ok<T>(c, N) &&
+      // Beyond one CTA's shared memory the same linear convolution is computed with segment
+      // FFTs of the table size, entirely on chip (measured 2.3x faster than the split
+      // transform at 1024 x 16384 float64, K = 165).  One long FFT split over three kernels
+      // with a global scratch (long_fft_kernels.cuh) -- the reference's own method,
+      // fftconv.hpp:338-380 -- serves taps too long for a segment FFT, or everything with
+      // FFTCONV_CUDA_CONV_SINGLE_FFT=1, while the direct O(N K) spectrum evaluation stays cheap.
+      const bool oa_feasible = optimal_fft_size(klen) <= max_generic_fft<T>(c, klen);
+      const bool prefer_long = env_int("FFTCONV_CUDA_CONV_SINGLE_FFT", 0) || !oa_feasible;
+      const bool want_long = prefer_long && !env_int("FFTCONV_CUDA_CONV_LONG_AS_OA", 0) && long_ok<T>(c, N) &&
                              (double)N * (double)klen <= 536870912.0;
       if (want_long) {
         Tables *tbig = nullptr;

@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q -k "hilbert" > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
-python bench_configs.py --config c4 --no-cpu 2>/dev/null | cut -c1-260
-FFTCONV_CUDA_NO_PERSISTENT_HILBERT=1 python bench_configs.py --config c4 --no-cpu 2>/dev/null | cut -c1-200
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+python bench_configs.py --config all --no-cpu > gpurun_out/configs_r2.log 2>/dev/null; cut -c1-330 gpurun_out/configs_r2.log

@@ -418,17 +418,20 @@ def test_convolve_one_long_fft(cuda, dt, n, klen, monkeypatch):
     a = rng.standard_normal((3, n)).astype(dt)
     k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(dt)
     tol = H.TOL[np.dtype(dt)]
+    monkeypatch.setenv("FFTCONV_CUDA_CONV_SINGLE_FFT", "1")
     before = fc.launch_count()
     for mode in ("full", "same"):
         got = fc.convolve(a, k, mode)
         assert O.rel_l2(got, O.conv_exact(a, k, mode)) < tol, (dt, n, klen, mode)
         assert O.rel_l2(got, O.convolve(a, k, mode)) < tol
     launches_long = fc.launch_count() - before
-    monkeypatch.setenv("FFTCONV_CUDA_CONV_LONG_AS_OA", "1")
-    if klen <= 4096:
-        alt = fc.convolve(a, k, "full")
-        assert O.rel_l2(alt, O.conv_exact(a, k, "full")) < tol
     assert launches_long >= 2 * 4   # spectrum + outer fwd + inner + outer inv, per call
+    # the default beyond one CTA's FFT: segment FFTs where the taps allow (two launches per call)
+    monkeypatch.delenv("FFTCONV_CUDA_CONV_SINGLE_FFT")
+    before = fc.launch_count()
+    alt = fc.convolve(a, k, "full")
+    assert O.rel_l2(alt, O.conv_exact(a, k, "full")) < tol
+    assert fc.launch_count() - before == (2 if klen <= 4096 else 4)
 
 
 @pytest.mark.parametrize("dt,n", [(np.float32, 32768), (np.float32, 262144), (np.float64, 16384), (np.float64, 131072)])
