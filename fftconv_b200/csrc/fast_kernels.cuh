@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
   using T = scalar_t<D>;
   using L = Lanes<D>;
   constexpr int N = P::N, NL = L::N;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int f = threadIdx.x / P::THREADS, tid = threadIdx.x % P::THREADS;
   const int tail_len = p.klen - 1;
   cx<D> *buf = reinterpret_cast<cx<D> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
   using T = scalar_t<D>;
   using L = Lanes<D>;
   constexpr int NL = L::N;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int f = threadIdx.x / P::THREADS, tid = threadIdx.x % P::THREADS;
   cx<D> *buf = reinterpret_cast<cx<D> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
   const cx<T> *W = reinterpret_cast<const cx<T> *>(p.W);

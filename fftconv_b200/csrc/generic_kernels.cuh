@@ -82,7 +82,7 @@ template <typename T> struct OaArgs {
 };
 
 template <typename T> __global__ void oa_generic_kernel(const OaArgs<T> p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = 1 << p.log2n;
   cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
   cx<T> *tails = buf + N; // 2 x (klen - 1)
@@ -180,7 +180,7 @@ template <typename T> struct HilbertArgs {
 };
 
 template <typename T> __global__ void hilbert_pow2_kernel(const HilbertArgs<T> p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = 1 << p.log2n;
   cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);
   const long long r0 = (long long)blockIdx.x * 2, r1 = r0 + 1;
@@ -230,7 +230,7 @@ template <typename T> struct HilbertBluesteinArgs {
 };
 
 template <typename T> __global__ void hilbert_bluestein_kernel(const HilbertBluesteinArgs<T> p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int M = 1 << p.log2m;
   const int n = (int)p.n;
   cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw);

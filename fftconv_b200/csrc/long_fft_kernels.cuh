@@ -116,7 +116,7 @@ template <typename T, int LOG2N, int FPC>
 __global__ void __launch_bounds__(fast::Plan<LOG2N>::THREADS *FPC)
     inner_kernel(cx<T> *scratch, long long n_subs, const cx<T> *W, const cx<T> *Hbig) {
   using P = fast::Plan<LOG2N>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int f = threadIdx.x / P::THREADS, tid = threadIdx.x % P::THREADS;
   cx<T> *buf = reinterpret_cast<cx<T> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
   long long g = (long long)blockIdx.x * FPC + f;
