@@ -158,4 +158,45 @@ void convolve_batched(std::span<const T> signals, std::size_t n, std::span<const
   internal::cv<T>(signals.data(), batch, n, n, kernel, output.data(), out_len, out_len, Mode, stream);
 }
 
+// ---- filter handle (new) --------------------------------------
+// The reference transforms the kernel on every call (fftconv.hpp:391-392 there).  A Filter
+// owns the taps and their spectrum on the current device, so repeated calls launch the
+// overlap-add kernel alone.  Move-only; spans may view host or device memory.
+template <FloatOrDouble T> class Filter {
+public:
+  explicit Filter(std::span<const T> kernel) : klen_(kernel.size()) {
+    if constexpr (std::is_same_v<T, float>)
+      internal::check(fftconv_cuda_filter_create_f32(kernel.data(), kernel.size(), &h_));
+    else
+      internal::check(fftconv_cuda_filter_create_f64(kernel.data(), kernel.size(), &h_));
+  }
+  Filter(const Filter &) = delete;
+  Filter &operator=(const Filter &) = delete;
+  Filter(Filter &&o) noexcept : h_(o.h_), klen_(o.klen_) { o.h_ = nullptr; }
+  ~Filter() { fftconv_cuda_filter_destroy(h_); }
+  [[nodiscard]] std::size_t size() const { return klen_; }
+
+  template <ConvMode Mode = ConvMode::Same>
+  void oaconvolve(std::span<const T> input, std::span<T> output, void *stream = nullptr) const {
+    oaconvolve_batched<Mode>(input, input.size(), output, stream);
+  }
+  template <ConvMode Mode = ConvMode::Same>
+  void oaconvolve_batched(std::span<const T> signals, std::size_t n, std::span<T> output, void *stream = nullptr) const {
+    if (n == 0 || signals.size() % n != 0) throw std::runtime_error("fftconv: signals.size() must be a multiple of n");
+    const std::size_t batch = signals.size() / n;
+    const std::size_t out_len = Mode == ConvMode::Full ? n + klen_ - 1 : n;
+    if (output.size() != batch * out_len) throw std::runtime_error("fftconv: output.size() must be batch * row length");
+    if constexpr (std::is_same_v<T, float>)
+      internal::check(fftconv_cuda_filter_oaconvolve_f32(h_, signals.data(), batch, n, n, output.data(), out_len,
+                                                         out_len, internal::c_mode(Mode), stream));
+    else
+      internal::check(fftconv_cuda_filter_oaconvolve_f64(h_, signals.data(), batch, n, n, output.data(), out_len,
+                                                         out_len, internal::c_mode(Mode), stream));
+  }
+
+private:
+  void *h_ = nullptr;
+  std::size_t klen_;
+};
+
 } // namespace fftconv
