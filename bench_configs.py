@@ -150,7 +150,7 @@ def main():
               "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None},
               "algorithmic_bytes": alg, "l2": "flushed between iterations (256 MB write)",
-              "method": "segment FFTs of 1024 points on chip (default beyond one CTA's FFT; same linear convolution)",
+              "method": "on-chip segment FFTs of 2048 points (default beyond one CTA's FFT; same linear convolution)",
               "alt_one_long_fft": {"ms_per_step": ms_one, "value": out.numel() / (ms_one * 1e-3) / 1e9,
                                    "frac": alg / (ms_one * 1e-3) / 1e9 / peak,
                                    "note": "FFTCONV_CUDA_CONV_SINGLE_FFT=1: one FFT of length 32768 per row pair "
@@ -168,6 +168,27 @@ def main():
                            "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None},
               "algorithmic_bytes": alg, "l2": "inputs (268 MB) exceed L2",
               "cpu_baseline": None if args.no_cpu else cpu_leg("hilbert", np.float32, 8192, 8192, 0)})
+
+    if "ksweep" in which and world == 1:
+        # batched overlap-add at the headline shape for one K per row of the segment-size table
+        # (include/fftconv/fftconv.hpp:38-49): which kernel serves it and how far from the roofline
+        rows, n = 4096, 65536
+        for dt, name in ((torch.float32, "f32"), (torch.float64, "f64")):
+            r = rows if dt == torch.float32 else rows // 2
+            a = torch.randn((r, n), device=dev, generator=g, dtype=dt)
+            for klen in (6, 20, 35, 65, 165, 245, 500, 1000, 3000):
+                k = torch.randn(klen, device=dev, generator=g, dtype=dt)
+                out = torch.empty((r, n + klen - 1), device=dev, dtype=dt)
+                try:
+                    ms = time_cuda(lambda: fc.oaconvolve_(a, k, out, "full"), max(3, args.steps // 2), 3)
+                except RuntimeError as e:
+                    emit({"config": "ksweep", "dtype": name, "k": klen, "error": str(e)[:120]})
+                    continue
+                alg = (a.numel() + out.numel() + klen) * a.element_size()
+                emit({"config": "ksweep", "dtype": name, "k": klen, "fft_size": fc.optimal_fft_size(klen), "rows": r,
+                      "n": n, "ms_per_step": ms, "value": out.numel() / (ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+                      "frac_of_measured_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak})
+            del a
 
     if "c5" in which:
         n = 1 << args.log2n

@@ -516,6 +516,14 @@ int oa2048_engine() {
   return e == 2 ? 2 : 1;
 }
 
+// engine for one call: the dedicated kernels take float32, N = 2048, 8 <= K <= 410 (staging
+// area and tail buffers are sized for that); the warp-pair engine only its table row
+template <typename T> int oa2048_engine_for(size_t N, size_t klen) {
+  if (!std::is_same<T, float>::value || N != 2048 || klen < 8 || klen > 410) return 0;
+  const int e = oa2048_engine();
+  return (e == 2 && klen < 221) ? 1 : e;
+}
+
 // ---- overlap-add on device pointers -------------------------------------------------
 template <typename T>
 int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride,
@@ -526,7 +534,7 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
   const size_t step = N - (klen - 1);
   const long long segs = (long long)((n + step - 1) / step);
 
-  const int engine2048 = (std::is_same<T, float>::value && N == 2048) ? oa2048_engine() : 0;
+  const int engine2048 = oa2048_engine_for<T>(N, klen);
   if (engine2048 == 2) {
     if constexpr (std::is_same<T, float>::value) {
       if (int r = get_w2_tables(c)) return r;
@@ -751,6 +759,32 @@ int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t 
 
 enum Op { OP_OA, OP_CONV, OP_HILBERT };
 
+// Segment FFT size for overlap-add.  The reference's table (fftconv.hpp:38-66) is a CPU cost
+// model, N (log2 N + 1) / (N - K + 1) per output sample; on this machine a segment also has a
+// fixed cost (barriers, exposed latencies, the fraction of a CTA it keeps busy) that the model
+// does not see, and tiny segments are slower by an order of magnitude (measured, DESIGN.md
+// section 4: K = 20 -> N = 64 takes 4.7 ms at 4096 x 65536, the N = 2048 kernel 0.58 ms).  The
+// table therefore stays the rule for small jobs -- where it also decides the latency of one
+// short call -- and for every K it was measured best; for large jobs short kernels are moved to
+// the size whose kernel is fastest.  Any N > K - 1 computes the same linear convolution.
+// FFTCONV_CUDA_STRICT_TABLE=1 restores the reference's choice, FFTCONV_CUDA_OA_FFT_SIZE forces one.
+template <typename T> size_t throughput_oa_size(const DeviceCtx &c, size_t klen, size_t batch, size_t n, size_t table_n) {
+  if (env_int("FFTCONV_CUDA_STRICT_TABLE", 0)) return table_n;
+  const int forced = env_int("FFTCONV_CUDA_OA_FFT_SIZE", 0);
+  if (forced >= 16 && (forced & (forced - 1)) == 0 && (size_t)forced >= 2 * klen && (size_t)forced >= table_n / 64)
+    return (size_t)forced;
+  if ((double)batch * (double)n < 4194304.0) return table_n;
+  (void)c;
+  if (std::is_same<T, float>::value) {
+    if (klen >= 8 && klen < 221 && oa2048_engine() == 1) return 2048;
+    if (klen < 8) return 512;
+  } else {
+    if (klen < 221) return 2048;                       // measured: 0.68-0.72 ms against 0.79-0.92 (N = 1024)
+    if (table_n == 8192 && klen <= 1024) return 4096;  // 1.15 ms against 1.44: the 8192-point float64 CTA is register-starved
+  }
+  return table_n;
+}
+
 template <typename T>
 int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, size_t n,
                 size_t a_stride, const T *k, size_t klen, T *out, size_t out_len,
@@ -758,6 +792,8 @@ int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, 
   size_t N;
   if (op == OP_OA) {
     N = optimal_fft_size(klen);
+    if (tl_filter && tl_filter->taps == (const void *)k) N = tl_filter->N; // the handle's spectrum
+    else N = throughput_oa_size<T>(c, klen, batch, n, N);
   } else {
     // single FFT of length >= n + K - 1 (any such length gives the same linear
     // convolution as the reference's exact-length transform, fftconv.hpp:458)
@@ -782,7 +818,7 @@ int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, 
         return long_device<T>(c, st, a, batch, n, a_stride, out, out_len, out_stride,
                               mode == FFTCONV_CUDA_SAME ? (int)(klen / 2) : 0, N, H, false);
       }
-      N = optimal_fft_size(klen);
+      N = throughput_oa_size<T>(c, klen, batch, n, optimal_fft_size(klen));
     }
   }
   if (N > max_generic_fft<T>(c, klen))
@@ -959,8 +995,7 @@ template <typename T> int add_entry(T *dst, const T *src, size_t n, void *stream
 }
 
 template <typename T> int oa_layout_for(const DeviceCtx &c, size_t N, size_t klen) {
-  if (std::is_same<T, float>::value && N == 2048 && oa2048_engine())
-    return oa2048_engine() == 2 ? fc::generic::LAYOUT_W2 : fc::generic::LAYOUT_N2048;
+  if (const int e = oa2048_engine_for<T>(N, klen)) return e == 2 ? fc::generic::LAYOUT_W2 : fc::generic::LAYOUT_N2048;
   return fast_ok<T>(c, N, klen) ? fc::generic::LAYOUT_FAST : fc::generic::LAYOUT_DIF;
 }
 
@@ -969,7 +1004,8 @@ template <typename T> int filter_create(const T *k, size_t klen, void **out) {
   if (!k || klen == 0 || !out) return fail(FFTCONV_CUDA_ERR_ARG, "filter_create: empty kernel or null output");
   DeviceCtx *c = nullptr;
   if (int r = get_ctx(&c)) return r;
-  const size_t N = optimal_fft_size(klen);
+  // a handle is for repeated, large calls: the segment size of the throughput rule
+  const size_t N = throughput_oa_size<T>(*c, klen, 1 << 16, 1 << 16, optimal_fft_size(klen));
   if (N > max_generic_fft<T>(*c, klen))
     return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "filter_create: " + std::to_string(klen) + " taps need FFT size " +
                                                  std::to_string(N) + ", beyond the single-CTA FFT");

@@ -1,5 +1,7 @@
-python bench.py > gpurun_out/bench_r1_final.log 2> gpurun_out/bench_r1_final.err; cut -c1-200 gpurun_out/bench_r1_final.log
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1_ref.log 2> gpurun_out/bench_r1_ref.err; cut -c1-300 gpurun_out/bench_r1_ref.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v8.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_l.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:oa_n2048 -c 1 -s 2 -o gpurun_out/prof_v8 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_v8.log 2>&1
-tail -1 gpurun_out/ncu_v8.log | cut -c1-80
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+python bench_configs.py --config ksweep --no-cpu > gpurun_out/ksweep.log 2>gpurun_out/ksweep.err; cat gpurun_out/ksweep.log | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d.get('dtype'),d.get('k'),d.get('fft_size'),round(d.get('ms_per_step',0),3),round(d.get('frac_of_measured_hbm_peak',0),3),d.get('error',''))
+"
+python bench_configs.py --config c3 --no-cpu 2>/dev/null | cut -c1-300

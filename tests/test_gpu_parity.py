@@ -475,8 +475,9 @@ def test_cuda_array_interface_inputs(cuda):
 
 @pytest.mark.parametrize("dt,klen", [(np.float32, 245), (np.float32, 65), (np.float64, 165), (np.float32, 7)])
 def test_filter_handle_reuses_the_spectrum(cuda, dt, klen):
-    """a filter handle gives the same samples as the plain call (bit for
-    bit: same kernels, same H) and launches no spectrum kernel."""
+    """a filter handle gives the same samples as the plain call and launches no
+    spectrum kernel (a handle always uses the large-job segment size, a small plain call the
+    reference's table, so bit-equality holds only where the two coincide)."""
     import torch
 
     import fftconv_b200 as fc
@@ -493,7 +494,9 @@ def test_filter_handle_reuses_the_spectrum(cuda, dt, klen):
         got = f.oaconvolve(ta, mode)
         torch.cuda.synchronize()
         assert fc.launch_count() - before == 1            # the overlap-add kernel alone
-        assert torch.equal(got, want)
+        if klen == 245:                                   # same segment size either way: bit for bit
+            assert torch.equal(got, want)
+        assert O.rel_l2(got.cpu().numpy(), want.cpu().numpy()) < H.TOL[np.dtype(dt)]
         _check(got.cpu().numpy(), a, k, mode, ("filter", klen, mode))
     # host arrays go through the same handle
     _check(f.oaconvolve(a, "full"), a, k, "full", ("filter-host", klen))
@@ -528,3 +531,28 @@ def test_streaming_overlap_add_across_calls(cuda, dt, klen, pieces):
     # the state is reset by flush: a second pass gives the same answer
     again = torch.cat([s.push(ta), s.flush(ta)], dim=1).cpu().numpy()
     assert O.rel_l2(again, got) < H.TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("klen", [1, 3, 7, 8, 20, 65, 165, 220])
+def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch):
+    """Jobs of >= 4 Mi samples move short kernels off the reference's (CPU cost model) segment
+    size onto the fastest kernel's; the samples are the same linear convolution either way."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(klen)
+    a = rng.standard_normal((64, 65536)).astype(dt)
+    k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(dt)
+    ta, tk = _t(a, cuda), _t(k, cuda)
+    tol = H.TOL[np.dtype(dt)]
+    for mode in ("full", "same"):
+        y = fc.oaconvolve(ta, tk, mode)
+        monkeypatch.setenv("FFTCONV_CUDA_STRICT_TABLE", "1")
+        y_table = fc.oaconvolve(ta, tk, mode)
+        monkeypatch.delenv("FFTCONV_CUDA_STRICT_TABLE")
+        torch.cuda.synchronize()
+        assert O.rel_l2(y.cpu().numpy(), y_table.cpu().numpy()) < tol
+        pick = [0, 1, 31, 63]
+        assert O.rel_l2(y[pick].cpu().numpy(), O.conv_exact(a[pick], k, mode)) < tol, (klen, mode)
