@@ -169,6 +169,74 @@ def main():
               "algorithmic_bytes": alg, "l2": "inputs (268 MB) exceed L2",
               "cpu_baseline": None if args.no_cpu else cpu_leg("hilbert", np.float32, 8192, 8192, 0)})
 
+    if "rf" in which and world == 1:
+        # the chain configs 2 + 4 imply: band-pass FIR, envelope, log
+        # compression, decimation -- one library call (two kernels, post-processing in the store of
+        # the second) against the same steps as separate passes over HBM
+        rows, n, klen, dec = 8192, 8192, 245, 4
+        x = torch.randn((rows, n), device=dev, generator=g)
+        k = torch.randn(klen, device=dev, generator=g) / klen ** 0.5
+        out = torch.empty((rows, n // dec), device=dev)
+        kw = dict(log_compress=True, ref=1.0, dynamic_range_db=60.0, decimate=dec)
+        ms_chain = time_cuda(lambda: fc.rf_envelope_(x, k, out, **kw), args.steps, args.warmup)
+        ms_env = time_cuda(lambda: fc.envelope_(x, out, **kw), args.steps, args.warmup)
+        filt, env = torch.empty_like(x), torch.empty_like(x)
+
+        def separate():
+            fc.oaconvolve_(x, k, filt, "same")
+            fc.hilbert_(filt, env)
+            return torch.clamp(1.0 + 20.0 * torch.log10(env[:, ::dec]) / 60.0, 0.0, 1.0)
+
+        ms_sep = time_cuda(separate, args.steps, args.warmup)
+        ms_hil = time_cuda(lambda: fc.hilbert_(x, env), args.steps, args.warmup)
+        ms_post = time_cuda(lambda: torch.clamp(1.0 + 20.0 * torch.log10(env[:, ::dec]) / 60.0, 0.0, 1.0),
+                            args.steps, args.warmup)
+        alg = rows * (n + n // dec) * 4 + klen * 4
+        emit({"config": "rf", "workload": f"RF chain f32 {rows} x {n}: band-pass k={klen} (same) -> envelope -> "
+                                          f"log compression -> decimate by {dec}",
+              "ms_per_step": ms_chain, "value": rows * n / (ms_chain * 1e-3) / 1e9, "unit": "Ginput-samples/s",
+              "roofline": {"bound": "hbm", "achieved": alg / (ms_chain * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": alg / (ms_chain * 1e-3) / 1e9 / peak, "traffic": None},
+              "algorithmic_bytes": alg,
+              "separate_passes_ms": ms_sep, "envelope_fused_ms": ms_env, "hilbert_plain_ms": ms_hil,
+              "torch_postprocessing_ms": ms_post,
+              "note": "separate = oaconvolve_ + hilbert_ + torch log10/clamp on a strided view"})
+
+    if "pcie" in which and world == 1:
+        # what the host-pointer path can reach at best: pinned copies alone and in both directions at once
+        nbytes = 1 << 30
+        hin = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        din = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dout = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def wall(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps
+
+        def h2d():
+            with torch.cuda.stream(s1):
+                din.copy_(hin, non_blocking=True)
+
+        def d2h():
+            with torch.cuda.stream(s2):
+                hout.copy_(dout, non_blocking=True)
+
+        def both():
+            h2d()
+            d2h()
+
+        t_h2d, t_d2h, t_both = wall(h2d), wall(d2h), wall(both)
+        emit({"config": "pcie", "bytes_each_way": nbytes, "h2d_gbs": nbytes / t_h2d / 1e9, "d2h_gbs": nbytes / t_d2h / 1e9,
+              "both_gbs_each_way": nbytes / t_both / 1e9,
+              "c2_e2e_floor_ms": max(1073742804, 1077739520) / (nbytes / t_both) * 1e3})
+
     if "ksweep" in which and world == 1:
         # batched overlap-add at the headline shape for one K per row of the segment-size table
         # (include/fftconv/fftconv.hpp:38-49): which kernel serves it and how far from the roofline

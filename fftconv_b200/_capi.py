@@ -24,8 +24,16 @@ SYMBOLS = [
     for name in ("oaconvolve", "oaconvolve_batched", "convolve", "convolve_batched",
                  "hilbert", "hilbert_batched", "add",
                  "filter_create", "filter_oaconvolve", "stream_create", "stream_push",
-                 "stream_flush")
+                 "stream_flush", "envelope_batched", "rf_envelope_batched")
 ] + ["fftconv_cuda_filter_destroy", "fftconv_cuda_stream_destroy"]
+
+
+
+class EnvelopeOpts(C.Structure):
+    """fftconv_cuda_envelope_opts (include/fftconv_cuda.h)."""
+    _fields_ = [("log_compress", C.c_int), ("ref", C.c_double), ("dynamic_range_db", C.c_double),
+                ("decimate", C.c_size_t)]
+
 
 _lib = None
 
@@ -68,6 +76,10 @@ def lib():
         f.restype, f.argtypes = i, [vp, vp, sz, sz, vp, sz, vp]
         f = getattr(L, f"fftconv_cuda_stream_flush_{sfx}")
         f.restype, f.argtypes = i, [vp, vp, sz, vp]
+        f = getattr(L, f"fftconv_cuda_envelope_batched_{sfx}")
+        f.restype, f.argtypes = i, [vp, sz, sz, sz, vp, sz, sz, C.POINTER(EnvelopeOpts), vp]
+        f = getattr(L, f"fftconv_cuda_rf_envelope_batched_{sfx}")
+        f.restype, f.argtypes = i, [vp, sz, sz, sz, vp, sz, vp, sz, sz, C.POINTER(EnvelopeOpts), vp]
     L.fftconv_cuda_filter_destroy.restype, L.fftconv_cuda_filter_destroy.argtypes = i, [vp]
     L.fftconv_cuda_stream_destroy.restype, L.fftconv_cuda_stream_destroy.argtypes = i, [vp]
     _lib = L

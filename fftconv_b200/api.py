@@ -201,6 +201,82 @@ def hilbert(a):
     return out
 
 
+def _envelope_opts(log_compress, ref, dynamic_range_db, decimate):
+    decimate = int(decimate)
+    if decimate < 1:
+        raise RuntimeError("decimate must be >= 1")
+    return _capi.EnvelopeOpts(1 if log_compress else 0, float(ref), float(dynamic_range_db), decimate)
+
+
+def envelope_out_len(n: int, decimate: int = 1) -> int:
+    return (int(n) + int(decimate) - 1) // int(decimate)
+
+
+def _envelope_(a, k, out, log_compress, ref, dynamic_range_db, decimate) -> None:
+    A, O = _Buf(a, "a"), _Buf(out, "out")
+    opts = _envelope_opts(log_compress, ref, dynamic_range_db, decimate)
+    if A.ndim not in (1, 2) or O.ndim != A.ndim:
+        raise RuntimeError("envelope: a and out must both be 1-D or both 2-D")
+    n = A.shape[-1]
+    batch = 1 if A.ndim == 1 else A.shape[0]
+    want = envelope_out_len(n, opts.decimate)
+    if O.shape[-1] != want or (A.ndim == 2 and O.shape[0] != batch):
+        raise RuntimeError(f"envelope: out must hold {want} samples per row (ceil(n / decimate))")
+    if A.dtype != O.dtype:
+        raise TypeError("a and out must share one dtype")
+    if A.is_cuda != O.is_cuda:
+        raise RuntimeError("a and out must live on the same side (host or device)")
+    stream = None
+    sfx = _SFX[A.dtype]
+    if k is None:
+        fn = getattr(_capi.lib(), f"fftconv_cuda_envelope_batched_{sfx}")
+        args = (A.ptr, batch, n, A.row_stride, O.ptr, want, O.row_stride)
+    else:
+        K = _Buf(k, "k")
+        if K.ndim != 1 or K.dtype != A.dtype:
+            raise RuntimeError("rf_envelope: k must be 1-D and share a's dtype")
+        if n < K.shape[0]:
+            raise RuntimeError("a should be no shorter than k")  # py/main.cpp:88-91
+        fn = getattr(_capi.lib(), f"fftconv_cuda_rf_envelope_batched_{sfx}")
+        args = (A.ptr, batch, n, A.row_stride, K.ptr, K.shape[0], O.ptr, want, O.row_stride)
+    if A.is_cuda:
+        with _device_of(A):
+            rc = fn(*args, opts, _stream_of(A))
+    else:
+        rc = fn(*args, opts, stream)
+    _capi.check(rc)
+
+
+def envelope_(a, out, *, log_compress: bool = False, ref: float = 1.0, dynamic_range_db: float = 60.0,
+              decimate: int = 1) -> None:
+    """`hilbert` with the post-processing its callers apply next fused into the kernel's store
+    (SURVEY.md section 8f item 3): keep every `decimate`-th envelope sample, and with
+    `log_compress` map it to clamp(1 + 20 log10(env / ref) / dynamic_range_db, 0, 1)."""
+    _envelope_(a, None, out, log_compress, ref, dynamic_range_db, decimate)
+
+
+def envelope(a, *, log_compress: bool = False, ref: float = 1.0, dynamic_range_db: float = 60.0,
+             decimate: int = 1):
+    out = _empty_like_rows(a, envelope_out_len(a.shape[-1], decimate))
+    envelope_(a, out, log_compress=log_compress, ref=ref, dynamic_range_db=dynamic_range_db, decimate=decimate)
+    return out
+
+
+def rf_envelope_(a, k, out, *, log_compress: bool = False, ref: float = 1.0, dynamic_range_db: float = 60.0,
+                 decimate: int = 1) -> None:
+    """Band-pass `oaconvolve(a, k, "same")`, then `envelope` of the filtered rows; the filtered
+    rows stay on the device between the two kernels."""
+    _envelope_(a, k, out, log_compress, ref, dynamic_range_db, decimate)
+
+
+def rf_envelope(a, k, *, log_compress: bool = False, ref: float = 1.0, dynamic_range_db: float = 60.0,
+                decimate: int = 1):
+    out = _empty_like_rows(a, envelope_out_len(a.shape[-1], decimate))
+    rf_envelope_(a, k, out, log_compress=log_compress, ref=ref, dynamic_range_db=dynamic_range_db,
+                 decimate=decimate)
+    return out
+
+
 def optimal_fft_size(klen: int) -> int:
     """Segment FFT size for `klen` taps (include/fftconv/fftconv.hpp:53-66)."""
     return int(_capi.lib().fftconv_cuda_optimal_fft_size(int(klen)))

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
 
 // Hilbert envelope of rows of length N (power of two): rows 2b, 2b+1 (or 4b .. 4b+3) per FFT.
 // G (position order) = -j sgn(f) / N with DC and Nyquist zeroed (hilbert.hpp:39-51).
-template <typename D, int LOG2N, int FPC>
+template <typename D, int LOG2N, int FPC, bool PLAIN = true>
 __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<LOG2N>::THREADS * FPC>())
     hilbert_fast_kernel(const generic::HilbertArgs<scalar_t<D>> p) {
   using P = Plan<LOG2N>;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
       L::split(v[s0 + s], h);
 #pragma unroll
       for (int l = 0; l < NL; ++l)
-        if (has[l]) e[l][i] = sqrt(a[s][l] * a[s][l] + h[l] * h[l]);
+        if (has[l]) env_store<PLAIN>(p.epi, e[l], i, (T)sqrt(a[s][l] * a[s][l] + h[l] * h[l]));
     }
   }
 }
@@ -236,7 +236,7 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 //   * the NEXT unit's rows are requested as soon as the last inverse pass has read the buffer,
 //     so they land while this unit's envelope is computed and stored.
 // Requires 16-byte aligned rows (base and stride); other layouts take hilbert_fast_kernel.
-template <int LOG2N, int FPC>
+template <int LOG2N, int FPC, bool PLAIN = true>
 __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, 1)
     hilbert_pk_persistent_kernel(const generic::HilbertArgs<float> p) {
   using P = Plan<LOG2N>;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, 1)
           float h[4];
           Lanes<f2>::split(v[s0 + s], h);
 #pragma unroll
-          for (int l = 0; l < 4; ++l) e[l][i] = fast_sqrt(a[s][l] * a[s][l] + h[l] * h[l]);
+          for (int l = 0; l < 4; ++l) env_store<PLAIN>(p.epi, e[l], i, fast_sqrt(a[s][l] * a[s][l] + h[l] * h[l]));
         }
       }
     } else {
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, 1)
         for (int l = 0; l < 4; ++l)
           if (has[l]) {
             const float a = __ldg(x[l] + i);
-            e[l][i] = fast_sqrt(a * a + h[l] * h[l]);
+            env_store<PLAIN>(p.epi, e[l], i, fast_sqrt(a * a + h[l] * h[l]));
           }
       }
     }

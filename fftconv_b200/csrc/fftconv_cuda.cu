@@ -94,6 +94,10 @@ struct StreamWs {         // per stream
   size_t taps_bytes = 0;
   void *H = nullptr;
   size_t h_bytes = 0;
+  void *rf = nullptr;     // filtered rows between the two launches of rf_envelope
+  size_t rf_bytes = 0;
+  void *part = nullptr;   // partial convolution with one block of a long kernel
+  size_t part_bytes = 0;
 };
 
 constexpr int kPipe = 3;
@@ -109,7 +113,8 @@ struct DeviceCtx {
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
   void *stage_in[kPipe] = {nullptr, nullptr, nullptr};
   void *stage_out[kPipe] = {nullptr, nullptr, nullptr};
-  size_t cap_in[kPipe] = {0, 0, 0}, cap_out[kPipe] = {0, 0, 0};
+  void *stage_tmp[kPipe] = {nullptr, nullptr, nullptr}; // filtered rows between the two steps of OP_RF
+  size_t cap_in[kPipe] = {0, 0, 0}, cap_out[kPipe] = {0, 0, 0}, cap_tmp[kPipe] = {0, 0, 0};
   std::map<const void *, size_t> smem_set; // kernel -> opted-in dynamic smem
   void *scratch = nullptr;                 // long-FFT intermediate (grow only)
   size_t scratch_bytes = 0;
@@ -161,15 +166,18 @@ void free_ctx(DeviceCtx &c) {
   for (auto &kv : c.ws) {
     cudaFree(kv.second.taps);
     cudaFree(kv.second.H);
+    cudaFree(kv.second.rf);
+    cudaFree(kv.second.part);
   }
   c.ws.clear();
   for (int i = 0; i < kPipe; ++i) {
     if (c.pipe[i]) cudaStreamDestroy(c.pipe[i]);
     cudaFree(c.stage_in[i]);
     cudaFree(c.stage_out[i]);
+    cudaFree(c.stage_tmp[i]);
     c.pipe[i] = nullptr;
-    c.stage_in[i] = c.stage_out[i] = nullptr;
-    c.cap_in[i] = c.cap_out[i] = 0;
+    c.stage_in[i] = c.stage_out[i] = c.stage_tmp[i] = nullptr;
+    c.cap_in[i] = c.cap_out[i] = c.cap_tmp[i] = 0;
   }
 }
 
@@ -362,6 +370,24 @@ struct Filter {
 };
 thread_local const Filter *tl_filter = nullptr; // set around a call made through a handle
 
+// Envelope post-processing of the call in flight (fftconv_cuda_envelope_* / rf_envelope_*): set
+// around entry(), read where the Hilbert kernels are launched.  dec == 0 means "plain hilbert".
+struct EnvOpts {
+  int log = 0;
+  size_t dec = 0;
+  double a = 0.0, b = 0.0;
+};
+thread_local EnvOpts tl_env;
+template <typename T> fc::EnvEpilogue<T> current_epilogue(size_t n) {
+  if (tl_env.dec == 0 || (tl_env.dec == 1 && !tl_env.log)) return fc::plain_epilogue<T>();
+  // i / dec == umulhi(i, floor(2^32 / dec) + 1) for every i < n when n * dec < 2^32
+  unsigned magic = 0;
+  if (tl_env.dec > 1 && (double)n * (double)tl_env.dec < 4294967296.0)
+    magic = (unsigned)(4294967296ULL / tl_env.dec) + 1u;
+  return fc::EnvEpilogue<T>{0, tl_env.log, (int)tl_env.dec, magic, (T)tl_env.a, (T)tl_env.b};
+}
+size_t env_out_len(size_t n) { return tl_env.dec > 1 ? (n + tl_env.dec - 1) / tl_env.dec : n; }
+
 template <typename T>
 int prepare_spectrum(DeviceCtx &c, cudaStream_t st, const T *k, size_t klen, size_t N, int layout,
                      Tables &tab, const cx<T> **H_out) {
@@ -457,7 +483,8 @@ int launch_hilbert_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::Hilber
       const size_t smem = packed_smem(LOG2N, 0);
       const bool aligned = (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (p.in_stride & 3) == 0;
       if (aligned && !env_int("FFTCONV_CUDA_NO_PERSISTENT_HILBERT", 0)) {
-        auto pk = fc::fast::hilbert_pk_persistent_kernel<LOG2N, FPC>;
+        auto pk = p.epi.plain ? fc::fast::hilbert_pk_persistent_kernel<LOG2N, FPC, true>
+                              : fc::fast::hilbert_pk_persistent_kernel<LOG2N, FPC, false>;
         if (int r = ensure_smem(c, pk, smem + 16)) return r;
         const long long units = (p.batch + 4 * FPC - 1) / (4 * FPC);
         pk<<<(unsigned)std::min<long long>(units, c.sm_count), fc::fast::Plan<LOG2N>::THREADS * FPC, smem + 16, st>>>(p);
@@ -465,7 +492,8 @@ int launch_hilbert_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::Hilber
         ++g_launches;
         return 0;
       }
-      auto kern = fc::fast::hilbert_fast_kernel<fc::f2, LOG2N, FPC>;
+      auto kern = p.epi.plain ? fc::fast::hilbert_fast_kernel<fc::f2, LOG2N, FPC, true>
+                              : fc::fast::hilbert_fast_kernel<fc::f2, LOG2N, FPC, false>;
       if (int r = ensure_smem(c, kern, smem)) return r;
       const long long grid = (p.batch + 4 * FPC - 1) / (4 * FPC);
       kern<<<(unsigned)grid, fc::fast::Plan<LOG2N>::THREADS * FPC, smem, st>>>(p);
@@ -476,7 +504,8 @@ int launch_hilbert_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::Hilber
   }
   constexpr int FPC = fast_fpc<T>(LOG2N);
   const size_t smem = fast_smem<T>(LOG2N, 0);
-  auto kern = fc::fast::hilbert_fast_kernel<T, LOG2N, FPC>;
+  auto kern = p.epi.plain ? fc::fast::hilbert_fast_kernel<T, LOG2N, FPC, true>
+                          : fc::fast::hilbert_fast_kernel<T, LOG2N, FPC, false>;
   if (int r = ensure_smem(c, kern, smem)) return r;
   const long long grid = (p.batch + 2 * FPC - 1) / (2 * FPC);
   kern<<<(unsigned)grid, fc::fast::Plan<LOG2N>::THREADS * FPC, smem, st>>>(p);
@@ -736,6 +765,7 @@ int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t 
   la.scratch = reinterpret_cast<fc::fast::cx<T> *>(c.scratch);
   la.TWbig = reinterpret_cast<const fc::fast::cx<T> *>(tbig->TWbig);
   la.hilbert = hilbert ? 1 : 0;
+  la.epi = current_epilogue<T>(n);
   const int threads = 256;
   for (size_t p0 = 0; p0 < pairs_total; p0 += pairs_per) {
     const size_t np = std::min(pairs_per, pairs_total - p0);
@@ -757,7 +787,7 @@ int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t 
   return 0;
 }
 
-enum Op { OP_OA, OP_CONV, OP_HILBERT };
+enum Op { OP_OA, OP_CONV, OP_HILBERT, OP_RF /* overlap-add (Same) then Hilbert envelope */ };
 
 // Segment FFT size for overlap-add.  The reference's table (fftconv.hpp:38-66) is a CPU cost
 // model, N (log2 N + 1) / (N - K + 1) per output sample; on this machine a segment also has a
@@ -783,6 +813,37 @@ template <typename T> size_t throughput_oa_size(const DeviceCtx &c, size_t klen,
     if (table_n == 8192 && klen <= 1024) return 4096;  // 1.15 ms against 1.44: the 8192-point float64 CTA is register-starved
   }
   return table_n;
+}
+
+// Kernels longer than a segment FFT can hold (N > max_generic_fft): the taps are cut into blocks of
+// Kb taps, every block is convolved with segment FFTs of 4 Kb points (75 % of each segment is new
+// output) into a per-stream temporary, and the partial results are summed in block order.  The
+// reference handles such kernels with one ever larger FFT (fftconv.hpp:61-65); the linear
+// convolution is the same.
+template <typename T>
+int partitioned_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride, const T *k,
+                       size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
+  const size_t Kb = std::is_same<T, float>::value ? 4096 : 2048, N = 4 * Kb;
+  if (!fast_ok<T>(c, N, Kb)) return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "long kernel: block FFT does not fit this device");
+  const size_t part_max = n + Kb - 1;
+  StreamWs &ws = c.ws[st];
+  if (ws.part_bytes < batch * part_max * sizeof(T)) CU_TRY(cudaStreamSynchronize(st));
+  if (int r = grow(&ws.part, &ws.part_bytes, batch * part_max * sizeof(T))) return r;
+  T *part = static_cast<T *>(ws.part);
+  const long long pad = mode == FFTCONV_CUDA_SAME ? (long long)(klen / 2) : 0;
+  const long long total = (long long)batch * (long long)out_len;
+  const int threads = 256;
+  if ((total + threads - 1) / threads > 0x7fffffffLL) return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "batch too large for one launch");
+  for (size_t p0 = 0, blk = 0; p0 < klen; p0 += Kb, ++blk) {
+    const size_t kp = std::min(Kb, klen - p0), plen = n + kp - 1;
+    if (int r = oa_device<T>(c, st, a, batch, n, a_stride, k + p0, kp, part, plen, plen, FFTCONV_CUDA_FULL, N)) return r;
+    fc::generic::partition_accumulate_kernel<T><<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
+        part, (long long)batch, (long long)plen, out, (long long)out_len, (long long)out_stride, (long long)p0 - pad,
+        blk == 0 ? 1 : 0);
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+  }
+  return 0;
 }
 
 template <typename T>
@@ -821,10 +882,11 @@ int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, 
       N = throughput_oa_size<T>(c, klen, batch, n, optimal_fft_size(klen));
     }
   }
-  if (N > max_generic_fft<T>(c, klen))
-    return fail(FFTCONV_CUDA_ERR_UNSUPPORTED,
-                "kernel of " + std::to_string(klen) + " taps needs FFT size " + std::to_string(N) +
-                    ", beyond the single-CTA shared-memory FFT");
+  if (N > max_generic_fft<T>(c, klen)) {
+    if (tl_filter && tl_filter->taps == (const void *)k)
+      return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "filter handle: kernel too long for a segment FFT");
+    return partitioned_device<T>(c, st, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+  }
   return oa_device<T>(c, st, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode, N);
 }
 
@@ -854,6 +916,7 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
     p.W = static_cast<const cx<T> *>(tabm->W);
     p.B = static_cast<const cx<T> *>(bt->B);
     p.chirp = static_cast<const cx<T> *>(bt->chirp);
+    p.epi = current_epilogue<T>(n);
     if (int r = ensure_smem(c, fc::generic::hilbert_bluestein_kernel<T>, std::max<size_t>(smem_b, 16))) return r;
     const long long gridb = ((long long)batch + 1) / 2;
     const int threadsb = (int)std::min<size_t>(512, std::max<size_t>(32, M / 4));
@@ -880,7 +943,7 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
       CU_TRY(cudaMalloc(&tbig->Glong, n * sizeof(cx<T>)));
       CU_TRY(cudaMemcpy(tbig->Glong, g.data(), n * sizeof(cx<T>), cudaMemcpyHostToDevice));
     }
-    return long_device<T>(c, st, x, batch, n, x_stride, env, n, env_stride, 0, n,
+    return long_device<T>(c, st, x, batch, n, x_stride, env, env_out_len(n), env_stride, 0, n,
                           static_cast<const cx<T> *>(tbig->Glong), true);
   }
   const size_t smem = n * sizeof(cx<T>);
@@ -901,6 +964,7 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
   p.log2n = ilog2(n);
   p.W = static_cast<const cx<T> *>(tab->W);
   p.G = static_cast<const cx<T> *>(use_fast ? tab->Gfast : tab->G);
+  p.epi = current_epilogue<T>(n);
   if (use_fast) {
     if (!tab->TWfast) {
       auto build = [&]() -> int { FAST_SWITCH(build_fast_twiddles, p.log2n, *tab) };
@@ -936,15 +1000,26 @@ int run_host(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_s
     if (int r = grow(&c.stage_out[s], &c.cap_out[s], rows_per_block * out_len * sizeof(T))) return r;
     T *din = static_cast<T *>(c.stage_in[s]);
     T *dout = static_cast<T *>(c.stage_out[s]);
-    CU_TRY(cudaMemcpy2DAsync(din, n * sizeof(T), a + r0 * a_stride, a_stride * sizeof(T),
-                             n * sizeof(T), rows, cudaMemcpyHostToDevice, c.pipe[s]));
+    if (a_stride == n) // contiguous rows: one linear copy
+      CU_TRY(cudaMemcpyAsync(din, a + r0 * n, rows * n * sizeof(T), cudaMemcpyHostToDevice, c.pipe[s]));
+    else
+      CU_TRY(cudaMemcpy2DAsync(din, n * sizeof(T), a + r0 * a_stride, a_stride * sizeof(T),
+                               n * sizeof(T), rows, cudaMemcpyHostToDevice, c.pipe[s]));
     int r;
     if (op == OP_HILBERT) r = hilbert_device<T>(c, c.pipe[s], din, rows, n, n, dout, out_len);
-    else r = conv_device<T>(c, c.pipe[s], op, din, rows, n, n, k, klen, dout, out_len, out_len, mode);
+    else if (op == OP_RF) {
+      if (int g = grow(&c.stage_tmp[s], &c.cap_tmp[s], rows_per_block * n * sizeof(T))) return g;
+      T *tmp = static_cast<T *>(c.stage_tmp[s]);
+      r = conv_device<T>(c, c.pipe[s], OP_OA, din, rows, n, n, k, klen, tmp, n, n, FFTCONV_CUDA_SAME);
+      if (!r) r = hilbert_device<T>(c, c.pipe[s], tmp, rows, n, n, dout, out_len);
+    } else r = conv_device<T>(c, c.pipe[s], op, din, rows, n, n, k, klen, dout, out_len, out_len, mode);
     if (r) return r;
-    CU_TRY(cudaMemcpy2DAsync(out + r0 * out_stride, out_stride * sizeof(T), dout,
-                             out_len * sizeof(T), out_len * sizeof(T), rows,
-                             cudaMemcpyDeviceToHost, c.pipe[s]));
+    if (out_stride == out_len)
+      CU_TRY(cudaMemcpyAsync(out + r0 * out_len, dout, rows * out_len * sizeof(T), cudaMemcpyDeviceToHost, c.pipe[s]));
+    else
+      CU_TRY(cudaMemcpy2DAsync(out + r0 * out_stride, out_stride * sizeof(T), dout,
+                               out_len * sizeof(T), out_len * sizeof(T), rows,
+                               cudaMemcpyDeviceToHost, c.pipe[s]));
   }
   for (int i = 0; i < kPipe; ++i) CU_TRY(cudaStreamSynchronize(c.pipe[i]));
   return 0;
@@ -958,7 +1033,12 @@ int entry(Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k
   if (batch == 0) return 0;
   if (n == 0) return fail(FFTCONV_CUDA_ERR_ARG, "empty signal");
   if (a_stride < n || out_stride < out_len) return fail(FFTCONV_CUDA_ERR_ARG, "row stride shorter than row");
-  if (op != OP_HILBERT) {
+  if (op == OP_RF) {
+    if (!k || klen == 0) return fail(FFTCONV_CUDA_ERR_ARG, "empty kernel");
+    if (out_len != env_out_len(n))
+      return fail(FFTCONV_CUDA_ERR_ARG, "rf_envelope: output length " + std::to_string(out_len) + ", expected " +
+                                            std::to_string(env_out_len(n)));
+  } else if (op != OP_HILBERT) {
     if (!k || klen == 0) return fail(FFTCONV_CUDA_ERR_ARG, "empty kernel");
     if (mode != FFTCONV_CUDA_FULL && mode != FFTCONV_CUDA_SAME)
       return fail(FFTCONV_CUDA_ERR_ARG, "Unsupported convolution mode: " + std::to_string(mode));
@@ -966,8 +1046,9 @@ int entry(Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k
     if (out_len != want)
       return fail(FFTCONV_CUDA_ERR_ARG, "output length " + std::to_string(out_len) + ", expected " +
                                             std::to_string(want));
-  } else if (out_len != n) {
-    return fail(FFTCONV_CUDA_ERR_ARG, "hilbert: output length must equal input length");
+  } else if (out_len != env_out_len(n)) {
+    return fail(FFTCONV_CUDA_ERR_ARG, tl_env.dec > 1 ? "envelope: output length must be ceil(n / decimate)"
+                                                     : "hilbert: output length must equal input length");
   }
   DeviceCtx *c = nullptr;
   if (int r = get_ctx(&c)) return r;
@@ -977,9 +1058,43 @@ int entry(Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k
   if (dev_in) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (op == OP_HILBERT) return hilbert_device<T>(*c, st, a, batch, n, a_stride, out, out_stride);
+    if (op == OP_RF) {
+      // the filtered rows live in a per-stream workspace (grow-only, stream-ordered reuse)
+      StreamWs &ws = c->ws[st];
+      if (ws.rf_bytes < batch * n * sizeof(T)) CU_TRY(cudaStreamSynchronize(st)); // before the old one is freed
+      if (int g = grow(&ws.rf, &ws.rf_bytes, batch * n * sizeof(T))) return g;
+      T *tmp = static_cast<T *>(ws.rf);
+      if (int r = conv_device<T>(*c, st, OP_OA, a, batch, n, a_stride, k, klen, tmp, n, n, FFTCONV_CUDA_SAME)) return r;
+      return hilbert_device<T>(*c, st, tmp, batch, n, n, out, out_stride);
+    }
     return conv_device<T>(*c, st, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
   }
   return run_host<T>(*c, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+}
+
+// fftconv_cuda_envelope_* / fftconv_cuda_rf_envelope_*: validate the options, publish them to
+// the launch sites through tl_env, run the Hilbert (or filter + Hilbert) path.
+template <typename T>
+int envelope_entry(Op op, const T *x, size_t batch, size_t n, size_t x_stride, const T *k, size_t klen, T *out,
+                   size_t out_len, size_t out_stride, const fftconv_cuda_envelope_opts *opts, void *stream) {
+  EnvOpts e;
+  e.dec = 1;
+  if (opts) {
+    e.dec = opts->decimate ? opts->decimate : 1;
+    e.log = opts->log_compress ? 1 : 0;
+    if (e.log) {
+      if (!(opts->ref > 0.0) || !(opts->dynamic_range_db > 0.0))
+        return fail(FFTCONV_CUDA_ERR_ARG, "envelope: log compression needs ref > 0 and dynamic_range_db > 0");
+      // 1 + 20 log10(env / ref) / DR  =  a log2(env) + b
+      e.a = 20.0 * std::log10(2.0) / opts->dynamic_range_db;
+      e.b = 1.0 - 20.0 * std::log10(opts->ref) / opts->dynamic_range_db;
+    }
+    if (e.dec > 0x7fffffffULL) return fail(FFTCONV_CUDA_ERR_ARG, "envelope: decimation factor too large");
+  }
+  tl_env = e;
+  const int r = entry<T>(op, x, batch, n, x_stride, k, klen, out, out_len, out_stride, FFTCONV_CUDA_SAME, stream);
+  tl_env = EnvOpts();
+  return r;
 }
 
 template <typename T> int add_entry(T *dst, const T *src, size_t n, void *stream) {
@@ -1170,6 +1285,23 @@ int fftconv_cuda_clear_cache(void) {
 
 FFTCONV_API(f32, float)
 FFTCONV_API(f64, double)
+
+#define FFTCONV_ENVELOPE_API(SFX, T)                                                                     \
+  int fftconv_cuda_envelope_batched_##SFX(const T *x, size_t batch, size_t n, size_t x_stride, T *out,   \
+                                          size_t out_len, size_t out_stride,                             \
+                                          const fftconv_cuda_envelope_opts *opts, void *stream) {        \
+    return envelope_entry<T>(OP_HILBERT, x, batch, n, x_stride, nullptr, 0, out, out_len, out_stride,    \
+                             opts, stream);                                                              \
+  }                                                                                                      \
+  int fftconv_cuda_rf_envelope_batched_##SFX(const T *x, size_t batch, size_t n, size_t x_stride,        \
+                                             const T *k, size_t klen, T *out, size_t out_len,            \
+                                             size_t out_stride, const fftconv_cuda_envelope_opts *opts,  \
+                                             void *stream) {                                             \
+    return envelope_entry<T>(OP_RF, x, batch, n, x_stride, k, klen, out, out_len, out_stride, opts,      \
+                             stream);                                                                    \
+  }
+FFTCONV_ENVELOPE_API(f32, float)
+FFTCONV_ENVELOPE_API(f64, double)
 
 #define FFTCONV_HANDLE_API(SFX, T)                                                                   \
   int fftconv_cuda_filter_create_##SFX(const T *k, size_t klen, void **filter_out) {                \

@@ -6,11 +6,15 @@
 // The f32 / N = 2048 overlap-add case has its own kernel (oa_n2048_kernel.cuh).
 #pragma once
 
+#include "envelope_epilogue.cuh"
 #include "fast_fft.cuh"
 #include "generic_fft.cuh"
 
 namespace fc {
 namespace generic {
+
+using fc::EnvEpilogue;
+using fc::env_store;
 
 // ---------------------------------------------------------------------------
 // Spectrum of the taps, evaluated directly in double:
@@ -177,6 +181,7 @@ template <typename T> struct HilbertArgs {
   int log2n;
   const cx<T> *W;
   const cx<T> *G;
+  EnvEpilogue<T> epi;
 };
 
 template <typename T> __global__ void hilbert_pow2_kernel(const HilbertArgs<T> p) {
@@ -202,10 +207,10 @@ template <typename T> __global__ void hilbert_pow2_kernel(const HilbertArgs<T> p
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const cx<T> h = buf[i];
     const T a = x0[i];
-    e0[i] = sqrt(a * a + h.x * h.x);
+    env_store(p.epi, e0, i, sqrt(a * a + h.x * h.x));
     if (has1) {
       const T b = x1[i];
-      e1[i] = sqrt(b * b + h.y * h.y);
+      env_store(p.epi, e1, i, sqrt(b * b + h.y * h.y));
     }
   }
 }
@@ -227,6 +232,7 @@ template <typename T> struct HilbertBluesteinArgs {
   const cx<T> *W;     // M twiddles
   const cx<T> *B;     // M, DIF order, 1/M folded in
   const cx<T> *chirp; // n
+  EnvEpilogue<T> epi;
 };
 
 template <typename T> __global__ void hilbert_bluestein_kernel(const HilbertBluesteinArgs<T> p) {
@@ -277,10 +283,10 @@ template <typename T> __global__ void hilbert_bluestein_kernel(const HilbertBlue
     const cx<T> w = cmul(buf[m], p.chirp[m]); // conj(h) * n
     const T h0 = w.x * inv_n, h1 = -w.y * inv_n;
     const T a = x0[m];
-    e0[m] = sqrt(a * a + h0 * h0);
+    env_store(p.epi, e0, m, sqrt(a * a + h0 * h0));
     if (has1) {
       const T b = x1[m];
-      e1[m] = sqrt(b * b + h1 * h1);
+      env_store(p.epi, e1, m, sqrt(b * b + h1 * h1));
     }
   }
 }
@@ -289,6 +295,25 @@ template <typename T> __global__ void hilbert_bluestein_kernel(const HilbertBlue
 template <typename T> __global__ void add_inplace_kernel(T *dst, const T *src, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
+}
+
+// Taps too long for one segment FFT are split into blocks k_p = k[p Kb : (p + 1) Kb]:
+//   a * k = sum_p shift(a * k_p, p Kb)
+// `part` holds rows of part_len = n + len(k_p) - 1 samples (the Full convolution with block p);
+// out[o] (+)= part[o + pad - shift], summed in block order -> deterministic.  The first block
+// assigns (and zero-fills what it does not reach), like the reference's fill(out, 0)
+// (/root/reference/include/fftconv/fftconv.hpp:385).
+template <typename T>
+__global__ void partition_accumulate_kernel(const T *__restrict__ part, long long rows, long long part_len,
+                                            T *__restrict__ out, long long out_len, long long out_stride,
+                                            long long shift_minus_pad, int first) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * out_len) return;
+  const long long r = idx / out_len, o = idx - r * out_len;
+  const long long i = o - shift_minus_pad;
+  const T v = (i >= 0 && i < part_len) ? part[r * part_len + i] : (T)0;
+  T *dst = out + r * out_stride + o;
+  *dst = first ? v : *dst + v;
 }
 
 // Streaming overlap-add across calls: `full` holds rows of n + K - 1 samples (this

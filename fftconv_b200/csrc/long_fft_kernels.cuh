@@ -16,6 +16,7 @@
 // (s, idx) is s + 16 * freq_sub(idx).
 #pragma once
 
+#include "envelope_epilogue.cuh"
 #include "fast_fft.cuh"
 
 namespace fc {
@@ -34,6 +35,7 @@ template <typename T> struct LongArgs {
   cx<T> *scratch;     // pairs * 16 * N_sub
   const cx<T> *TWbig; // 15 * N_sub: [(s-1) N_sub + p] = W_Nbig^{p s}
   int hilbert;        // outer_inv: write the envelope instead of the convolution
+  EnvEpilogue<T> epi; // hilbert only
 };
 
 template <typename T> __global__ void outer_fwd_kernel(const LongArgs<T> a) {
@@ -88,10 +90,10 @@ template <typename T> __global__ void outer_inv_kernel(const LongArgs<T> a) {
       const long long i = p + (long long)q * nsub;
       if (i < a.n) {
         const T u = x0[i];
-        o0[i] = sqrt(u * u + v[q].x * v[q].x);
+        env_store(a.epi, o0, i, sqrt(u * u + v[q].x * v[q].x));
         if (has1) {
           const T w = x1[i];
-          o1[i] = sqrt(w * w + v[q].y * v[q].y);
+          env_store(a.epi, o1, i, sqrt(w * w + v[q].y * v[q].y));
         }
       }
     }

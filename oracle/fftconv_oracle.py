@@ -159,6 +159,27 @@ def hilbert(x):
     return np.sqrt(x * x + h * h).astype(x.dtype)         # :59-63
 
 
+def envelope(x, log_compress: bool = False, ref: float = 1.0, dynamic_range_db: float = 60.0, decimate: int = 1):
+    """Envelope post-processing (include/fftconv_cuda.h, fftconv_cuda_envelope_*; SURVEY.md section
+    8f item 3) restated on top of the reference's hilbert (include/fftconv/hilbert.hpp:16-66):
+    env = hilbert(x); y[j] = env[j * decimate]; with log_compress
+    y = clamp(1 + 20 log10(y / ref) / dynamic_range_db, 0, 1).  The reference has no such
+    function: the definition is this one, the envelope underneath is the reference's."""
+    env = hilbert(x)
+    y = env[..., ::int(decimate)]
+    if log_compress:
+        with np.errstate(divide="ignore"):
+            db = 20.0 * np.log10(y.astype(np.float64) / float(ref))
+        y = np.clip(1.0 + db / float(dynamic_range_db), 0.0, 1.0).astype(env.dtype)
+    return np.ascontiguousarray(y)
+
+
+def rf_envelope(x, k, log_compress: bool = False, ref: float = 1.0, dynamic_range_db: float = 60.0,
+                decimate: int = 1):
+    """oaconvolve_fftw<T, Same> (include/fftconv/fftconv.hpp:474-480) row by row, then `envelope`."""
+    return envelope(oaconvolve(x, k, "same"), log_compress, ref, dynamic_range_db, decimate)
+
+
 # ---------------------------------------------------------------------------
 # float64 ground truth by the mathematical definition (the reference tests'
 # oracle is arma::conv = direct convolution, test/test_fftconv.cpp:100,116,137).

@@ -148,6 +148,36 @@ int main() {
     fftconv::hilbert<float>(inf, outf);
     for (int i = 0; i < 10; ++i) EXPECT(std::abs(outf[i] - expect[i]) < 1e-6 * 5);
   }
+  { // envelope with fused post-processing: decimated + log-compressed samples of hilbert()
+    const size_t batch = 3, n = 1000, dec = 3;
+    auto x = randn<double>(batch * n, 23);
+    std::vector<double> env(batch * n);
+    fftconv::hilbert_batched<double>(std::span<const double>(x), n, std::span<double>(env));
+    fftconv::EnvelopeOptions opt;
+    opt.decimate = dec;
+    opt.log_compress = true;
+    opt.ref = 2.0;
+    opt.dynamic_range_db = 40.0;
+    const size_t m = opt.out_len(n);
+    EXPECT(m == 334);
+    std::vector<double> got(batch * m);
+    fftconv::envelope_batched<double>(std::span<const double>(x), n, std::span<double>(got), opt);
+    for (size_t b = 0; b < batch; ++b)
+      for (size_t j = 0; j < m; ++j) {
+        double want = 1.0 + 20.0 * std::log10(env[b * n + j * dec] / 2.0) / 40.0;
+        want = want < 0 ? 0 : (want > 1 ? 1 : want);
+        EXPECT(std::abs(got[b * m + j] - want) < 1e-12);
+      }
+    // rf_envelope == envelope of the Same-mode overlap-add
+    auto k = randn<double>(65, 24);
+    std::vector<double> filt(batch * n), want2(batch * n), got2(batch * n);
+    fftconv::oaconvolve_batched<double, ConvMode::Same>(std::span<const double>(x), n, std::span<const double>(k),
+                                                        std::span<double>(filt));
+    fftconv::hilbert_batched<double>(std::span<const double>(filt), n, std::span<double>(want2));
+    fftconv::rf_envelope_batched<double>(std::span<const double>(x), n, std::span<const double>(k),
+                                         std::span<double>(got2));
+    for (size_t i = 0; i < got2.size(); ++i) EXPECT(std::abs(got2[i] - want2[i]) < 1e-12 * 50);
+  }
   { // errors surface as exceptions (the reference only asserts)
     bool threw = false;
     std::vector<double> a(10), k(3), out(10);

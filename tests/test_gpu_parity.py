@@ -556,3 +556,117 @@ def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch)
         assert O.rel_l2(y.cpu().numpy(), y_table.cpu().numpy()) < tol
         pick = [0, 1, 31, 63]
         assert O.rel_l2(y[pick].cpu().numpy(), O.conv_exact(a[pick], k, mode)) < tol, (klen, mode)
+
+
+# ---- envelope with fused post-processing --------------------------
+ENV_CASES = [
+    # (dtype, rows, n, device tensors, what it exercises)
+    (np.float32, 1300, 8192, True),    # packed persistent TMA-fed kernel (config 4 shape)
+    (np.float32, 37, 8192, True),      # two rows per FFT (small batch)
+    (np.float32, 5, 64, False),        # small power of two, host pointers
+    (np.float32, 6, 1000, False),      # chirp-z
+    (np.float32, 3, 32768, True),      # one long FFT through global scratch
+    (np.float64, 9, 4096, True),
+    (np.float64, 4, 777, False),
+]
+
+
+@pytest.mark.parametrize("dt,rows,n,on_device", ENV_CASES)
+@pytest.mark.parametrize("dec,log", [(1, True), (3, False), (4, True), (7, True)])
+def test_envelope_epilogue_matches_oracle(cuda, dt, rows, n, on_device, dec, log):
+    """fftconv_cuda_envelope_*: decimation and log compression in the store of every Hilbert
+    kernel, against the oracle restatement (reference hilbert + the stated post-processing)."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(n + 13 * dec + rows)
+    x = (rng.standard_normal((rows, n)) * np.exp(rng.uniform(-4, 1, (rows, 1)))).astype(dt)
+    kw = dict(log_compress=log, ref=1.5, dynamic_range_db=50.0, decimate=dec)
+    if on_device:
+        got = fc.envelope(_t(x, cuda), **kw)
+        torch.cuda.synchronize()
+        got = got.cpu().numpy()
+    else:
+        got = fc.envelope(x, **kw)
+    pick = np.unique(np.concatenate([np.arange(0, rows, max(1, rows // 24)), np.arange(max(0, rows - 5), rows)]))
+    want = O.envelope(x[pick], **kw)
+    assert got.shape == (rows, (n + dec - 1) // dec) and got.dtype == x.dtype
+    assert np.all(np.isfinite(got))
+    if log:
+        assert got.min() >= 0.0 and got.max() <= 1.0
+        # absolute: outputs live in [0, 1]; 1e-5 / 1e-12 of full scale per sample on average
+        err = np.linalg.norm(got[pick].astype(np.float64) - want) / np.sqrt(want.size)
+        assert err < H.TOL[np.dtype(dt)] * 4, err
+    else:
+        assert O.rel_l2(got[pick], want) < H.TOL[np.dtype(dt)]
+
+
+def test_envelope_plain_options_equal_hilbert(cuda):
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(5)
+    for dt, n in ((np.float32, 2048), (np.float64, 300)):
+        x = rng.standard_normal((7, n)).astype(dt)
+        assert np.array_equal(fc.envelope(x), fc.hilbert(x))
+    with pytest.raises(RuntimeError):
+        fc.envelope_(x, np.empty((7, 300), dtype=np.float64), decimate=2)   # wrong output length
+    with pytest.raises(RuntimeError):
+        fc.envelope(x, log_compress=True, ref=0.0)
+
+
+@pytest.mark.parametrize("dt,rows,n,klen,on_device", [(np.float32, 600, 8192, 245, True), (np.float32, 9, 5000, 65, False),
+                                                      (np.float64, 12, 4096, 95, True)])
+def test_rf_envelope_chain(cuda, dt, rows, n, klen, on_device):
+    """Band-pass (oaconvolve Same) then envelope without leaving the device, against the oracle
+    chain and against the two separate public calls."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(klen + rows)
+    x = rng.standard_normal((rows, n)).astype(dt)
+    t = np.arange(klen) - klen // 2
+    k = (np.hamming(klen) * np.cos(2 * np.pi * 0.12 * t)).astype(dt)
+    k /= np.abs(k).sum()
+    kw = dict(log_compress=True, ref=0.2, dynamic_range_db=45.0, decimate=2)
+    if on_device:
+        tx, tk = _t(x, cuda), _t(k, cuda)
+        got = fc.rf_envelope(tx, tk, **kw)
+        lin = fc.rf_envelope(tx, tk)
+        two = fc.hilbert(fc.oaconvolve(tx, tk, "same"))
+        torch.cuda.synchronize()
+        got, lin, two = got.cpu().numpy(), lin.cpu().numpy(), two.cpu().numpy()
+    else:
+        got, lin = fc.rf_envelope(x, k, **kw), fc.rf_envelope(x, k)
+        two = fc.hilbert(fc.oaconvolve(x, k, "same"))
+    assert np.array_equal(lin, two)
+    pick = np.arange(0, rows, max(1, rows // 16))
+    tol = H.TOL[np.dtype(dt)]
+    assert O.rel_l2(lin[pick], O.rf_envelope(x[pick], k)) < tol * 3   # two chained transforms
+    want = O.rf_envelope(x[pick], k, **kw)
+    assert np.linalg.norm(got[pick].astype(np.float64) - want) / np.sqrt(want.size) < tol * 4
+
+
+@pytest.mark.parametrize("dt,n,klen", [(np.float32, 30000, 10000), (np.float32, 9000, 8999), (np.float64, 20000, 5000),
+                                       (np.float64, 70000, 4097)])
+def test_kernels_longer_than_a_segment_fft(cuda, dt, n, klen):
+    """The reference keeps doubling the segment FFT for long kernels (fftconv.hpp:61-65); here the
+    taps are cut into blocks and the partial convolutions summed in order: same linear
+    convolution, Full and Same, host and device pointers, oaconvolve and convolve."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(klen)
+    a = rng.standard_normal((3, n)).astype(dt)
+    k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(dt)
+    tol = H.TOL[np.dtype(dt)]
+    for mode in ("full", "same"):
+        want = O.conv_exact(a, k, mode)
+        got = fc.oaconvolve(a, k, mode)
+        assert O.rel_l2(got, want) < tol, (mode, O.rel_l2(got, want))
+        tgot = fc.oaconvolve(_t(a, cuda), _t(k, cuda), mode)
+        torch.cuda.synchronize()
+        assert np.array_equal(tgot.cpu().numpy(), got)
+    assert O.rel_l2(fc.convolve(a[0], k, "full"), O.conv_exact(a[0], k, "full")) < tol

@@ -131,3 +131,24 @@ def test_python_binding_cases_on_oracle():
         for mode in ("full", "same"):
             np.testing.assert_allclose(fn(a, k, mode), np.convolve(a, k, mode), rtol=1e-5, atol=1e-8)
     np.testing.assert_allclose(O.hilbert(a), O.hilbert_exact(a), rtol=1e-5, atol=1e-8)
+
+
+def test_envelope_restatement_against_scipy():
+    """oracle.envelope / rf_envelope (post-processing of fftconv_cuda_envelope_*): the envelope
+    underneath is the reference's hilbert; decimation and log compression follow the formula in
+    include/fftconv_cuda.h, checked here against an independent float64 evaluation."""
+    from scipy import signal
+
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((4, 1000))
+    env = np.abs(signal.hilbert(x, axis=-1))
+    got = O.envelope(x, log_compress=True, ref=2.0, dynamic_range_db=40.0, decimate=3)
+    want = np.clip(1.0 + 20.0 * np.log10(env[:, ::3] / 2.0) / 40.0, 0.0, 1.0)
+    assert got.shape == (4, 334)
+    assert np.max(np.abs(got - want)) < 1e-12
+    assert np.array_equal(O.envelope(x), O.hilbert(x))
+    k = rng.standard_normal(65)
+    filt = np.stack([np.convolve(r, k, "full")[32:32 + 1000] for r in x])
+    assert O.rel_l2(O.rf_envelope(x, k), np.abs(signal.hilbert(filt, axis=-1))) < 1e-12
+    z = np.zeros((1, 16))
+    assert np.array_equal(O.envelope(z, log_compress=True), z)   # log of 0 clamps to 0
