@@ -109,6 +109,7 @@ struct DeviceCtx {
   std::map<std::pair<size_t, int>, Tables> tables;
   std::map<std::pair<size_t, int>, BluesteinTables> bluestein;
   fc::n2048::cpair *tw1 = nullptr, *tw2 = nullptr, *tw_w2 = nullptr;
+  fc::n2048::CPairT<double> *tw1d = nullptr, *tw2d = nullptr; // the float64 instantiation's tables
   std::map<cudaStream_t, StreamWs> ws;
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
   void *stage_in[kPipe] = {nullptr, nullptr, nullptr};
@@ -162,7 +163,10 @@ void free_ctx(DeviceCtx &c) {
   cudaFree(c.tw1);
   cudaFree(c.tw2);
   cudaFree(c.tw_w2);
+  cudaFree(c.tw1d);
+  cudaFree(c.tw2d);
   c.tw1 = c.tw2 = c.tw_w2 = nullptr;
+  c.tw1d = c.tw2d = nullptr;
   for (auto &kv : c.ws) {
     cudaFree(kv.second.taps);
     cudaFree(kv.second.H);
@@ -300,15 +304,28 @@ template <typename T> int get_bluestein(DeviceCtx &c, size_t n, BluesteinTables 
   return 0;
 }
 
-int get_n2048_tables(DeviceCtx &c) {
-  if (c.tw1) return 0;
-  std::vector<fc::n2048::cpair> t1(2048), t2(128);
-  fc::n2048::fill_tw1(t1.data());
-  fc::n2048::fill_tw2(t2.data());
-  CU_TRY(cudaMalloc((void **)&c.tw1, t1.size() * sizeof(fc::n2048::cpair)));
-  CU_TRY(cudaMalloc((void **)&c.tw2, t2.size() * sizeof(fc::n2048::cpair)));
-  CU_TRY(cudaMemcpy(c.tw1, t1.data(), t1.size() * sizeof(fc::n2048::cpair), cudaMemcpyHostToDevice));
-  CU_TRY(cudaMemcpy(c.tw2, t2.data(), t2.size() * sizeof(fc::n2048::cpair), cudaMemcpyHostToDevice));
+template <typename S>
+int get_n2048_tables(DeviceCtx &c, const fc::n2048::CPairT<S> **tw1_out, const fc::n2048::CPairT<S> **tw2_out) {
+  using CP = fc::n2048::CPairT<S>;
+  CP **tw1, **tw2;
+  if constexpr (std::is_same<S, float>::value) {
+    tw1 = &c.tw1;
+    tw2 = &c.tw2;
+  } else {
+    tw1 = &c.tw1d;
+    tw2 = &c.tw2d;
+  }
+  if (!*tw1) {
+    std::vector<CP> t1(2048), t2(128);
+    fc::n2048::fill_tw1(t1.data());
+    fc::n2048::fill_tw2(t2.data());
+    CU_TRY(cudaMalloc((void **)tw1, t1.size() * sizeof(CP)));
+    CU_TRY(cudaMalloc((void **)tw2, t2.size() * sizeof(CP)));
+    CU_TRY(cudaMemcpy(*tw1, t1.data(), t1.size() * sizeof(CP), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(*tw2, t2.data(), t2.size() * sizeof(CP), cudaMemcpyHostToDevice));
+  }
+  *tw1_out = *tw1;
+  *tw2_out = *tw2;
   return 0;
 }
 
@@ -545,11 +562,12 @@ int oa2048_engine() {
   return e == 2 ? 2 : 1;
 }
 
-// engine for one call: the dedicated kernels take float32, N = 2048, 8 <= K <= 410 (staging
-// area and tail buffers are sized for that); the warp-pair engine only its table row
+// engine for one call: the dedicated kernels take N = 2048, 8 <= K <= 410 (staging area and tail
+// buffers are sized for that); the warp-pair engine only float32 and its table row
 template <typename T> int oa2048_engine_for(size_t N, size_t klen) {
-  if (!std::is_same<T, float>::value || N != 2048 || klen < 8 || klen > 410) return 0;
+  if (N != 2048 || klen < 8 || klen > 410) return 0;
   const int e = oa2048_engine();
+  if (!std::is_same<T, float>::value) return (e && !env_int("FFTCONV_CUDA_NO_N2048_F64", 0)) ? 1 : 0;
   return (e == 2 && klen < 221) ? 1 : e;
 }
 
@@ -599,46 +617,50 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
     }
   }
   if (engine2048 == 1) {
-    if constexpr (std::is_same<T, float>::value) {
-      if (int r = get_n2048_tables(c)) return r;
-      const cx<float> *H = nullptr;
-      if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_N2048, *tab, &H))
-        return r;
-      int G = env_int("FFTCONV_CUDA_N2048_GROUPS", 4);
-      if (G < 1 || G > 4) G = 4;
-      const long long slots = (long long)c.sm_count * G;
-      // streams per row: enough quads to fill every group, but never so many that
-      // the per-chunk warm-up segment costs more than ~6 %
-      long long chunks = 1;
-      if ((long long)batch < 4 * slots) {
-        chunks = (4 * slots + (long long)batch - 1) / (long long)batch;
-        const long long max_chunks = std::max<long long>(1, segs / 16);
-        chunks = std::min(chunks, max_chunks);
-      }
-      fc::n2048::OaParams p{};
-      fc::n2048::fill_params(p, a, out, (long long)batch, (long long)n, (long long)a_stride,
-                             (long long)out_stride, (long long)out_len, (int)klen, mode, chunks);
-      p.tw1 = c.tw1;
-      p.tw2 = c.tw2;
-      p.hs = reinterpret_cast<const fc::n2048::cpair *>(H);
-      const size_t smem = fc::n2048::smem_bytes(G, (int)klen);
-      const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
-      const bool recomp = env_int("FFTCONV_CUDA_TW_RECOMPUTE", 1) != 0;
-#define FC_LAUNCH_N2048(GG, RR)                                                         \
-  {                                                                                     \
-    if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<GG, RR>, smem)) return r;     \
-    fc::n2048::oa_n2048_kernel<GG, RR><<<(unsigned)grid, 128 * GG, smem, st>>>(p);      \
-  }
-      if (G == 4 && recomp) FC_LAUNCH_N2048(4, true)
-      else if (G == 4) FC_LAUNCH_N2048(4, false)
-      else if (G == 3) FC_LAUNCH_N2048(3, false)
-      else if (G == 2) FC_LAUNCH_N2048(2, false)
-      else FC_LAUNCH_N2048(1, false)
-#undef FC_LAUNCH_N2048
-      CU_TRY(cudaGetLastError());
-      ++g_launches;
-      return 0;
+    using D = typename fc::DataOf<T>::D;
+    constexpr int NL = fc::DataTraits<D>::NL;
+    const fc::n2048::CPairT<T> *tw1 = nullptr, *tw2 = nullptr;
+    if (int r = get_n2048_tables<T>(c, &tw1, &tw2)) return r;
+    const cx<T> *H = nullptr;
+    if (int r = prepare_spectrum<T>(c, st, k, klen, N, fc::generic::LAYOUT_N2048, *tab, &H)) return r;
+    int G = env_int("FFTCONV_CUDA_N2048_GROUPS", 4);
+    if (G < 1 || G > 4) G = 4;
+    const bool want_recomp = env_int("FFTCONV_CUDA_TW_RECOMPUTE", 1) != 0;
+    // float64 with the longest kernels (K > ~390: two 16-byte tail buffers of K - 1 points per
+    // group) does not fit four groups: drop to three
+    while (G > 1 && fc::n2048::smem_bytes<T>(G, (int)klen, want_recomp && G == 4) > c.smem_optin) --G;
+    const long long slots = (long long)c.sm_count * G;
+    // streams per row: enough quads to fill every group, but never so many that
+    // the per-chunk warm-up segment costs more than ~6 %
+    long long chunks = 1;
+    if ((long long)batch < NL * slots) {
+      chunks = (NL * slots + (long long)batch - 1) / (long long)batch;
+      const long long max_chunks = std::max<long long>(1, segs / 16);
+      chunks = std::min(chunks, max_chunks);
     }
+    fc::n2048::OaParamsT<T> p{};
+    fc::n2048::fill_params(p, a, out, (long long)batch, (long long)n, (long long)a_stride,
+                           (long long)out_stride, (long long)out_len, (int)klen, mode, chunks);
+    p.tw1 = tw1;
+    p.tw2 = tw2;
+    p.hs = reinterpret_cast<const fc::n2048::CPairT<T> *>(H);
+    const bool recomp = want_recomp && G == 4;
+    const size_t smem = fc::n2048::smem_bytes<T>(G, (int)klen, recomp);
+    const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
+#define FC_LAUNCH_N2048(GG, RR)                                                            \
+  {                                                                                        \
+    if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<D, GG, RR>, smem)) return r;     \
+    fc::n2048::oa_n2048_kernel<D, GG, RR><<<(unsigned)grid, 128 * GG, smem, st>>>(p);      \
+  }
+    if (G == 4 && recomp) FC_LAUNCH_N2048(4, true)
+    else if (G == 4) FC_LAUNCH_N2048(4, false)
+    else if (G == 3) FC_LAUNCH_N2048(3, false)
+    else if (G == 2) FC_LAUNCH_N2048(2, false)
+    else FC_LAUNCH_N2048(1, false)
+#undef FC_LAUNCH_N2048
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+    return 0;
   }
 
   const bool use_fast = fast_ok<T>(c, N, klen);
@@ -882,7 +904,11 @@ int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, 
       N = throughput_oa_size<T>(c, klen, batch, n, optimal_fft_size(klen));
     }
   }
-  if (N > max_generic_fft<T>(c, klen)) {
+  // beyond one CTA's shared memory -- or inside the narrow window where the segment fits only the
+  // plain radix-4 kernel (measured 7.8 ms against ~3 ms at 2048 x 65536 float64, K = 3000)
+  const bool slow_window = N >= 4096 && !fast_ok<T>(c, N, klen) && !(tl_filter && tl_filter->taps == (const void *)k) &&
+                           !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0);
+  if (N > max_generic_fft<T>(c, klen) || slow_window) {
     if (tl_filter && tl_filter->taps == (const void *)k)
       return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "filter handle: kernel too long for a segment FFT");
     return partitioned_device<T>(c, st, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);

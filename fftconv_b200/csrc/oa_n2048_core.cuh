@@ -30,6 +30,11 @@
 //
 // Everything here is __host__ __device__ so tests can emulate the 128 threads
 // phase by phase on the CPU (tests/cpu/emulate_oa_n2048.cpp).
+//
+// The engine is a template over its data type D (packed_f32x2.cuh, DataTraits):
+//   D = f2      float32, FOUR real segments per group (as described above);
+//   D = double  float64, TWO real segments per group (real / imaginary part), the
+//               same 16-byte points, layouts, phases and barrier count.
 #pragma once
 
 #include "packed_f32x2.cuh"
@@ -41,26 +46,37 @@ constexpr int kN = 2048;
 constexpr int kThreads = 128; // per group
 constexpr int kPts = 16;      // points per thread
 
-struct pt4 {                  // one complex point of both packed FFTs (16 B)
-  float reA, reB, imA, imB;
+template <typename D> struct PtT { // one complex point (16 B): f2 -> (reA, reB, imA, imB)
+  D re, im;
 };
+using pt4 = PtT<f2>;
 
-struct Regs {
-  f2 re[kPts];
-  f2 im[kPts];
+template <typename D> struct RegsT {
+  D re[kPts];
+  D im[kPts];
 };
+using Regs = RegsT<f2>;
 
 constexpr float kC8 = 0.70710678118654752440f;  // cos(pi/4)
 constexpr float kC16 = 0.92387953251128675613f; // cos(pi/8)
 constexpr float kS16 = 0.38268343236508977173f; // sin(pi/8)
+template <typename S> struct Consts;
+template <> struct Consts<float> {
+  static constexpr float c8 = kC8, c16 = kC16, s16 = kS16;
+};
+template <> struct Consts<double> {
+  static constexpr double c8 = 0.70710678118654752440084436210485, c16 = 0.92387953251128675612818318939679,
+                          s16 = 0.38268343236508977172845998403040;
+};
+template <typename D> using scalar_of_t = typename DataTraits<D>::S;
 
 // 4-point DFT, sign S (-1 forward, +1 inverse), in place on 4 named slots.
-template <int S>
-FC_HD void bfly4(f2 &r0, f2 &i0, f2 &r1, f2 &i1, f2 &r2, f2 &i2, f2 &r3, f2 &i3) {
-  const f2 s0r = add2(r0, r2), s0i = add2(i0, i2);
-  const f2 d0r = sub2(r0, r2), d0i = sub2(i0, i2);
-  const f2 s1r = add2(r1, r3), s1i = add2(i1, i3);
-  const f2 d1r = sub2(r1, r3), d1i = sub2(i1, i3);
+template <int S, typename D>
+FC_HD void bfly4(D &r0, D &i0, D &r1, D &i1, D &r2, D &i2, D &r3, D &i3) {
+  const D s0r = add2(r0, r2), s0i = add2(i0, i2);
+  const D d0r = sub2(r0, r2), d0i = sub2(i0, i2);
+  const D s1r = add2(r1, r3), s1i = add2(i1, i3);
+  const D d1r = sub2(r1, r3), d1i = sub2(i1, i3);
   r0 = add2(s0r, s1r); i0 = add2(s0i, s1i);
   r2 = sub2(s0r, s1r); i2 = sub2(s0i, s1i);
   if (S < 0) { // X1 = d0 - j d1, X3 = d0 + j d1
@@ -73,23 +89,26 @@ FC_HD void bfly4(f2 &r0, f2 &i0, f2 &r1, f2 &i1, f2 &r2, f2 &i2, f2 &r3, f2 &i3)
 }
 
 // multiply by -j (S<0) or +j (S>0)
-template <int S> FC_HD void rot90(f2 &r, f2 &i) {
-  const f2 t = r;
-  if (S < 0) { r = i; i = muls2(t, -1.0f); }
-  else       { r = muls2(i, -1.0f); i = t; }
+template <int S, typename D> FC_HD void rot90(D &r, D &i) {
+  using Sc = scalar_of_t<D>;
+  const D t = r;
+  if (S < 0) { r = i; i = muls2(t, (Sc)-1); }
+  else       { r = muls2(i, (Sc)-1); i = t; }
 }
 
 // 16-point DFT of v.re/im[0..15], natural order in, natural order out.
 //   m = m0 + 4 m1, k = k1 + 4 k0:
 //   X[k1 + 4 k0] = sum_m0 W4^{m0 k0} W16^{m0 k1} sum_m1 x[m0 + 4 m1] W4^{m1 k1}
-template <int S> FC_HD void dft16(Regs &v) {
+template <int S, typename D> FC_HD void dft16(RegsT<D> &v) {
+  using Sc = scalar_of_t<D>;
+  constexpr Sc kC8 = Consts<Sc>::c8, kC16 = Consts<Sc>::c16, kS16 = Consts<Sc>::s16;
   // step A: 4-point DFTs over m1 for each m0; result A[m0][k1] stays in slot m0 + 4 k1
 #pragma unroll
   for (int m0 = 0; m0 < 4; ++m0)
     bfly4<S>(v.re[m0], v.im[m0], v.re[m0 + 4], v.im[m0 + 4], v.re[m0 + 8], v.im[m0 + 8],
              v.re[m0 + 12], v.im[m0 + 12]);
   // step B: twiddles W16^{m0 k1} on slot m0 + 4 k1   (imag sign follows S)
-  const float s = (S < 0) ? -1.0f : 1.0f;
+  const Sc s = (S < 0) ? (Sc)-1 : (Sc)1;
   cmul2(v.re[1 + 4], v.im[1 + 4], kC16, s * kS16);    // e = 1
   cmul2(v.re[2 + 4], v.im[2 + 4], kC8, s * kC8);      // e = 2
   cmul2(v.re[3 + 4], v.im[3 + 4], kS16, s * kC16);    // e = 3
@@ -111,16 +130,18 @@ FC_HD constexpr int slot16(int k) { return 4 * (k & 3) + (k >> 2); }
 // 8-point DFT on slots base..base+7, natural in, output k in slot base + slot8(k).
 //   m = m0 + 2 m1, k = k1 + 4 k0:
 //   X[k1 + 4 k0] = sum_m0 W2^{m0 k0} W8^{m0 k1} sum_m1 x[m0 + 2 m1] W4^{m1 k1}
-template <int S> FC_HD void dft8(f2 *re, f2 *im) {
+template <int S, typename D> FC_HD void dft8(D *re, D *im) {
+  using Sc = scalar_of_t<D>;
+  constexpr Sc kC8 = Consts<Sc>::c8;
   bfly4<S>(re[0], im[0], re[2], im[2], re[4], im[4], re[6], im[6]); // m0 = 0: A[0][k1] in slot 2 k1
   bfly4<S>(re[1], im[1], re[3], im[3], re[5], im[5], re[7], im[7]); // m0 = 1: A[1][k1] in slot 2 k1 + 1
-  const float s = (S < 0) ? -1.0f : 1.0f;
+  const Sc s = (S < 0) ? (Sc)-1 : (Sc)1;
   cmul2(re[3], im[3], kC8, s * kC8);    // W8^1
   rot90<S>(re[5], im[5]);               // W8^2
   cmul2(re[7], im[7], -kC8, s * kC8);   // W8^3
 #pragma unroll
   for (int k1 = 0; k1 < 4; ++k1) {      // X[k1] -> slot 2 k1, X[k1 + 4] -> slot 2 k1 + 1
-    const f2 ar = re[2 * k1], ai = im[2 * k1], br = re[2 * k1 + 1], bi = im[2 * k1 + 1];
+    const D ar = re[2 * k1], ai = im[2 * k1], br = re[2 * k1 + 1], bi = im[2 * k1 + 1];
     re[2 * k1] = add2(ar, br); im[2 * k1] = add2(ai, bi);
     re[2 * k1 + 1] = sub2(ar, br); im[2 * k1 + 1] = sub2(ai, bi);
   }
@@ -134,15 +155,16 @@ FC_HD int x1_addr(int t, int k2) { // t = 8 t1 + t0
 }
 FC_HD int x2_addr(int c, int t0) { return c * 8 + ((t0 + c) & 7); }
 
-FC_HD void put(pt4 *buf, int addr, f2 re, f2 im) {
-  pt4 p;
-  p.reA = re.x; p.reB = re.y; p.imA = im.x; p.imB = im.y;
-  buf[addr] = p;
+template <typename D> FC_HD void put(PtT<D> *buf, int addr, D re, D im) {
+  PtT<D> p;
+  p.re = re;
+  p.im = im;
+  buf[addr] = p; // one 128-bit store
 }
-FC_HD void get(const pt4 *buf, int addr, f2 &re, f2 &im) {
-  const pt4 p = buf[addr];
-  re = make_f2(p.reA, p.reB);
-  im = make_f2(p.imA, p.imB);
+template <typename D> FC_HD void get(const PtT<D> *buf, int addr, D &re, D &im) {
+  const PtT<D> p = buf[addr];
+  re = p.re;
+  im = p.im;
 }
 
 // Twiddle / spectrum tables (float2-like pairs), shared by all groups of a CTA:
@@ -150,7 +172,8 @@ FC_HD void get(const pt4 *buf, int addr, f2 &re, f2 &im) {
 //   tw2[k1a * 8 + t0]   = W_128^{t0 k1a}      k1a = 0..15
 //   hs[slot * 128 + c0] = H[k] / 2048, slot = 8 h + k1b, c = c0 + 128 h,
 //                         k = 16 (c & 15) + 256 k1b + (c >> 4)
-struct cpair { float re, im; };
+template <typename S> struct CPairT { S re, im; };
+using cpair = CPairT<float>;
 
 // frequency handled by thread c0 in register slot s of phase P2
 FC_HD int p2_freq(int c0, int s) {
@@ -163,19 +186,23 @@ FC_HD int p2_freq(int c0, int s) {
 // the shared-memory crossbar is this kernel's bottleneck and the FP32 pipe has
 // slack, so 11 fewer 8-byte loads are worth 44 scalar multiply-adds.  Products are
 // at most three deep (k = 15 = 8 * (4 * (1 * 2))): relative twiddle error <= ~2e-7.
-FC_HD cpair cpair_mul(cpair a, cpair b) {
-  cpair r;
+template <typename S> FC_HD CPairT<S> cpair_mul(CPairT<S> a, CPairT<S> b) {
+  CPairT<S> r;
   r.re = a.re * b.re - a.im * b.im;
   r.im = a.re * b.im + a.im * b.re;
   return r;
 }
-template <bool RECOMP, class Use>
-FC_HD void for_each_twiddle(const cpair *col /* entry k = 0 */, int stride, Use &&use) {
+// COMPACT (with RECOMP): the table holds only the four rows that are read, row r = entry k = 2^r.
+template <bool RECOMP, bool COMPACT = false, typename S, class Use>
+FC_HD void for_each_twiddle(const CPairT<S> *col /* entry k = 0 */, int stride, Use &&use) {
+  using cpair = CPairT<S>;
+  static_assert(RECOMP || !COMPACT, "the compact table only serves twiddle recomputation");
   if (!RECOMP) {
 #pragma unroll
     for (int k = 1; k < 16; ++k) use(k, col[k * stride]);
   } else {
-    const cpair w1 = col[1 * stride], w2 = col[2 * stride], w4 = col[4 * stride], w8 = col[8 * stride];
+    const cpair w1 = col[(COMPACT ? 0 : 1) * stride], w2 = col[(COMPACT ? 1 : 2) * stride],
+                w4 = col[(COMPACT ? 2 : 4) * stride], w8 = col[(COMPACT ? 3 : 8) * stride];
     use(1, w1); use(2, w2); use(4, w4); use(8, w8);
     const cpair w3 = cpair_mul(w1, w2); use(3, w3);
     const cpair w5 = cpair_mul(w4, w1); use(5, w5);
@@ -195,23 +222,27 @@ FC_HD void for_each_twiddle(const cpair *col /* entry k = 0 */, int stride, Use 
 // P0: v holds x[t + 128 m] in slot m.  Split in two so that a barrier can sit
 // between the last read of the (aliased) input staging area and the first write
 // of the exchange buffer.
-template <bool RECOMP = false> FC_HD void phase0_compute(int t, Regs &v, const cpair *tw1) {
+template <bool RECOMP = false, bool COMPACT = false, typename D>
+FC_HD void phase0_compute(int t, RegsT<D> &v, const CPairT<scalar_of_t<D>> *tw1) {
+  using cpair = CPairT<scalar_of_t<D>>;
   dft16<-1>(v);
-  for_each_twiddle<RECOMP>(tw1 + t, 128, [&](int k2, cpair w) {
+  for_each_twiddle<RECOMP, COMPACT>(tw1 + t, 128, [&](int k2, cpair w) {
     const int s = slot16(k2);
     cmul2(v.re[s], v.im[s], w.re, w.im);
   });
 }
-FC_HD void phase0_put(int t, const Regs &v, pt4 *xb) {
+template <typename D> FC_HD void phase0_put(int t, const RegsT<D> &v, PtT<D> *xb) {
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) put(xb, x1_addr(t, k2), v.re[slot16(k2)], v.im[slot16(k2)]);
 }
-FC_HD void phase0(int t, Regs &v, pt4 *xb, const cpair *tw1) {
-  phase0_compute<false>(t, v, tw1);
+template <typename D> FC_HD void phase0(int t, RegsT<D> &v, PtT<D> *xb, const CPairT<scalar_of_t<D>> *tw1) {
+  phase0_compute<false, false>(t, v, tw1);
   phase0_put(t, v, xb);
 }
 
-template <bool RECOMP = false> FC_HD void phase1(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
+template <bool RECOMP = false, typename D>
+FC_HD void phase1(int tau, RegsT<D> &v, PtT<D> *xb, const CPairT<scalar_of_t<D>> *tw2) {
+  using cpair = CPairT<scalar_of_t<D>>;
   const int t0 = tau & 7, k2 = tau >> 3;
 #pragma unroll
   for (int t1 = 0; t1 < 16; ++t1) get(xb, x1_addr(8 * t1 + t0, k2), v.re[t1], v.im[t1]);
@@ -227,7 +258,8 @@ template <bool RECOMP = false> FC_HD void phase1(int tau, Regs &v, pt4 *xb, cons
   }
 }
 
-FC_HD void phase2(int c0, Regs &v, pt4 *xb, const cpair *hs) {
+template <typename D> FC_HD void phase2(int c0, RegsT<D> &v, PtT<D> *xb, const CPairT<scalar_of_t<D>> *hs) {
+  using cpair = CPairT<scalar_of_t<D>>;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int c = c0 + 128 * h;
@@ -236,7 +268,7 @@ FC_HD void phase2(int c0, Regs &v, pt4 *xb, const cpair *hs) {
     dft8<-1>(&v.re[8 * h], &v.im[8 * h]);
     // spectrum multiply; dft8 output k1b sits in slot slot8(k1b).  The inverse
     // dft8 wants natural order in, so gather while multiplying.
-    f2 yr[8], yi[8];
+    D yr[8], yi[8];
 #pragma unroll
     for (int k1b = 0; k1b < 8; ++k1b) {
       const cpair w = hs[(8 * h + k1b) * 128 + c0];
@@ -250,7 +282,9 @@ FC_HD void phase2(int c0, Regs &v, pt4 *xb, const cpair *hs) {
   }
 }
 
-template <bool RECOMP = false> FC_HD void phase3(int tau, Regs &v, pt4 *xb, const cpair *tw2) {
+template <bool RECOMP = false, typename D>
+FC_HD void phase3(int tau, RegsT<D> &v, PtT<D> *xb, const CPairT<scalar_of_t<D>> *tw2) {
+  using cpair = CPairT<scalar_of_t<D>>;
   const int t0 = tau & 7, k2 = tau >> 3;
 #pragma unroll
   for (int k1a = 0; k1a < 16; ++k1a) get(xb, x2_addr(k2 * 16 + k1a, t0), v.re[k1a], v.im[k1a]);
@@ -264,14 +298,16 @@ template <bool RECOMP = false> FC_HD void phase3(int tau, Regs &v, pt4 *xb, cons
 // P4: leaves y[t + 128 m] in slot slot16(m).  Split so that a barrier (and the
 // request for the next inputs, which land in the exchange buffer) can follow the
 // last read of the buffer.
-template <bool RECOMP = false> FC_HD void phase4_read(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
+template <bool RECOMP = false, bool COMPACT = false, typename D>
+FC_HD void phase4_read(int t, RegsT<D> &v, const PtT<D> *xb, const CPairT<scalar_of_t<D>> *tw1) {
+  using cpair = CPairT<scalar_of_t<D>>;
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) get(xb, x1_addr(t, k2), v.re[k2], v.im[k2]);
-  for_each_twiddle<RECOMP>(tw1 + t, 128, [&](int k2, cpair w) { cmul2(v.re[k2], v.im[k2], w.re, -w.im); });
+  for_each_twiddle<RECOMP, COMPACT>(tw1 + t, 128, [&](int k2, cpair w) { cmul2(v.re[k2], v.im[k2], w.re, -w.im); });
 }
-FC_HD void phase4_compute(Regs &v) { dft16<+1>(v); }
-FC_HD void phase4(int t, Regs &v, const pt4 *xb, const cpair *tw1) {
-  phase4_read<false>(t, v, xb, tw1);
+template <typename D> FC_HD void phase4_compute(RegsT<D> &v) { dft16<+1>(v); }
+template <typename D> FC_HD void phase4(int t, RegsT<D> &v, const PtT<D> *xb, const CPairT<scalar_of_t<D>> *tw1) {
+  phase4_read<false, false>(t, v, xb, tw1);
   phase4_compute(v);
 }
 

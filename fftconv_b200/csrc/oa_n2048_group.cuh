@@ -33,9 +33,12 @@
 namespace fc {
 namespace n2048 {
 
-struct OaParams {
-  const float *in;
-  float *out;
+// S = scalar type (float: four streams per quad, double: two).  The word "quad" is kept for
+// the set of NL streams that one group transforms together.
+template <typename S> struct OaParamsT {
+  static constexpr int NL = DataTraits<typename DataOf<S>::D>::NL;
+  const S *in;
+  S *out;
   long long batch;      // rows
   long long n;          // samples per row
   long long in_stride;  // elements between rows
@@ -48,23 +51,33 @@ struct OaParams {
   long long chunks;     // streams per row
   long long segs_per_chunk;
   long long n_streams;  // batch * chunks
-  long long n_quads;    // ceil(n_streams / 4)
+  long long n_quads;    // ceil(n_streams / NL)
   long long total_work; // n_quads * segs_per_chunk
-  const cpair *tw1, *tw2, *hs; // global tables (see oa_n2048_core.cuh)
+  const CPairT<S> *tw1, *tw2, *hs; // global tables (see oa_n2048_core.cuh)
 };
+using OaParams = OaParamsT<float>;
 
-struct Lane {
-  const float *in;
-  float *out;
+template <typename S> struct LaneT {
+  const S *in;
+  S *out;
   long long seg0;
   long long cnt;
   bool active;
 };
+using Lane = LaneT<float>;
 
-FC_HD void make_lanes(const OaParams &p, long long quad, Lane (&ln)[4]) {
+template <typename S> FC_HD void make_lanes(const OaParamsT<S> &p, long long quad, LaneT<S> (&ln)[4]) {
+  constexpr int NL = OaParamsT<S>::NL;
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
-    const long long sid = quad * 4 + l;
+    const long long sid = quad * NL + l;
+    if (l >= NL) { // unused slots of a two-lane (float64) quad
+      ln[l].active = false;
+      ln[l].seg0 = ln[l].cnt = 0;
+      ln[l].in = p.in;
+      ln[l].out = p.out;
+      continue;
+    }
     ln[l].active = sid < p.n_streams;
     const long long row = ln[l].active ? sid / p.chunks : 0;
     const long long chunk = ln[l].active ? sid - row * p.chunks : 0;
@@ -77,7 +90,7 @@ FC_HD void make_lanes(const OaParams &p, long long quad, Lane (&ln)[4]) {
 }
 
 // does any lane of this quad have a predecessor segment at chunk-local index j?
-FC_HD bool needs_warmup(const Lane (&ln)[4], long long j) {
+template <typename S> FC_HD bool needs_warmup(const LaneT<S> (&ln)[4], long long j) {
   bool w = false;
 #pragma unroll
   for (int l = 0; l < 4; ++l) w = w || (ln[l].active && j < ln[l].cnt && ln[l].seg0 + j > 0);
@@ -89,42 +102,48 @@ FC_HD bool needs_warmup(const Lane (&ln)[4], long long j) {
 // for a warm-up) into the packed registers, zero padded.
 //   lane 0 -> re, half A    lane 1 -> im, half A
 //   lane 2 -> re, half B    lane 3 -> im, half B
-FC_HD void io_load(int t, Regs &v, const OaParams &p, const Lane (&ln)[4], long long j) {
-  float x[4][kPts];
+template <typename D, typename S>
+FC_HD void io_load(int t, RegsT<D> &v, const OaParamsT<S> &p, const LaneT<S> (&ln)[4], long long j) {
+  constexpr int NL = DataTraits<D>::NL;
+  S x[NL][kPts];
 #pragma unroll
-  for (int l = 0; l < 4; ++l) {
+  for (int l = 0; l < NL; ++l) {
     const long long seg = ln[l].seg0 + j;
     const bool on = ln[l].active && seg >= 0 && j < ln[l].cnt;
     const long long pos = seg * p.step;
     long long len = on ? p.n - pos : 0;
     if (len > p.step) len = p.step;
-    const float *src = ln[l].in + (on ? pos : 0);
+    const S *src = ln[l].in + (on ? pos : 0);
     const int ilen = (int)len;
 #pragma unroll
     for (int m = 0; m < kPts; ++m) {
       const int i = t + 128 * m;
 #if defined(__CUDA_ARCH__)
-      x[l][m] = (i < ilen) ? __ldg(src + i) : 0.0f;
+      x[l][m] = (i < ilen) ? __ldg(src + i) : (S)0;
 #else
-      x[l][m] = (i < ilen) ? src[i] : 0.0f;
+      x[l][m] = (i < ilen) ? src[i] : (S)0;
 #endif
     }
   }
 #pragma unroll
   for (int m = 0; m < kPts; ++m) {
-    v.re[m] = make_f2(x[0][m], x[2][m]);
-    v.im[m] = make_f2(x[1][m], x[3][m]);
+    S xm[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) xm[l] = x[l][m];
+    DataTraits<D>::pack(xm, v.re[m], v.im[m]);
   }
 }
 
 // v holds y[t + 128 m] in slot slot16(m).  Adds the incoming tail, saves the
 // outgoing tail, stores the samples this segment owns.
-FC_HD void io_store(int t, const Regs &v, const OaParams &p, const Lane (&ln)[4], long long j,
-                    const pt4 *tail_prev, pt4 *tail_next, bool add_tail, bool warm) {
-  int limit[4];
-  long long obase[4]; // output index of y[0]
+template <typename D, typename S>
+FC_HD void io_store(int t, const RegsT<D> &v, const OaParamsT<S> &p, const LaneT<S> (&ln)[4], long long j,
+                    const PtT<D> *tail_prev, PtT<D> *tail_next, bool add_tail, bool warm) {
+  constexpr int NL = DataTraits<D>::NL;
+  int limit[NL];
+  long long obase[NL]; // output index of y[0]
 #pragma unroll
-  for (int l = 0; l < 4; ++l) {
+  for (int l = 0; l < NL; ++l) {
     const long long seg = ln[l].seg0 + j;
     const bool on = !warm && ln[l].active && j < ln[l].cnt;
     const long long pos = seg * p.step;
@@ -141,17 +160,18 @@ FC_HD void io_store(int t, const Regs &v, const OaParams &p, const Lane (&ln)[4]
   for (int m = 0; m < kPts; ++m) {
     const int i = t + 128 * m;
     const int s = slot16(m);
-    f2 yr = v.re[s], yi = v.im[s];
+    D yr = v.re[s], yi = v.im[s];
     if (add_tail && i < tail_len) {
-      f2 tr, ti;
+      D tr, ti;
       get(tail_prev, i, tr, ti);
       yr = add2(yr, tr);
       yi = add2(yi, ti);
     }
     if (i >= p.step) put(tail_next, i - p.step, yr, yi);
-    const float y[4] = {yr.x, yi.x, yr.y, yi.y};
+    S y[NL];
+    DataTraits<D>::unpack(yr, yi, y);
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
+    for (int l = 0; l < NL; ++l) {
       const long long o = obase[l] + i;
       if (i < limit[l] && o >= 0) ln[l].out[o] = y[l];
     }
@@ -159,16 +179,19 @@ FC_HD void io_store(int t, const Regs &v, const OaParams &p, const Lane (&ln)[4]
 }
 
 // ---- fast path: staged through shared memory ------------------------------------
-// staging buffers hold 4 lanes of `ls` floats each, ls = (3 + step + 3) & ~3 (oa_n2048_kernel.cuh)
+// staging buffers hold NL lanes of `ls` elements each, ls = (A - 1 + step + A - 1) & ~(A - 1) with
+// A = 16 / sizeof(S) elements per 16-byte unit (oa_n2048_kernel.cuh)
 
-FC_HD int align_shift(const void *ptr) { return (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ULL); }
+// elements between `ptr` and the 16-byte boundary below it
+FC_HD int align_shift(const float *ptr) { return (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ULL); }
+FC_HD int align_shift(const double *ptr) { return (int)((reinterpret_cast<unsigned long long>(ptr) >> 3) & 1ULL); }
 
 // Per-thread constants of the fast path (depend on t, K only).
 struct ThreadMasks {
   unsigned in_zero;   // bit m: t + 128 m >= step  (padding region: value is 0, no load)
   unsigned tail_add;  // bit m: t + 128 m <  K - 1 (incoming tail is added)
 };
-FC_HD ThreadMasks make_masks(int t, const OaParams &p) {
+template <typename S> FC_HD ThreadMasks make_masks(int t, const OaParamsT<S> &p) {
   ThreadMasks k;
   k.in_zero = 0;
   k.tail_add = 0;
@@ -182,50 +205,56 @@ FC_HD ThreadMasks make_masks(int t, const OaParams &p) {
 }
 
 // staged input -> registers.  `in` is the group's input staging buffer.
-FC_HD void fast_load(int t, Regs &v, const float *in, int ls, const int (&shift)[4], unsigned in_zero) {
-  const float *b0 = in + 0 * ls + shift[0] + t;
-  const float *b1 = in + 1 * ls + shift[1] + t;
-  const float *b2 = in + 2 * ls + shift[2] + t;
-  const float *b3 = in + 3 * ls + shift[3] + t;
+template <typename D, typename S>
+FC_HD void fast_load(int t, RegsT<D> &v, const S *in, int ls, const int (&shift)[4], unsigned in_zero) {
+  constexpr int NL = DataTraits<D>::NL;
+  const S *b[NL];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) b[l] = in + l * ls + shift[l] + t;
 #pragma unroll
   for (int m = 0; m < kPts; ++m) {
     // step >= 2048 - 409: only m >= 12 can fall into the padding region
     const bool z = (m >= 12) && ((in_zero >> m) & 1u);
-    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+    S x[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) x[l] = (S)0;
     if (!z) {
-      x0 = b0[128 * m];
-      x1 = b1[128 * m];
-      x2 = b2[128 * m];
-      x3 = b3[128 * m];
+#pragma unroll
+      for (int l = 0; l < NL; ++l) x[l] = b[l][128 * m];
     }
-    v.re[m] = make_f2(x0, x2);
-    v.im[m] = make_f2(x1, x3);
+    DataTraits<D>::pack(x, v.re[m], v.im[m]);
   }
 }
 
 // registers -> the four lanes' outputs (+ tail hand-over).  b_l points at y[t] of
 // lane l -- in a shared staging buffer or directly in global memory (one coalesced
 // 128-byte line per warp instruction); element y[t + 128 m] goes to b_l[128 m].
-FC_HD void fast_store_to(int t, const Regs &v, float *b0, float *b1, float *b2, float *b3, const ThreadMasks &k,
-                         const pt4 *tail_prev, pt4 *tail_next, bool add_tail, bool stage, int step);
+template <typename D, typename S>
+FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const ThreadMasks &k, const PtT<D> *tail_prev,
+                         PtT<D> *tail_next, bool add_tail, bool stage, int step);
 
 // registers -> staged output (+ tail hand-over).  `out` is the output staging buffer.
-FC_HD void fast_store(int t, const Regs &v, float *out, int ls, const int (&shift)[4], const ThreadMasks &k,
-                      const pt4 *tail_prev, pt4 *tail_next, bool add_tail, bool stage, int step) {
-  fast_store_to(t, v, out + 0 * ls + shift[0] + t, out + 1 * ls + shift[1] + t, out + 2 * ls + shift[2] + t,
-                out + 3 * ls + shift[3] + t, k, tail_prev, tail_next, add_tail, stage, step);
+template <typename D, typename S>
+FC_HD void fast_store(int t, const RegsT<D> &v, S *out, int ls, const int (&shift)[4], const ThreadMasks &k,
+                      const PtT<D> *tail_prev, PtT<D> *tail_next, bool add_tail, bool stage, int step) {
+  S *const b[4] = {out + 0 * ls + shift[0] + t, out + 1 * ls + shift[1] + t, out + 2 * ls + shift[2] + t,
+                   out + 3 * ls + shift[3] + t};
+  fast_store_to(t, v, b, k, tail_prev, tail_next, add_tail, stage, step);
 }
 
-FC_HD void fast_store_to(int t, const Regs &v, float *b0, float *b1, float *b2, float *b3, const ThreadMasks &k,
-                         const pt4 *tail_prev, pt4 *tail_next, bool add_tail, bool stage, int step) {
+// b[l] points at y[t] of lane l (entries l >= NL are ignored)
+template <typename D, typename S>
+FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const ThreadMasks &k, const PtT<D> *tail_prev,
+                         PtT<D> *tail_next, bool add_tail, bool stage, int step) {
+  constexpr int NL = DataTraits<D>::NL;
 #pragma unroll
   for (int m = 0; m < kPts; ++m) {
     const int i = t + 128 * m;
     const int s = slot16(m);
-    f2 yr = v.re[s], yi = v.im[s];
+    D yr = v.re[s], yi = v.im[s];
     if (m < 4) { // K - 1 <= 409 < 512
       if (add_tail && ((k.tail_add >> m) & 1u)) {
-        f2 tr, ti;
+        D tr, ti;
         get(tail_prev, i, tr, ti);
         yr = add2(yr, tr);
         yi = add2(yi, ti);
@@ -235,10 +264,10 @@ FC_HD void fast_store_to(int t, const Regs &v, float *b0, float *b1, float *b2, 
     if (in_tail) {
       put(tail_next, i - step, yr, yi);
     } else if (stage) {
-      b0[128 * m] = yr.x;
-      b1[128 * m] = yi.x;
-      b2[128 * m] = yr.y;
-      b3[128 * m] = yi.y;
+      S y[NL];
+      DataTraits<D>::unpack(yr, yi, y);
+#pragma unroll
+      for (int l = 0; l < NL; ++l) b[l][128 * m] = y[l];
     }
   }
 }
@@ -265,7 +294,7 @@ struct WorkIter {
     quad = j = jend = jfirst = 0;
   }
   // returns false when the slice is exhausted; `ln` is refreshed on a new quad
-  FC_HD bool next(const OaParams &p, Lane (&ln)[4], IterDesc &d) {
+  template <typename S> FC_HD bool next(const OaParamsT<S> &p, LaneT<S> (&ln)[4], IterDesc &d) {
     if (!in_visit) {
       if (w >= w1) return false;
       quad = w / p.segs_per_chunk;
@@ -289,81 +318,98 @@ struct WorkIter {
   }
 };
 
-struct SchedSlot {      // private scheduler state of one warp leader
+template <typename S> struct SchedSlotT { // private scheduler state of one warp leader
   WorkIter it;
-  Lane ln[4];
+  LaneT<S> ln[4];
   long long pad_;
 };
+using SchedSlot = SchedSlotT<float>;
 
 // tail buffers: two (ping-pong) arrays of tail_pts(K) points per group
 FC_HD int tail_pts(int klen) { return ((klen - 1) + 7) & ~7; }
 
-struct Packet {        // one iteration of one group, produced by thread 0
+template <typename S> struct PacketT { // one iteration of one group, one lane per warp leader
   int valid;           // 0: the slice is exhausted
   int warm;
   int first;           // no incoming tail
-  int in_fast[4];      // per lane; the quad takes the fast path when all four are set
-  int out_fast[4];
+  int in_fast[4];      // per lane; the quad takes the fast path when all lanes are set
+  int out_fast[4];     //   (slots >= NL of a two-lane quad are preset to 1)
   int in_shift[4];
   int out_shift[4];
   int in_bytes[4];     // bulk-load size per lane (fast path)
-  const float *in_src[4];
-  float *out_dst[4];
-  Lane ln[4];          // slow path only
+  const S *in_src[4];
+  S *out_dst[4];
+  LaneT<S> ln[4];      // slow path only
   long long j;
 };
+using Packet = PacketT<float>;
 
 struct GroupLayout {   // byte offsets inside a group's shared-memory block
   int lane_stride;     // floats per lane of the staging area (which aliases xb)
   int xb, tails, packets, sched, mbar, total;
 };
-// The input and output staging areas alias the exchange buffer: 4 lanes x
-// lane_stride floats <= 4 * 1832 * 4 B = 29312 B <= 32768 B.
-FC_HD GroupLayout group_layout(int klen) {
+// The input and output staging areas alias the exchange buffer: NL lanes x lane_stride
+// elements, e.g. 4 * 1832 * 4 B = 29312 B (float, K = 245) <= 32768 B.
+template <typename S = float> FC_HD GroupLayout group_layout(int klen) {
+  constexpr int A = 16 / (int)sizeof(S);
   GroupLayout g;
   const int step = kN - (klen - 1);
-  g.lane_stride = (3 + step + 3) & ~3;
+  g.lane_stride = (A - 1 + step + A - 1) & ~(A - 1);
   int off = 0;
-  g.xb = off;      off += kN * (int)sizeof(pt4);
-  g.tails = off;   off += 2 * tail_pts(klen) * (int)sizeof(pt4);
-  g.packets = off; off += 3 * (((int)sizeof(Packet) + 15) & ~15);
-  g.sched = off;   off += 4 * (int)sizeof(SchedSlot);
+  g.xb = off;      off += kN * 16;
+  g.tails = off;   off += 2 * tail_pts(klen) * 16;
+  g.packets = off; off += 3 * (((int)sizeof(PacketT<S>) + 15) & ~15);
+  g.sched = off;   off += 4 * (int)sizeof(SchedSlotT<S>);
   g.mbar = off;    off += 16;
   g.total = off;
   return g;
 }
-inline size_t smem_bytes(int groups, int klen) {
-  return (size_t)(2048 + 2048 + 128) * sizeof(cpair) + (size_t)groups * group_layout(klen).total;
+// tw1 rows kept in shared memory: all 16, or with twiddle recomputation only k2 = 1, 2, 4, 8
+// (row r of the compact table holds k2 = 2^r)
+FC_HD constexpr int tw1_rows(bool recomp) { return recomp ? 4 : 16; }
+template <typename S = float> inline size_t smem_bytes(int groups, int klen, bool recomp = false) {
+  return (size_t)(2048 + tw1_rows(recomp) * 128 + 128) * sizeof(CPairT<S>) + (size_t)groups * group_layout<S>(klen).total;
 }
 
 // One lane of the description of the next iteration.  The group's four warp
 // leaders each own one lane (`slot` holds that leader's private copy of the work
 // iterator and of the quad's lanes, so the leaders never wait for one another);
 // lane 0 also writes the fields shared by the quad.
-FC_HD void fill_packet_lane(const OaParams &p, SchedSlot &slot, Packet *pk, int lane) {
+template <typename S>
+FC_HD void fill_packet_lane(const OaParamsT<S> &p, SchedSlotT<S> &slot, PacketT<S> *pk, int lane) {
+  constexpr int NL = OaParamsT<S>::NL, A = 16 / (int)sizeof(S);
   IterDesc d;
   if (!slot.it.next(p, slot.ln, d)) {
     if (lane == 0) pk->valid = 0;
     return;
   }
-  const Lane ln = slot.ln[lane];
+  if (lane >= NL) { // no such stream in a two-lane quad: never blocks the fast path
+    pk->in_fast[lane] = pk->out_fast[lane] = 1;
+    pk->in_shift[lane] = pk->out_shift[lane] = pk->in_bytes[lane] = 0;
+    pk->in_src[lane] = p.in;
+    pk->out_dst[lane] = p.out;
+    pk->ln[lane] = slot.ln[lane];
+    return;
+  }
+  const LaneT<S> ln = slot.ln[lane];
   const long long seg = ln.seg0 + d.j;
   const bool on = ln.active && seg >= 0 && d.j < ln.cnt;
   const long long pos = seg * p.step;
   // input: a full segment whose 16-byte aligned span stays inside the tensor
-  const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
+  const S *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
   const bool full = on && (p.n - pos >= p.step);
-  const float *a = ln.in + (full ? pos : 0);
+  const S *a = ln.in + (full ? pos : 0);
   const int ish = align_shift(a);
-  const int bytes = ((ish + p.step) * 4 + 15) & ~15;
+  const int bytes = ((ish + p.step) * (int)sizeof(S) + 15) & ~15;
   pk->in_shift[lane] = ish;
   pk->in_src[lane] = a - ish;
   pk->in_bytes[lane] = bytes;
-  pk->in_fast[lane] = full && (a - ish + bytes / 4 <= tensor_end);
+  pk->in_fast[lane] = full && (a - ish + bytes / (int)sizeof(S) <= tensor_end);
+  (void)A;
   // output: an interior segment owns exactly y[0..step), all of it inside the row
   const long long o0 = pos - p.pad;
   const bool interior = on && seg < p.segs - 1 && o0 >= 0;
-  float *dst = ln.out + (interior ? o0 : 0);
+  S *dst = ln.out + (interior ? o0 : 0);
   pk->out_dst[lane] = dst;
   pk->out_shift[lane] = align_shift(dst);
   pk->out_fast[lane] = interior && !d.warm;

@@ -78,45 +78,43 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 
 // Thread 0: start the bulk copies of a fast-path packet into the staging area
 // (= the exchange buffer, which must be idle).
-__device__ __forceinline__ void issue_loads(const Packet *pk, float *stage, int lane_stride, uint32_t mbar) {
+template <typename S>
+__device__ __forceinline__ void issue_loads(const PacketT<S> *pk, S *stage, int lane_stride, uint32_t mbar) {
+  constexpr int NL = OaParamsT<S>::NL;
   if (pk->valid && all4(pk->in_fast)) {
     dev::fence_proxy_async(); // the area was last touched through the generic proxy
-    dev::mbar_expect_tx(mbar, (uint32_t)(pk->in_bytes[0] + pk->in_bytes[1] + pk->in_bytes[2] + pk->in_bytes[3]));
+    uint32_t bytes = 0;
 #pragma unroll
-    for (int l = 0; l < 4; ++l)
+    for (int l = 0; l < NL; ++l) bytes += (uint32_t)pk->in_bytes[l];
+    dev::mbar_expect_tx(mbar, bytes);
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
       dev::bulk_load(dev::smem_u32(stage + l * lane_stride), pk->in_src[l], (uint32_t)pk->in_bytes[l], mbar);
   }
 }
 
-// Thread 0: send the staged outputs of this iteration to global memory.
-__device__ __forceinline__ void flush_out(const Packet *pk, const float *stage, int lane_stride, int step) {
-#pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    const int d = pk->out_shift[l];
-    const FlushSplit f = flush_split(d, step);
-    float *dst = pk->out_dst[l];
-    const float *src = stage + l * lane_stride + d;
-    dev::bulk_store(dst + f.head, dev::smem_u32(src + f.head), (uint32_t)f.nb * 4u);
-    for (int i = 0; i < f.head; ++i) dst[i] = src[i];
-    for (int i = f.head + f.nb; i < step; ++i) dst[i] = src[i];
-  }
-  dev::bulk_commit();
-}
-
-template <int G, bool RECOMP>
-__global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_constant__ OaParams p) {
+// D = f2 (float32, four segments per group iteration) or double (float64, two).
+template <typename D, int G, bool RECOMP>
+__global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_constant__ OaParamsT<scalar_of_t<D>> p) {
+  using S = scalar_of_t<D>;
+  using cpair = CPairT<S>;
+  using Packet = PacketT<S>;
+  using SchedSlot = SchedSlotT<S>;
+  using Lane = LaneT<S>;
+  using Regs = RegsT<D>;
+  using pt = PtT<D>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cpair *hs = reinterpret_cast<cpair *>(smem_raw);
-  cpair *tw1 = hs + 2048;
-  cpair *tw2 = tw1 + 2048;
+  cpair *tw1 = hs + 2048;                         // RECOMP: rows k2 = 1, 2, 4, 8 only
+  cpair *tw2 = tw1 + tw1_rows(RECOMP) * 128;
   unsigned char *grp0 = reinterpret_cast<unsigned char *>(tw2 + 128);
 
-  const GroupLayout L = group_layout(p.klen);
+  const GroupLayout L = group_layout<S>(p.klen);
   const int g = threadIdx.x >> 7, t = threadIdx.x & 127;
   unsigned char *base = grp0 + (size_t)g * L.total;
-  pt4 *xb = reinterpret_cast<pt4 *>(base + L.xb);
-  float *stage = reinterpret_cast<float *>(base + L.xb); // input staging aliases xb
-  pt4 *tails = reinterpret_cast<pt4 *>(base + L.tails);
+  pt *xb = reinterpret_cast<pt *>(base + L.xb);
+  S *stage = reinterpret_cast<S *>(base + L.xb); // input staging aliases xb
+  pt *tails = reinterpret_cast<pt *>(base + L.tails);
   const int pk_stride = ((int)sizeof(Packet) + 15) & ~15;
   // ring of three packets, addressed arithmetically so that every access stays a
   // shared-memory access (an array of pointers would live in local memory)
@@ -126,10 +124,9 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   const int tpts = tail_pts(p.klen);
   const int LS = L.lane_stride;
 
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
-    tw1[i] = p.tw1[i];
-    hs[i] = p.hs[i];
-  }
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) hs[i] = p.hs[i];
+  for (int i = threadIdx.x; i < tw1_rows(RECOMP) * 128; i += blockDim.x)
+    tw1[i] = RECOMP ? p.tw1[(128 << (i >> 7)) + (i & 127)] : p.tw1[i];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) tw2[i] = p.tw2[i];
 
   const long long slot = (long long)blockIdx.x * G + g;
@@ -175,7 +172,7 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_load(t, v, p, ln, cur->j);
     }
-    phase0_compute<RECOMP>(t, v, tw1);
+    phase0_compute<RECOMP, RECOMP>(t, v, tw1);
     dev::bar_sync(bar_id); // every thread has read its inputs out of the staging area
     phase0_put(t, v, xb);
     dev::bar_sync(bar_id);
@@ -185,17 +182,17 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     dev::bar_sync(bar_id);
     phase3<RECOMP>(t, v, xb, tw2);
     dev::bar_sync(bar_id);
-    phase4_read<RECOMP>(t, v, xb, tw1);
+    phase4_read<RECOMP, RECOMP>(t, v, xb, tw1);
     dev::bar_sync(bar_id); // every thread has read its points: the exchange buffer is idle
     const int ni = ci == 2 ? 0 : ci + 1, nni = ni == 2 ? 0 : ni + 1;
     // request the next inputs now: they land while this iteration's last DFT and stores run
     if (t == 0) issue_loads(PK(ni), stage, LS, mbar);
     phase4_compute(v);
-    pt4 *tail_prev = tails + (parity ^ 1) * tpts, *tail_next = tails + parity * tpts;
+    pt *tail_prev = tails + (parity ^ 1) * tpts, *tail_next = tails + parity * tpts;
     if (out_fast || warm) {
-      // 4-byte coalesced stores straight from registers (one 128-byte line per warp instruction)
-      fast_store_to(t, v, cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t, cur->out_dst[3] + t,
-                    masks, tail_prev, tail_next, add_tail, out_fast, p.step);
+      // coalesced element stores straight from registers (full 128-byte lines per warp instruction)
+      S *const dst[4] = {cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t, cur->out_dst[3] + t};
+      fast_store_to(t, v, dst, masks, tail_prev, tail_next, add_tail, out_fast, p.step);
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_store(t, v, p, ln, cur->j, tail_prev, tail_next, add_tail, warm);

@@ -99,6 +99,49 @@ FC_HD f2 fmas2(f2 a, float s, f2 c) { return make_f2(a.x * s + c.x, a.y * s + c.
 FC_HD f2 fmss2(f2 a, float s, f2 c) { return make_f2(a.x * s - c.x, a.y * s - c.y); }
 #endif
 
+// The same vocabulary for a plain double: the N = 2048 overlap-add engine is a template over
+// its data type (f2: two float transforms per thread; double: one double transform).
+FC_HD double add2(double a, double b) { return a + b; }
+FC_HD double sub2(double a, double b) { return a - b; }
+FC_HD double muls2(double a, double s) { return a * s; }
+FC_HD double fmas2(double a, double s, double c) { return a * s + c; }
+FC_HD double fmss2(double a, double s, double c) { return a * s - c; }
+FC_HD void cmul2(double &re, double &im, double wr, double wi) {
+  const double nre = re * wr - im * wi;
+  im = re * wi + im * wr;
+  re = nre;
+}
+
+// Data-type traits of the overlap-add engines: scalar type and how many real streams ("lanes")
+// ride in one complex value -- f2: lane 0 = re half A, 1 = im half A, 2 = re half B, 3 = im half B;
+// double: lane 0 = re, lane 1 = im.
+template <typename D> struct DataTraits;
+template <> struct DataTraits<f2> {
+  using S = float;
+  static constexpr int NL = 4;
+  static FC_HD void pack(const float (&x)[4], f2 &re, f2 &im) {
+    re = make_f2(x[0], x[2]);
+    im = make_f2(x[1], x[3]);
+  }
+  static FC_HD void unpack(f2 re, f2 im, float (&y)[4]) {
+    y[0] = re.x; y[1] = im.x; y[2] = re.y; y[3] = im.y;
+  }
+};
+template <> struct DataTraits<double> {
+  using S = double;
+  static constexpr int NL = 2;
+  static FC_HD void pack(const double (&x)[2], double &re, double &im) {
+    re = x[0];
+    im = x[1];
+  }
+  static FC_HD void unpack(double re, double im, double (&y)[2]) {
+    y[0] = re; y[1] = im;
+  }
+};
+template <typename S> struct DataOf;            // scalar type -> data type of the engine
+template <> struct DataOf<float> { using D = f2; };
+template <> struct DataOf<double> { using D = double; };
+
 // (re + i im) *= (wr + i wi), both lanes, scalar twiddle.
 FC_HD void cmul2(f2 &re, f2 &im, float wr, float wi) {
   const f2 t = muls2(im, -wi);     // the negation is on the scalar (free for constants)

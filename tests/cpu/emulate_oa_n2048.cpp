@@ -4,9 +4,10 @@
 // with the barriers replaced by loop boundaries and the bulk (TMA) copies by
 // memcpy.  Checked against direct convolution in double.
 //
-// usage: emulate_oa_n2048 batch n K mode(0 full,1 same) chunks n_slots [misalign]
-//   misalign: shifts the input/output base pointers by that many floats (0..3)
+// usage: emulate_oa_n2048 batch n K mode(0 full,1 same) chunks n_slots [misalign [recomp [f64]]]
+//   misalign: shifts the input/output base pointers by that many elements (0..3 float, 0..1 double)
 //   recomp:   1 (default) = twiddles k = 3, 5..7, 9..15 formed as products in registers
+//   f64:      1 = the float64 instantiation (two streams per group); its error bound is 1e-13
 #include "../../fftconv_b200/csrc/oa_n2048_group.cuh"
 #include "../../fftconv_b200/csrc/oa_n2048_tables.h"
 
@@ -22,29 +23,33 @@ using namespace fc::n2048;
 
 static long long g_fast_in = 0, g_fast_out = 0, g_iters = 0;
 
-struct HostGroup {
+template <typename D> struct HostGroup {
+  using S = scalar_of_t<D>;
+  using OaParams = OaParamsT<S>;
+  using Packet = PacketT<S>;
+  using SchedSlot = SchedSlotT<S>;
+  using pt = PtT<D>;
+  static constexpr int NL = DataTraits<D>::NL;
   const OaParams &p;
   GroupLayout L;
-  std::vector<pt4> xb, tails;
-  float *stage; // aliases xb, exactly as in the kernel
-  std::vector<Regs> regs;
-  Packet pk[2];
+  std::vector<pt> xb, tails;
+  S *stage; // aliases xb, exactly as in the kernel
+  std::vector<RegsT<D>> regs;
   int tpts;
 
   explicit HostGroup(const OaParams &pp)
-      : p(pp), L(group_layout(pp.klen)), xb(kN), tails(2 * tail_pts(pp.klen)), regs(kThreads),
+      : p(pp), L(group_layout<S>(pp.klen)), xb(kN), tails(2 * tail_pts(pp.klen)), regs(kThreads),
         tpts(tail_pts(pp.klen)) {
-    std::memset(pk, 0, sizeof(pk));
-    stage = reinterpret_cast<float *>(xb.data());
-    if (4 * L.lane_stride * 4 > kN * (int)sizeof(pt4)) { std::printf("staging does not fit xb\n"); std::exit(4); }
+    stage = reinterpret_cast<S *>(xb.data());
+    if (NL * L.lane_stride * (int)sizeof(S) > kN * 16) { std::printf("staging does not fit xb\n"); std::exit(4); }
   }
 
   void poison() { // whatever was in the exchange buffer must never be consumed as data
-    for (int i = 0; i < kN * 4; ++i) stage[i] = NAN;
+    for (int i = 0; i < kN * 16 / (int)sizeof(S); ++i) stage[i] = (S)NAN;
   }
   void issue(const Packet *q) { // the bulk (TMA) loads of a fast-path packet
     if (q->valid && all4(q->in_fast))
-      for (int l = 0; l < 4; ++l) std::memcpy(stage + l * L.lane_stride, q->in_src[l], q->in_bytes[l]);
+      for (int l = 0; l < NL; ++l) std::memcpy(stage + l * L.lane_stride, q->in_src[l], q->in_bytes[l]);
   }
 
   template <bool RECOMP> void run(long long w0, long long w1) {
@@ -89,12 +94,12 @@ struct HostGroup {
       poison();
       issue(&ring[ni]);
 
-      pt4 *tail_prev = tails.data() + (parity ^ 1) * tpts, *tail_next = tails.data() + parity * tpts;
+      pt *tail_prev = tails.data() + (parity ^ 1) * tpts, *tail_next = tails.data() + parity * tpts;
       for (int t = 0; t < kThreads; ++t) {
         phase4_compute(regs[t]);
         if (out_fast || warm) {
-          fast_store_to(t, regs[t], cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t,
-                        cur->out_dst[3] + t, masks[t], tail_prev, tail_next, add_tail, out_fast, p.step);
+          S *const dst[4] = {cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t, cur->out_dst[3] + t};
+          fast_store_to(t, regs[t], dst, masks[t], tail_prev, tail_next, add_tail, out_fast, p.step);
         } else {
           io_store(t, regs[t], p, cur->ln, cur->j, tail_prev, tail_next, add_tail, warm);
         }
@@ -107,20 +112,17 @@ struct HostGroup {
   }
 };
 
-int main(int argc, char **argv) {
-  if (argc < 7) { std::fprintf(stderr, "usage\n"); return 2; }
-  const long long batch = atoll(argv[1]), n = atoll(argv[2]);
-  const int K = atoi(argv[3]), mode = atoi(argv[4]);
-  const long long chunks = atoll(argv[5]), n_slots = atoll(argv[6]);
-  const int mis = argc > 7 ? atoi(argv[7]) : 0;
-  const int recomp = argc > 8 ? atoi(argv[8]) : 1; // twiddle recomputation (the kernel's default)
-
+template <typename D>
+int run_case(long long batch, long long n, int K, int mode, long long chunks, long long n_slots, int mis, int recomp,
+             double bound) {
+  using S = scalar_of_t<D>;
+  using cpair = CPairT<S>;
   std::mt19937 rng(1234);
-  std::normal_distribution<float> nd(0.f, 1.f);
+  std::normal_distribution<S> nd((S)0, (S)1);
   const long long out_len = mode ? n : n + K - 1;
   // 16-byte aligned backing stores, then an optional misalignment of the views
-  std::vector<float> a_store(batch * n + 8), out_store(batch * out_len + 8, NAN), k(K);
-  float *a = a_store.data(), *out = out_store.data();
+  std::vector<S> a_store(batch * n + 8), out_store(batch * out_len + 8, (S)NAN), k(K);
+  S *a = a_store.data(), *out = out_store.data();
   while (reinterpret_cast<unsigned long long>(a) & 15ULL) ++a;
   while (reinterpret_cast<unsigned long long>(out) & 15ULL) ++out;
   a += mis;
@@ -128,7 +130,7 @@ int main(int argc, char **argv) {
   for (long long i = 0; i < batch * n; ++i) a[i] = nd(rng);
   for (auto &v : k) v = nd(rng);
 
-  OaParams p{};
+  OaParamsT<S> p{};
   std::vector<cpair> tw1(2048), tw2(128), hs(2048);
   fill_tw1(tw1.data());
   fill_tw2(tw2.data());
@@ -138,9 +140,9 @@ int main(int argc, char **argv) {
 
   for (long long s = 0; s < n_slots; ++s) {
     const long long w0 = p.total_work * s / n_slots, w1 = p.total_work * (s + 1) / n_slots;
-    HostGroup grp(p);
-    if (recomp) grp.run<true>(w0, w1);
-    else grp.run<false>(w0, w1);
+    HostGroup<D> grp(p);
+    if (recomp) grp.template run<true>(w0, w1);
+    else grp.template run<false>(w0, w1);
   }
 
   double num = 0, den = 0;
@@ -158,5 +160,17 @@ int main(int argc, char **argv) {
     }
   const double err = std::sqrt(num / (den > 0 ? den : 1));
   std::printf("%.3e iters %lld fast_in %lld fast_out %lld\n", err, g_iters, g_fast_in, g_fast_out);
-  return (err < 2e-6 && std::isfinite(err)) ? 0 : 1;
+  return (err < bound && std::isfinite(err)) ? 0 : 1;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 7) { std::fprintf(stderr, "usage\n"); return 2; }
+  const long long batch = atoll(argv[1]), n = atoll(argv[2]);
+  const int K = atoi(argv[3]), mode = atoi(argv[4]);
+  const long long chunks = atoll(argv[5]), n_slots = atoll(argv[6]);
+  const int mis = argc > 7 ? atoi(argv[7]) : 0;
+  const int recomp = argc > 8 ? atoi(argv[8]) : 1; // twiddle recomputation (the kernel's default)
+  const int f64 = argc > 9 ? atoi(argv[9]) : 0;
+  if (f64) return run_case<double>(batch, n, K, mode, chunks, n_slots, mis, recomp, 1e-13);
+  return run_case<f2>(batch, n, K, mode, chunks, n_slots, mis, recomp, 2e-6);
 }

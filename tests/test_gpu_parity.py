@@ -670,3 +670,53 @@ def test_kernels_longer_than_a_segment_fft(cuda, dt, n, klen):
         torch.cuda.synchronize()
         assert np.array_equal(tgot.cpu().numpy(), got)
     assert O.rel_l2(fc.convolve(a[0], k, "full"), O.conv_exact(a[0], k, "full")) < tol
+
+
+N2048_F64_CASES = [
+    # batch, n, K
+    (4, 65536, 245), (5, 10000, 245), (1, 100000, 245), (3, 5000, 300), (2, 1804, 245), (1, 300, 245),
+    (6, 7000, 410), (2, 4000, 221), (7, 1805, 245), (9, 3607, 256), (33, 40000, 245), (1024, 16384, 165),
+]
+
+
+@pytest.mark.parametrize("batch,n,klen", N2048_F64_CASES)
+@pytest.mark.parametrize("mode", ["full", "same"])
+def test_n2048_kernel_float64(cuda, batch, n, klen, mode, monkeypatch):
+    """oa_n2048_kernel<double, ...>: the same engine with one float64 transform per thread (two
+    streams per group): ragged last segments, odd batches, rows cut into chunks, rows at an
+    8-byte offset; config 3's shape (1024 x 16384, K = 165) rides on it through the throughput
+    rule.  Dense check on a subset of rows for the large case; bit-equality with the register-
+    blocked engine is not expected, 1e-12 relative L2 with the definition is."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(batch * 1000 + n + klen)
+    a = rng.standard_normal((batch, n))
+    k = rng.standard_normal(klen) / np.sqrt(klen)
+    ta, tk = _t(a, cuda), _t(k, cuda)
+    before = fc.launch_count()
+    y = fc.oaconvolve(ta, tk, mode) if batch < 1000 else fc.convolve(ta, tk, mode)
+    torch.cuda.synchronize()
+    assert fc.launch_count() - before == 2          # spectrum + one fused kernel
+    pick = np.arange(batch) if batch < 64 else np.unique(np.r_[np.arange(0, batch, 97), batch - 3, batch - 2, batch - 1])
+    _check(y[pick].cpu().numpy(), a[pick], k, mode, (batch, n, klen, mode))
+    assert torch.isfinite(y).all()
+    # the register-blocked engine on the same input
+    monkeypatch.setenv("FFTCONV_CUDA_NO_N2048_F64", "1")
+    y2 = fc.oaconvolve(ta, tk, mode)
+    torch.cuda.synchronize()
+    assert O.rel_l2(y[pick].cpu().numpy(), y2[pick].cpu().numpy()) < 1e-13
+    monkeypatch.delenv("FFTCONV_CUDA_NO_N2048_F64")
+    # misaligned rows: 8 bytes off a 16-byte boundary, odd stride
+    if batch <= 9:
+        store = torch.zeros(batch * (n + 1) + 1, dtype=torch.float64, device=cuda)
+        view = store[1:].view(batch, n + 1)[:, :n]
+        view.copy_(ta)
+        out_len = y.shape[-1]
+        ostore = torch.full((batch * (out_len + 3) + 1,), float("nan"), dtype=torch.float64, device=cuda)
+        oview = ostore[1:].view(batch, out_len + 3)[:, :out_len]
+        fc.oaconvolve_(view, tk, oview, mode)
+        torch.cuda.synchronize()
+        assert torch.equal(oview, y)
+        assert torch.isnan(ostore[1:].view(batch, out_len + 3)[:, out_len:]).all()   # nothing written past a row
