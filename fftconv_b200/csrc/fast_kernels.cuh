@@ -236,28 +236,29 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 //   * the NEXT unit's rows are requested as soon as the last inverse pass has read the buffer,
 //     so they land while this unit's envelope is computed and stored.
 // Requires 16-byte aligned rows (base and stride); other layouts take hilbert_fast_kernel.
-template <int LOG2N, int FPC, bool PLAIN = true>
-__global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, 1)
+template <int LOG2N, int FPC, bool PLAIN = true, typename D = f2, int CTAS_PER_SM = 1>
+__global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, CTAS_PER_SM)
     hilbert_pk_persistent_kernel(const generic::HilbertArgs<float> p) {
   using P = Plan<LOG2N>;
   namespace dev = n2048::dev;
   constexpr int N = P::N;
+  constexpr int NL = Lanes<D>::N; // rows per FFT: 4 (packed) or 2 (D = float: two CTAs per SM, see the launcher)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int f = threadIdx.x / P::THREADS, tid = threadIdx.x % P::THREADS;
-  cx<f2> *buf = reinterpret_cast<cx<f2> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
-  const float *stage = reinterpret_cast<const float *>(buf); // [4][N], aliases the exchange buffer
-  const uint32_t mbar = dev::smem_u32(smem_raw + (size_t)FPC * P::SMEM_ELEMS * sizeof(cx<f2>));
+  cx<D> *buf = reinterpret_cast<cx<D> *>(smem_raw) + (size_t)f * P::SMEM_ELEMS;
+  const float *stage = reinterpret_cast<const float *>(buf); // [NL][N], aliases the exchange buffer
+  const uint32_t mbar = dev::smem_u32(smem_raw + (size_t)FPC * P::SMEM_ELEMS * sizeof(cx<D>));
   const cx<float> *W = reinterpret_cast<const cx<float> *>(p.W);
-  const long long units = (p.batch + 4 * FPC - 1) / (4 * FPC);
+  const long long units = (p.batch + NL * FPC - 1) / (NL * FPC);
 
   auto request = [&](long long unit) { // thread 0: bulk loads of every valid row of `unit`
-    const long long r0 = unit * 4 * FPC;
+    const long long r0 = unit * NL * FPC;
     long long rows = p.batch - r0;
-    if (rows > 4 * FPC) rows = 4 * FPC;
+    if (rows > NL * FPC) rows = NL * FPC;
     dev::fence_proxy_async();
     dev::mbar_expect_tx(mbar, (uint32_t)(rows * N * 4));
     for (int r = 0; r < (int)rows; ++r) {
-      unsigned char *dst = smem_raw + (size_t)(r >> 2) * P::SMEM_ELEMS * sizeof(cx<f2>) + (size_t)(r & 3) * N * 4;
+      unsigned char *dst = smem_raw + (size_t)(r / NL) * P::SMEM_ELEMS * sizeof(cx<D>) + (size_t)(r % NL) * N * 4;
       dev::bulk_load(dev::smem_u32(dst), p.in + (r0 + r) * p.in_stride, (uint32_t)(N * 4), mbar);
     }
   };
@@ -272,12 +273,12 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, 1)
   CtaSync sync;
   const HilbertSpectrum<float> G{(float)(1.0 / (double)N)};
   for (; unit < units; unit += gridDim.x) {
-    bool has[4];
-    const float *x[4];
-    float *e[4];
+    bool has[NL];
+    const float *x[NL];
+    float *e[NL];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const long long r = (unit * FPC + f) * 4 + l;
+    for (int l = 0; l < NL; ++l) {
+      const long long r = (unit * FPC + f) * NL + l;
       has[l] = r < p.batch;
       x[l] = p.in + (has[l] ? r : 0) * p.in_stride;
       e[l] = p.out + (has[l] ? r : 0) * p.out_stride;
@@ -285,47 +286,49 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, 1)
     while (!dev::mbar_try_wait(mbar, phase)) {
     }
     phase ^= 1;
-    cx<f2> v[16];
+    cx<D> v[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
       const int i = pass0_index<LOG2N>(tid, s);
-      float a[4];
+      float a[NL];
 #pragma unroll
-      for (int l = 0; l < 4; ++l) a[l] = has[l] ? stage[l * N + i] : 0.0f; // rows past the batch were not loaded
-      v[s] = Lanes<f2>::make(a);
+      for (int l = 0; l < NL; ++l) a[l] = has[l] ? stage[l * N + i] : 0.0f; // rows past the batch were not loaded
+      v[s] = Lanes<D>::make(a);
     }
     __syncthreads(); // the staged rows have been read; pass 0 overwrites them
     conv_core_with<LOG2N>(tid, v, buf, W, G, sync);
     __syncthreads(); // the last inverse pass has read the buffer: it is idle until the next unit
     if (threadIdx.x == 0 && unit + gridDim.x < units) request(unit + gridDim.x);
-    const bool all = has[0] && has[1] && has[2] && has[3];
+    bool all = true;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) all = all && has[l];
     if (all) {
 #pragma unroll
       for (int s0 = 0; s0 < 16; s0 += 4) {
-        float a[4][4];
+        float a[4][NL];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           const int i = pass0_index<LOG2N>(tid, s0 + s);
 #pragma unroll
-          for (int l = 0; l < 4; ++l) a[s][l] = __ldg(x[l] + i);
+          for (int l = 0; l < NL; ++l) a[s][l] = __ldg(x[l] + i);
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           const int i = pass0_index<LOG2N>(tid, s0 + s);
-          float h[4];
-          Lanes<f2>::split(v[s0 + s], h);
+          float h[NL];
+          Lanes<D>::split(v[s0 + s], h);
 #pragma unroll
-          for (int l = 0; l < 4; ++l) env_store<PLAIN>(p.epi, e[l], i, fast_sqrt(a[s][l] * a[s][l] + h[l] * h[l]));
+          for (int l = 0; l < NL; ++l) env_store<PLAIN>(p.epi, e[l], i, fast_sqrt(a[s][l] * a[s][l] + h[l] * h[l]));
         }
       }
     } else {
 #pragma unroll
       for (int s = 0; s < 16; ++s) {
         const int i = pass0_index<LOG2N>(tid, s);
-        float h[4];
-        Lanes<f2>::split(v[s], h);
+        float h[NL];
+        Lanes<D>::split(v[s], h);
 #pragma unroll
-        for (int l = 0; l < 4; ++l)
+        for (int l = 0; l < NL; ++l)
           if (has[l]) {
             const float a = __ldg(x[l] + i);
             env_store<PLAIN>(p.epi, e[l], i, fast_sqrt(a * a + h[l] * h[l]));

@@ -246,11 +246,17 @@ void host_fft_ld(std::vector<long double> &re, std::vector<long double> &im) {
     }
   }
   const long double pi = 3.14159265358979323846264338327950288L;
+  std::vector<long double> cr(n / 2 + 1), ci(n / 2 + 1); // exp(-2 pi i j / n), evaluated once
+  for (size_t j = 0; j < n / 2; ++j) {
+    const long double a = -2.0L * pi * (long double)j / (long double)n;
+    cr[j] = cosl(a);
+    ci[j] = sinl(a);
+  }
   for (size_t len = 2; len <= n; len <<= 1) {
+    const size_t stride = n / len;
     for (size_t i = 0; i < n; i += len)
       for (size_t k = 0; k < len / 2; ++k) {
-        const long double a = -2.0L * pi * (long double)k / (long double)len;
-        const long double wr = cosl(a), wi = sinl(a);
+        const long double wr = cr[k * stride], wi = ci[k * stride];
         const size_t u = i + k, v = i + k + len / 2;
         const long double tr = re[v] * wr - im[v] * wi, ti = re[v] * wi + im[v] * wr;
         re[v] = re[u] - tr;
@@ -261,7 +267,7 @@ void host_fft_ld(std::vector<long double> &re, std::vector<long double> &im) {
   }
 }
 
-template <typename T> int get_bluestein(DeviceCtx &c, size_t n, BluesteinTables **out) {
+template <typename T> int get_bluestein(DeviceCtx &c, size_t n, BluesteinTables **out, bool long_layout = false) {
   auto key = std::make_pair(n, dtype_id<T>());
   auto it = c.bluestein.find(key);
   if (it == c.bluestein.end()) {
@@ -287,8 +293,14 @@ template <typename T> int get_bluestein(DeviceCtx &c, size_t n, BluesteinTables 
     }
     host_fft_ld(br, bi);
     std::vector<cx<T>> B(M);
+    const size_t nsub = M / 16;
+    const int l2s = ilog2(M) - 4;
     for (size_t pos = 0; pos < M; ++pos) {
-      const size_t k = fc::generic::dif_freq_of_pos((unsigned)pos, (unsigned)M);
+      // long layout (long_fft_kernels.cuh): entry (s, idx_sub) holds frequency s + 16 freq_sub(idx_sub)
+      const size_t k = long_layout
+                           ? pos / nsub + 16 * (size_t)fc::fast::freq_of_pos(
+                                                   fc::fast::pos_of_table_index((unsigned)(pos % nsub), l2s), l2s)
+                           : fc::generic::dif_freq_of_pos((unsigned)pos, (unsigned)M);
       B[pos].x = (T)(br[k] / (long double)M);
       B[pos].y = (T)(bi[k] / (long double)M);
     }
@@ -499,6 +511,20 @@ int launch_hilbert_fast(DeviceCtx &c, cudaStream_t st, const fc::generic::Hilber
       constexpr int FPC = packed_fpc(LOG2N);
       const size_t smem = packed_smem(LOG2N, 0);
       const bool aligned = (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (p.in_stride & 3) == 0;
+      // experiment (FFTCONV_CUDA_HILBERT_2CTA=1, 8192-point lines): two rows per FFT in plain float and
+      // TWO independent CTAs per SM, so that one CTA's shared-memory phases overlap the other's arithmetic
+      if constexpr (LOG2N == 13) {
+        if (aligned && p.epi.plain && env_int("FFTCONV_CUDA_HILBERT_2CTA", 0)) {
+          auto pk2 = fc::fast::hilbert_pk_persistent_kernel<LOG2N, 1, true, float, 2>;
+          const size_t smem2 = fc::fast::Plan<LOG2N>::SMEM_ELEMS * sizeof(cx<float>) + 16;
+          if (int r = ensure_smem(c, pk2, smem2)) return r;
+          const long long units = (p.batch + 1) / 2;
+          pk2<<<(unsigned)std::min<long long>(units, 2LL * c.sm_count), fc::fast::Plan<LOG2N>::THREADS, smem2, st>>>(p);
+          CU_TRY(cudaGetLastError());
+          ++g_launches;
+          return 0;
+        }
+      }
       if (aligned && !env_int("FFTCONV_CUDA_NO_PERSISTENT_HILBERT", 0)) {
         auto pk = p.epi.plain ? fc::fast::hilbert_pk_persistent_kernel<LOG2N, FPC, true>
                               : fc::fast::hilbert_pk_persistent_kernel<LOG2N, FPC, false>;
@@ -747,7 +773,8 @@ int launch_inner(DeviceCtx &c, cudaStream_t st, cx<T> *scratch, long long n_subs
 // Hbig: spectrum table of N_big entries in LAYOUT_LONG order (1/N_big folded in)
 template <typename T>
 int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride, T *out,
-                size_t out_len, size_t out_stride, int pad, size_t Nbig, const cx<T> *Hbig, bool hilbert) {
+                size_t out_len, size_t out_stride, int pad, size_t Nbig, const cx<T> *Hbig, bool hilbert,
+                const cx<T> *chirp = nullptr /* chirp-z Hilbert: Hbig is the chirp filter's spectrum */) {
   const size_t nsub = Nbig / 16;
   const int l2s = ilog2(nsub);
   Tables *tbig = nullptr, *tsub = nullptr;
@@ -771,9 +798,11 @@ int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t 
   const size_t pairs_total = (batch + 1) / 2;
   const size_t pair_bytes = Nbig * sizeof(cx<T>);
   const size_t budget = (size_t)env_int("FFTCONV_CUDA_SCRATCH_MB", 512) << 20;
-  size_t pairs_per = std::max<size_t>(1, std::min<size_t>(pairs_total, budget / pair_bytes));
+  const size_t bufs = chirp ? 2 : 1; // chirp-z keeps the sequence between its two convolutions
+  size_t pairs_per = std::max<size_t>(1, std::min<size_t>(pairs_total, budget / (bufs * pair_bytes)));
   pairs_per = std::min<size_t>(pairs_per, 65535);
-  if (int r = grow(&c.scratch, &c.scratch_bytes, pairs_per * pair_bytes)) return r;
+  if (c.scratch_bytes < bufs * pairs_per * pair_bytes) CU_TRY(cudaDeviceSynchronize()); // other streams may still use it
+  if (int r = grow(&c.scratch, &c.scratch_bytes, bufs * pairs_per * pair_bytes)) return r;
   fc::longfft::LongArgs<T> la{};
   la.in = a;
   la.out = out;
@@ -788,23 +817,29 @@ int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t 
   la.TWbig = reinterpret_cast<const fc::fast::cx<T> *>(tbig->TWbig);
   la.hilbert = hilbert ? 1 : 0;
   la.epi = current_epilogue<T>(n);
+  la.bluestein = 0;
+  la.chirp = reinterpret_cast<const fc::fast::cx<T> *>(chirp);
+  la.cbuf = reinterpret_cast<fc::fast::cx<T> *>(c.scratch) + pairs_per * Nbig;
   const int threads = 256;
   for (size_t p0 = 0; p0 < pairs_total; p0 += pairs_per) {
     const size_t np = std::min(pairs_per, pairs_total - p0);
     la.pair0 = (long long)p0;
     la.pairs = (long long)np;
     const dim3 grid((unsigned)((nsub + threads - 1) / threads), (unsigned)np);
-    fc::longfft::outer_fwd_kernel<T><<<grid, threads, 0, st>>>(la);
-    CU_TRY(cudaGetLastError());
-    ++g_launches;
     auto inner = [&]() -> int {
       FAST_SWITCH(launch_inner, l2s, c, st, static_cast<cx<T> *>(c.scratch), (long long)np * 16,
                   static_cast<const cx<T> *>(tsub->TWfast), Hbig)
     };
-    if (int r = inner()) return r;
-    fc::longfft::outer_inv_kernel<T><<<grid, threads, 0, st>>>(la);
-    CU_TRY(cudaGetLastError());
-    ++g_launches;
+    for (int pass = 0; pass < (chirp ? 2 : 1); ++pass) {
+      la.bluestein = chirp ? pass + 1 : 0;
+      fc::longfft::outer_fwd_kernel<T><<<grid, threads, 0, st>>>(la);
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+      if (int r = inner()) return r;
+      fc::longfft::outer_inv_kernel<T><<<grid, threads, 0, st>>>(la);
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+    }
   }
   return 0;
 }
@@ -923,10 +958,17 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
     size_t M = 1;
     while (M < 2 * n - 1) M *= 2;
     const size_t smem_b = M * sizeof(cx<T>);
-    if (smem_b > c.smem_optin)
-      return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
-                                                   " needs a chirp-z FFT of " + std::to_string(M) +
-                                                   " points, beyond the single-CTA shared-memory FFT");
+    if (smem_b > c.smem_optin) {
+      // the chirp filter's two convolutions as split FFTs of M = 16 N_sub points through global scratch
+      if (!long_ok<T>(c, M))
+        return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
+                                                     " needs a chirp-z FFT of " + std::to_string(M) +
+                                                     " points, beyond the split (16 x 16384) FFT");
+      BluesteinTables *btl = nullptr;
+      if (int r = get_bluestein<T>(c, n, &btl, true)) return r;
+      return long_device<T>(c, st, x, batch, n, x_stride, env, env_out_len(n), env_stride, 0, M,
+                            static_cast<const cx<T> *>(btl->B), true, static_cast<const cx<T> *>(btl->chirp));
+    }
     BluesteinTables *bt = nullptr;
     if (int r = get_bluestein<T>(c, n, &bt)) return r;
     Tables *tabm = nullptr;
@@ -1018,10 +1060,27 @@ int run_host(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_s
   const size_t target = (size_t)env_int("FFTCONV_CUDA_HOST_BLOCK_MB", 32) << 20;
   size_t rows_per_block = std::max<size_t>(1, target / std::max<size_t>(1, row_bytes));
   rows_per_block = std::min(rows_per_block, batch);
-  const size_t nblocks = (batch + rows_per_block - 1) / rows_per_block;
-  for (size_t b = 0; b < nblocks; ++b) {
+  // Block schedule: full blocks in the middle, blocks of 1/8, 1/4, 1/2 of that at both ends -- the
+  // first upload and the last download are the only copies nothing else overlaps with.
+  std::vector<size_t> blocks;
+  {
+    std::vector<size_t> ramp;
+    if (rows_per_block >= 8 && batch >= 6 * rows_per_block && !env_int("FFTCONV_CUDA_HOST_NO_RAMP", 0))
+      for (size_t r = rows_per_block / 8; r < rows_per_block; r *= 2) ramp.push_back(r);
+    size_t ramp_rows = 0;
+    for (size_t r : ramp) ramp_rows += r;
+    blocks = ramp;
+    for (size_t left = batch - 2 * ramp_rows; left > 0;) {
+      const size_t rows = std::min(rows_per_block, left);
+      blocks.push_back(rows);
+      left -= rows;
+    }
+    blocks.insert(blocks.end(), ramp.rbegin(), ramp.rend());
+  }
+  size_t r0 = 0;
+  for (size_t b = 0; b < blocks.size(); r0 += blocks[b], ++b) {
     const int s = (int)(b % kPipe);
-    const size_t r0 = b * rows_per_block, rows = std::min(rows_per_block, batch - r0);
+    const size_t rows = blocks[b];
     if (int r = grow(&c.stage_in[s], &c.cap_in[s], rows_per_block * n * sizeof(T))) return r;
     if (int r = grow(&c.stage_out[s], &c.cap_out[s], rows_per_block * out_len * sizeof(T))) return r;
     T *din = static_cast<T *>(c.stage_in[s]);

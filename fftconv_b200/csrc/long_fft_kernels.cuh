@@ -36,6 +36,14 @@ template <typename T> struct LongArgs {
   const cx<T> *TWbig; // 15 * N_sub: [(s-1) N_sub + p] = W_Nbig^{p s}
   int hilbert;        // outer_inv: write the envelope instead of the convolution
   EnvEpilogue<T> epi; // hilbert only
+  // Chirp-z (Bluestein) Hilbert envelope of a line whose length n is not a power of two, N_big =
+  // M >= 2 n - 1: two convolutions with the chirp filter (generic_kernels.cuh, hilbert_bluestein_kernel,
+  // is the single-CTA form of the same recipe):
+  //   bluestein = 1: load (x0 + i x1) chirp, store u = chirp conj(Hilbert(chirp * y)) into cbuf
+  //   bluestein = 2: load cbuf, store the envelope from conj(chirp * y) / n
+  int bluestein;
+  const cx<T> *chirp; // n: exp(-pi i j^2 / n)
+  cx<T> *cbuf;        // pairs * N_big
 };
 
 template <typename T> __global__ void outer_fwd_kernel(const LongArgs<T> a) {
@@ -48,11 +56,18 @@ template <typename T> __global__ void outer_fwd_kernel(const LongArgs<T> a) {
   const T *x0 = a.in + r0 * a.in_stride;
   const T *x1 = a.in + (has1 ? r1 : r0) * a.in_stride;
   cx<T> v[16];
+  if (a.bluestein == 2) {
+    const cx<T> *src = a.cbuf + pair * 16 * nsub + p;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const long long i = p + (long long)q * nsub;
-    v[q].x = i < a.n ? x0[i] : (T)0;
-    v[q].y = (has1 && i < a.n) ? x1[i] : (T)0;
+    for (int q = 0; q < 16; ++q) v[q] = src[(long long)q * nsub];
+  } else {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const long long i = p + (long long)q * nsub;
+      v[q].x = i < a.n ? x0[i] : (T)0;
+      v[q].y = (has1 && i < a.n) ? x1[i] : (T)0;
+      if (a.bluestein == 1 && i < a.n) v[q] = fast::cmul(v[q], a.chirp[i]);
+    }
   }
   fast::dft16<-1>(v);
   cx<T> *dst = a.scratch + pair * 16 * nsub + p;
@@ -82,7 +97,43 @@ template <typename T> __global__ void outer_inv_kernel(const LongArgs<T> a) {
   fast::dft16<+1>(v);
   T *o0 = a.out + r0 * a.out_stride;
   T *o1 = a.out + (has1 ? r1 : r0) * a.out_stride;
-  if (a.hilbert) {
+  if (a.bluestein == 1) {
+    // X[k] = chirp[k] v[k]; Z = -j X (0 < k < n/2), +j X (k > n/2), 0 at DC / Nyquist
+    // (/root/reference/include/fftconv/hilbert.hpp:39-51); the inverse DFT is conj(DFT(conj(Z))) / n
+    cx<T> *dst = a.cbuf + pair * 16 * nsub + p;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const long long k = p + (long long)q * nsub;
+      cx<T> u = {(T)0, (T)0};
+      if (k < a.n && k != 0 && 2 * k != a.n) {
+        const cx<T> c = a.chirp[k];
+        const cx<T> X = fast::cmul(v[q], c);
+        cx<T> Zc; // conj(Z)
+        if (2 * k < a.n) { Zc.x = X.y; Zc.y = X.x; }
+        else             { Zc.x = -X.y; Zc.y = -X.x; }
+        u = fast::cmul(Zc, c);
+      }
+      dst[(long long)q * nsub] = u;
+    }
+  } else if (a.bluestein == 2) {
+    const T *x0 = a.in + r0 * a.in_stride;
+    const T *x1 = a.in + (has1 ? r1 : r0) * a.in_stride;
+    const T inv_n = (T)(1.0 / (double)a.n);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const long long m = p + (long long)q * nsub;
+      if (m < a.n) {
+        const cx<T> w = fast::cmul(v[q], a.chirp[m]); // conj(h) * n
+        const T h0 = w.x * inv_n, h1 = -w.y * inv_n;
+        const T u = x0[m];
+        env_store(a.epi, o0, m, sqrt(u * u + h0 * h0));
+        if (has1) {
+          const T t = x1[m];
+          env_store(a.epi, o1, m, sqrt(t * t + h1 * h1));
+        }
+      }
+    }
+  } else if (a.hilbert) {
     const T *x0 = a.in + r0 * a.in_stride;
     const T *x1 = a.in + (has1 ? r1 : r0) * a.in_stride;
 #pragma unroll

@@ -1,7 +1,3 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -8 gpurun_out/pytest_gpu.log
-python bench_configs.py --config ksweep --no-cpu > gpurun_out/ksweep.log 2>gpurun_out/ksweep.err; cat gpurun_out/ksweep.log | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print(d.get('dtype'),d.get('k'),d.get('fft_size'),round(d.get('ms_per_step',0),3),round(d.get('frac_of_measured_hbm_peak',0),3),d.get('error',''))
-"
-python bench_configs.py --config c3 --no-cpu > gpurun_out/c3.log 2>/dev/null; cut -c1-300 gpurun_out/c3.log
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -12 gpurun_out/pytest_gpu.log
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_v9.log 2>gpurun_out/bench_v9.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_v9.log').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['e2e'], d['roofline']['frac'])"

@@ -97,6 +97,27 @@ def test_n2048_kernel_logic_emulated_on_cpu(built, case):
     assert float(r.stdout.split()[0]) < 1e-6
 
 
+EMU_F64_CASES = [
+    # batch n K mode chunks slots misalign(0..1 doubles) recomp
+    (4, 32768, 245, 0, 1, 7, 0, 1),   # work split mid-row (warm-up path)
+    (5, 10000, 165, 1, 1, 3, 0, 1),   # config 3's kernel length on the throughput segment size, odd batch
+    (1, 60000, 245, 0, 4, 5, 0, 1),   # one long row cut into chunks
+    (2, 1804, 245, 0, 1, 1, 0, 0),    # exactly one full segment, full twiddle table
+    (3, 7000, 410, 0, 3, 2, 1, 1),    # largest K, base pointers 8 bytes off 16-byte alignment
+    (2, 4000, 8, 1, 1, 1, 1, 1),      # smallest K the staged path serves
+    (3, 9001, 246, 1, 1, 2, 1, 0),    # odd step: the staging shift alternates between segments
+]
+
+
+@pytest.mark.parametrize("case", EMU_F64_CASES)
+def test_n2048_float64_kernel_logic_emulated_on_cpu(built, case):
+    """The float64 instantiation of the same engine (two streams per group), error bound 1e-13."""
+    exe = os.path.join(ROOT, "tests", "cpu", "emulate_oa_n2048")
+    r = subprocess.run([exe, *map(str, case), "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (case, r.stdout, r.stderr)
+    assert float(r.stdout.split()[0]) < 1e-13
+
+
 @pytest.mark.parametrize("case", EMU_CASES + [(8, 20000, 410, 0, 1, 2), (8, 20000, 221, 1, 1, 3, 2)])
 def test_w2_kernel_logic_emulated_on_cpu(built, case):
     """The warp-pair engine (oa_w2_*.cuh): same method, tests/cpu/emulate_oa_w2.cpp."""

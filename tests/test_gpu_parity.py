@@ -720,3 +720,30 @@ def test_n2048_kernel_float64(cuda, batch, n, klen, mode, monkeypatch):
         torch.cuda.synchronize()
         assert torch.equal(oview, y)
         assert torch.isnan(ostore[1:].view(batch, out_len + 3)[:, out_len:]).all()   # nothing written past a row
+
+
+@pytest.mark.parametrize("dt,n", [(np.float32, 10000), (np.float32, 12345), (np.float32, 50001), (np.float32, 131072 - 3),
+                                  (np.float64, 5000), (np.float64, 6001), (np.float64, 40000)])
+def test_hilbert_long_lines_of_any_length(cuda, dt, n):
+    """hilbert.hpp:16-66 accepts any n: lines that are not a power of two and whose chirp-z FFT
+    (M >= 2 n - 1) exceeds a CTA's shared memory run the chirp filter's two convolutions as split
+    FFTs through global scratch (long_fft_kernels.cuh).  Odd row count: unpaired last row."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((3, n)).astype(dt)
+    t = np.arange(n)
+    x[1] = (np.exp(-0.5 * ((t - n // 3) / 200.0) ** 2) * np.cos(2 * np.pi * 0.07 * t)).astype(dt)
+    want = O.hilbert_exact(x)
+    got = fc.hilbert(x)
+    tol = H.TOL[np.dtype(dt)]
+    assert O.rel_l2(got, want) < tol, (n, dt, O.rel_l2(got, want))
+    tx = _t(x, cuda)
+    tgot = fc.hilbert(tx)
+    dec = fc.envelope(tx, decimate=5, log_compress=True, ref=1.0, dynamic_range_db=50.0)
+    torch.cuda.synchronize()
+    assert np.array_equal(tgot.cpu().numpy(), got)
+    wdec = O.envelope(x, log_compress=True, ref=1.0, dynamic_range_db=50.0, decimate=5)
+    assert np.linalg.norm(dec.cpu().numpy().astype(np.float64) - wdec) / np.sqrt(wdec.size) < tol * 4
