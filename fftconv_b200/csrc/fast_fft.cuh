@@ -333,12 +333,27 @@ template <int LOG2N, typename D, class Spectrum> FCF_HD void last_fused(int tid,
   for (int q = 0; q < 16; ++q) buf[phys(base + q)] = v[q];
 }
 
+// Synchronisation between two passes.  A pass whose sub-transforms have 2^LM <= 512 points keeps
+// every warp inside its own 512-point region ([512 w, 512 w + 512), w = warp index within the FFT:
+// mid pass blocks tid >> (LM - 4), last pass points 16 tid ...), so an exchange whose wider side is
+// such a pass is warp-local: `sync.warp()` (__syncwarp) replaces the barrier among all the FFT's
+// threads.  For N = 8192 that is two of six boundaries (mid2 -> last, last -> inverse mid2), for
+// N <= 4096 two of four: the warps of an FFT drift apart there and one warp's shared-memory phase
+// overlaps another's arithmetic.
+template <int LM, class Sync> FCF_HD void pass_sync(Sync &sync) {
+  if constexpr (LM <= 9) sync.warp();
+  else sync();
+}
+template <int LOG2N, int J> struct MidLm { // log2 of the sub-transform length of middle pass J
+  static constexpr int value = LOG2N - Plan<LOG2N>::R0 - 4 * (J - 1);
+};
+
 // compile-time loops over the middle passes
 template <int LOG2N, int J, typename T> struct FwdMids { // T = data type
   template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<scalar_t<T>> *W, Sync &sync) {
     if constexpr (J <= Plan<LOG2N>::P - 2) {
       fwd_mid<LOG2N, J>(tid, buf, W);
-      sync();
+      pass_sync<MidLm<LOG2N, J>::value>(sync); // the next pass is narrower
       FwdMids<LOG2N, J + 1, T>::run(tid, buf, W, sync);
     }
   }
@@ -347,7 +362,7 @@ template <int LOG2N, int J, typename T> struct InvMids {
   template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<scalar_t<T>> *W, Sync &sync) {
     if constexpr (J >= 1) {
       inv_mid<LOG2N, J>(tid, buf, W);
-      sync();
+      pass_sync<(J > 1 ? MidLm<LOG2N, (J > 1 ? J - 1 : 1)>::value : LOG2N)>(sync); // the next pass is wider
       InvMids<LOG2N, J - 1, T>::run(tid, buf, W, sync);
     }
   }
@@ -359,10 +374,10 @@ template <int LOG2N, typename T, class Spectrum, class Sync>
 FCF_HD void conv_core_with(int tid, cx<T> *v, cx<T> *buf, const cx<scalar_t<T>> *W /* pass twiddle tables */,
                            const Spectrum &H, Sync &sync) {
   fwd_pass0<LOG2N>(tid, v, buf, W);
-  sync();
+  pass_sync<LOG2N>(sync);
   FwdMids<LOG2N, 1, T>::run(tid, buf, W, sync);
   last_fused<LOG2N>(tid, buf, H);
-  sync();
+  pass_sync<8>(sync); // the last middle pass always has 256-point sub-transforms
   InvMids<LOG2N, Plan<LOG2N>::P - 2, T>::run(tid, buf, W, sync);
   inv_pass0<LOG2N>(tid, v, buf, W);
 }
@@ -370,13 +385,7 @@ template <int LOG2N, typename T, class Sync>
 FCF_HD void conv_core(int tid, cx<T> *v, cx<T> *buf, const cx<scalar_t<T>> *W /* pass twiddle tables */,
                       const cx<scalar_t<T>> *Htab, Sync &sync) {
   const TableSpectrum<scalar_t<T>> H{Htab, Plan<LOG2N>::THREADS};
-  fwd_pass0<LOG2N>(tid, v, buf, W);
-  sync();
-  FwdMids<LOG2N, 1, T>::run(tid, buf, W, sync);
-  last_fused<LOG2N>(tid, buf, H);
-  sync();
-  InvMids<LOG2N, Plan<LOG2N>::P - 2, T>::run(tid, buf, W, sync);
-  inv_pass0<LOG2N>(tid, v, buf, W);
+  conv_core_with<LOG2N>(tid, v, buf, W, H, sync);
 }
 
 // Host: fill the per-pass twiddle tables (TW_ELEMS entries) in long double.

@@ -23,6 +23,7 @@ template <typename D, int CTA_THREADS> constexpr int min_blocks() {
 
 struct CtaSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
+  __device__ __forceinline__ void warp() const { __syncwarp(); } // warp-local exchange (fast_fft.cuh, pass_sync)
 };
 
 // The real streams ("lanes") that ride in one complex value of data type D:

@@ -26,9 +26,9 @@ using fc::env_store;
 enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1, LAYOUT_FAST = 2, LAYOUT_LONG = 3, LAYOUT_W2 = 4 };
 
 __device__ __forceinline__ unsigned n2048_freq_of_index(unsigned idx) {
-  // idx = slot * 128 + c0 (see fc::n2048::p2_freq)
-  const unsigned s = idx >> 7, c0 = idx & 127;
-  const unsigned h = s >> 3, k1b = s & 7, c = c0 + 128 * h;
+  // idx = slot * 128 + t (see fc::n2048::p2_freq, p2_col)
+  const unsigned s = idx >> 7, t = idx & 127;
+  const unsigned h = s >> 3, k1b = s & 7, c = 64 * (t >> 5) + 32 * h + (t & 31);
   return 16 * (c & 15) + 256 * k1b + (c >> 4);
 }
 

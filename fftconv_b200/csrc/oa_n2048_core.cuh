@@ -18,8 +18,8 @@
 //   W_N^{nk} = W_16^{m k2} W_2048^{t k2}  W_16^{t1 k1a} W_128^{t0 k1a}  W_8^{t0 k1b}
 //   P0 (thread t):        radix-16 over m  -> k2,  twiddle W_2048^{t k2}
 //   P1 (thread t0 + 8k2): radix-16 over t1 -> k1a, twiddle W_128^{t0 k1a}
-//   P2 (thread c, c+128; c = 16 k2 + k1a): radix-8 over t0 -> k1b, times H[k],
-//                         inverse radix-8 back to t0
+//   P2 (thread t: columns c = p2_col(t, 0), p2_col(t, 1); c = 16 k2 + k1a): radix-8 over
+//                         t0 -> k1b, times H[k], inverse radix-8 back to t0
 //   P3 / P4 mirror P1 / P0 with conjugated twiddles; 1/N is folded into H.
 // The three exchanges go through ONE 32 KB shared buffer of 16-byte points
 // (reA, reB, imA, imB).  Its layouts are chosen so that every phase writes
@@ -170,14 +170,20 @@ template <typename D> FC_HD void get(const PtT<D> *buf, int addr, D &re, D &im) 
 // Twiddle / spectrum tables (float2-like pairs), shared by all groups of a CTA:
 //   tw1[k2 * 128 + t]   = W_2048^{t k2}       k2 = 0..15
 //   tw2[k1a * 8 + t0]   = W_128^{t0 k1a}      k1a = 0..15
-//   hs[slot * 128 + c0] = H[k] / 2048, slot = 8 h + k1b, c = c0 + 128 h,
+//   hs[slot * 128 + t]  = H[k] / 2048, slot = 8 h + k1b, c = p2_col(t, h),
 //                         k = 16 (c & 15) + 256 k1b + (c >> 4)
 template <typename S> struct CPairT { S re, im; };
 using cpair = CPairT<float>;
 
-// frequency handled by thread c0 in register slot s of phase P2
-FC_HD int p2_freq(int c0, int s) {
-  const int h = s >> 3, k1b = s & 7, c = c0 + 128 * h;
+// Phase P2: thread t handles two columns c (h = 0, 1) of 8 points each.  Warp w = t >> 5 takes
+// c in [64 w, 64 w + 64): exactly the points [512 w, 512 w + 512) that the same warp wrote in P1
+// (c = 16 k2 + k1a, k2 = 4 w .. 4 w + 3) and reads back in P3, so the exchanges P1 -> P2 -> P3
+// are warp-local and need __syncwarp() only; the group barrier is kept where data crosses warps
+// (P0 -> P1, P3 -> P4, and around the aliased staging area).
+FC_HD int p2_col(int t, int h) { return 64 * (t >> 5) + 32 * h + (t & 31); }
+// frequency handled by thread t in register slot s of phase P2
+FC_HD int p2_freq(int t, int s) {
+  const int h = s >> 3, k1b = s & 7, c = p2_col(t, h);
   return 16 * (c & 15) + 256 * k1b + (c >> 4);
 }
 
@@ -262,7 +268,7 @@ template <typename D> FC_HD void phase2(int c0, RegsT<D> &v, PtT<D> *xb, const C
   using cpair = CPairT<scalar_of_t<D>>;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int c = c0 + 128 * h;
+    const int c = p2_col(c0, h);
 #pragma unroll
     for (int t0 = 0; t0 < 8; ++t0) get(xb, x2_addr(c, t0), v.re[8 * h + t0], v.im[8 * h + t0]);
     dft8<-1>(&v.re[8 * h], &v.im[8 * h]);

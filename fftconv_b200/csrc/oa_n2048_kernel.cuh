@@ -11,7 +11,7 @@
 //                      TMA, issued by thread 0 at the end of the previous
 //                      iteration)
 //   LDS.32 x 64        x[t + 128 m] of the four lanes -> packed registers
-//   P0 compute | bar | P0 put | bar | P1 | bar | P2 | bar | P3 | bar | P4 reads | bar
+//   P0 compute | bar | P0 put | bar | P1 | warp | P2 | warp | P3 | bar | P4 reads | bar
 //   thread 0           requests the NEXT inputs (the buffer is idle from here on)
 //                      and then builds the packet of the iteration after next
 //   P4 DFT, tail hand-over (K-1 samples, separate small ping-pong buffers),
@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     phase0_put(t, v, xb);
     dev::bar_sync(bar_id);
     phase1<RECOMP>(t, v, xb, tw2);
-    dev::bar_sync(bar_id);
+    __syncwarp(); // P1 -> P2 -> P3 exchange inside each warp's own 512 points (oa_n2048_core.cuh, p2_col)
     phase2(t, v, xb, hs);
-    dev::bar_sync(bar_id);
+    __syncwarp();
     phase3<RECOMP>(t, v, xb, tw2);
     dev::bar_sync(bar_id);
     phase4_read<RECOMP, RECOMP>(t, v, xb, tw1);
