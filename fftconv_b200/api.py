@@ -8,9 +8,9 @@
 Same names, argument meaning, defaults and error behaviour (RuntimeError for a
 kernel longer than the signal or an unknown mode).  Extensions over the reference:
 2-D inputs are batches of rows convolved with the same taps (the reference's
-binding rejects ndim != 1), and CUDA `torch.Tensor`s -- or any object with
-`__cuda_array_interface__` (CuPy, Numba) in the `_` forms -- are processed in place on
-the device on the caller's stream (no host round trip).
+binding rejects ndim != 1), and CUDA `torch.Tensor`s -- or, in the `_` forms, any object with
+`__cuda_array_interface__` (CuPy, Numba) or `__dlpack__` on a CUDA device -- are processed in
+place on the device on the caller's stream (no host round trip).
 
 Everything goes through the C ABI of libfftconv_cuda.so; nothing here computes.
 """
@@ -45,6 +45,10 @@ class _Buf:
     """pointer + shape view of a numpy array or a torch tensor (rows contiguous)."""
 
     def __init__(self, x, name: str):
+        if (torch is not None and not _is_tensor(x) and not isinstance(x, np.ndarray)
+                and not hasattr(x, "__cuda_array_interface__") and hasattr(x, "__dlpack__")
+                and hasattr(x, "__dlpack_device__") and int(x.__dlpack_device__()[0]) == 2):
+            x = torch.from_dlpack(x)     # any DLPack exporter on a CUDA device: zero-copy view
         self.obj = x
         if not _is_tensor(x) and hasattr(x, "__cuda_array_interface__"):
             # CuPy / Numba / any CUDA array: taken in place, no torch needed

@@ -473,6 +473,33 @@ def test_cuda_array_interface_inputs(cuda):
     assert O.rel_l2(env.cpu().numpy(), O.hilbert_exact(a[:, :8192])) < 1e-5
 
 
+def test_dlpack_inputs(cuda):
+    """Any DLPack exporter on a CUDA device is taken in place (a minimal wrapper that exposes only
+    __dlpack__ / __dlpack_device__ stands in for JAX / CuPy arrays)."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    class DL:
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, *a, **kw):
+            return self.t.__dlpack__(*a, **kw)
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    rng = np.random.default_rng(78)
+    a = rng.standard_normal((5, 7000))
+    k = rng.standard_normal(165) / 13
+    ta, tk = _t(a, cuda), _t(k, cuda)
+    out = torch.full((5, 7164), float("nan"), dtype=torch.float64, device=cuda)
+    fc.oaconvolve_(DL(ta), DL(tk), DL(out), "full")
+    torch.cuda.synchronize()
+    _check(out.cpu().numpy(), a, k, "full", "dlpack")
+
+
 @pytest.mark.parametrize("dt,klen", [(np.float32, 245), (np.float32, 65), (np.float64, 165), (np.float32, 7)])
 def test_filter_handle_reuses_the_spectrum(cuda, dt, klen):
     """a filter handle gives the same samples as the plain call and launches no
