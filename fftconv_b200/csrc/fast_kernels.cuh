@@ -26,6 +26,18 @@ struct CtaSync {
   __device__ __forceinline__ void warp() const { __syncwarp(); } // warp-local exchange (fast_fft.cuh, pass_sync)
 };
 
+// Barrier among the threads of ONE of the FPC FFTs that share a CTA (named barrier f of 16): the
+// FFTs of a CTA are independent, so they need not wait for one another -- while one is in a
+// shared-memory exchange another is in its butterflies.  Kernels that use it must not call
+// __syncthreads() in the same phase (that is barrier 0).
+struct FftSync {
+  int id, threads;
+  __device__ __forceinline__ void operator()() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+  }
+  __device__ __forceinline__ void warp() const { __syncwarp(); }
+};
+
 // The real streams ("lanes") that ride in one complex value of data type D:
 //   D = T:   lane 0 = real part, lane 1 = imaginary part
 //   D = f2:  lane 0 = re half A, lane 1 = im half A, lane 2 = re half B, lane 3 = im half B
@@ -99,7 +111,9 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
       }
     }
 
-  CtaSync sync;
+  // one barrier domain per FFT (the trip count stays CTA-uniform, so every domain executes the same
+  // number of barriers); a single FFT per CTA is the CTA barrier itself
+  const FftSync sync{FPC > 1 ? f : 0, FPC > 1 ? P::THREADS : P::THREADS * FPC};
   int parity = 0;
   bool add_tail = false;
   for (long long j = warm_needed ? -1 : 0; j < max_cnt; ++j) {
@@ -147,7 +161,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
         if (i < limit[l] && o >= 0) dst[l][o] = ys[l];
       }
     }
-    __syncthreads(); // tails and the exchange buffer are reused by the next segment
+    sync(); // tails and the exchange buffer (both per FFT) are reused by the next segment
     parity ^= 1;
     add_tail = true;
   }
@@ -189,7 +203,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
     v[s] = L::make(a);
     if constexpr (kKeep) keep[s] = v[s];
   }
-  CtaSync sync;
+  const FftSync sync{FPC > 1 ? f : 0, FPC > 1 ? P::THREADS : P::THREADS * FPC};
   const HilbertSpectrum<T> G{(T)(1.0 / (double)P::N)};
   conv_core_with<LOG2N>(tid, v, buf, W, G, sync);
   // envelope; the inputs are re-read (L2) in batches so that their latencies overlap

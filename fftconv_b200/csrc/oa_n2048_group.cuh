@@ -226,21 +226,11 @@ FC_HD void fast_load(int t, RegsT<D> &v, const S *in, int ls, const int (&shift)
   }
 }
 
-// registers -> the four lanes' outputs (+ tail hand-over).  b_l points at y[t] of
-// lane l -- in a shared staging buffer or directly in global memory (one coalesced
-// 128-byte line per warp instruction); element y[t + 128 m] goes to b_l[128 m].
+// registers -> the lanes' outputs in GLOBAL memory (+ tail hand-over).  b_l points at y[t] of
+// lane l (one coalesced 128-byte line per warp instruction); element y[t + 128 m] goes to b_l[128 m].
 template <typename D, typename S>
 FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const ThreadMasks &k, const PtT<D> *tail_prev,
                          PtT<D> *tail_next, bool add_tail, bool stage, int step);
-
-// registers -> staged output (+ tail hand-over).  `out` is the output staging buffer.
-template <typename D, typename S>
-FC_HD void fast_store(int t, const RegsT<D> &v, S *out, int ls, const int (&shift)[4], const ThreadMasks &k,
-                      const PtT<D> *tail_prev, PtT<D> *tail_next, bool add_tail, bool stage, int step) {
-  S *const b[4] = {out + 0 * ls + shift[0] + t, out + 1 * ls + shift[1] + t, out + 2 * ls + shift[2] + t,
-                   out + 3 * ls + shift[3] + t};
-  fast_store_to(t, v, b, k, tail_prev, tail_next, add_tail, stage, step);
-}
 
 // b[l] points at y[t] of lane l (entries l >= NL are ignored)
 template <typename D, typename S>
@@ -267,7 +257,7 @@ FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const Threa
       S y[NL];
       DataTraits<D>::unpack(yr, yi, y);
 #pragma unroll
-      for (int l = 0; l < NL; ++l) b[l][128 * m] = y[l];
+      for (int l = 0; l < NL; ++l) b[l][128 * m] = y[l]; // (streaming st.global.cs was measured: 1 % slower)
     }
   }
 }

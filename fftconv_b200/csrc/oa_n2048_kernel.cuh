@@ -176,10 +176,17 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     dev::bar_sync(bar_id); // every thread has read its inputs out of the staging area
     phase0_put(t, v, xb);
     dev::bar_sync(bar_id);
+    // P1 -> P2 -> P3 exchange inside each warp's own 512 points (oa_n2048_core.cuh, p2_col): a warp
+    // barrier suffices.  Measured: float32 2 % faster with it (the warps of a group drift apart and
+    // overlap), float64 2 % slower (0.55 -> 0.56 ms at 2048 x 65536) -- that one keeps the group barrier.
+    auto mid_sync = [&]() {
+      if constexpr (sizeof(S) == 4) __syncwarp();
+      else dev::bar_sync(bar_id);
+    };
     phase1<RECOMP>(t, v, xb, tw2);
-    __syncwarp(); // P1 -> P2 -> P3 exchange inside each warp's own 512 points (oa_n2048_core.cuh, p2_col)
+    mid_sync();
     phase2(t, v, xb, hs);
-    __syncwarp();
+    mid_sync();
     phase3<RECOMP>(t, v, xb, tw2);
     dev::bar_sync(bar_id);
     phase4_read<RECOMP, RECOMP>(t, v, xb, tw1);
