@@ -590,11 +590,18 @@ int oa2048_engine() {
 
 // engine for one call: the dedicated kernels take N = 2048, 8 <= K <= 410 (staging area and tail
 // buffers are sized for that); the warp-pair engine only float32 and its table row
+// (the WIDE instantiations: up to 1024 taps in float32, 640 in float64 -- what three groups' tail
+// buffers leave room for; reached through the throughput rule only, the table gives such kernels
+// larger segments)
+template <typename T> size_t oa2048_max_taps() {
+  if (env_int("FFTCONV_CUDA_NO_N2048_WIDE", 0)) return fc::n2048::kMaxTapsNarrow;
+  return std::is_same<T, float>::value ? (size_t)fc::n2048::kMaxTapsWide : 640;
+}
 template <typename T> int oa2048_engine_for(size_t N, size_t klen) {
-  if (N != 2048 || klen < 8 || klen > 410) return 0;
+  if (N != 2048 || klen < 8 || klen > oa2048_max_taps<T>()) return 0;
   const int e = oa2048_engine();
   if (!std::is_same<T, float>::value) return (e && !env_int("FFTCONV_CUDA_NO_N2048_F64", 0)) ? 1 : 0;
-  return (e == 2 && klen < 221) ? 1 : e;
+  return (e == 2 && (klen < 221 || klen > 410)) ? 1 : e;
 }
 
 // ---- overlap-add on device pointers -------------------------------------------------
@@ -654,7 +661,9 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
     const bool want_recomp = env_int("FFTCONV_CUDA_TW_RECOMPUTE", 1) != 0;
     // float64 with the longest kernels (K > ~390: two 16-byte tail buffers of K - 1 points per
     // group) does not fit four groups: drop to three
-    while (G > 1 && fc::n2048::smem_bytes<T>(G, (int)klen, want_recomp && G == 4) > c.smem_optin) --G;
+    const bool wide_k = klen > (size_t)fc::n2048::kMaxTapsNarrow || env_int("FFTCONV_CUDA_N2048_FORCE_WIDE", 0);
+    if (wide_k && G < 3) G = 4; // the wide instantiations exist for four and three groups, always with twiddle recomputation
+    while (G > (wide_k ? 3 : 1) && fc::n2048::smem_bytes<T>(G, (int)klen, wide_k || (want_recomp && G == 4)) > c.smem_optin) --G;
     const long long slots = (long long)c.sm_count * G;
     // streams per row: enough quads to fill every group, but never so many that
     // the per-chunk warm-up segment costs more than ~6 %
@@ -670,19 +679,23 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
     p.tw1 = tw1;
     p.tw2 = tw2;
     p.hs = reinterpret_cast<const fc::n2048::CPairT<T> *>(H);
-    const bool recomp = want_recomp && G == 4;
+    const bool wide = wide_k;
+    const bool recomp = wide || (want_recomp && G == 4);
     const size_t smem = fc::n2048::smem_bytes<T>(G, (int)klen, recomp);
     const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
-#define FC_LAUNCH_N2048(GG, RR)                                                            \
-  {                                                                                        \
-    if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<D, GG, RR>, smem)) return r;     \
-    fc::n2048::oa_n2048_kernel<D, GG, RR><<<(unsigned)grid, 128 * GG, smem, st>>>(p);      \
+#define FC_LAUNCH_N2048(GG, RR, WW)                                                            \
+  {                                                                                            \
+    if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<D, GG, RR, WW>, smem)) return r;     \
+    fc::n2048::oa_n2048_kernel<D, GG, RR, WW><<<(unsigned)grid, 128 * GG, smem, st>>>(p);      \
   }
-    if (G == 4 && recomp) FC_LAUNCH_N2048(4, true)
-    else if (G == 4) FC_LAUNCH_N2048(4, false)
-    else if (G == 3) FC_LAUNCH_N2048(3, false)
-    else if (G == 2) FC_LAUNCH_N2048(2, false)
-    else FC_LAUNCH_N2048(1, false)
+    if (wide) {
+      if (G == 4) FC_LAUNCH_N2048(4, true, true)
+      else FC_LAUNCH_N2048(3, true, true)
+    } else if (G == 4 && recomp) FC_LAUNCH_N2048(4, true, false)
+    else if (G == 4) FC_LAUNCH_N2048(4, false, false)
+    else if (G == 3) FC_LAUNCH_N2048(3, false, false)
+    else if (G == 2) FC_LAUNCH_N2048(2, false, false)
+    else FC_LAUNCH_N2048(1, false, false)
 #undef FC_LAUNCH_N2048
     CU_TRY(cudaGetLastError());
     ++g_launches;
@@ -867,8 +880,12 @@ template <typename T> size_t throughput_oa_size(const DeviceCtx &c, size_t klen,
     if (klen < 8) return 512;
   } else {
     if (klen < 221) return 2048;                       // measured: 0.68-0.72 ms against 0.79-0.92 (N = 1024)
-    if (table_n == 8192 && klen <= 1024) return 4096;  // 1.15 ms against 1.44: the 8192-point float64 CTA is register-starved
   }
+  // 411 .. 1024 (float64: 640) taps: 2048-point segments on the dedicated kernel rather than the
+  // table's 4096 / 8192 points on the register-blocked engine (measured)
+  if (klen > 410 && klen <= oa2048_max_taps<T>() && oa2048_engine() != 0 && oa2048_engine_for<T>(2048, klen)) return 2048;
+  if (!std::is_same<T, float>::value && table_n == 8192 && klen <= 1024)
+    return 4096;  // 1.15 ms against 1.44: the 8192-point float64 CTA is register-starved
   return table_n;
 }
 

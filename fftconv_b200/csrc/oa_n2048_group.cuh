@@ -205,7 +205,18 @@ template <typename S> FC_HD ThreadMasks make_masks(int t, const OaParamsT<S> &p)
 }
 
 // staged input -> registers.  `in` is the group's input staging buffer.
-template <typename D, typename S>
+// The kernel is specialised for the table row it was built for, 8 <= K <= 410 (WIDE = false): the
+// incoming tail touches only y[i], i < 512 (register slots m < 4), the zero padding / outgoing tail
+// only i >= 1536 (m >= 12).  WIDE = true serves 411 <= K <= 1024 on the same 2048-point segments
+// (m < 8 / m >= 8): for large jobs that beats the reference's larger segment on the generic engine
+// (fftconv_cuda.cu, throughput_oa_size).  1024 is the end: the tail (K - 1 samples) must not be
+// longer than the step (2049 - K), or it would reach past the next segment and the one-segment
+// warm-up of a stream that starts in mid-row would not recover it.
+template <bool WIDE> FC_HD constexpr int tail_in_slots() { return WIDE ? 8 : 4; }
+template <bool WIDE> FC_HD constexpr int pad_first_slot() { return WIDE ? 8 : 12; }
+constexpr int kMaxTapsNarrow = 410, kMaxTapsWide = 1024;
+
+template <bool WIDE = false, typename D, typename S>
 FC_HD void fast_load(int t, RegsT<D> &v, const S *in, int ls, const int (&shift)[4], unsigned in_zero) {
   constexpr int NL = DataTraits<D>::NL;
   const S *b[NL];
@@ -213,8 +224,8 @@ FC_HD void fast_load(int t, RegsT<D> &v, const S *in, int ls, const int (&shift)
   for (int l = 0; l < NL; ++l) b[l] = in + l * ls + shift[l] + t;
 #pragma unroll
   for (int m = 0; m < kPts; ++m) {
-    // step >= 2048 - 409: only m >= 12 can fall into the padding region
-    const bool z = (m >= 12) && ((in_zero >> m) & 1u);
+    // step >= 2048 - 409 (narrow): only m >= 12 can fall into the padding region
+    const bool z = (m >= pad_first_slot<WIDE>()) && ((in_zero >> m) & 1u);
     S x[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) x[l] = (S)0;
@@ -228,12 +239,8 @@ FC_HD void fast_load(int t, RegsT<D> &v, const S *in, int ls, const int (&shift)
 
 // registers -> the lanes' outputs in GLOBAL memory (+ tail hand-over).  b_l points at y[t] of
 // lane l (one coalesced 128-byte line per warp instruction); element y[t + 128 m] goes to b_l[128 m].
-template <typename D, typename S>
-FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const ThreadMasks &k, const PtT<D> *tail_prev,
-                         PtT<D> *tail_next, bool add_tail, bool stage, int step);
-
 // b[l] points at y[t] of lane l (entries l >= NL are ignored)
-template <typename D, typename S>
+template <bool WIDE = false, typename D, typename S>
 FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const ThreadMasks &k, const PtT<D> *tail_prev,
                          PtT<D> *tail_next, bool add_tail, bool stage, int step) {
   constexpr int NL = DataTraits<D>::NL;
@@ -242,7 +249,7 @@ FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const Threa
     const int i = t + 128 * m;
     const int s = slot16(m);
     D yr = v.re[s], yi = v.im[s];
-    if (m < 4) { // K - 1 <= 409 < 512
+    if (m < tail_in_slots<WIDE>()) { // K - 1 <= 409 < 512 (narrow)
       if (add_tail && ((k.tail_add >> m) & 1u)) {
         D tr, ti;
         get(tail_prev, i, tr, ti);
@@ -250,7 +257,7 @@ FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const Threa
         yi = add2(yi, ti);
       }
     }
-    const bool in_tail = (m >= 12) && ((k.in_zero >> m) & 1u); // i >= step
+    const bool in_tail = (m >= pad_first_slot<WIDE>()) && ((k.in_zero >> m) & 1u); // i >= step
     if (in_tail) {
       put(tail_next, i - step, yr, yi);
     } else if (stage) {

@@ -94,7 +94,7 @@ __device__ __forceinline__ void issue_loads(const PacketT<S> *pk, S *stage, int 
 }
 
 // D = f2 (float32, four segments per group iteration) or double (float64, two).
-template <typename D, int G, bool RECOMP>
+template <typename D, int G, bool RECOMP, bool WIDE = false>
 __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_constant__ OaParamsT<scalar_of_t<D>> p) {
   using S = scalar_of_t<D>;
   using cpair = CPairT<S>;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
       while (!dev::mbar_try_wait(mbar, in_phase)) {
       }
       in_phase ^= 1;
-      fast_load(t, v, stage, LS, sh, masks.in_zero);
+      fast_load<WIDE>(t, v, stage, LS, sh, masks.in_zero);
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_load(t, v, p, ln, cur->j);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     if (out_fast || warm) {
       // coalesced element stores straight from registers (full 128-byte lines per warp instruction)
       S *const dst[4] = {cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t, cur->out_dst[3] + t};
-      fast_store_to(t, v, dst, masks, tail_prev, tail_next, add_tail, out_fast, p.step);
+      fast_store_to<WIDE>(t, v, dst, masks, tail_prev, tail_next, add_tail, out_fast, p.step);
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
       io_store(t, v, p, ln, cur->j, tail_prev, tail_next, add_tail, warm);

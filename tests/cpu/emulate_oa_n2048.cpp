@@ -52,7 +52,7 @@ template <typename D> struct HostGroup {
       for (int l = 0; l < NL; ++l) std::memcpy(stage + l * L.lane_stride, q->in_src[l], q->in_bytes[l]);
   }
 
-  template <bool RECOMP> void run(long long w0, long long w1) {
+  template <bool RECOMP, bool WIDE> void run(long long w0, long long w1) {
     SchedSlot slots[4];
     Packet ring[3];
     std::memset(ring, 0, sizeof(ring));
@@ -77,7 +77,7 @@ template <typename D> struct HostGroup {
       for (int t = 0; t < kThreads; ++t) {
         if (in_fast) {
           int sh[4] = {cur->in_shift[0], cur->in_shift[1], cur->in_shift[2], cur->in_shift[3]};
-          fast_load(t, regs[t], stage, L.lane_stride, sh, masks[t].in_zero);
+          fast_load<WIDE>(t, regs[t], stage, L.lane_stride, sh, masks[t].in_zero);
         } else {
           io_load(t, regs[t], p, cur->ln, cur->j);
         }
@@ -99,7 +99,7 @@ template <typename D> struct HostGroup {
         phase4_compute(regs[t]);
         if (out_fast || warm) {
           S *const dst[4] = {cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t, cur->out_dst[3] + t};
-          fast_store_to(t, regs[t], dst, masks[t], tail_prev, tail_next, add_tail, out_fast, p.step);
+          fast_store_to<WIDE>(t, regs[t], dst, masks[t], tail_prev, tail_next, add_tail, out_fast, p.step);
         } else {
           io_store(t, regs[t], p, cur->ln, cur->j, tail_prev, tail_next, add_tail, warm);
         }
@@ -141,8 +141,10 @@ int run_case(long long batch, long long n, int K, int mode, long long chunks, lo
   for (long long s = 0; s < n_slots; ++s) {
     const long long w0 = p.total_work * s / n_slots, w1 = p.total_work * (s + 1) / n_slots;
     HostGroup<D> grp(p);
-    if (recomp) grp.template run<true>(w0, w1);
-    else grp.template run<false>(w0, w1);
+    // kernels of more than 410 taps take the WIDE instantiation, exactly as the dispatcher does
+    if (K > kMaxTapsNarrow) grp.template run<true, true>(w0, w1);
+    else if (recomp) grp.template run<true, false>(w0, w1);
+    else grp.template run<false, false>(w0, w1);
   }
 
   double num = 0, den = 0;

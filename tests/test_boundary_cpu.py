@@ -85,9 +85,15 @@ EMU_CASES = [
     (8, 30000, 247, 0, 2, 3, 2),
     (4, 9020, 245, 0, 1, 1),      # n an exact multiple of step: last segment is full
 ]
+EMU_WIDE_CASES = [
+    (6, 20000, 411, 0, 1, 3),     # more than 410 taps: the WIDE instantiation (tails reach register slots < 8)
+    (5, 30000, 500, 1, 2, 3, 1),
+    (4, 30000, 768, 0, 1, 2, 3),
+    (3, 30000, 1024, 1, 1, 2),    # tail as long as the step allows
+]
 
 
-@pytest.mark.parametrize("case", EMU_CASES)
+@pytest.mark.parametrize("case", EMU_CASES + EMU_WIDE_CASES)
 def test_n2048_kernel_logic_emulated_on_cpu(built, case):
     """Runs the kernel's own __host__ __device__ phase functions thread by thread on
     the CPU (tests/cpu/emulate_oa_n2048.cpp) against direct convolution in double."""
@@ -106,6 +112,7 @@ EMU_F64_CASES = [
     (3, 7000, 410, 0, 3, 2, 1, 1),    # largest K, base pointers 8 bytes off 16-byte alignment
     (2, 4000, 8, 1, 1, 1, 1, 1),      # smallest K the staged path serves
     (3, 9001, 246, 1, 1, 2, 1, 0),    # odd step: the staging shift alternates between segments
+    (4, 30000, 640, 0, 1, 3, 1, 1),   # WIDE instantiation, longest float64 kernel it serves
 ]
 
 

@@ -561,7 +561,7 @@ def test_streaming_overlap_add_across_calls(cuda, dt, klen, pieces):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("klen", [1, 3, 7, 8, 20, 65, 165, 220])
+@pytest.mark.parametrize("klen", [1, 3, 7, 8, 20, 65, 165, 220, 411, 500, 560, 561, 640, 641, 768, 1024, 1025])
 def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch):
     """Jobs of >= 4 Mi samples move short kernels off the reference's (CPU cost model) segment
     size onto the fastest kernel's; the samples are the same linear convolution either way."""
@@ -570,12 +570,15 @@ def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch)
     import fftconv_b200 as fc
 
     rng = np.random.default_rng(klen)
-    a = rng.standard_normal((64, 65536)).astype(dt)
+    a = rng.standard_normal((64 if klen < 400 else 67, 65536)).astype(dt)
     k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(dt)
     ta, tk = _t(a, cuda), _t(k, cuda)
     tol = H.TOL[np.dtype(dt)]
     for mode in ("full", "same"):
+        before = fc.launch_count()
         y = fc.oaconvolve(ta, tk, mode)
+        if 8 <= klen <= (1024 if dt == np.float32 else 640):
+            assert fc.launch_count() - before == 2     # spectrum + the N = 2048 kernel (wide form beyond 410 taps)
         monkeypatch.setenv("FFTCONV_CUDA_STRICT_TABLE", "1")
         y_table = fc.oaconvolve(ta, tk, mode)
         monkeypatch.delenv("FFTCONV_CUDA_STRICT_TABLE")
