@@ -244,7 +244,7 @@ def main():
         for dt, name in ((torch.float32, "f32"), (torch.float64, "f64")):
             r = rows if dt == torch.float32 else rows // 2
             a = torch.randn((r, n), device=dev, generator=g, dtype=dt)
-            for klen in (6, 20, 35, 65, 165, 245, 500, 1000, 3000):
+            for klen in (6, 20, 35, 65, 165, 245, 500, 768, 1000, 3000):
                 k = torch.randn(klen, device=dev, generator=g, dtype=dt)
                 out = torch.empty((r, n + klen - 1), device=dev, dtype=dt)
                 try:
