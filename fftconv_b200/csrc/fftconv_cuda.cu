@@ -11,6 +11,7 @@
 // table as the reference (fftconv.hpp:38-66).
 #include "../../include/fftconv_cuda.h"
 
+#include "direct_kernels.cuh"
 #include "fast_kernels.cuh"
 #include "generic_kernels.cuh"
 #include "long_fft_kernels.cuh"
@@ -920,10 +921,54 @@ int partitioned_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, 
   return 0;
 }
 
+// Short kernels: direct time-domain evaluation (direct_kernels.cuh), one launch, no spectrum.
+// Measured at 4096 x 65536 float32 / 2048 x 65536 float64, Full, direct
+// against the FFT path: K <= 8: 0.42 / 0.44 ms against 0.53-0.89 / 0.54-0.68; 9..16: 0.47 / 0.54
+// against 0.51-0.53 / 0.53-0.54; 17..24: 0.53 / 0.68 against 0.50-0.53 / 0.53-0.54.  So float32 goes
+// direct up to 16 taps and float64 up to 8 (FFTCONV_CUDA_DIRECT_MAX_TAPS overrides, at most 16).
+template <typename T> size_t direct_max_taps() {
+  const int dflt = std::is_same<T, float>::value ? 16 : 8;
+  return (size_t)std::min(16, std::max(0, env_int("FFTCONV_CUDA_DIRECT_MAX_TAPS", dflt)));
+}
+template <typename T>
+int direct_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride, const T *k,
+                  size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
+  StreamWs &ws = c.ws[st];
+  const T *taps_dev = k;
+  if (!is_device_ptr(k)) {
+    if (int r = grow(&ws.taps, &ws.taps_bytes, klen * sizeof(T))) return r;
+    CU_TRY(cudaMemcpyAsync(ws.taps, k, klen * sizeof(T), cudaMemcpyHostToDevice, st));
+    taps_dev = static_cast<const T *>(ws.taps);
+  }
+  fc::direct::DirectArgs<T> p{};
+  p.in = a;
+  p.out = out;
+  p.taps = taps_dev;
+  p.batch = (long long)batch;
+  p.n = (long long)n;
+  p.in_stride = (long long)a_stride;
+  p.out_stride = (long long)out_stride;
+  p.out_len = (long long)out_len;
+  p.klen = (int)klen;
+  p.pad = mode == FFTCONV_CUDA_SAME ? (int)(klen / 2) : 0;
+  p.tiles_per_row = ((long long)out_len + fc::direct::kTile - 1) / fc::direct::kTile;
+  const long long total = p.batch * p.tiles_per_row;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(total, 8LL * c.sm_count));
+  if (klen <= 8) fc::direct::direct_conv_kernel<T, 8><<<grid, fc::direct::kThreads, 0, st>>>(p);
+  else fc::direct::direct_conv_kernel<T, 16><<<grid, fc::direct::kThreads, 0, st>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
 template <typename T>
 int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, size_t n,
                 size_t a_stride, const T *k, size_t klen, T *out, size_t out_len,
                 size_t out_stride, int mode) {
+  if (klen <= direct_max_taps<T>() && !tl_filter && !env_int("FFTCONV_CUDA_NO_DIRECT", 0) &&
+      !env_int("FFTCONV_CUDA_STRICT_TABLE", 0) && !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) &&
+      !env_int("FFTCONV_CUDA_OA_FFT_SIZE", 0) && !env_int("FFTCONV_CUDA_CONV_SINGLE_FFT", 0))
+    return direct_device<T>(c, st, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
   size_t N;
   if (op == OP_OA) {
     N = optimal_fft_size(klen);

@@ -345,7 +345,9 @@ def test_launch_counter_and_errors(cuda):
 
     before = fc.launch_count()
     fc.oaconvolve(np.ones(100, np.float32), np.ones(5, np.float32))
-    assert fc.launch_count() >= before + 2   # spectrum + segment kernel
+    assert fc.launch_count() == before + 1   # 5 taps: the direct kernel
+    fc.oaconvolve(np.ones(100, np.float32), np.ones(25, np.float32))
+    assert fc.launch_count() == before + 3   # spectrum + segment kernel
     with pytest.raises(RuntimeError, match="expected"):
         fc.oaconvolve_(np.ones(100), np.ones(5), np.empty(100), "full")
 
@@ -577,7 +579,9 @@ def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch)
     for mode in ("full", "same"):
         before = fc.launch_count()
         y = fc.oaconvolve(ta, tk, mode)
-        if 8 <= klen <= (1024 if dt == np.float32 else 640):
+        if klen <= (16 if dt == np.float32 else 8):
+            assert fc.launch_count() - before == 1     # direct time-domain kernel
+        elif klen <= (1024 if dt == np.float32 else 640):
             assert fc.launch_count() - before == 2     # spectrum + the N = 2048 kernel (wide form beyond 410 taps)
         monkeypatch.setenv("FFTCONV_CUDA_STRICT_TABLE", "1")
         y_table = fc.oaconvolve(ta, tk, mode)
@@ -777,3 +781,56 @@ def test_hilbert_long_lines_of_any_length(cuda, dt, n):
     assert np.array_equal(tgot.cpu().numpy(), got)
     wdec = O.envelope(x, log_compress=True, ref=1.0, dynamic_range_db=50.0, decimate=5)
     assert np.linalg.norm(dec.cpu().numpy().astype(np.float64) - wdec) / np.sqrt(wdec.size) < tol * 4
+
+
+DIRECT_CASES = [
+    # batch, n, K
+    (1, 1, 1), (1, 5, 3), (3, 100, 5), (2, 4352, 8), (5, 1023, 7), (4, 1024, 8), (3, 1025, 2), (7, 5000, 4),
+    (2, 70001, 6), (64, 65536, 3), (33, 40000, 8), (1, 3000000, 5), (3, 4352, 16), (5, 9000, 9), (6, 4100, 13),
+]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("batch,n,klen", DIRECT_CASES)
+def test_direct_kernel_for_short_kernels(cuda, dt, batch, n, klen, monkeypatch):
+    """Kernels of at most 16 (float32) / 8 (float64) taps are evaluated in the time domain (direct_kernels.cuh): against the
+    definition, against the FFT path on the same input (FFTCONV_CUDA_NO_DIRECT=1), Full and Same,
+    host and device pointers, rows at every 4-byte / 8-byte alignment (odd output strides), and
+    nothing written past a row."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    if klen > n:
+        pytest.skip("binding requires n >= K")
+    rng = np.random.default_rng(batch * 131 + n + klen)
+    a = rng.standard_normal((batch, n)).astype(dt)
+    k = rng.standard_normal(klen).astype(dt)
+    tol = H.TOL[np.dtype(dt)]
+    ta, tk = _t(a, cuda), _t(k, cuda)
+    for mode in ("full", "same"):
+        want = O.conv_exact(a, k, mode)
+        y = fc.oaconvolve(ta, tk, mode)
+        torch.cuda.synchronize()
+        assert O.rel_l2(y.cpu().numpy(), want) < tol, (mode, O.rel_l2(y.cpu().numpy(), want))
+        if n <= 70001:
+            assert O.rel_l2(fc.convolve(a, k, mode), want) < tol       # host pointers, convolve entry
+        monkeypatch.setenv("FFTCONV_CUDA_NO_DIRECT", "1")
+        y_fft = fc.oaconvolve(ta, tk, mode)
+        monkeypatch.delenv("FFTCONV_CUDA_NO_DIRECT")
+        torch.cuda.synchronize()
+        assert O.rel_l2(y.cpu().numpy(), y_fft.cpu().numpy()) < tol * 2
+        # misaligned rows in and out, NaN guard band after every output row
+        if batch <= 7:
+            out_len = y.shape[-1]
+            for off in (1, 2, 3):
+                store = torch.zeros(batch * (n + 3) + off, dtype=ta.dtype, device=cuda)
+                view = store[off:].view(batch, n + 3)[:, :n]
+                view.copy_(ta)
+                ostore = torch.full((batch * (out_len + 5) + off,), float("nan"), dtype=ta.dtype, device=cuda)
+                full_view = ostore[off:].view(batch, out_len + 5)
+                fc.oaconvolve_(view, tk, full_view[:, :out_len], mode)
+                torch.cuda.synchronize()
+                assert torch.equal(full_view[:, :out_len], y), (mode, off)
+                assert torch.isnan(full_view[:, out_len:]).all()
+                assert torch.isnan(ostore[:off]).all()
