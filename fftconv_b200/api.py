@@ -102,7 +102,10 @@ class _device_of:
     arrays are taken to live on the current device, as their own libraries assume)."""
 
     def __init__(self, buf: _Buf):
-        self.ctx = torch.cuda.device(buf.obj.device) if _is_tensor(buf.obj) else None
+        # switching devices costs several microseconds per call: only when it is not current already
+        self.ctx = None
+        if _is_tensor(buf.obj) and buf.obj.device.index not in (None, torch.cuda.current_device()):
+            self.ctx = torch.cuda.device(buf.obj.device)
 
     def __enter__(self):
         if self.ctx is not None:

@@ -143,3 +143,45 @@ __global__ void __launch_bounds__(kThreads) direct_conv_kernel(const DirectArgs<
 
 } // namespace direct
 } // namespace fc
+
+// ---- small jobs: one thread per output sample ----------------------------------------------------
+// A single short signal (the reference's own benchmark case is n = 4352, K = 65, 17.2 us per call
+// on a CPU, /root/reference/README.md:99-102) is bound by launch latency, not by arithmetic: the
+// FFT path needs two launches (kernel spectrum, segments) and a few dependent passes.  When the
+// whole job is at most a few million multiply-adds the definition is evaluated directly, one
+// thread per output, accumulating in double; taps of up to kInlineTaps ride in the kernel
+// arguments so that a host-pointer call needs no separate copy for them.
+namespace fc {
+namespace direct {
+
+constexpr int kInlineTaps = 96;
+
+template <typename T> struct SmallArgs {
+  const T *in;
+  T *out;
+  const T *taps;     // used when klen > kInlineTaps or the taps already live on the device
+  long long batch, n, in_stride, out_stride, out_len;
+  int klen, pad, inline_taps;
+  T tap[kInlineTaps];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) direct_small_kernel(const __grid_constant__ SmallArgs<T> p) {
+  __shared__ T ks[256];
+  for (int j = threadIdx.x; j < p.klen; j += blockDim.x) ks[j] = p.inline_taps ? p.tap[j] : p.taps[j];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.batch * p.out_len) return;
+  const long long row = idx / p.out_len, o = idx - row * p.out_len;
+  const T *a = p.in + row * p.in_stride;
+  // out[o] = sum_j k[j] a[o + pad - j], 0 <= o + pad - j < n
+  const long long hi = o + p.pad;                              // index for j = 0
+  int j0 = hi >= p.n ? (int)(hi - p.n + 1) : 0;
+  int j1 = hi < p.klen - 1 ? (int)hi : p.klen - 1;             // inclusive
+  double acc = 0.0;
+  for (int j = j0; j <= j1; ++j) acc += (double)ks[j] * (double)a[hi - j];
+  p.out[row * p.out_stride + o] = (T)acc;
+}
+
+} // namespace direct
+} // namespace fc

@@ -961,10 +961,49 @@ int direct_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_
   return 0;
 }
 
+// Small jobs (at most 4 Mi multiply-adds, at most 256 taps): the definition, one thread per output,
+// one launch (direct_kernels.cuh, direct_small_kernel) -- config 1 is such a job.
+template <typename T>
+int direct_small_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n, size_t a_stride, const T *k,
+                        size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
+  fc::direct::SmallArgs<T> p{};
+  p.in = a;
+  p.out = out;
+  p.batch = (long long)batch;
+  p.n = (long long)n;
+  p.in_stride = (long long)a_stride;
+  p.out_stride = (long long)out_stride;
+  p.out_len = (long long)out_len;
+  p.klen = (int)klen;
+  p.pad = mode == FFTCONV_CUDA_SAME ? (int)(klen / 2) : 0;
+  if (is_device_ptr(k)) {
+    p.taps = k;
+  } else if (klen <= (size_t)fc::direct::kInlineTaps) {
+    p.inline_taps = 1;
+    std::memcpy(p.tap, k, klen * sizeof(T));
+  } else {
+    StreamWs &ws = c.ws[st];
+    if (int r = grow(&ws.taps, &ws.taps_bytes, klen * sizeof(T))) return r;
+    CU_TRY(cudaMemcpyAsync(ws.taps, k, klen * sizeof(T), cudaMemcpyHostToDevice, st));
+    p.taps = static_cast<const T *>(ws.taps);
+  }
+  const long long total = p.batch * p.out_len;
+  fc::direct::direct_small_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
 template <typename T>
 int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, size_t n,
                 size_t a_stride, const T *k, size_t klen, T *out, size_t out_len,
                 size_t out_stride, int mode) {
+  const bool fft_forced = env_int("FFTCONV_CUDA_NO_DIRECT", 0) || env_int("FFTCONV_CUDA_STRICT_TABLE", 0) ||
+                          env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) || env_int("FFTCONV_CUDA_OA_FFT_SIZE", 0) ||
+                          env_int("FFTCONV_CUDA_CONV_SINGLE_FFT", 0);
+  if (!tl_filter && !fft_forced && klen <= 256 && !env_int("FFTCONV_CUDA_NO_SMALL_DIRECT", 0) &&
+      (double)batch * (double)out_len * (double)klen <= 4194304.0)
+    return direct_small_device<T>(c, st, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
   if (klen <= direct_max_taps<T>() && !tl_filter && !env_int("FFTCONV_CUDA_NO_DIRECT", 0) &&
       !env_int("FFTCONV_CUDA_STRICT_TABLE", 0) && !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) &&
       !env_int("FFTCONV_CUDA_OA_FFT_SIZE", 0) && !env_int("FFTCONV_CUDA_CONV_SINGLE_FFT", 0))

@@ -29,3 +29,12 @@ def cuda(built):
     if not torch.cuda.is_available():
         pytest.fail("gpu-marked test running without a CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _fft_path_for_small_jobs(monkeypatch):
+    """The library evaluates SMALL jobs (<= 4 Mi multiply-adds) directly, one thread per output
+    (direct_small_kernel).  Most parity tests use small shapes precisely to exercise the FFT kernels
+    cheaply, so they switch that rule off; the tests of the rule itself
+    (tests/test_gpu_parity.py::test_small_jobs_*) switch it back on."""
+    monkeypatch.setenv("FFTCONV_CUDA_NO_SMALL_DIRECT", "1")

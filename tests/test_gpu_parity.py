@@ -834,3 +834,64 @@ def test_direct_kernel_for_short_kernels(cuda, dt, batch, n, klen, monkeypatch):
                 assert torch.equal(full_view[:, :out_len], y), (mode, off)
                 assert torch.isnan(full_view[:, out_len:]).all()
                 assert torch.isnan(ostore[:off]).all()
+
+
+def test_small_jobs_take_one_launch_and_match_the_reference_cases(cuda, monkeypatch):
+    """Default dispatch for small jobs (<= 4 Mi multiply-adds, <= 256 taps): direct_small_kernel, one
+    launch.  Replays the reference's own small cases through it: golden vectors (tests/golden), the
+    Python binding cases (py/test/test_fftconv.py:9-70), the GTest shapes (test/test_fftconv.cpp:93-218)
+    and the test_script sizes (test/test_script.cpp:29-34, config 1)."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    monkeypatch.delenv("FFTCONV_CUDA_NO_SMALL_DIRECT", raising=False)
+    g, names = H.golden_conv_cases()
+    for name in names:
+        a, k = g[f"{name}__a"], g[f"{name}__k"]
+        fn = fc.oaconvolve if name.startswith("oa_") else fc.convolve
+        for mode in ("full", "same"):
+            before = fc.launch_count()
+            got = fn(a, k, mode)
+            if a.shape[-1] * k.size * (1 if a.ndim == 1 else a.shape[0]) <= 2 ** 21 and k.size <= 256:
+                assert fc.launch_count() - before == 1, name
+            assert O.rel_l2(got, g[f"{name}__{mode}"]) < H.TOL[a.dtype], (name, mode)
+    a = np.array([1, 2, 3, 4, 5], dtype=np.float64)
+    k = np.array([0.2, 0.5, 0.2], dtype=np.float64)
+    for mode in ("full", "same"):
+        assert np.allclose(fc.convolve(a, k, mode), np.convolve(a, k, mode=mode), rtol=1e-5, atol=1e-8)
+        assert np.allclose(fc.oaconvolve(a, k, mode), np.convolve(a, k, mode=mode), rtol=1e-5, atol=1e-8)
+    rng = np.random.default_rng(9)
+    for dt in (np.float64, np.float32):
+        for n, klen in ((1000, 95), (2000, 95), (3000, 95), (200, 95), (350, 95), (500, 95), (4, 4), (13, 13), (94, 94),
+                        (1664, 65), (2816, 65), (2304, 65), (4352, 65), (4352, 256), (300, 245)):
+            a, k = rng.standard_normal(n).astype(dt), rng.standard_normal(klen).astype(dt)
+            for mode in ("full", "same"):
+                before = fc.launch_count()
+                y = fc.oaconvolve(_t(a, cuda), _t(k, cuda), mode)
+                torch.cuda.synchronize()
+                assert fc.launch_count() - before == 1
+                _check(y.cpu().numpy(), a, k, mode, (n, klen, dt, mode))
+                _check(fc.convolve(a, k, mode), a, k, mode, ("host", n, klen, dt, mode))
+    # a batch with padded strides and a guard band
+    a = rng.standard_normal((7, 900)).astype(np.float32)
+    k = rng.standard_normal(33).astype(np.float32)
+    store = torch.full((7, 940), float("nan"), device=cuda)
+    fc.oaconvolve_(_t(a, cuda), _t(k, cuda), store[:, :932], "full")
+    torch.cuda.synchronize()
+    _check(store[:, :932].cpu().numpy(), a, k, "full", "strided")
+    assert torch.isnan(store[:, 932:]).all()
+
+
+def test_small_jobs_rule_boundaries(cuda, monkeypatch):
+    """Just above the limits (work, taps) the FFT path serves the call; both agree."""
+    import fftconv_b200 as fc
+
+    monkeypatch.delenv("FFTCONV_CUDA_NO_SMALL_DIRECT", raising=False)
+    rng = np.random.default_rng(10)
+    for n, klen, launches in ((16000, 257, 2), (70000, 65, 2), (4352, 65, 1)):
+        a, k = rng.standard_normal(n).astype(np.float32), rng.standard_normal(klen).astype(np.float32)
+        before = fc.launch_count()
+        y = fc.oaconvolve(a, k, "full")
+        assert fc.launch_count() - before == launches, (n, klen)
+        _check(y, a, k, "full", (n, klen))
