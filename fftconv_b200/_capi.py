@@ -17,7 +17,7 @@ FULL, SAME = 0, 1
 # every symbol include/fftconv_cuda.h declares
 SYMBOLS = [
     "fftconv_cuda_version", "fftconv_cuda_last_error", "fftconv_cuda_optimal_fft_size",
-    "fftconv_cuda_clear_cache", "fftconv_cuda_launch_count",
+    "fftconv_cuda_clear_cache", "fftconv_cuda_launch_count", "fftconv_cuda_set_reserved_sms",
 ] + [
     f"fftconv_cuda_{name}_{sfx}"
     for sfx in ("f32", "f64")
@@ -53,6 +53,7 @@ def lib():
     L.fftconv_cuda_optimal_fft_size.argtypes = [C.c_size_t]
     L.fftconv_cuda_clear_cache.restype = C.c_int
     L.fftconv_cuda_launch_count.restype = C.c_ulonglong
+    L.fftconv_cuda_set_reserved_sms.restype, L.fftconv_cuda_set_reserved_sms.argtypes = C.c_int, [C.c_int]
     vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
     for sfx in ("f32", "f64"):
         for name in ("oaconvolve", "convolve"):

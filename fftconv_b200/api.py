@@ -408,6 +408,20 @@ class Stream:
         return out
 
 
+class reserved_sms:
+    """Context: the persistent overlap-add kernel leaves `n` SMs free while a collective runs beside it
+    (fftconv_cuda_set_reserved_sms)."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+
+    def __enter__(self):
+        self.prev = int(_capi.lib().fftconv_cuda_set_reserved_sms(self.n))
+
+    def __exit__(self, *exc):
+        _capi.lib().fftconv_cuda_set_reserved_sms(self.prev)
+
+
 def launch_count() -> int:
     return int(_capi.lib().fftconv_cuda_launch_count())
 

@@ -42,6 +42,7 @@ using fc::generic::cx;
 thread_local std::string g_err;
 std::mutex g_mu;
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_reserved_sms{0}; // SMs the persistent kernels leave free (fftconv_cuda_set_reserved_sms)
 
 int fail(int code, const std::string &msg) {
   g_err = msg;
@@ -665,7 +666,11 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
     const bool wide_k = klen > (size_t)fc::n2048::kMaxTapsNarrow || env_int("FFTCONV_CUDA_N2048_FORCE_WIDE", 0);
     if (wide_k && G < 3) G = 4; // the wide instantiations exist for four and three groups, always with twiddle recomputation
     while (G > (wide_k ? 3 : 1) && fc::n2048::smem_bytes<T>(G, (int)klen, wide_k || (want_recomp && G == 4)) > c.smem_optin) --G;
-    const long long slots = (long long)c.sm_count * G;
+    // a caller that runs a collective beside this kernel (the K-1 tail exchange of a long signal)
+    // asks for a few SMs to be left free: a persistent grid that owns every SM would make the
+    // collective's kernel wait for it, or wait for the collective's kernel on the SM it took
+    const int sms = std::max(1, c.sm_count - std::max(0, g_reserved_sms.load()));
+    const long long slots = (long long)sms * G;
     // streams per row: enough quads to fill every group, but never so many that
     // the per-chunk warm-up segment costs more than ~6 %
     long long chunks = 1;
@@ -683,7 +688,7 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
     const bool wide = wide_k;
     const bool recomp = wide || (want_recomp && G == 4);
     const size_t smem = fc::n2048::smem_bytes<T>(G, (int)klen, recomp);
-    const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
+    const long long grid = std::max<long long>(1, std::min<long long>(sms, (p.total_work + G - 1) / G));
 #define FC_LAUNCH_N2048(GG, RR, WW)                                                            \
   {                                                                                            \
     if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<D, GG, RR, WW>, smem)) return r;     \
@@ -1420,6 +1425,10 @@ const char *fftconv_cuda_version(void) { return FFTCONV_CUDA_VERSION; }
 const char *fftconv_cuda_last_error(void) { return g_err.c_str(); }
 size_t fftconv_cuda_optimal_fft_size(size_t klen) { return optimal_fft_size(klen); }
 unsigned long long fftconv_cuda_launch_count(void) { return g_launches.load(); }
+int fftconv_cuda_set_reserved_sms(int sms) {
+  const int prev = g_reserved_sms.exchange(sms < 0 ? 0 : sms);
+  return prev;
+}
 
 int fftconv_cuda_clear_cache(void) {
   std::lock_guard<std::mutex> lock(g_mu);

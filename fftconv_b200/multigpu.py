@@ -42,6 +42,22 @@ def chunk_bounds(n: int, world: int, rank: int, align: int = 4) -> Tuple[int, in
     return cut(rank), cut(rank + 1)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One exchange stream per device for the life of the process.  A fresh stream per call walks
+    through torch's pool of 32, and the caching allocator keeps blocks per stream: the first ~40
+    calls then each pay cudaMalloc for their small temporaries (measured at 8 GPUs: 1.2 ms per step
+    falling to 0.6 ms)."""
+    import torch
+
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
                     conv: Optional[Callable] = None, add: Optional[Callable] = None):
     """Full-mode overlap-add convolution of one long signal split across ranks.
@@ -55,6 +71,7 @@ def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
     import torch
     import torch.distributed as dist
 
+    own_conv = conv is None
     if conv is None or add is None:
         from . import api
 
@@ -73,7 +90,7 @@ def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
     # samples swap roles: conv is commutative and the API wants signal >= kernel) on a
     # side stream and sent at once; the exchange then overlaps the main kernel.
     on_cuda = bool(getattr(a_chunk, "is_cuda", False))
-    side = torch.cuda.Stream(device=a_chunk.device) if on_cuda else None
+    side = _side_stream(a_chunk.device) if on_cuda else None
     recv_buf = torch.empty(tail_len, dtype=a_chunk.dtype, device=a_chunk.device) if rank > 0 else None
 
     def exchange():
@@ -92,7 +109,22 @@ def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
             reqs, send_buf = exchange()
     else:
         reqs, send_buf = exchange()
-    y = conv(a_chunk, k)                      # m + K - 1 samples, main stream
+    # the main kernel is persistent (one CTA per SM): it leaves a few SMs to the exchange's kernel,
+    # or the two wait for each other's SMs
+    import os
+
+    # measured in steady state (2^31 samples, K = 245): 2 ranks 2.47 / 2.26 / 2.31 ms with 0 / 1 / 4 SMs
+    # left free (main kernel alone 2.18); 8 ranks 0.65-0.68 / 0.60 / 0.60-0.63 / 0.62-0.66 ms with
+    # 0 / 2 / 4 / 8 (alone 0.57): interior ranks send and receive
+    dflt = "1" if world == 2 else "2"
+    reserve = int(os.environ.get("FFTCONV_B200_EXCHANGE_SMS", dflt)) if on_cuda and own_conv else 0
+    if reserve:
+        from . import api
+
+        with api.reserved_sms(reserve):
+            y = conv(a_chunk, k)              # m + K - 1 samples, main stream
+    else:
+        y = conv(a_chunk, k)
     for req in reqs:
         req.wait()                            # the current stream waits for the exchange
     if on_cuda:
