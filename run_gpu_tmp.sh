@@ -1,3 +1,7 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29525 bench_configs.py --config c5 --gpus 2 --steps 10 --warmup 3 > gpurun_out/c5_2gpu_v12.log 2>gpurun_out/c5_2gpu_v12.err; tail -1 gpurun_out/c5_2gpu_v12.log | cut -c1-200
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29526 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_2gpu_v12.log 2>gpurun_out/bench_2gpu_v12.err; tail -1 gpurun_out/bench_2gpu_v12.log | cut -c1-200
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py > gpurun_out/bench_v12.log 2>gpurun_out/bench_v12.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_v12.log').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['e2e']['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['cpu_baseline']['value'])"
+python bench.py --impl reference > gpurun_out/bench_v12_ref.log 2>gpurun_out/bench_v12_ref.err; tail -c 300 gpurun_out/bench_v12_ref.log
+python bench_configs.py --config all > gpurun_out/configs_v12.log 2>gpurun_out/configs_v12.err
+python bench_configs.py --config rf --no-cpu >> gpurun_out/configs_v12.log 2>>gpurun_out/configs_v12.err
+cut -c1-170 gpurun_out/configs_v12.log
