@@ -16,6 +16,13 @@
 // shared loads; four rounds of four outputs per thread, each stored as one 128-bit store (the
 // row's first 0..3 outputs are peeled off so that tiles start on a 16-byte boundary of the output
 // row).  Grid-stride loop over (row, tile).
+//
+// ncu (profiles/r01_ncu_v12_direct_conv_*): LSU data pipe 78 %, DRAM 61 % of ncu's peak -- the
+// scattered scalar stores that lay the window out cost a 4-way bank conflict each.  The obvious
+// cure (load both aligned vectors a misaligned logical vector straddles, assemble it in registers,
+// one aligned 128-bit store) was measured and is SLOWER: 0.50-0.52 ms against 0.40-0.42 (float32),
+// 0.85 against 0.44 (float64) -- twice the global loads in flight per thread costs more than the
+// conflicts.
 #pragma once
 
 #include <cstdint>
