@@ -76,12 +76,12 @@ class _Buf:
         else:
             x = np.asarray(x)
             self.obj = x
-            self.dtype = str(x.dtype)
+            self.dtype = x.dtype.name                     # (str(dtype) costs ~6 us)
             self.shape = x.shape
             if x.ndim >= 1 and x.shape[-1] > 1 and x.strides[-1] != x.itemsize:
                 raise RuntimeError(f"{name}: last dimension must be contiguous")
             self.row_stride = (x.strides[0] // x.itemsize) if x.ndim == 2 else (x.shape[-1] if x.ndim else 1)
-            self.ptr = x.ctypes.data
+            self.ptr = x.__array_interface__["data"][0]   # (x.ctypes.data costs ~3 us per array)
             self.is_cuda = False
         if self.dtype not in _SFX:
             raise TypeError(f"{name}: float32 or float64 expected, got {self.dtype}")
