@@ -563,7 +563,8 @@ def test_streaming_overlap_add_across_calls(cuda, dt, klen, pieces):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("klen", [1, 3, 7, 8, 20, 65, 165, 220, 411, 500, 560, 561, 640, 641, 768, 1024, 1025])
+@pytest.mark.parametrize("klen", [1, 3, 7, 8, 9, 16, 17, 20, 65, 165, 220, 221, 410, 411, 500, 560, 561, 640, 641, 768,
+                                  1024, 1025])
 def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch):
     """Jobs of >= 4 Mi samples move short kernels off the reference's (CPU cost model) segment
     size onto the fastest kernel's; the samples are the same linear convolution either way."""
