@@ -285,7 +285,10 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, CTAS_PER_SM)
   long long unit = blockIdx.x;
   if (threadIdx.x == 0 && unit < units) request(unit);
   uint32_t phase = 0;
-  CtaSync sync;
+  // inside the transform every FFT of the CTA has its own barrier (ids 1 .. FPC; barrier 0 stays the
+  // CTA barrier around the staged rows, which all FFTs share); sixteen FFTs would need one id too many
+  constexpr bool kOwnBarrier = FPC > 1 && FPC <= 15;
+  const FftSync sync{kOwnBarrier ? f + 1 : 0, kOwnBarrier ? P::THREADS : P::THREADS * FPC};
   const HilbertSpectrum<float> G{(float)(1.0 / (double)N)};
   for (; unit < units; unit += gridDim.x) {
     bool has[NL];
