@@ -340,9 +340,12 @@ template <int LOG2N, typename D, class Spectrum> FCF_HD void last_fused(int tid,
 // threads.  For N = 8192 that is two of six boundaries (mid2 -> last, last -> inverse mid2), for
 // N <= 4096 two of four: the warps of an FFT drift apart there and one warp's shared-memory phase
 // overlaps another's arithmetic.
-template <int LM, class Sync> FCF_HD void pass_sync(Sync &sync) {
+// Between those extremes the threads that must meet are the 2^LM / 16 threads of one sub-transform
+// (after the radix-2 first pass of N = 8192 the two 4096-point halves are independent until the
+// mirrored last pass): `sync.sub<LM>(tid)` lets a kernel give every such block its own named barrier.
+template <int LM, class Sync> FCF_HD void pass_sync(Sync &sync, int tid) {
   if constexpr (LM <= 9) sync.warp();
-  else sync();
+  else sync.template sub<LM>(tid);
 }
 template <int LOG2N, int J> struct MidLm { // log2 of the sub-transform length of middle pass J
   static constexpr int value = LOG2N - Plan<LOG2N>::R0 - 4 * (J - 1);
@@ -353,7 +356,7 @@ template <int LOG2N, int J, typename T> struct FwdMids { // T = data type
   template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<scalar_t<T>> *W, Sync &sync) {
     if constexpr (J <= Plan<LOG2N>::P - 2) {
       fwd_mid<LOG2N, J>(tid, buf, W);
-      pass_sync<MidLm<LOG2N, J>::value>(sync); // the next pass is narrower
+      pass_sync<MidLm<LOG2N, J>::value>(sync, tid); // the next pass is narrower
       FwdMids<LOG2N, J + 1, T>::run(tid, buf, W, sync);
     }
   }
@@ -362,7 +365,7 @@ template <int LOG2N, int J, typename T> struct InvMids {
   template <class Sync> static FCF_HD void run(int tid, cx<T> *buf, const cx<scalar_t<T>> *W, Sync &sync) {
     if constexpr (J >= 1) {
       inv_mid<LOG2N, J>(tid, buf, W);
-      pass_sync<(J > 1 ? MidLm<LOG2N, (J > 1 ? J - 1 : 1)>::value : LOG2N)>(sync); // the next pass is wider
+      pass_sync<(J > 1 ? MidLm<LOG2N, (J > 1 ? J - 1 : 1)>::value : LOG2N)>(sync, tid); // the next pass is wider
       InvMids<LOG2N, J - 1, T>::run(tid, buf, W, sync);
     }
   }
@@ -374,10 +377,10 @@ template <int LOG2N, typename T, class Spectrum, class Sync>
 FCF_HD void conv_core_with(int tid, cx<T> *v, cx<T> *buf, const cx<scalar_t<T>> *W /* pass twiddle tables */,
                            const Spectrum &H, Sync &sync) {
   fwd_pass0<LOG2N>(tid, v, buf, W);
-  pass_sync<LOG2N>(sync);
+  pass_sync<LOG2N>(sync, tid);
   FwdMids<LOG2N, 1, T>::run(tid, buf, W, sync);
   last_fused<LOG2N>(tid, buf, H);
-  pass_sync<8>(sync); // the last middle pass always has 256-point sub-transforms
+  pass_sync<8>(sync, tid); // the last middle pass always has 256-point sub-transforms
   InvMids<LOG2N, Plan<LOG2N>::P - 2, T>::run(tid, buf, W, sync);
   inv_pass0<LOG2N>(tid, v, buf, W);
 }

@@ -24,6 +24,7 @@ template <typename D, int CTA_THREADS> constexpr int min_blocks() {
 struct CtaSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
   __device__ __forceinline__ void warp() const { __syncwarp(); } // warp-local exchange (fast_fft.cuh, pass_sync)
+  template <int LM> __device__ __forceinline__ void sub(int) const { __syncthreads(); }
 };
 
 // Barrier among the threads of ONE of the FPC FFTs that share a CTA (named barrier f of 16): the
@@ -32,10 +33,20 @@ struct CtaSync {
 // __syncthreads() in the same phase (that is barrier 0).
 struct FftSync {
   int id, threads;
+  int sub_base = -1; // >= 0: named barriers sub_base, sub_base + 1, ... are free for the sub-transforms of this FFT
   __device__ __forceinline__ void operator()() const {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
   }
   __device__ __forceinline__ void warp() const { __syncwarp(); }
+  // the 2^LM / 16 threads that share one sub-transform of 2^LM points (mid pass: block tid >> (LM - 4))
+  template <int LM> __device__ __forceinline__ void sub(int tid) const {
+    constexpr int TB = (1 << LM) / 16;
+    if (sub_base >= 0 && TB < threads) {
+      asm volatile("bar.sync %0, %1;" ::"r"(sub_base + tid / TB), "r"(TB) : "memory");
+    } else {
+      (*this)();
+    }
+  }
 };
 
 // The real streams ("lanes") that ride in one complex value of data type D:
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
 
   // one barrier domain per FFT (the trip count stays CTA-uniform, so every domain executes the same
   // number of barriers); a single FFT per CTA is the CTA barrier itself
-  const FftSync sync{FPC > 1 ? f : 0, FPC > 1 ? P::THREADS : P::THREADS * FPC};
+  const FftSync sync{FPC > 1 ? f : 0, FPC > 1 ? P::THREADS : P::THREADS * FPC, FPC == 1 ? 1 : -1};
   int parity = 0;
   bool add_tail = false;
   for (long long j = warm_needed ? -1 : 0; j < max_cnt; ++j) {
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, min_blocks<D, Plan<
     v[s] = L::make(a);
     if constexpr (kKeep) keep[s] = v[s];
   }
-  const FftSync sync{FPC > 1 ? f : 0, FPC > 1 ? P::THREADS : P::THREADS * FPC};
+  const FftSync sync{FPC > 1 ? f : 0, FPC > 1 ? P::THREADS : P::THREADS * FPC, FPC == 1 ? 1 : -1};
   const HilbertSpectrum<T> G{(T)(1.0 / (double)P::N)};
   conv_core_with<LOG2N>(tid, v, buf, W, G, sync);
   // envelope; the inputs are re-read (L2) in batches so that their latencies overlap
@@ -288,7 +299,8 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, CTAS_PER_SM)
   // inside the transform every FFT of the CTA has its own barrier (ids 1 .. FPC; barrier 0 stays the
   // CTA barrier around the staged rows, which all FFTs share); sixteen FFTs would need one id too many
   constexpr bool kOwnBarrier = FPC > 1 && FPC <= 15;
-  const FftSync sync{kOwnBarrier ? f + 1 : 0, kOwnBarrier ? P::THREADS : P::THREADS * FPC};
+  // a single FFT per CTA (8192-sample lines): its independent sub-transforms get barriers 1, 2, ...
+  const FftSync sync{kOwnBarrier ? f + 1 : 0, kOwnBarrier ? P::THREADS : P::THREADS * FPC, FPC == 1 ? 1 : -1};
   const HilbertSpectrum<float> G{(float)(1.0 / (double)N)};
   for (; unit < units; unit += gridDim.x) {
     bool has[NL];

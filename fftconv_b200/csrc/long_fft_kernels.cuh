@@ -163,6 +163,7 @@ template <typename T> __global__ void outer_inv_kernel(const LongArgs<T> a) {
 struct CtaSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
   __device__ __forceinline__ void warp() const { __syncwarp(); } // warp-local exchange (fast_fft.cuh, pass_sync)
+  template <int LM> __device__ __forceinline__ void sub(int) const { __syncthreads(); }
 };
 
 // one sub-transform per FFT slot, FPC slots per CTA; H = Hbig + (sub index) * N_sub
