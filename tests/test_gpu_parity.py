@@ -896,3 +896,44 @@ def test_small_jobs_rule_boundaries(cuda, monkeypatch):
         y = fc.oaconvolve(a, k, "full")
         assert fc.launch_count() - before == launches, (n, klen)
         _check(y, a, k, "full", (n, klen))
+
+
+def test_concurrent_callers(cuda):
+    """Any thread may call any entry point (include/fftconv_cuda.h): four Python threads (ctypes
+    releases the GIL) mixing host-pointer and device-pointer calls, float32 and float64, overlap-add,
+    Hilbert and the envelope options; every result is checked."""
+    import threading
+
+    import torch
+
+    import fftconv_b200 as fc
+
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for it in range(6):
+                dt = np.float32 if (seed + it) % 2 == 0 else np.float64
+                tol = H.TOL[np.dtype(dt)]
+                a = rng.standard_normal((3 + seed, 3000 + 500 * it)).astype(dt)
+                k = (rng.standard_normal(20 + 60 * seed) / 8).astype(dt)
+                if it % 2 == 0:
+                    y = fc.oaconvolve(a, k, "full")
+                else:
+                    y = fc.oaconvolve(_t(a, cuda), _t(k, cuda), "full").cpu().numpy()
+                assert O.rel_l2(y, O.conv_exact(a, k, "full")) < tol
+                x = rng.standard_normal((5, 1024)).astype(dt)
+                assert O.rel_l2(fc.hilbert(x), O.hilbert_exact(x)) < tol
+                e = fc.envelope(x, decimate=2 + seed)
+                assert O.rel_l2(e, O.envelope(x, decimate=2 + seed)) < tol
+        except Exception as exc:  # noqa: BLE001 - reported below with the thread's seed
+            errors.append((seed, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
