@@ -11,6 +11,10 @@
 #include "generic_kernels.cuh"
 #include "oa_n2048_kernel.cuh" // the TMA / mbarrier wrappers (n2048::dev)
 
+#ifndef FC_ENV_BATCH
+#define FC_ENV_BATCH 8 // envelope: input samples re-read per batch (x 4 rows in flight per thread); measured on config 4: 4 -> 0.214 ms, 8 -> 0.209, 16 -> 0.210
+#endif
+
 namespace fc {
 namespace fast {
 
@@ -333,17 +337,18 @@ __global__ void __launch_bounds__(Plan<LOG2N>::THREADS *FPC, CTAS_PER_SM)
 #pragma unroll
     for (int l = 0; l < NL; ++l) all = all && has[l];
     if (all) {
+      constexpr int EB = PLAIN ? FC_ENV_BATCH : 4; // (the post-processing store needs the registers: 8 measured slower there)
 #pragma unroll
-      for (int s0 = 0; s0 < 16; s0 += 4) {
-        float a[4][NL];
+      for (int s0 = 0; s0 < 16; s0 += EB) {
+        float a[EB][NL];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < EB; ++s) {
           const int i = pass0_index<LOG2N>(tid, s0 + s);
 #pragma unroll
           for (int l = 0; l < NL; ++l) a[s][l] = __ldg(x[l] + i);
         }
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < EB; ++s) {
           const int i = pass0_index<LOG2N>(tid, s0 + s);
           float h[NL];
           Lanes<D>::split(v[s0 + s], h);
