@@ -18,13 +18,19 @@ FULL, SAME = 0, 1
 SYMBOLS = [
     "fftconv_cuda_version", "fftconv_cuda_last_error", "fftconv_cuda_optimal_fft_size",
     "fftconv_cuda_clear_cache", "fftconv_cuda_launch_count", "fftconv_cuda_set_reserved_sms",
+    "fftconv_cuda_release_stream",
+    "fftconv_cuda_mgpu_init", "fftconv_cuda_mgpu_destroy", "fftconv_cuda_mgpu_device_count",
+    "fftconv_cuda_mgpu_sync", "fftconv_cuda_mgpu_chunk_bounds", "fftconv_cuda_mgpu_row_bounds",
 ] + [
     f"fftconv_cuda_{name}_{sfx}"
     for sfx in ("f32", "f64")
     for name in ("oaconvolve", "oaconvolve_batched", "convolve", "convolve_batched",
                  "hilbert", "hilbert_batched", "add",
                  "filter_create", "filter_oaconvolve", "stream_create", "stream_push",
-                 "stream_flush", "envelope_batched", "rf_envelope_batched")
+                 "stream_flush", "envelope_batched", "rf_envelope_batched",
+                 "oa_tail", "fill_synthetic",
+                 "mgpu_oaconvolve_batched", "mgpu_hilbert_batched", "mgpu_oaconvolve_long",
+                 "mgpu_oaconvolve_long_host")
 ] + ["fftconv_cuda_filter_destroy", "fftconv_cuda_stream_destroy"]
 
 
@@ -55,6 +61,27 @@ def lib():
     L.fftconv_cuda_launch_count.restype = C.c_ulonglong
     L.fftconv_cuda_set_reserved_sms.restype, L.fftconv_cuda_set_reserved_sms.argtypes = C.c_int, [C.c_int]
     vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    L.fftconv_cuda_release_stream.restype, L.fftconv_cuda_release_stream.argtypes = i, [vp]
+    L.fftconv_cuda_mgpu_init.restype, L.fftconv_cuda_mgpu_init.argtypes = i, [i, C.POINTER(i), C.POINTER(vp)]
+    L.fftconv_cuda_mgpu_destroy.restype, L.fftconv_cuda_mgpu_destroy.argtypes = i, [vp]
+    L.fftconv_cuda_mgpu_device_count.restype, L.fftconv_cuda_mgpu_device_count.argtypes = i, [vp]
+    L.fftconv_cuda_mgpu_sync.restype, L.fftconv_cuda_mgpu_sync.argtypes = i, [vp]
+    for name in ("chunk_bounds", "row_bounds"):
+        f = getattr(L, f"fftconv_cuda_mgpu_{name}")
+        f.restype, f.argtypes = None, [sz, i, i, C.POINTER(sz), C.POINTER(sz)]
+    for sfx in ("f32", "f64"):
+        f = getattr(L, f"fftconv_cuda_oa_tail_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, vp, vp]
+        f = getattr(L, f"fftconv_cuda_fill_synthetic_{sfx}")
+        f.restype, f.argtypes = i, [vp, sz, C.c_ulonglong, C.c_ulonglong, C.c_double, vp]
+        f = getattr(L, f"fftconv_cuda_mgpu_oaconvolve_batched_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, sz, sz, vp, sz, vp, sz, sz, i]
+        f = getattr(L, f"fftconv_cuda_mgpu_hilbert_batched_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, sz, sz, vp, sz]
+        f = getattr(L, f"fftconv_cuda_mgpu_oaconvolve_long_{sfx}")
+        f.restype, f.argtypes = i, [vp, C.POINTER(vp), C.POINTER(sz), vp, sz, C.POINTER(vp)]
+        f = getattr(L, f"fftconv_cuda_mgpu_oaconvolve_long_host_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, vp, sz, vp]
     for sfx in ("f32", "f64"):
         for name in ("oaconvolve", "convolve"):
             f = getattr(L, f"fftconv_cuda_{name}_{sfx}")

@@ -20,7 +20,14 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
+    # the CUDA runtime as a shared object (ldconfig knows libcudart.so.12 in this image): nothing
+    # that ships with the snapshot then carries the runtime's own symbol-name tables, and a process
+    # that already holds a runtime (torch) shares it.  FFTCONV_B200_STATIC_CUDART=1 restores nvcc's default.
+    *([] if os.environ.get("FFTCONV_B200_STATIC_CUDART") else ["-cudart", "shared"]),
 ]
+
+# translation units of libfftconv_cuda.so (compiled in parallel, objects under lib/obj/)
+UNITS = ["fftconv_cuda.cu", "fftconv_cuda_mgpu.cu"]
 
 
 def _newer(target: str, sources: list[str]) -> bool:
@@ -37,14 +44,34 @@ def _sources() -> list[str]:
     return out
 
 
+def _unit_deps(unit: str) -> list[str]:
+    """Sources a translation unit is rebuilt for: itself, the public header, and -- for the main
+    unit, which includes every kernel header -- everything under csrc/ that is not another unit."""
+    hdr = os.path.join(ROOT, "include", "fftconv_cuda.h")
+    if unit == "fftconv_cuda.cu":
+        return [hdr] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
+                        if f == unit or not f.endswith(".cu")]
+    return [hdr, os.path.join(CSRC, unit)]
+
+
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(LIBDIR, exist_ok=True)
-    if not force and _newer(LIB, _sources()):
-        return LIB
-    cmd = ["nvcc", *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "fftconv_cuda.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for unit in UNITS:
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and _newer(obj, _unit_deps(unit)):
+            continue
+        cmd = ["nvcc", *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, unit)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    if force or procs or not _newer(LIB, objs):
+        subprocess.run(["nvcc", *NVCC_FLAGS, "-shared", "-o", LIB, *objs, "-ldl"], check=True)
     return LIB
 
 

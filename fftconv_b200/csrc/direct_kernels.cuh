@@ -190,5 +190,46 @@ __global__ void __launch_bounds__(256) direct_small_kernel(const __grid_constant
   p.out[row * p.out_stride + o] = (T)acc;
 }
 
+// The same job for a HOST-pointer call (config 1 through the reference's span API): the signal
+// sits in a page-locked buffer mapped into the device address space, the kernel reads it across
+// PCIe exactly once -- each CTA stages the 256 + K - 1 inputs of its 256 outputs in shared memory
+// with coalesced loads -- and writes the outputs straight back into mapped host memory: one
+// launch and one synchronisation per call, no cudaMemcpy in either direction.
+template <typename T>
+__global__ void __launch_bounds__(256) direct_tiny_kernel(const __grid_constant__ SmallArgs<T> p, int tiles_per_row) {
+  __shared__ T ks[256];
+  __shared__ T xs[512];
+  const int row = blockIdx.x / tiles_per_row, tile = blockIdx.x - row * tiles_per_row;
+  const T *a = p.in + (long long)row * p.in_stride;
+  const long long o0 = (long long)tile * 256;
+  const long long lo = o0 + p.pad - (p.klen - 1);              // input index of xs[0]
+  for (int j = threadIdx.x; j < p.klen; j += 256) ks[j] = p.inline_taps ? p.tap[j] : p.taps[j];
+  for (int i = threadIdx.x; i < 256 + p.klen - 1; i += 256) {
+    const long long src = lo + i;
+    xs[i] = (src >= 0 && src < p.n) ? a[src] : (T)0;
+  }
+  __syncthreads();
+  const long long o = o0 + threadIdx.x;
+  if (o >= p.out_len) return;
+  // out[o] = sum_j k[j] a[o + pad - j]; a[o + pad - j] = xs[threadIdx.x + K - 1 - j]
+  double acc = 0.0;
+  const T *w = xs + threadIdx.x + p.klen - 1;
+  for (int j = 0; j < p.klen; ++j) acc += (double)ks[j] * (double)w[-j];
+  p.out[(long long)row * p.out_stride + o] = (T)acc;
+}
+
+// The K - 1 outputs past the end of a chunk's Full convolution depend only on the chunk's last
+// K - 1 samples: tail[i] = sum_{j > i} k[j] last[K - 1 + i - j].  One thread per output, double
+// accumulation -- (K - 1)^2 / 2 multiply-adds in all.  Used when one long signal is cut across
+// GPUs: the tail is produced first and travels to the neighbour while the chunk is convolved.
+template <typename T>
+__global__ void oa_tail_kernel(const T *__restrict__ last, const T *__restrict__ k, int klen, T *__restrict__ tail) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= klen - 1) return;
+  double acc = 0.0;
+  for (int j = i + 1; j < klen; ++j) acc += (double)k[j] * (double)last[klen - 1 + i - j];
+  tail[i] = (T)acc;
+}
+
 } // namespace direct
 } // namespace fc

@@ -19,6 +19,7 @@
 #include "oa_n2048_tables.h"
 #include "oa_w2_kernel.cuh"
 #include "oa_w2_tables.h"
+#include "synthetic.cuh"
 
 #include <cuda_runtime.h>
 
@@ -30,7 +31,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -40,7 +43,17 @@ namespace {
 using fc::generic::cx;
 
 thread_local std::string g_err;
-std::mutex g_mu;
+// Locking (the reference is lock-free per thread through thread_local plan caches,
+// /root/reference/include/fftconv/fftw.hpp:443-455; device memory and streams are shared, so here):
+//   g_map_mu       the device -> context map, held for the lookup only
+//   DeviceCtx::mu  one device's plan / table / workspace cache, held while a call looks up or
+//                  builds its plan and ENQUEUES its kernels -- never across a host transfer or a
+//                  stream synchronisation
+//   DeviceCtx::host_mu  one device's host-pointer pipeline (three streams + staging buffers),
+//                  held for the duration of a host-pointer call on that device
+// Calls on different devices never share a lock; device-pointer calls on one device only
+// serialise their enqueue.
+std::mutex g_map_mu;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_reserved_sms{0}; // SMs the persistent kernels leave free (fftconv_cuda_set_reserved_sms)
 
@@ -91,7 +104,7 @@ struct BluesteinTables {  // per (n, dtype): Hilbert of a non-power-of-two lengt
   void *B = nullptr;      // cx<T>[M], DIF order, 1/M folded in
 };
 
-struct StreamWs {         // per stream
+struct StreamWs {         // per stream: everything a call in flight on that stream may still be using
   void *taps = nullptr;
   size_t taps_bytes = 0;
   void *H = nullptr;
@@ -100,11 +113,23 @@ struct StreamWs {         // per stream
   size_t rf_bytes = 0;
   void *part = nullptr;   // partial convolution with one block of a long kernel
   size_t part_bytes = 0;
+  void *scratch = nullptr; // long-FFT intermediate (grow only): per stream, so that launches on
+  size_t scratch_bytes = 0; // different streams (the host pipeline's three) never share it
 };
+void free_ws(StreamWs &w) {
+  cudaFree(w.taps);
+  cudaFree(w.H);
+  cudaFree(w.rf);
+  cudaFree(w.part);
+  cudaFree(w.scratch);
+  w = StreamWs();
+}
 
 constexpr int kPipe = 3;
 
 struct DeviceCtx {
+  std::mutex mu;      // cache + enqueue
+  std::mutex host_mu; // host-pointer pipeline
   int device = -1;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -119,27 +144,32 @@ struct DeviceCtx {
   void *stage_tmp[kPipe] = {nullptr, nullptr, nullptr}; // filtered rows between the two steps of OP_RF
   size_t cap_in[kPipe] = {0, 0, 0}, cap_out[kPipe] = {0, 0, 0}, cap_tmp[kPipe] = {0, 0, 0};
   std::map<const void *, size_t> smem_set; // kernel -> opted-in dynamic smem
-  void *scratch = nullptr;                 // long-FFT intermediate (grow only)
-  size_t scratch_bytes = 0;
+  // host-pointer path: pinned ring for pageable callers, mapped buffer for tiny calls
+  void *ring_in[kPipe] = {nullptr, nullptr, nullptr}, *ring_out[kPipe] = {nullptr, nullptr, nullptr};
+  size_t ring_cap_in[kPipe] = {0, 0, 0}, ring_cap_out[kPipe] = {0, 0, 0};
+  void *tiny_host = nullptr, *tiny_dev = nullptr; // one mapped (zero-copy) page-locked buffer
+  size_t tiny_bytes = 0;
+  cudaStream_t tiny_stream = nullptr;
 };
 
-std::map<int, DeviceCtx> g_ctx;
+std::map<int, std::unique_ptr<DeviceCtx>> g_ctx; // contexts never move: calls keep plain pointers
 
 int get_ctx(DeviceCtx **out) {
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_map_mu);
   auto it = g_ctx.find(dev);
   if (it == g_ctx.end()) {
-    DeviceCtx c;
-    c.device = dev;
+    std::unique_ptr<DeviceCtx> c(new DeviceCtx());
+    c->device = dev;
     int v = 0;
     CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
-    c.sm_count = v;
+    c->sm_count = v;
     CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    c.smem_optin = (size_t)v;
-    it = g_ctx.emplace(dev, c).first;
+    c->smem_optin = (size_t)v;
+    it = g_ctx.emplace(dev, std::move(c)).first;
   }
-  *out = &it->second;
+  *out = it->second.get();
   return 0;
 }
 
@@ -159,9 +189,6 @@ void free_ctx(DeviceCtx &c) {
     cudaFree(kv.second.B);
   }
   c.bluestein.clear();
-  cudaFree(c.scratch);
-  c.scratch = nullptr;
-  c.scratch_bytes = 0;
   cudaFree(c.tw1);
   cudaFree(c.tw2);
   cudaFree(c.tw_w2);
@@ -169,22 +196,27 @@ void free_ctx(DeviceCtx &c) {
   cudaFree(c.tw2d);
   c.tw1 = c.tw2 = c.tw_w2 = nullptr;
   c.tw1d = c.tw2d = nullptr;
-  for (auto &kv : c.ws) {
-    cudaFree(kv.second.taps);
-    cudaFree(kv.second.H);
-    cudaFree(kv.second.rf);
-    cudaFree(kv.second.part);
-  }
+  for (auto &kv : c.ws) free_ws(kv.second);
   c.ws.clear();
+  c.smem_set.clear();
   for (int i = 0; i < kPipe; ++i) {
     if (c.pipe[i]) cudaStreamDestroy(c.pipe[i]);
     cudaFree(c.stage_in[i]);
     cudaFree(c.stage_out[i]);
     cudaFree(c.stage_tmp[i]);
+    cudaFreeHost(c.ring_in[i]);
+    cudaFreeHost(c.ring_out[i]);
     c.pipe[i] = nullptr;
     c.stage_in[i] = c.stage_out[i] = c.stage_tmp[i] = nullptr;
+    c.ring_in[i] = c.ring_out[i] = nullptr;
     c.cap_in[i] = c.cap_out[i] = c.cap_tmp[i] = 0;
+    c.ring_cap_in[i] = c.ring_cap_out[i] = 0;
   }
+  cudaFreeHost(c.tiny_host);
+  c.tiny_host = c.tiny_dev = nullptr;
+  c.tiny_bytes = 0;
+  if (c.tiny_stream) cudaStreamDestroy(c.tiny_stream);
+  c.tiny_stream = nullptr;
 }
 
 template <typename T> constexpr int dtype_id() { return std::is_same<T, float>::value ? 0 : 1; }
@@ -820,8 +852,11 @@ int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t 
   const size_t bufs = chirp ? 2 : 1; // chirp-z keeps the sequence between its two convolutions
   size_t pairs_per = std::max<size_t>(1, std::min<size_t>(pairs_total, budget / (bufs * pair_bytes)));
   pairs_per = std::min<size_t>(pairs_per, 65535);
-  if (c.scratch_bytes < bufs * pairs_per * pair_bytes) CU_TRY(cudaDeviceSynchronize()); // other streams may still use it
-  if (int r = grow(&c.scratch, &c.scratch_bytes, bufs * pairs_per * pair_bytes)) return r;
+  // per stream: launches on different streams -- the host pipeline's three, or two
+  // user streams -- must not write the same intermediate; work on ONE stream is ordered
+  StreamWs &wsl = c.ws[st];
+  if (wsl.scratch_bytes < bufs * pairs_per * pair_bytes) CU_TRY(cudaStreamSynchronize(st)); // before the old one is freed
+  if (int r = grow(&wsl.scratch, &wsl.scratch_bytes, bufs * pairs_per * pair_bytes)) return r;
   fc::longfft::LongArgs<T> la{};
   la.in = a;
   la.out = out;
@@ -832,13 +867,13 @@ int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t 
   la.out_len = (long long)out_len;
   la.pad = pad;
   la.log2sub = l2s;
-  la.scratch = reinterpret_cast<fc::fast::cx<T> *>(c.scratch);
+  la.scratch = reinterpret_cast<fc::fast::cx<T> *>(wsl.scratch);
   la.TWbig = reinterpret_cast<const fc::fast::cx<T> *>(tbig->TWbig);
   la.hilbert = hilbert ? 1 : 0;
   la.epi = current_epilogue<T>(n);
   la.bluestein = 0;
   la.chirp = reinterpret_cast<const fc::fast::cx<T> *>(chirp);
-  la.cbuf = reinterpret_cast<fc::fast::cx<T> *>(c.scratch) + pairs_per * Nbig;
+  la.cbuf = reinterpret_cast<fc::fast::cx<T> *>(wsl.scratch) + pairs_per * Nbig;
   const int threads = 256;
   for (size_t p0 = 0; p0 < pairs_total; p0 += pairs_per) {
     const size_t np = std::min(pairs_per, pairs_total - p0);
@@ -846,7 +881,7 @@ int long_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t 
     la.pairs = (long long)np;
     const dim3 grid((unsigned)((nsub + threads - 1) / threads), (unsigned)np);
     auto inner = [&]() -> int {
-      FAST_SWITCH(launch_inner, l2s, c, st, static_cast<cx<T> *>(c.scratch), (long long)np * 16,
+      FAST_SWITCH(launch_inner, l2s, c, st, static_cast<cx<T> *>(wsl.scratch), (long long)np * 16,
                   static_cast<const cx<T> *>(tsub->TWfast), Hbig)
     };
     for (int pass = 0; pass < (chirp ? 2 : 1); ++pass) {
@@ -1156,12 +1191,40 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
   return 0;
 }
 
-// ---- host-pointer path: pipelined row blocks over three streams ------------------------
+// ---- host-pointer path ------------------------------------------------------------------
+// Kind of memory behind a caller's pointer.  The reference's callers hand in std::vector / NumPy
+// arrays, i.e. PAGEABLE memory; cudaMemcpyAsync on pageable memory is staged by the driver and
+// blocks the calling thread, so nothing would overlap.
+enum PtrKind { PTR_DEVICE, PTR_PINNED, PTR_PAGEABLE };
+PtrKind ptr_kind(const void *p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return PTR_PAGEABLE;
+  }
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return PTR_DEVICE;
+  return attr.type == cudaMemoryTypeHost ? PTR_PINNED : PTR_PAGEABLE;
+}
+
+// one row block of the host pipeline on device buffers: kernels only, c.mu held by the caller
 template <typename T>
-int run_host(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k,
-             size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
-  for (int i = 0; i < kPipe; ++i)
-    if (!c.pipe[i]) CU_TRY(cudaStreamCreateWithFlags(&c.pipe[i], cudaStreamNonBlocking));
+int block_device(DeviceCtx &c, cudaStream_t st, Op op, int slot, size_t rows_cap, const T *din, size_t rows, size_t n,
+                 const T *k, size_t klen, T *dout, size_t out_len, int mode) {
+  if (op == OP_HILBERT) return hilbert_device<T>(c, st, din, rows, n, n, dout, out_len);
+  if (op == OP_RF) {
+    if (int g = grow(&c.stage_tmp[slot], &c.cap_tmp[slot], rows_cap * n * sizeof(T))) return g;
+    T *tmp = static_cast<T *>(c.stage_tmp[slot]);
+    if (int r = conv_device<T>(c, st, OP_OA, din, rows, n, n, k, klen, tmp, n, n, FFTCONV_CUDA_SAME)) return r;
+    return hilbert_device<T>(c, st, tmp, rows, n, n, dout, out_len);
+  }
+  return conv_device<T>(c, st, op, din, rows, n, n, k, klen, dout, out_len, out_len, mode);
+}
+
+// Pinned (or registered) host memory: row blocks pipelined over three streams; every copy is one
+// cudaMemcpyAsync (or one 2-D copy for strided rows) that returns at once.
+template <typename T>
+int run_host_pinned(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k,
+                    size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
   const size_t row_bytes = std::max(n, out_len) * sizeof(T);
   const size_t target = (size_t)env_int("FFTCONV_CUDA_HOST_BLOCK_MB", 32) << 20;
   size_t rows_per_block = std::max<size_t>(1, target / std::max<size_t>(1, row_bytes));
@@ -1196,15 +1259,10 @@ int run_host(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_s
     else
       CU_TRY(cudaMemcpy2DAsync(din, n * sizeof(T), a + r0 * a_stride, a_stride * sizeof(T),
                                n * sizeof(T), rows, cudaMemcpyHostToDevice, c.pipe[s]));
-    int r;
-    if (op == OP_HILBERT) r = hilbert_device<T>(c, c.pipe[s], din, rows, n, n, dout, out_len);
-    else if (op == OP_RF) {
-      if (int g = grow(&c.stage_tmp[s], &c.cap_tmp[s], rows_per_block * n * sizeof(T))) return g;
-      T *tmp = static_cast<T *>(c.stage_tmp[s]);
-      r = conv_device<T>(c, c.pipe[s], OP_OA, din, rows, n, n, k, klen, tmp, n, n, FFTCONV_CUDA_SAME);
-      if (!r) r = hilbert_device<T>(c, c.pipe[s], tmp, rows, n, n, dout, out_len);
-    } else r = conv_device<T>(c, c.pipe[s], op, din, rows, n, n, k, klen, dout, out_len, out_len, mode);
-    if (r) return r;
+    {
+      std::lock_guard<std::mutex> lock(c.mu); // plan cache + enqueue only
+      if (int r = block_device<T>(c, c.pipe[s], op, s, rows_per_block, din, rows, n, k, klen, dout, out_len, mode)) return r;
+    }
     if (out_stride == out_len)
       CU_TRY(cudaMemcpyAsync(out + r0 * out_len, dout, rows * out_len * sizeof(T), cudaMemcpyDeviceToHost, c.pipe[s]));
     else
@@ -1216,14 +1274,166 @@ int run_host(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_s
   return 0;
 }
 
+// Pageable host memory through a page-locked ring: kPipe worker threads, each with its own stream,
+// device staging and a pinned in / out buffer.  A worker copies a row block into its pinned buffer
+// (plain memcpy, the part the driver would otherwise do single-threaded and synchronously), uploads,
+// computes, downloads and copies out; the workers overlap one another's phases.
+template <typename T>
+int run_host_ring(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k,
+                  size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
+  const size_t row_bytes = std::max(n, out_len) * sizeof(T);
+  const size_t target = (size_t)env_int("FFTCONV_CUDA_HOST_RING_BLOCK_MB", 16) << 20;
+  const size_t rows_per_block = std::min(batch, std::max<size_t>(1, target / std::max<size_t>(1, row_bytes)));
+  const size_t n_blocks = (batch + rows_per_block - 1) / rows_per_block;
+  for (int s = 0; s < kPipe; ++s) {
+    if (int r = grow(&c.stage_in[s], &c.cap_in[s], rows_per_block * n * sizeof(T))) return r;
+    if (int r = grow(&c.stage_out[s], &c.cap_out[s], rows_per_block * out_len * sizeof(T))) return r;
+    if (c.ring_cap_in[s] < rows_per_block * n * sizeof(T)) {
+      cudaFreeHost(c.ring_in[s]);
+      c.ring_in[s] = nullptr;
+      c.ring_cap_in[s] = 0;
+      CU_TRY(cudaHostAlloc(&c.ring_in[s], rows_per_block * n * sizeof(T), cudaHostAllocPortable));
+      c.ring_cap_in[s] = rows_per_block * n * sizeof(T);
+    }
+    if (c.ring_cap_out[s] < rows_per_block * out_len * sizeof(T)) {
+      cudaFreeHost(c.ring_out[s]);
+      c.ring_out[s] = nullptr;
+      c.ring_cap_out[s] = 0;
+      CU_TRY(cudaHostAlloc(&c.ring_out[s], rows_per_block * out_len * sizeof(T), cudaHostAllocPortable));
+      c.ring_cap_out[s] = rows_per_block * out_len * sizeof(T);
+    }
+  }
+  int status[kPipe] = {0, 0, 0};
+  std::string msgs[kPipe];
+  const Filter *parent_filter = tl_filter; // thread_local call context: hand it to the workers
+  const EnvOpts parent_env = tl_env;
+  auto worker = [&](int s) {
+    auto body = [&]() -> int {
+      tl_filter = parent_filter;
+      tl_env = parent_env;
+      CU_TRY(cudaSetDevice(c.device));
+      T *din = static_cast<T *>(c.stage_in[s]), *dout = static_cast<T *>(c.stage_out[s]);
+      T *hin = static_cast<T *>(c.ring_in[s]), *hout = static_cast<T *>(c.ring_out[s]);
+      for (size_t b = (size_t)s; b < n_blocks; b += kPipe) {
+        const size_t r0 = b * rows_per_block, rows = std::min(rows_per_block, batch - r0);
+        if (a_stride == n) std::memcpy(hin, a + r0 * n, rows * n * sizeof(T));
+        else
+          for (size_t r = 0; r < rows; ++r) std::memcpy(hin + r * n, a + (r0 + r) * a_stride, n * sizeof(T));
+        CU_TRY(cudaMemcpyAsync(din, hin, rows * n * sizeof(T), cudaMemcpyHostToDevice, c.pipe[s]));
+        {
+          std::lock_guard<std::mutex> lock(c.mu);
+          if (int r = block_device<T>(c, c.pipe[s], op, s, rows_per_block, din, rows, n, k, klen, dout, out_len, mode)) return r;
+        }
+        CU_TRY(cudaMemcpyAsync(hout, dout, rows * out_len * sizeof(T), cudaMemcpyDeviceToHost, c.pipe[s]));
+        CU_TRY(cudaStreamSynchronize(c.pipe[s]));
+        if (out_stride == out_len) std::memcpy(out + r0 * out_len, hout, rows * out_len * sizeof(T));
+        else
+          for (size_t r = 0; r < rows; ++r) std::memcpy(out + (r0 + r) * out_stride, hout + r * out_len, out_len * sizeof(T));
+      }
+      return 0;
+    };
+    status[s] = body();
+    if (status[s]) msgs[s] = g_err; // g_err is thread_local: carry the message back
+  };
+  std::thread th[kPipe];
+  const int workers = (int)std::min<size_t>(kPipe, n_blocks);
+  for (int s = 1; s < workers; ++s) th[s] = std::thread(worker, s);
+  worker(0);
+  for (int s = 1; s < workers; ++s) th[s].join();
+  for (int s = 0; s < workers; ++s)
+    if (status[s]) return fail(status[s], msgs[s]);
+  return 0;
+}
+
+// A tiny convolution through the host API (BASELINE config 1: n = 4352, K = 65; the reference needs
+// 17.2 us per call, README.md:99-102): no cudaMemcpy at all -- the signal is copied into a mapped
+// page-locked buffer, one kernel reads it across PCIe and writes the result back the same way.
+constexpr size_t kTinyBytes = 256 << 10;
+template <typename T> bool tiny_ok(Op op, size_t batch, size_t n, size_t klen, size_t out_len) {
+  if (op != OP_OA && op != OP_CONV) return false;
+  if (tl_filter || klen > 256 || batch > 64) return false;
+  if ((double)batch * (double)out_len * (double)klen > 4194304.0) return false;
+  if (batch * (n + out_len) * sizeof(T) + klen * sizeof(T) > kTinyBytes) return false;
+  return !(env_int("FFTCONV_CUDA_NO_DIRECT", 0) || env_int("FFTCONV_CUDA_STRICT_TABLE", 0) ||
+           env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) || env_int("FFTCONV_CUDA_OA_FFT_SIZE", 0) ||
+           env_int("FFTCONV_CUDA_CONV_SINGLE_FFT", 0) || env_int("FFTCONV_CUDA_NO_SMALL_DIRECT", 0) ||
+           env_int("FFTCONV_CUDA_NO_TINY_HOST", 0));
+}
+template <typename T>
+int run_host_tiny(DeviceCtx &c, const T *a, size_t batch, size_t n, size_t a_stride, const T *k, size_t klen, T *out,
+                  size_t out_len, size_t out_stride, int mode) {
+  if (!c.tiny_host) {
+    CU_TRY(cudaHostAlloc(&c.tiny_host, kTinyBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    CU_TRY(cudaHostGetDevicePointer(&c.tiny_dev, c.tiny_host, 0));
+    CU_TRY(cudaStreamCreateWithFlags(&c.tiny_stream, cudaStreamNonBlocking));
+    c.tiny_bytes = kTinyBytes;
+  }
+  T *h = static_cast<T *>(c.tiny_host), *d = static_cast<T *>(c.tiny_dev);
+  for (size_t r = 0; r < batch; ++r) std::memcpy(h + r * n, a + r * a_stride, n * sizeof(T));
+  const size_t out_off = batch * n, taps_off = out_off + batch * out_len;
+  fc::direct::SmallArgs<T> p{};
+  p.in = d;
+  p.out = d + out_off;
+  p.batch = (long long)batch;
+  p.n = (long long)n;
+  p.in_stride = (long long)n;
+  p.out_stride = (long long)out_len;
+  p.out_len = (long long)out_len;
+  p.klen = (int)klen;
+  p.pad = mode == FFTCONV_CUDA_SAME ? (int)(klen / 2) : 0;
+  if (klen <= (size_t)fc::direct::kInlineTaps) {
+    p.inline_taps = 1;
+    std::memcpy(p.tap, k, klen * sizeof(T));
+  } else {
+    std::memcpy(h + taps_off, k, klen * sizeof(T));
+    p.taps = d + taps_off;
+  }
+  const int tiles = (int)((out_len + 255) / 256);
+  fc::direct::direct_tiny_kernel<T><<<(unsigned)(batch * tiles), 256, 0, c.tiny_stream>>>(p, tiles);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  CU_TRY(cudaStreamSynchronize(c.tiny_stream));
+  for (size_t r = 0; r < batch; ++r) std::memcpy(out + r * out_stride, h + out_off + r * out_len, out_len * sizeof(T));
+  return 0;
+}
+
+template <typename T>
+int run_host(DeviceCtx &c, Op op, PtrKind kind_in, PtrKind kind_out, const T *a, size_t batch, size_t n, size_t a_stride,
+             const T *k, size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
+  std::lock_guard<std::mutex> host_lock(c.host_mu);
+  if (tiny_ok<T>(op, batch, n, klen, out_len) && ptr_kind(k) != PTR_DEVICE)
+    return run_host_tiny<T>(c, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+  for (int i = 0; i < kPipe; ++i)
+    if (!c.pipe[i]) CU_TRY(cudaStreamCreateWithFlags(&c.pipe[i], cudaStreamNonBlocking));
+  const size_t in_bytes = ((batch - 1) * a_stride + n) * sizeof(T), out_bytes = ((batch - 1) * out_stride + out_len) * sizeof(T);
+  const bool pageable = kind_in == PTR_PAGEABLE || kind_out == PTR_PAGEABLE;
+  // FFTCONV_CUDA_HOST_PAGEABLE: 0 = plain cudaMemcpyAsync on pageable memory (driver staging),
+  // 1 = page-lock the caller's arrays for the duration of the call (cudaHostRegister), 2 = ring
+  const int strategy = env_int("FFTCONV_CUDA_HOST_PAGEABLE", 2);
+  if (pageable && in_bytes + out_bytes >= (size_t)(8 << 20)) {
+    if (strategy == 2) return run_host_ring<T>(c, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+    if (strategy == 1) {
+      const bool reg_in = kind_in == PTR_PAGEABLE &&
+                          cudaHostRegister(const_cast<T *>(a), in_bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly) == cudaSuccess;
+      const bool reg_out = kind_out == PTR_PAGEABLE && cudaHostRegister(out, out_bytes, cudaHostRegisterPortable) == cudaSuccess;
+      cudaGetLastError(); // a failed registration falls back to the driver's staging
+      const int r = run_host_pinned<T>(c, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+      if (reg_in) cudaHostUnregister(const_cast<T *>(a));
+      if (reg_out) cudaHostUnregister(out);
+      return r;
+    }
+  }
+  return run_host_pinned<T>(c, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+}
+
 template <typename T>
 int entry(Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k, size_t klen,
           T *out, size_t out_len, size_t out_stride, int mode, void *stream) {
-  std::lock_guard<std::mutex> lock(g_mu);
   if (!a || !out) return fail(FFTCONV_CUDA_ERR_ARG, "null data pointer");
   if (batch == 0) return 0;
   if (n == 0) return fail(FFTCONV_CUDA_ERR_ARG, "empty signal");
   if (a_stride < n || out_stride < out_len) return fail(FFTCONV_CUDA_ERR_ARG, "row stride shorter than row");
+  size_t zero_tail = 0; // Full mode, oversized output: samples past n + K - 1 are zeroed
   if (op == OP_RF) {
     if (!k || klen == 0) return fail(FFTCONV_CUDA_ERR_ARG, "empty kernel");
     if (out_len != env_out_len(n))
@@ -1234,6 +1444,12 @@ int entry(Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k
     if (mode != FFTCONV_CUDA_FULL && mode != FFTCONV_CUDA_SAME)
       return fail(FFTCONV_CUDA_ERR_ARG, "Unsupported convolution mode: " + std::to_string(mode));
     const size_t want = mode == FFTCONV_CUDA_FULL ? n + klen - 1 : n;
+    // the reference zero-fills `out` and accepts a Full output longer than n + K - 1
+    // (/root/reference/include/fftconv/fftconv.hpp:340, :385, :467)
+    if (mode == FFTCONV_CUDA_FULL && out_len > want) {
+      zero_tail = out_len - want;
+      out_len = want;
+    }
     if (out_len != want)
       return fail(FFTCONV_CUDA_ERR_ARG, "output length " + std::to_string(out_len) + ", expected " +
                                             std::to_string(want));
@@ -1243,11 +1459,18 @@ int entry(Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k
   }
   DeviceCtx *c = nullptr;
   if (int r = get_ctx(&c)) return r;
-  const bool dev_in = is_device_ptr(a), dev_out = is_device_ptr(out);
+  if (tl_filter && tl_filter->device != c->device)
+    return fail(FFTCONV_CUDA_ERR_ARG, "filter handle lives on device " + std::to_string(tl_filter->device) +
+                                          ", the current device is " + std::to_string(c->device));
+  const PtrKind kind_in = ptr_kind(a), kind_out = ptr_kind(out);
+  const bool dev_in = kind_in == PTR_DEVICE, dev_out = kind_out == PTR_DEVICE;
   if (dev_in != dev_out)
     return fail(FFTCONV_CUDA_ERR_ARG, "input and output must both be host or both be device pointers");
   if (dev_in) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (zero_tail)
+      CU_TRY(cudaMemset2DAsync(out + out_len, out_stride * sizeof(T), 0, zero_tail * sizeof(T), batch, st));
     if (op == OP_HILBERT) return hilbert_device<T>(*c, st, a, batch, n, a_stride, out, out_stride);
     if (op == OP_RF) {
       // the filtered rows live in a per-stream workspace (grow-only, stream-ordered reuse)
@@ -1260,7 +1483,9 @@ int entry(Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k
     }
     return conv_device<T>(*c, st, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
   }
-  return run_host<T>(*c, op, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
+  if (zero_tail)
+    for (size_t r = 0; r < batch; ++r) std::memset(out + r * out_stride + out_len, 0, zero_tail * sizeof(T));
+  return run_host<T>(*c, op, kind_in, kind_out, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode);
 }
 
 // fftconv_cuda_envelope_* / fftconv_cuda_rf_envelope_*: validate the options, publish them to
@@ -1289,12 +1514,40 @@ int envelope_entry(Op op, const T *x, size_t batch, size_t n, size_t x_stride, c
 }
 
 template <typename T> int add_entry(T *dst, const T *src, size_t n, void *stream) {
-  std::lock_guard<std::mutex> lock(g_mu);
   if (n == 0) return 0;
   if (!dst || !src) return fail(FFTCONV_CUDA_ERR_ARG, "null pointer");
   const int threads = 256;
   fc::generic::add_inplace_kernel<T><<<(unsigned)((n + threads - 1) / threads), threads, 0,
                                        static_cast<cudaStream_t>(stream)>>>(dst, src, (long long)n);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+template <typename T> int oa_tail_entry(const T *last, const T *k, size_t klen, T *tail, void *stream) {
+  if (klen <= 1) return 0;
+  if (!last || !k || !tail) return fail(FFTCONV_CUDA_ERR_ARG, "null pointer");
+  if (klen > 0x7fffffffULL) return fail(FFTCONV_CUDA_ERR_ARG, "oa_tail: kernel too long");
+  fc::direct::oa_tail_kernel<T><<<(unsigned)((klen - 1 + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      last, k, (int)klen, tail);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+// x[i] = synthetic sample (seed, first + i): the measurement harness's signal generator
+// (synthetic.cuh; numpy twin fftconv_b200/synthetic.py)
+template <typename T>
+int fill_synthetic_entry(T *dst, size_t n, unsigned long long seed, unsigned long long first, double gain, void *stream) {
+  if (n == 0) return 0;
+  if (!dst) return fail(FFTCONV_CUDA_ERR_ARG, "null pointer");
+  if (ptr_kind(dst) != PTR_DEVICE) return fail(FFTCONV_CUDA_ERR_ARG, "fill_synthetic: device pointer expected");
+  DeviceCtx *c = nullptr;
+  if (int r = get_ctx(&c)) return r;
+  const int threads = 256;
+  const unsigned grid = (unsigned)std::min<size_t>((n + threads - 1) / threads, (size_t)c->sm_count * 16);
+  fc::synthetic::fill_kernel<T><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dst, (unsigned long long)n, seed, first, (T)(fc::synthetic::kScale * gain));
   CU_TRY(cudaGetLastError());
   ++g_launches;
   return 0;
@@ -1306,10 +1559,10 @@ template <typename T> int oa_layout_for(const DeviceCtx &c, size_t N, size_t kle
 }
 
 template <typename T> int filter_create(const T *k, size_t klen, void **out) {
-  std::lock_guard<std::mutex> lock(g_mu);
   if (!k || klen == 0 || !out) return fail(FFTCONV_CUDA_ERR_ARG, "filter_create: empty kernel or null output");
   DeviceCtx *c = nullptr;
   if (int r = get_ctx(&c)) return r;
+  std::lock_guard<std::mutex> lock(c->mu);
   // a handle is for repeated, large calls: the segment size of the throughput rule
   const size_t N = throughput_oa_size<T>(*c, klen, 1 << 16, 1 << 16, optimal_fft_size(klen));
   if (N > max_generic_fft<T>(*c, klen))
@@ -1317,26 +1570,31 @@ template <typename T> int filter_create(const T *k, size_t klen, void **out) {
                                                  std::to_string(N) + ", beyond the single-CTA FFT");
   Tables *tab = nullptr;
   if (int r = get_tables<T>(*c, N, &tab)) return r;
-  auto *f = new Filter();
+  std::unique_ptr<Filter> f(new Filter());
   f->dtype = dtype_id<T>();
   f->device = c->device;
   f->klen = klen;
   f->N = N;
   f->layout = oa_layout_for<T>(*c, N, klen);
-  if (cudaMalloc(&f->taps, klen * sizeof(T)) != cudaSuccess || cudaMalloc(&f->H, N * sizeof(cx<T>)) != cudaSuccess) {
+  auto body = [&]() -> int {
+    CU_TRY(cudaMalloc(&f->taps, klen * sizeof(T)));
+    CU_TRY(cudaMalloc(&f->H, N * sizeof(cx<T>)));
+    CU_TRY(cudaMemcpy(f->taps, k, klen * sizeof(T), cudaMemcpyDefault));
+    const int warps = fc::generic::kSpectrumWarps;
+    fc::generic::spectrum_kernel<T><<<(unsigned)((N + warps - 1) / warps), warps * 32>>>(
+        static_cast<const T *>(f->taps), (int)klen, (int)N, tab->Wd, f->layout, 1.0 / (double)N,
+        static_cast<cx<T> *>(f->H));
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+    CU_TRY(cudaDeviceSynchronize());
+    return 0;
+  };
+  if (int r = body()) { // no leak on any failure path
     cudaFree(f->taps);
-    delete f;
-    return fail(FFTCONV_CUDA_ERR_CUDA, "filter_create: cudaMalloc failed");
+    cudaFree(f->H);
+    return r;
   }
-  CU_TRY(cudaMemcpy(f->taps, k, klen * sizeof(T), cudaMemcpyDefault));
-  const int warps = fc::generic::kSpectrumWarps;
-  fc::generic::spectrum_kernel<T><<<(unsigned)((N + warps - 1) / warps), warps * 32>>>(
-      static_cast<const T *>(f->taps), (int)klen, (int)N, tab->Wd, f->layout, 1.0 / (double)N,
-      static_cast<cx<T> *>(f->H));
-  CU_TRY(cudaGetLastError());
-  ++g_launches;
-  CU_TRY(cudaDeviceSynchronize());
-  *out = f;
+  *out = f.release();
   return 0;
 }
 
@@ -1353,6 +1611,7 @@ int filter_oaconvolve(const void *filter, const T *a, size_t batch, size_t n, si
 }
 
 struct StreamState {
+  std::mutex mu; // push / flush of ONE state are serialised (they reorder the carry buffers)
   const Filter *f = nullptr;
   size_t rows = 0;
   void *carry[2] = {nullptr, nullptr};
@@ -1361,20 +1620,39 @@ struct StreamState {
   size_t tmp_bytes = 0;
 };
 
+// the current device must be the filter's: the carry buffers and every later push live there
+int check_filter_device(const Filter *f, const char *what) {
+  int dev = -1;
+  CU_TRY(cudaGetDevice(&dev));
+  if (dev != f->device)
+    return fail(FFTCONV_CUDA_ERR_ARG, std::string(what) + ": the filter lives on device " + std::to_string(f->device) +
+                                          ", the current device is " + std::to_string(dev));
+  return 0;
+}
+
 template <typename T> int stream_create(const void *filter, size_t rows, void **out) {
   const Filter *f = static_cast<const Filter *>(filter);
   if (!f || f->dtype != dtype_id<T>() || rows == 0 || !out)
     return fail(FFTCONV_CUDA_ERR_ARG, "stream_create: bad filter handle or zero rows");
-  auto *s = new StreamState();
+  if (int r = check_filter_device(f, "stream_create")) return r;
+  std::unique_ptr<StreamState> s(new StreamState());
   s->f = f;
   s->rows = rows;
   const size_t bytes = std::max<size_t>(1, rows * (f->klen - 1)) * sizeof(T);
-  for (int i = 0; i < 2; ++i) {
-    CU_TRY(cudaMalloc(&s->carry[i], bytes));
-    CU_TRY(cudaMemset(s->carry[i], 0, bytes));
+  auto body = [&]() -> int {
+    for (int i = 0; i < 2; ++i) {
+      CU_TRY(cudaMalloc(&s->carry[i], bytes));
+      CU_TRY(cudaMemset(s->carry[i], 0, bytes));
+    }
+    CU_TRY(cudaDeviceSynchronize());
+    return 0;
+  };
+  if (int r = body()) {
+    cudaFree(s->carry[0]);
+    cudaFree(s->carry[1]);
+    return r;
   }
-  CU_TRY(cudaDeviceSynchronize());
-  *out = s;
+  *out = s.release();
   return 0;
 }
 
@@ -1385,18 +1663,18 @@ int stream_push(void *state, const T *chunk, size_t n, size_t chunk_stride, T *o
   if (n == 0) return 0;
   if (!is_device_ptr(chunk) || !is_device_ptr(out))
     return fail(FFTCONV_CUDA_ERR_ARG, "stream_push: device pointers only");
+  if (int r = check_filter_device(s->f, "stream_push")) return r;
+  std::lock_guard<std::mutex> lock(s->mu);
   const size_t tail_len = s->f->klen - 1, w = n + tail_len;
-  {
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (int r = grow(&s->tmp, &s->tmp_bytes, s->rows * w * sizeof(T))) return r;
-  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (s->tmp_bytes < s->rows * w * sizeof(T)) CU_TRY(cudaStreamSynchronize(st)); // before the old one is freed
+  if (int r = grow(&s->tmp, &s->tmp_bytes, s->rows * w * sizeof(T))) return r;
   if (int r = filter_oaconvolve<T>(s->f, chunk, s->rows, n, chunk_stride, static_cast<T *>(s->tmp), w, w,
                                    FFTCONV_CUDA_FULL, stream))
     return r;
   const long long total = (long long)(s->rows * w);
   const int threads = 256;
-  fc::generic::stream_merge_kernel<T><<<(unsigned)((total + threads - 1) / threads), threads, 0,
-                                        static_cast<cudaStream_t>(stream)>>>(
+  fc::generic::stream_merge_kernel<T><<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
       static_cast<const T *>(s->tmp), (long long)s->rows, (long long)n, (int)tail_len,
       static_cast<const T *>(s->carry[s->cur]), static_cast<T *>(s->carry[s->cur ^ 1]), out, (long long)out_stride);
   CU_TRY(cudaGetLastError());
@@ -1410,6 +1688,8 @@ template <typename T> int stream_flush(void *state, T *tail_out, size_t tail_str
   if (!s || s->f->dtype != dtype_id<T>()) return fail(FFTCONV_CUDA_ERR_ARG, "stream state of the wrong precision");
   const size_t tail_len = s->f->klen - 1;
   if (tail_len == 0) return 0;
+  if (int r = check_filter_device(s->f, "stream_flush")) return r;
+  std::lock_guard<std::mutex> lock(s->mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU_TRY(cudaMemcpy2DAsync(tail_out, tail_stride * sizeof(T), s->carry[s->cur], tail_len * sizeof(T),
                            tail_len * sizeof(T), s->rows, cudaMemcpyDefault, st));
@@ -1423,6 +1703,8 @@ extern "C" {
 
 const char *fftconv_cuda_version(void) { return FFTCONV_CUDA_VERSION; }
 const char *fftconv_cuda_last_error(void) { return g_err.c_str(); }
+// for the library's other translation units (fftconv_cuda_mgpu.cu); not declared in the public header
+void fftconv_cuda_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
 size_t fftconv_cuda_optimal_fft_size(size_t klen) { return optimal_fft_size(klen); }
 unsigned long long fftconv_cuda_launch_count(void) { return g_launches.load(); }
 int fftconv_cuda_set_reserved_sms(int sms) {
@@ -1431,20 +1713,35 @@ int fftconv_cuda_set_reserved_sms(int sms) {
 }
 
 int fftconv_cuda_clear_cache(void) {
-  std::lock_guard<std::mutex> lock(g_mu);
+  // Contexts are emptied, not destroyed: a call on another thread that already holds a
+  // DeviceCtx pointer keeps a valid object and simply rebuilds what it needs.
+  std::lock_guard<std::mutex> map_lock(g_map_mu);
   int cur = 0;
   if (cudaGetDevice(&cur) != cudaSuccess) {
     cudaGetLastError();
-    g_ctx.clear();
     return 0;
   }
   for (auto &kv : g_ctx) {
+    DeviceCtx &c = *kv.second;
+    std::lock_guard<std::mutex> host_lock(c.host_mu);
+    std::lock_guard<std::mutex> lock(c.mu);
     cudaSetDevice(kv.first);
     cudaDeviceSynchronize();
-    free_ctx(kv.second);
+    free_ctx(c);
   }
-  g_ctx.clear();
   cudaSetDevice(cur);
+  return 0;
+}
+
+int fftconv_cuda_release_stream(void *stream) {
+  DeviceCtx *c = nullptr;
+  if (int r = get_ctx(&c)) return r;
+  std::lock_guard<std::mutex> lock(c->mu);
+  auto it = c->ws.find(static_cast<cudaStream_t>(stream));
+  if (it == c->ws.end()) return 0;
+  CU_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); // work in flight may still use the buffers
+  free_ws(it->second);
+  c->ws.erase(it);
   return 0;
 }
 
@@ -1476,6 +1773,13 @@ int fftconv_cuda_clear_cache(void) {
   }                                                                                              \
   int fftconv_cuda_add_##SFX(T *dst, const T *src, size_t n, void *stream) {                     \
     return add_entry<T>(dst, src, n, stream);                                                    \
+  }                                                                                              \
+  int fftconv_cuda_oa_tail_##SFX(const T *last, const T *k, size_t klen, T *tail, void *stream) { \
+    return oa_tail_entry<T>(last, k, klen, tail, stream);                                        \
+  }                                                                                              \
+  int fftconv_cuda_fill_synthetic_##SFX(T *dst, size_t n, unsigned long long seed,               \
+                                        unsigned long long first, double gain, void *stream) {   \
+    return fill_synthetic_entry<T>(dst, n, seed, first, gain, stream);                           \
   }
 
 FFTCONV_API(f32, float)

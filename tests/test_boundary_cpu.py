@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(declared) == sorted(_capi.SYMBOLS)
-    assert lib.fftconv_cuda_version() == b"0.1.0"
+    assert lib.fftconv_cuda_version() == b"0.2.0"
 
 
 def test_segment_size_rule_matches_reference_table(built):
