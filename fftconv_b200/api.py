@@ -93,8 +93,10 @@ def _stream_of(buf: _Buf):
         return None
     if _is_tensor(buf.obj):
         return torch.cuda.current_stream(buf.obj.device).cuda_stream
-    s = getattr(buf, "cai_stream", None)     # __cuda_array_interface__ v3: None / 1 = default stream
-    return None if s in (None, 1, 2) else int(s)
+    s = getattr(buf, "cai_stream", None)     # __cuda_array_interface__ v3: None / 1 = legacy default stream,
+    if s == 2:                                # 2 = per-thread default stream (cudaStreamPerThread, handle 0x2)
+        return 2
+    return None if s in (None, 1) else int(s)
 
 
 class _device_of:
@@ -420,6 +422,106 @@ class reserved_sms:
 
     def __exit__(self, *exc):
         _capi.lib().fftconv_cuda_set_reserved_sms(self.prev)
+
+
+def oa_tail_(last, k, tail) -> None:
+    """tail[i] = sum_{j > i} k[j] last[K - 1 + i - j]: the K-1 outputs past the end of a chunk's Full
+    convolution, from the chunk's last K-1 samples (1-D CUDA tensors)."""
+    Lb, K, Tb = _Buf(last, "last"), _Buf(k, "k"), _Buf(tail, "tail")
+    klen = K.shape[0]
+    if not (Lb.is_cuda and K.is_cuda and Tb.is_cuda) or Lb.shape != (klen - 1,) or Tb.shape != (klen - 1,):
+        raise RuntimeError("oa_tail_: CUDA tensors of K-1, K and K-1 samples expected")
+    if Lb.dtype != K.dtype or Tb.dtype != K.dtype:
+        raise TypeError("last, k and tail must share one dtype")
+    fn = getattr(_capi.lib(), f"fftconv_cuda_oa_tail_{_SFX[K.dtype]}")
+    with _device_of(Lb):
+        _capi.check(fn(Lb.ptr, K.ptr, klen, Tb.ptr, _stream_of(Lb)))
+
+
+def release_stream(stream=None) -> None:
+    """Free the workspace the library keeps for `stream` (a torch.cuda.Stream; default: the current one)."""
+    st = torch.cuda.current_stream() if stream is None else stream
+    _capi.check(_capi.lib().fftconv_cuda_release_stream(st.cuda_stream))
+
+
+class MultiGpu:
+    """One process driving several GPUs through the C ABI (`fftconv_cuda_mgpu_*`): batches are split
+    by rows with no collective; one long signal is split into contiguous chunks whose K-1 sample
+    tails go to the neighbouring GPU by ncclSend / ncclRecv.  The one-process-
+    per-GPU form over `torch.distributed` is `fftconv_b200.multigpu`."""
+
+    def __init__(self, devices=None):
+        n = torch.cuda.device_count() if devices is None else len(devices)
+        ids = list(range(n)) if devices is None else [int(d) for d in devices]
+        arr = (_capi.C.c_int * n)(*ids)
+        self._h = _capi.C.c_void_p()
+        _capi.check(_capi.lib().fftconv_cuda_mgpu_init(n, arr, _capi.C.byref(self._h)))
+        self.devices = ids
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _capi.lib().fftconv_cuda_mgpu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def sync(self) -> None:
+        _capi.check(_capi.lib().fftconv_cuda_mgpu_sync(self._h))
+
+    def chunk_bounds(self, n: int, d: int):
+        lo, hi = _capi.C.c_size_t(), _capi.C.c_size_t()
+        _capi.lib().fftconv_cuda_mgpu_chunk_bounds(n, len(self.devices), d, _capi.C.byref(lo), _capi.C.byref(hi))
+        return int(lo.value), int(hi.value)
+
+    def oaconvolve_batched(self, a, k, mode: str = "full"):
+        """Host arrays: rows of `a` (2-D numpy) sharded over the GPUs."""
+        a = np.ascontiguousarray(a)
+        k = np.ascontiguousarray(k, dtype=a.dtype)
+        n, klen = a.shape[1], k.shape[0]
+        m = _mode(mode)
+        out = np.empty((a.shape[0], n if m == _capi.SAME else n + klen - 1), dtype=a.dtype)
+        fn = getattr(_capi.lib(), f"fftconv_cuda_mgpu_oaconvolve_batched_{_SFX[a.dtype.name]}")
+        _capi.check(fn(self._h, a.ctypes.data, a.shape[0], n, n, k.ctypes.data, klen, out.ctypes.data,
+                       out.shape[1], out.shape[1], m))
+        return out
+
+    def hilbert_batched(self, x):
+        x = np.ascontiguousarray(x)
+        out = np.empty_like(x)
+        fn = getattr(_capi.lib(), f"fftconv_cuda_mgpu_hilbert_batched_{_SFX[x.dtype.name]}")
+        _capi.check(fn(self._h, x.ctypes.data, x.shape[0], x.shape[1], x.shape[1], out.ctypes.data, x.shape[1]))
+        return out
+
+    def oaconvolve_long_host(self, a, k):
+        """Host arrays: one long 1-D signal, Full mode."""
+        a = np.ascontiguousarray(a)
+        k = np.ascontiguousarray(k, dtype=a.dtype)
+        out = np.empty(a.shape[0] + k.shape[0] - 1, dtype=a.dtype)
+        fn = getattr(_capi.lib(), f"fftconv_cuda_mgpu_oaconvolve_long_host_{_SFX[a.dtype.name]}")
+        _capi.check(fn(self._h, a.ctypes.data, a.shape[0], k.ctypes.data, k.shape[0], out.ctypes.data))
+        return out
+
+    def oaconvolve_long_(self, a_chunks, k, out_chunks) -> None:
+        """Device-resident: `a_chunks[d]` / `out_chunks[d]` are 1-D CUDA tensors on device d; out chunk d
+        holds len(a_chunks[d]) + K - 1 samples.  `k` is a host (numpy) array.  Enqueues; `sync()` waits.
+        The inputs must be complete (synchronise their producers first)."""
+        nd = len(self.devices)
+        k = np.ascontiguousarray(k)
+        sfx = _SFX[k.dtype.name]
+        klen = k.shape[0]
+        if len(a_chunks) != nd or len(out_chunks) != nd:
+            raise RuntimeError("one chunk per device expected")
+        for d in range(nd):
+            if a_chunks[d].device.index != self.devices[d] or out_chunks[d].device.index != self.devices[d]:
+                raise RuntimeError(f"chunk {d} must live on device {self.devices[d]}")
+            if out_chunks[d].numel() < a_chunks[d].numel() + klen - 1:
+                raise RuntimeError("out chunk must hold len(a chunk) + K - 1 samples")
+        vp = _capi.C.c_void_p
+        ap = (vp * nd)(*[int(t.data_ptr()) for t in a_chunks])
+        op = (vp * nd)(*[int(t.data_ptr()) for t in out_chunks])
+        ln = (_capi.C.c_size_t * nd)(*[int(t.numel()) for t in a_chunks])
+        fn = getattr(_capi.lib(), f"fftconv_cuda_mgpu_oaconvolve_long_{sfx}")
+        _capi.check(fn(self._h, ap, ln, k.ctypes.data, klen, op))
 
 
 def launch_count() -> int:

@@ -126,10 +126,24 @@ def build_cpp_test(force: bool = False) -> str:
     return CPP_TEST
 
 
+CPP_BENCH = os.path.join(ROOT, "tests", "cpp", "bench_c1")
+
+
+def build_cpp_bench(force: bool = False) -> str:
+    src = CPP_BENCH + ".cpp"
+    if not force and _newer(CPP_BENCH, [src, LIB] + _headers()):
+        return CPP_BENCH
+    cmd = ["g++", "-O2", "-std=c++20", f"-I{os.path.join(ROOT, 'include')}", src,
+           f"-L{LIBDIR}", "-lfftconv_cuda", "-Wl,-rpath,$ORIGIN/../../fftconv_b200/lib", "-o", CPP_BENCH]
+    subprocess.run(cmd, check=True)
+    return CPP_BENCH
+
+
 def build_all(force: bool = False) -> None:
     build_lib(force)
     build_microbench(force)
     build_cpp_test(force)
+    build_cpp_bench(force)
     build_ref_binding(force)
 
 

@@ -72,9 +72,9 @@ def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
     import torch.distributed as dist
 
     own_conv = conv is None
-    if conv is None or add is None:
-        from . import api
+    from . import api
 
+    if conv is None or add is None:
         conv = conv or (lambda a, kk: api.oaconvolve(a, kk, "full"))
         add = add or api.add_
     klen = int(k.shape[0])
@@ -97,7 +97,12 @@ def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
         ops = []
         send_buf = None
         if rank < world - 1:
-            send_buf = conv(k, a_chunk[m - tail_len:].contiguous())[tail_len:].contiguous()
+            if own_conv and on_cuda:
+                # the dedicated (K-1)^2 / 2 multiply-add kernel (fftconv_cuda_oa_tail)
+                send_buf = torch.empty(tail_len, dtype=a_chunk.dtype, device=a_chunk.device)
+                api.oa_tail_(a_chunk[m - tail_len:], k, send_buf)
+            else:
+                send_buf = conv(k, a_chunk[m - tail_len:].contiguous())[tail_len:].contiguous()
             ops.append(dist.P2POp(dist.isend, send_buf, rank + 1, group))
         if rank > 0:
             ops.append(dist.P2POp(dist.irecv, recv_buf, rank - 1, group))
@@ -119,8 +124,6 @@ def oaconvolve_long(a_chunk, k, *, rank: int, world: int, group=None,
     dflt = "1" if world == 2 else "2"
     reserve = int(os.environ.get("FFTCONV_B200_EXCHANGE_SMS", dflt)) if on_cuda and own_conv else 0
     if reserve:
-        from . import api
-
         with api.reserved_sms(reserve):
             y = conv(a_chunk, k)              # m + K - 1 samples, main stream
     else:

@@ -9,11 +9,13 @@
 // test/test_common.hpp:9-18 (1e-9 double, 1e-5 float).  Needs a GPU.
 #include <fftconv/fftconv.hpp>
 #include <fftconv/hilbert.hpp>
+#include <fftconv/multi_gpu.hpp>
 
 #include <array>
 #include <cmath>
 #include <cstdio>
 #include <random>
+#include <thread>
 #include <vector>
 
 using fftconv::ConvMode;
@@ -186,6 +188,59 @@ int main() {
                                                      std::span<double>(out));
     } catch (const std::runtime_error &) { threw = true; }
     EXPECT(threw);
+  }
+  { // Full mode into an oversized output: the reference zero-fills `out` (fftconv.hpp:385) and
+    // accepts output.size() >= n + K - 1 (:340); the samples past n + K - 1 must come back zero
+    auto a = randn<double>(500, 31), k = randn<double>(33, 32);
+    std::vector<double> out(500 + 32 + 7, 123.0);
+    fftconv::oaconvolve_fftw<double, ConvMode::Full>(std::span<const double>(a), std::span<const double>(k),
+                                                     std::span<double>(out));
+    std::vector<double> head(out.begin(), out.begin() + 532);
+    near<double>(head, direct(a, k, ConvMode::Full));
+    for (size_t i = 532; i < out.size(); ++i) EXPECT(out[i] == 0.0);
+  }
+  { // one process, every visible GPU (fftconv_cuda_mgpu_*): rows sharded; one long signal cut
+    // into chunks with the K-1 tails exchanged over NCCL when there is more than one device
+    fftconv::MultiGpu mg;
+    std::printf("multi-GPU communicator over %d device(s)\n", mg.size());
+    const size_t batch = 11, n = 6000;
+    auto a = randn<float>(batch * n, 41), k = randn<float>(245, 42);
+    std::vector<float> got(batch * (n + 244)), want(batch * (n + 244));
+    fftconv::oaconvolve_batched<float, ConvMode::Full>(std::span<const float>(a), n, std::span<const float>(k),
+                                                       std::span<float>(want));
+    mg.oaconvolve_batched<float, ConvMode::Full>(std::span<const float>(a), n, std::span<const float>(k),
+                                                 std::span<float>(got));
+    // (not bit-identical across device counts: which rows share a complex FFT depends on the shard)
+    for (size_t i = 0; i < got.size(); ++i) EXPECT(std::abs(got[i] - want[i]) < 1e-4);
+    const size_t nl = 1 << 20;
+    auto x = randn<double>(nl, 43), kd = randn<double>(245, 44);
+    std::vector<double> yl(nl + 244);
+    mg.oaconvolve_long<double>(std::span<const double>(x), std::span<const double>(kd), std::span<double>(yl));
+    // exact check around every cut and at both ends
+    std::vector<size_t> probe = {0, 1, 243, 244, nl - 1, nl, nl + 243};
+    for (int d = 1; d < mg.size(); ++d) {
+      size_t lo = 0, hi = 0;
+      fftconv_cuda_mgpu_chunk_bounds(nl, mg.size(), d, &lo, &hi);
+      for (size_t o = lo - 250; o < lo + 250; ++o) probe.push_back(o);
+    }
+    for (size_t o : probe) {
+      double s = 0;
+      for (size_t j = 0; j < 245; ++j)
+        if (o >= j && o - j < nl) s += kd[j] * x[o - j];
+      EXPECT(std::abs(yl[o] - s) < 1e-9);
+    }
+    if (mg.size() >= 2) { // two host threads, two devices, host-pointer calls: they must not serialise on a lock
+      auto worker = [&](int dev, std::vector<float> *out) {
+        fftconv::MultiGpu one{std::vector<int>{dev}};
+        one.oaconvolve_batched<float, ConvMode::Full>(std::span<const float>(a), n, std::span<const float>(k),
+                                                      std::span<float>(*out));
+      };
+      std::vector<float> o0(want.size()), o1(want.size());
+      std::thread t0(worker, 0, &o0), t1(worker, 1, &o1);
+      t0.join();
+      t1.join();
+      for (size_t i = 0; i < want.size(); ++i) EXPECT(o0[i] == want[i] && o1[i] == want[i]); // same call, same device count
+    }
   }
   std::printf(g_fail ? "FAILED %d\n" : "ALL PASSED\n", g_fail);
   return g_fail ? 1 : 0;

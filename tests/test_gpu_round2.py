@@ -1,0 +1,409 @@
+"""GPU: round-2 parity cases -- the host pipeline's concurrency (per-stream scratch, per-device
+locks), pageable / tiny host paths, oversized Full outputs, the counter-based synthetic signal,
+64-bit indexing beyond 2^31 samples, and the multi-GPU paths (torch.distributed + NCCL, and the
+single-process C ABI `fftconv_cuda_mgpu_*`).  Tolerances are BASELINE.json's."""
+import json
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import fftconv_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _t(x, dev):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+# ---- the long-FFT scratch was shared by the host pipeline's three streams ------
+@pytest.mark.parametrize("dt,n", [(np.float32, 32768), (np.float64, 16384), (np.float32, 20001)])
+def test_host_hilbert_long_lines_many_blocks(cuda, dt, n, monkeypatch):
+    """Host-pointer Hilbert of lines that take the split (global-scratch) FFT, with the row-block size
+    forced down so that the batch runs as many blocks round-robin over the three pipeline streams."""
+    import fftconv_b200 as fc
+
+    monkeypatch.setenv("FFTCONV_CUDA_HOST_BLOCK_MB", "1")
+    rng = np.random.default_rng(n)
+    rows = 48 if n > 20001 else 64
+    x = rng.standard_normal((rows, n)).astype(dt)
+    for strategy in ("0", "2"):            # pinned-style pipeline on pageable memory, and the ring
+        monkeypatch.setenv("FFTCONV_CUDA_HOST_PAGEABLE", strategy)
+        monkeypatch.setenv("FFTCONV_CUDA_HOST_RING_BLOCK_MB", "1")
+        got = fc.hilbert(x)
+        assert O.rel_l2(got, O.hilbert_exact(x)) < H.TOL[np.dtype(dt)], strategy
+
+
+def test_host_convolve_single_long_fft_many_blocks(cuda, monkeypatch):
+    import fftconv_b200 as fc
+
+    monkeypatch.setenv("FFTCONV_CUDA_HOST_BLOCK_MB", "1")
+    monkeypatch.setenv("FFTCONV_CUDA_CONV_SINGLE_FFT", "1")
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((40, 30000))
+    k = rng.standard_normal(165)
+    got = fc.convolve(a, k, "full")
+    assert O.rel_l2(got, O.conv_exact(a, k, "full")) < 1e-12
+
+
+def test_two_streams_share_nothing(cuda):
+    """Device pointers on two user streams at once: long-FFT Hilbert on both, results checked."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(11)
+    xs = [rng.standard_normal((6, 65536)).astype(np.float32) for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = []
+    torch.cuda.synchronize()
+    for it in range(3):
+        outs = []
+        for x, st in zip(xs, streams):
+            with torch.cuda.stream(st):
+                xd = _t(x, cuda)
+                outs.append(fc.hilbert(xd))
+    torch.cuda.synchronize()
+    for x, y in zip(xs, outs):
+        assert O.rel_l2(y.cpu().numpy(), O.hilbert_exact(x)) < 1e-5
+    for st in streams:
+        fc.release_stream(st)              # frees that stream's workspace; later calls rebuild it
+    with torch.cuda.stream(streams[0]):
+        y = fc.hilbert(_t(xs[0], cuda))
+    torch.cuda.synchronize()
+    assert O.rel_l2(y.cpu().numpy(), O.hilbert_exact(xs[0])) < 1e-5
+
+
+# ---- Full mode into an oversized output (fftconv.hpp:340, :385) -------------------------
+@pytest.mark.parametrize("on_device", [False, True])
+def test_full_mode_oversized_output_is_zero_filled(cuda, on_device):
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((5, 3000)).astype(np.float32)
+    k = rng.standard_normal(245).astype(np.float32)
+    want = O.conv_exact(a, k, "full")
+    if on_device:
+        out = torch.full((5, 3300), float("nan"), device=cuda)
+        fc.oaconvolve_(_t(a, cuda), _t(k, cuda), out[:, :3260], "full")   # 3260 > 3244, row stride 3300
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+    else:
+        got = np.full((5, 3300), np.nan, np.float32)
+        fc.oaconvolve_(a, k, got[:, :3260], "full")
+    assert O.rel_l2(got[:, :3244], want) < 1e-5
+    assert np.all(got[:, 3244:3260] == 0)
+    assert np.all(np.isnan(got[:, 3260:]))
+    with pytest.raises(RuntimeError, match="output length"):
+        fc.oaconvolve_(a, k, np.empty((5, 3243), np.float32), "full")       # too short stays an error
+    with pytest.raises(RuntimeError, match="output length"):
+        fc.oaconvolve_(a, k, np.empty((5, 3001), np.float32), "same")       # Same stays exact
+
+
+# ---- tiny host calls: one zero-copy kernel --------------------------------------------------------
+def test_tiny_host_path_config1(cuda, monkeypatch):
+    """BASELINE config 1 (n = 4352, K = 65) and its neighbours through host pointers: mapped
+    page-locked buffer, one launch, no cudaMemcpy; must equal the device-pointer result bit for bit."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    monkeypatch.delenv("FFTCONV_CUDA_NO_SMALL_DIRECT", raising=False)
+    rng = np.random.default_rng(21)
+    for dt in (np.float32, np.float64):
+        for batch, n, klen in ((1, 4352, 65), (1, 1664, 65), (3, 700, 120), (1, 300, 245), (2, 1000, 7), (1, 5, 3)):
+            a = rng.standard_normal((batch, n)).astype(dt)
+            k = rng.standard_normal(klen).astype(dt)
+            for mode in ("full", "same"):
+                before = fc.launch_count()
+                got = fc.oaconvolve(a if batch > 1 else a[0], k, mode)
+                assert fc.launch_count() - before == 1
+                want = O.conv_exact(a if batch > 1 else a[0], k, mode)
+                assert O.rel_l2(got, want) < H.TOL[np.dtype(dt)], (dt, batch, n, klen, mode)
+                dev = fc.oaconvolve(_t(a if batch > 1 else a[0], cuda), _t(k, cuda), mode)
+                torch.cuda.synchronize()
+                assert np.array_equal(dev.cpu().numpy(), got), (dt, batch, n, klen, mode)
+    monkeypatch.setenv("FFTCONV_CUDA_NO_TINY_HOST", "1")
+    a, k = rng.standard_normal(4352).astype(np.float32), rng.standard_normal(65).astype(np.float32)
+    assert O.rel_l2(fc.oaconvolve(a, k, "full"), O.conv_exact(a, k, "full")) < 1e-5
+
+
+# ---- pageable host memory: three strategies, same samples ------------------------------------------
+def test_pageable_host_strategies_agree(cuda, monkeypatch):
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(31)
+    a = rng.standard_normal((300, 20000)).astype(np.float32)        # 24 MB in, 24 MB out: above the 8 MB floor
+    k = (rng.standard_normal(245) / 16).astype(np.float32)
+    want = O.conv_exact(a[:4], k, "full")
+    outs = []
+    for strategy in ("0", "1", "2"):
+        monkeypatch.setenv("FFTCONV_CUDA_HOST_PAGEABLE", strategy)
+        monkeypatch.setenv("FFTCONV_CUDA_HOST_RING_BLOCK_MB", "2")
+        y = fc.oaconvolve(a, k, "full")
+        assert O.rel_l2(y[:4], want) < 1e-5, strategy
+        outs.append(y)
+    # strided rows (views into wider arrays) through the ring
+    wide_in = rng.standard_normal((300, 20100)).astype(np.float32)
+    wide_out = np.full((300, 20300), np.nan, np.float32)
+    fc.oaconvolve_(wide_in[:, 50:20050], k, wide_out[:, :20244], "full")
+    assert O.rel_l2(wide_out[:3, :20244], O.conv_exact(wide_in[:3, 50:20050], k, "full")) < 1e-5
+    assert np.all(np.isnan(wide_out[:, 20244:]))
+    # the envelope options (thread-local call context) must reach the ring's worker threads
+    x = rng.standard_normal((600, 8192)).astype(np.float32)
+    e = fc.envelope(x, decimate=4, log_compress=True, ref=1.0, dynamic_range_db=50.0)
+    assert O.rel_l2(e[:5], O.envelope(x[:5], decimate=4, log_compress=True, ref=1.0, dynamic_range_db=50.0)) < 1e-4
+    assert O.rel_l2(e[-5:], O.envelope(x[-5:], decimate=4, log_compress=True, ref=1.0, dynamic_range_db=50.0)) < 1e-4
+
+
+# ---- synthetic generator: device == numpy twin, bit for bit ------------------------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_synthetic_fill_matches_numpy_twin(cuda, dt):
+    import torch
+
+    from fftconv_b200 import synthetic as syn
+
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    for first, n, gain in ((0, 100000, 1.0), (2 ** 33 + 12345, 4097, 0.25), (2 ** 31 - 50, 100, 1.0 / np.sqrt(245))):
+        x = torch.empty(n, device=cuda, dtype=tdt)
+        syn.fill_(x, syn.SEED_SIGNAL, first=first, gain=gain)
+        torch.cuda.synchronize()
+        assert np.array_equal(x.cpu().numpy(), syn.signal(syn.SEED_SIGNAL, first, n, dt, gain))
+    big = syn.signal(7, 0, 1 << 20, np.float64)
+    assert abs(big.mean()) < 5e-3 and abs(big.std() - 1.0) < 5e-3
+
+
+def test_oa_tail_kernel(cuda):
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(41)
+    for dt, klen in ((np.float32, 245), (np.float64, 165), (np.float32, 2)):
+        k = rng.standard_normal(klen).astype(dt)
+        last = rng.standard_normal(klen - 1).astype(dt)
+        tail = torch.empty(klen - 1, device=cuda, dtype=torch.float32 if dt == np.float32 else torch.float64)
+        fc.oa_tail_(_t(last, cuda), _t(k, cuda), tail)
+        torch.cuda.synchronize()
+        want = np.convolve(last.astype(np.float64), k.astype(np.float64))[klen - 1:]
+        assert O.rel_l2(tail.cpu().numpy(), want) < H.TOL[np.dtype(dt)]
+
+
+# ---- 64-bit indexing: one signal longer than 2^31 samples on ONE GPU (SURVEY section 7 hard part 5) ---
+def test_long_signal_beyond_int32_indices(cuda):
+    import torch
+
+    import fftconv_b200 as fc
+    from fftconv_b200 import synthetic as syn
+
+    free, _ = torch.cuda.mem_get_info()
+    n = 2 ** 31 + 4096 + 7
+    if free < 3 * 4 * n:
+        pytest.skip("needs ~26 GB of free device memory")
+    klen = 245
+    a = torch.empty(n, device=cuda)
+    syn.fill_(a, syn.SEED_SIGNAL)
+    taps = syn.signal(syn.SEED_TAPS, 0, klen, np.float32, gain=1.0 / np.sqrt(klen))
+    for mode, n_out, pad in (("full", n + klen - 1, 0), ("same", n, klen // 2)):
+        y = fc.oaconvolve(a, _t(taps, cuda), mode)
+        torch.cuda.synchronize()
+        assert y.shape[0] == n_out
+        idx = syn.cut_window_indices([2 ** 31 - 1, 2 ** 31, 2 ** 30], n_out, klen, extra_random=20000, tail=6000, seed=1)
+        want = syn.conv_at(syn.SEED_SIGNAL, n, taps, idx + pad)
+        got = y[torch.from_numpy(idx).to(cuda)].cpu().numpy()
+        assert np.sum(idx > 2 ** 31) > 6000
+        assert syn.rel_l2(got, want) < 1e-5, mode
+        # the far end on its own: every output index there exceeds INT32_MAX
+        far = idx[idx > 2 ** 31]
+        assert syn.rel_l2(y[torch.from_numpy(far).to(cuda)].cpu().numpy(), syn.conv_at(syn.SEED_SIGNAL, n, taps, far + pad)) < 1e-5
+        del y
+    del a
+    torch.cuda.empty_cache()
+
+
+# ---- multi-GPU ------------------------------------------------------------------------------------
+def _visible_gpus():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def test_long_signal_tail_exchange_over_nccl(cuda):
+    """BASELINE config 5 end to end under torchrun + NCCL: every rank checks, from the definition, the
+    outputs around ITS cut -- including the first K-1 after the cut, which are sums of its own
+    partial result and the tail its left neighbour sent (fftconv.hpp:387-410 across the cut)."""
+    g = _visible_gpus()
+    if g < 2:
+        pytest.skip("one GPU visible: the NCCL exchange needs two")
+    world = min(g, 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench_configs.py"),
+           "--config", "c5", "--log2n", "27", "--steps", "3", "--gpus", str(world)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    p = d["parity"]
+    assert d["n_gpus"] == world
+    assert p["exchanged_outputs_checked"] == (world - 1) * 244
+    assert p["rel_l2_first_K-1_after_each_cut"] < 1e-5, p
+    assert p["rel_l2"] < 1e-5, p
+
+
+def test_mgpu_c_abi(cuda):
+    """fftconv_cuda_mgpu_*: one process over every visible GPU (one GPU: the same code without the
+    exchange).  Batches by rows; one long signal host-to-host and device-resident."""
+    import torch
+
+    import fftconv_b200 as fc
+    from fftconv_b200 import synthetic as syn
+
+    g = _visible_gpus()
+    mg = fc.MultiGpu()
+    assert len(mg.devices) == g
+    rng = np.random.default_rng(51)
+    a = rng.standard_normal((37, 9000)).astype(np.float32)
+    k = (rng.standard_normal(245) / 16).astype(np.float32)
+    for mode in ("full", "same"):
+        assert O.rel_l2(mg.oaconvolve_batched(a, k, mode), O.conv_exact(a, k, mode)) < 1e-5
+    x = rng.standard_normal((19, 4096))
+    assert O.rel_l2(mg.hilbert_batched(x), O.hilbert_exact(x)) < 1e-12
+    # long signal, host arrays, float64
+    al = rng.standard_normal(3_000_000)
+    kl = rng.standard_normal(165)
+    yl = mg.oaconvolve_long_host(al, kl)
+    cuts = [mg.chunk_bounds(al.shape[0], d)[0] for d in range(1, g)]
+    idx = syn.cut_window_indices(cuts, yl.shape[0], 165, extra_random=3000, tail=1000)
+    assert O.rel_l2(yl[idx], O.conv_exact_at(al, kl, idx)) < 1e-12
+    # long signal, device resident, float32, synthetic: 2^26 samples
+    n, klen = 1 << 26, 245
+    taps = syn.signal(syn.SEED_TAPS, 0, klen, np.float32, gain=1.0 / np.sqrt(klen))
+    ins, outs, los = [], [], []
+    for d in range(g):
+        lo, hi = mg.chunk_bounds(n, d)
+        dev = torch.device("cuda", d)
+        t = torch.empty(hi - lo, device=dev)
+        syn.fill_(t, syn.SEED_SIGNAL, first=lo)
+        ins.append(t)
+        outs.append(torch.empty(hi - lo + klen - 1, device=dev))
+        los.append(lo)
+    for d in range(g):
+        torch.cuda.synchronize(d)
+    for _ in range(3):                     # repeated calls reuse the communicator's buffers
+        mg.oaconvolve_long_(ins, taps, outs)
+    mg.sync()
+    n_out = n + klen - 1
+    idx = syn.cut_window_indices(los[1:], n_out, klen, extra_random=5000, tail=2000)
+    want = syn.conv_at(syn.SEED_SIGNAL, n, taps, idx)
+    got = np.empty(idx.shape[0])
+    for d in range(g):
+        lo = los[d]
+        hi = los[d + 1] if d + 1 < g else n_out
+        m = (idx >= lo) & (idx < hi)
+        got[m] = outs[d][torch.from_numpy(idx[m] - lo).to(outs[d].device)].cpu().numpy()
+    assert syn.rel_l2(got, want) < 1e-5
+    mg.close()
+
+
+def test_two_threads_two_devices_do_not_serialise(cuda):
+    """Per-device locks: two host threads, each driving its own GPU through the
+    host-pointer API, must overlap -- together they take clearly less than twice one alone."""
+    import time
+
+    import torch
+
+    import fftconv_b200 as fc
+
+    if _visible_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(61)
+    a = rng.standard_normal((512, 65536)).astype(np.float32)
+    k = (rng.standard_normal(245) / 16).astype(np.float32)
+    pinned = [torch.from_numpy(a).pin_memory() for _ in range(2)]
+    outs = [torch.empty((512, 65536 + 244)).pin_memory() for _ in range(2)]
+
+    def run(d):
+        with torch.cuda.device(d):
+            fc.oaconvolve_(pinned[d].numpy(), k, outs[d].numpy(), "full")
+
+    for d in range(2):
+        run(d)                              # warm both devices' pipelines
+    t0 = time.perf_counter()
+    run(0)
+    alone = time.perf_counter() - t0
+    ths = [threading.Thread(target=run, args=(d,)) for d in range(2)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    both = time.perf_counter() - t0
+    assert torch.equal(outs[0], outs[1])
+    assert O.rel_l2(outs[1][:3].numpy(), O.conv_exact(a[:3], k, "full")) < 1e-5
+    assert both < 1.6 * alone, (alone, both)
+
+
+def test_threads_on_one_device_host_and_device_calls(cuda):
+    """One device, three threads: two on device pointers (own streams), one on host pointers."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(71)
+    a = rng.standard_normal((64, 30000)).astype(np.float32)
+    k = (rng.standard_normal(245) / 16).astype(np.float32)
+    want = O.conv_exact(a[:2], k, "full")
+    errors = []
+
+    def dev_worker():
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                ad, kd = _t(a, cuda), _t(k, cuda)
+                for _ in range(20):
+                    y = fc.oaconvolve(ad, kd, "full")
+                st.synchronize()
+            assert O.rel_l2(y[:2].cpu().numpy(), want) < 1e-5
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def host_worker():
+        try:
+            for _ in range(4):
+                y = fc.oaconvolve(a, k, "full")
+            assert O.rel_l2(y[:2], want) < 1e-5
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ths = [threading.Thread(target=dev_worker), threading.Thread(target=dev_worker), threading.Thread(target=host_worker)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+
+
+def test_filter_handle_device_mismatch_is_an_error(cuda):
+    import torch
+
+    import fftconv_b200 as fc
+
+    if _visible_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    k = np.ones(33, np.float32)
+    f = fc.Filter(k)                        # lives on device 0
+    a1 = torch.ones(1000, device="cuda:1")
+    with pytest.raises(RuntimeError, match="device"):
+        f.oaconvolve(a1, "full")
+    f.close()
