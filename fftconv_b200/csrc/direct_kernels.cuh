@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256) direct_small_kernel(const __grid_constant
 // with coalesced loads -- and writes the outputs straight back into mapped host memory: one
 // launch and one synchronisation per call, no cudaMemcpy in either direction.
 template <typename T>
-__global__ void __launch_bounds__(256) direct_tiny_kernel(const __grid_constant__ SmallArgs<T> p, int tiles_per_row) {
+__global__ void __launch_bounds__(256) direct_tiny_kernel(const __grid_constant__ SmallArgs<T> p, int tiles_per_row,
+                                                          unsigned *counter, unsigned *flag, unsigned epoch) {
   __shared__ T ks[256];
   __shared__ T xs[512];
   const int row = blockIdx.x / tiles_per_row, tile = blockIdx.x - row * tiles_per_row;
@@ -210,12 +211,25 @@ __global__ void __launch_bounds__(256) direct_tiny_kernel(const __grid_constant_
   }
   __syncthreads();
   const long long o = o0 + threadIdx.x;
-  if (o >= p.out_len) return;
-  // out[o] = sum_j k[j] a[o + pad - j]; a[o + pad - j] = xs[threadIdx.x + K - 1 - j]
-  double acc = 0.0;
-  const T *w = xs + threadIdx.x + p.klen - 1;
-  for (int j = 0; j < p.klen; ++j) acc += (double)ks[j] * (double)w[-j];
-  p.out[(long long)row * p.out_stride + o] = (T)acc;
+  if (o < p.out_len) {
+    // out[o] = sum_j k[j] a[o + pad - j]; a[o + pad - j] = xs[threadIdx.x + K - 1 - j]
+    double acc = 0.0;
+    const T *w = xs + threadIdx.x + p.klen - 1;
+    for (int j = 0; j < p.klen; ++j) acc += (double)ks[j] * (double)w[-j];
+    p.out[(long long)row * p.out_stride + o] = (T)acc;
+  }
+  // completion: every CTA's outputs are fenced system-wide before it is counted; the last CTA
+  // resets the counter for the next call and publishes the epoch to the host
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(counter, 1u) + 1u;
+    if (done == gridDim.x) {
+      *counter = 0u;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned *>(flag) = epoch;
+    }
+  }
 }
 
 // The K - 1 outputs past the end of a chunk's Full convolution depend only on the chunk's last

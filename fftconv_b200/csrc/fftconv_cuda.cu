@@ -17,8 +17,6 @@
 #include "long_fft_kernels.cuh"
 #include "oa_n2048_kernel.cuh"
 #include "oa_n2048_tables.h"
-#include "oa_w2_kernel.cuh"
-#include "oa_w2_tables.h"
 #include "synthetic.cuh"
 
 #include <cuda_runtime.h>
@@ -30,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -126,6 +125,12 @@ void free_ws(StreamWs &w) {
 }
 
 constexpr int kPipe = 3;
+constexpr int kRing = 8;  // worker threads (each: stream + device staging + page-locked in / out) for pageable callers
+struct RingSlot {
+  cudaStream_t st = nullptr;
+  void *din = nullptr, *dout = nullptr, *dtmp = nullptr, *hin = nullptr, *hout = nullptr;
+  size_t cap_din = 0, cap_dout = 0, cap_dtmp = 0, cap_hin = 0, cap_hout = 0;
+};
 
 struct DeviceCtx {
   std::mutex mu;      // cache + enqueue
@@ -135,7 +140,14 @@ struct DeviceCtx {
   size_t smem_optin = 0;
   std::map<std::pair<size_t, int>, Tables> tables;
   std::map<std::pair<size_t, int>, BluesteinTables> bluestein;
-  fc::n2048::cpair *tw1 = nullptr, *tw2 = nullptr, *tw_w2 = nullptr;
+  fc::n2048::cpair *tw1 = nullptr, *tw2 = nullptr;
+  // slice plans of the N = 2048 kernel, keyed by (dtype, batch, n, K, slices): where every group of
+  // the grid starts (oa_n2048_tables.h, plan_slices) -- computed once per shape, kept on the device
+  struct SlicePlanDev {
+    fc::n2048::SlotStart *starts = nullptr;
+    long long vrows = 1, vlen = 0, n_streams = 0, n_quads = 0;
+  };
+  std::map<std::array<long long, 5>, SlicePlanDev> slice_plans;
   fc::n2048::CPairT<double> *tw1d = nullptr, *tw2d = nullptr; // the float64 instantiation's tables
   std::map<cudaStream_t, StreamWs> ws;
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
@@ -145,11 +157,12 @@ struct DeviceCtx {
   size_t cap_in[kPipe] = {0, 0, 0}, cap_out[kPipe] = {0, 0, 0}, cap_tmp[kPipe] = {0, 0, 0};
   std::map<const void *, size_t> smem_set; // kernel -> opted-in dynamic smem
   // host-pointer path: pinned ring for pageable callers, mapped buffer for tiny calls
-  void *ring_in[kPipe] = {nullptr, nullptr, nullptr}, *ring_out[kPipe] = {nullptr, nullptr, nullptr};
-  size_t ring_cap_in[kPipe] = {0, 0, 0}, ring_cap_out[kPipe] = {0, 0, 0};
+  RingSlot ring[kRing];
   void *tiny_host = nullptr, *tiny_dev = nullptr; // one mapped (zero-copy) page-locked buffer
   size_t tiny_bytes = 0;
   cudaStream_t tiny_stream = nullptr;
+  unsigned *tiny_counter = nullptr;               // device: CTAs of the tiny kernel that have finished
+  unsigned tiny_epoch = 0;
 };
 
 std::map<int, std::unique_ptr<DeviceCtx>> g_ctx; // contexts never move: calls keep plain pointers
@@ -191,10 +204,11 @@ void free_ctx(DeviceCtx &c) {
   c.bluestein.clear();
   cudaFree(c.tw1);
   cudaFree(c.tw2);
-  cudaFree(c.tw_w2);
   cudaFree(c.tw1d);
   cudaFree(c.tw2d);
-  c.tw1 = c.tw2 = c.tw_w2 = nullptr;
+  c.tw1 = c.tw2 = nullptr;
+  for (auto &kv : c.slice_plans) cudaFree(kv.second.starts);
+  c.slice_plans.clear();
   c.tw1d = c.tw2d = nullptr;
   for (auto &kv : c.ws) free_ws(kv.second);
   c.ws.clear();
@@ -204,15 +218,22 @@ void free_ctx(DeviceCtx &c) {
     cudaFree(c.stage_in[i]);
     cudaFree(c.stage_out[i]);
     cudaFree(c.stage_tmp[i]);
-    cudaFreeHost(c.ring_in[i]);
-    cudaFreeHost(c.ring_out[i]);
     c.pipe[i] = nullptr;
     c.stage_in[i] = c.stage_out[i] = c.stage_tmp[i] = nullptr;
-    c.ring_in[i] = c.ring_out[i] = nullptr;
     c.cap_in[i] = c.cap_out[i] = c.cap_tmp[i] = 0;
-    c.ring_cap_in[i] = c.ring_cap_out[i] = 0;
+  }
+  for (RingSlot &r : c.ring) {
+    if (r.st) cudaStreamDestroy(r.st);
+    cudaFree(r.din);
+    cudaFree(r.dout);
+    cudaFree(r.dtmp);
+    cudaFreeHost(r.hin);
+    cudaFreeHost(r.hout);
+    r = RingSlot();
   }
   cudaFreeHost(c.tiny_host);
+  cudaFree(c.tiny_counter);
+  c.tiny_counter = nullptr;
   c.tiny_host = c.tiny_dev = nullptr;
   c.tiny_bytes = 0;
   if (c.tiny_stream) cudaStreamDestroy(c.tiny_stream);
@@ -372,15 +393,6 @@ int get_n2048_tables(DeviceCtx &c, const fc::n2048::CPairT<S> **tw1_out, const f
   }
   *tw1_out = *tw1;
   *tw2_out = *tw2;
-  return 0;
-}
-
-int get_w2_tables(DeviceCtx &c) {
-  if (c.tw_w2) return 0;
-  std::vector<fc::n2048::cpair> t(fc::w2::kTwElems);
-  fc::w2::fill_tw(t.data());
-  CU_TRY(cudaMalloc((void **)&c.tw_w2, t.size() * sizeof(fc::n2048::cpair)));
-  CU_TRY(cudaMemcpy(c.tw_w2, t.data(), t.size() * sizeof(fc::n2048::cpair), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -613,20 +625,17 @@ template <typename T, int LOG2N> int build_fast_twiddles(Tables &t) {
   default: return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "fast engine: bad size"); \
   }
 
-// Which kernel serves float32 overlap-add at FFT size 2048: 0 = the register-blocked engine,
-// 1 = oa_n2048_kernel (16 points per thread, 128-thread groups), 2 = oa_w2_kernel (32 points
-// per thread, warp pairs).  FFTCONV_CUDA_OA2048_ENGINE overrides the default.
+// Is the dedicated N = 2048 kernel (oa_n2048_kernel: 16 points per thread, 128-thread groups) in use?
+// (Round 1 also carried a warp-pair engine, oa_w2: measured 12 % slower, removed -- DESIGN.md 3.6.)
 int oa2048_engine() {
   if (env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) || env_int("FFTCONV_CUDA_NO_N2048", 0)) return 0;
-  const int e = env_int("FFTCONV_CUDA_OA2048_ENGINE", 1);
-  return e == 2 ? 2 : 1;
+  return 1;
 }
 
-// engine for one call: the dedicated kernels take N = 2048, 8 <= K <= 410 (staging area and tail
-// buffers are sized for that); the warp-pair engine only float32 and its table row
-// (the WIDE instantiations: up to 1024 taps in float32, 640 in float64 -- what three groups' tail
-// buffers leave room for; reached through the throughput rule only, the table gives such kernels
-// larger segments)
+// engine for one call: the dedicated kernel takes N = 2048, 8 <= K <= 410 (staging area and tail
+// buffers are sized for that) and, in its WIDE instantiations, up to 1024 taps in float32 / 640 in
+// float64 -- what three groups' tail buffers leave room for; those are reached through the
+// throughput rule only, the table gives such kernels larger segments
 template <typename T> size_t oa2048_max_taps() {
   if (env_int("FFTCONV_CUDA_NO_N2048_WIDE", 0)) return fc::n2048::kMaxTapsNarrow;
   return std::is_same<T, float>::value ? (size_t)fc::n2048::kMaxTapsWide : 640;
@@ -635,7 +644,40 @@ template <typename T> int oa2048_engine_for(size_t N, size_t klen) {
   if (N != 2048 || klen < 8 || klen > oa2048_max_taps<T>()) return 0;
   const int e = oa2048_engine();
   if (!std::is_same<T, float>::value) return (e && !env_int("FFTCONV_CUDA_NO_N2048_F64", 0)) ? 1 : 0;
-  return (e == 2 && (klen < 221 || klen > 410)) ? 1 : e;
+  return e;
+}
+
+// The plan of one launch of the N = 2048 kernel: stream geometry + where each group's slice starts.
+template <typename T>
+int get_slice_plan(DeviceCtx &c, fc::n2048::OaParamsT<T> &p, const T *a, T *out, size_t batch, size_t n, size_t a_stride,
+                   size_t out_stride, size_t out_len, size_t klen, int mode, long long n_slots) {
+  const std::array<long long, 5> key = {dtype_id<T>(), (long long)batch, (long long)n, (long long)klen, n_slots};
+  auto it = c.slice_plans.find(key);
+  if (it == c.slice_plans.end()) {
+    if (c.slice_plans.size() >= 512) { // shapes keep changing: start over (tables may still be read by kernels in flight)
+      CU_TRY(cudaDeviceSynchronize());
+      for (auto &kv : c.slice_plans) cudaFree(kv.second.starts);
+      c.slice_plans.clear();
+    }
+    const fc::n2048::SlicePlan plan = fc::n2048::plan_slices<T>(p, a, out, (long long)batch, (long long)n, (long long)a_stride,
+                                                               (long long)out_stride, (long long)out_len, (int)klen, mode, n_slots);
+    DeviceCtx::SlicePlanDev d;
+    d.vrows = plan.vrows; d.vlen = plan.vlen; d.n_streams = plan.n_streams; d.n_quads = plan.n_quads;
+    CU_TRY(cudaMalloc((void **)&d.starts, plan.starts.size() * sizeof(fc::n2048::SlotStart)));
+    CU_TRY(cudaMemcpy(d.starts, plan.starts.data(), plan.starts.size() * sizeof(fc::n2048::SlotStart), cudaMemcpyHostToDevice));
+    it = c.slice_plans.emplace(key, d).first;
+  }
+  const DeviceCtx::SlicePlanDev &d = it->second;
+  p.in = a; p.out = out;
+  p.batch = (long long)batch; p.n = (long long)n;
+  p.in_stride = (long long)a_stride; p.out_stride = (long long)out_stride; p.out_len = (long long)out_len;
+  p.klen = (int)klen;
+  p.step = fc::n2048::kN - ((int)klen - 1);
+  p.pad = mode == FFTCONV_CUDA_SAME ? (int)(klen / 2) : 0;
+  p.vrows = d.vrows; p.vlen = d.vlen; p.n_streams = d.n_streams; p.n_quads = d.n_quads;
+  p.n_slots = n_slots;
+  p.slots = d.starts;
+  return 0;
 }
 
 // ---- overlap-add on device pointers -------------------------------------------------
@@ -649,40 +691,6 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
   const long long segs = (long long)((n + step - 1) / step);
 
   const int engine2048 = oa2048_engine_for<T>(N, klen);
-  if (engine2048 == 2) {
-    if constexpr (std::is_same<T, float>::value) {
-      if (int r = get_w2_tables(c)) return r;
-      const cx<float> *H = nullptr;
-      if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_W2, *tab, &H)) return r;
-      int G = env_int("FFTCONV_CUDA_W2_PAIRS", 4);
-      if (G < 1 || G > 4) G = 4;
-      const long long slots = (long long)c.sm_count * G;
-      long long chunks = 1;
-      if ((long long)batch < 4 * slots) {
-        chunks = (4 * slots + (long long)batch - 1) / (long long)batch;
-        chunks = std::min(chunks, std::max<long long>(1, segs / 16));
-      }
-      fc::n2048::OaParams p{};
-      fc::n2048::fill_params(p, a, out, (long long)batch, (long long)n, (long long)a_stride,
-                             (long long)out_stride, (long long)out_len, (int)klen, mode, chunks);
-      const size_t smem = fc::w2::smem_bytes(G, (int)klen);
-      const long long grid = std::max<long long>(1, std::min<long long>(c.sm_count, (p.total_work + G - 1) / G));
-      const fc::n2048::cpair *hs = reinterpret_cast<const fc::n2048::cpair *>(H);
-#define FC_LAUNCH_W2(GG)                                                                  \
-  {                                                                                       \
-    if (int r = ensure_smem(c, fc::w2::oa_w2_kernel<GG>, smem)) return r;                 \
-    fc::w2::oa_w2_kernel<GG><<<(unsigned)grid, 64 * GG, smem, st>>>(p, c.tw_w2, hs);      \
-  }
-      if (G == 4) FC_LAUNCH_W2(4)
-      else if (G == 3) FC_LAUNCH_W2(3)
-      else if (G == 2) FC_LAUNCH_W2(2)
-      else FC_LAUNCH_W2(1)
-#undef FC_LAUNCH_W2
-      CU_TRY(cudaGetLastError());
-      ++g_launches;
-      return 0;
-    }
-  }
   if (engine2048 == 1) {
     using D = typename fc::DataOf<T>::D;
     constexpr int NL = fc::DataTraits<D>::NL;
@@ -702,25 +710,18 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
     // asks for a few SMs to be left free: a persistent grid that owns every SM would make the
     // collective's kernel wait for it, or wait for the collective's kernel on the SM it took
     const int sms = std::max(1, c.sm_count - std::max(0, g_reserved_sms.load()));
-    const long long slots = (long long)sms * G;
-    // streams per row: enough quads to fill every group, but never so many that
-    // the per-chunk warm-up segment costs more than ~6 %
-    long long chunks = 1;
-    if ((long long)batch < NL * slots) {
-      chunks = (NL * slots + (long long)batch - 1) / (long long)batch;
-      const long long max_chunks = std::max<long long>(1, segs / 16);
-      chunks = std::min(chunks, max_chunks);
-    }
+    // the grid: one CTA per SM unless there is less than one block per group to hand out
+    const long long blocks_total =
+        (long long)((batch + NL - 1) / NL) * (long long)((n + (N - klen)) / (N - klen + 1));
+    const long long grid = std::max<long long>(1, std::min<long long>(sms, (blocks_total + G - 1) / G));
     fc::n2048::OaParamsT<T> p{};
-    fc::n2048::fill_params(p, a, out, (long long)batch, (long long)n, (long long)a_stride,
-                           (long long)out_stride, (long long)out_len, (int)klen, mode, chunks);
+    if (int r = get_slice_plan<T>(c, p, a, out, batch, n, a_stride, out_stride, out_len, klen, mode, grid * G)) return r;
     p.tw1 = tw1;
     p.tw2 = tw2;
     p.hs = reinterpret_cast<const fc::n2048::CPairT<T> *>(H);
     const bool wide = wide_k;
     const bool recomp = wide || (want_recomp && G == 4);
     const size_t smem = fc::n2048::smem_bytes<T>(G, (int)klen, recomp);
-    const long long grid = std::max<long long>(1, std::min<long long>(sms, (p.total_work + G - 1) / G));
 #define FC_LAUNCH_N2048(GG, RR, WW)                                                            \
   {                                                                                            \
     if (int r = ensure_smem(c, fc::n2048::oa_n2048_kernel<D, GG, RR, WW>, smem)) return r;     \
@@ -1208,12 +1209,12 @@ PtrKind ptr_kind(const void *p) {
 
 // one row block of the host pipeline on device buffers: kernels only, c.mu held by the caller
 template <typename T>
-int block_device(DeviceCtx &c, cudaStream_t st, Op op, int slot, size_t rows_cap, const T *din, size_t rows, size_t n,
-                 const T *k, size_t klen, T *dout, size_t out_len, int mode) {
+int block_device(DeviceCtx &c, cudaStream_t st, Op op, void **tmp_buf, size_t *tmp_cap, size_t rows_cap, const T *din,
+                 size_t rows, size_t n, const T *k, size_t klen, T *dout, size_t out_len, int mode) {
   if (op == OP_HILBERT) return hilbert_device<T>(c, st, din, rows, n, n, dout, out_len);
   if (op == OP_RF) {
-    if (int g = grow(&c.stage_tmp[slot], &c.cap_tmp[slot], rows_cap * n * sizeof(T))) return g;
-    T *tmp = static_cast<T *>(c.stage_tmp[slot]);
+    if (int g = grow(tmp_buf, tmp_cap, rows_cap * n * sizeof(T))) return g;
+    T *tmp = static_cast<T *>(*tmp_buf);
     if (int r = conv_device<T>(c, st, OP_OA, din, rows, n, n, k, klen, tmp, n, n, FFTCONV_CUDA_SAME)) return r;
     return hilbert_device<T>(c, st, tmp, rows, n, n, dout, out_len);
   }
@@ -1261,7 +1262,9 @@ int run_host_pinned(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, siz
                                n * sizeof(T), rows, cudaMemcpyHostToDevice, c.pipe[s]));
     {
       std::lock_guard<std::mutex> lock(c.mu); // plan cache + enqueue only
-      if (int r = block_device<T>(c, c.pipe[s], op, s, rows_per_block, din, rows, n, k, klen, dout, out_len, mode)) return r;
+      if (int r = block_device<T>(c, c.pipe[s], op, &c.stage_tmp[s], &c.cap_tmp[s], rows_per_block, din, rows, n, k, klen,
+                                  dout, out_len, mode))
+        return r;
     }
     if (out_stride == out_len)
       CU_TRY(cudaMemcpyAsync(out + r0 * out_len, dout, rows * out_len * sizeof(T), cudaMemcpyDeviceToHost, c.pipe[s]));
@@ -1274,37 +1277,48 @@ int run_host_pinned(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, siz
   return 0;
 }
 
-// Pageable host memory through a page-locked ring: kPipe worker threads, each with its own stream,
-// device staging and a pinned in / out buffer.  A worker copies a row block into its pinned buffer
-// (plain memcpy, the part the driver would otherwise do single-threaded and synchronously), uploads,
-// computes, downloads and copies out; the workers overlap one another's phases.
+// Pageable host memory through a page-locked ring: up to kRing worker threads, each with its own
+// stream, device staging and a pinned in / out buffer.  A worker copies a row block into its pinned
+// buffer (plain memcpy -- the part the driver would otherwise do single-threaded and synchronously),
+// uploads, computes, downloads and copies out; the workers overlap one another's phases.  Measured on
+// the headline shape (profiles/r02_hostab.jsonl): driver staging 155 ms, cudaHostRegister per call
+// 162 ms, 3 workers x 16 MB 100 ms, and one numpy-style single-threaded copy of 1 GB alone takes 71 ms
+// -- the host memcpy is the bound, hence many workers.
+template <typename T> int ring_alloc(void **p, size_t *cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  CU_TRY(cudaHostAlloc(p, bytes, cudaHostAllocPortable));
+  *cap = bytes;
+  return 0;
+}
 template <typename T>
 int run_host_ring(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_t a_stride, const T *k,
                   size_t klen, T *out, size_t out_len, size_t out_stride, int mode) {
   const size_t row_bytes = std::max(n, out_len) * sizeof(T);
-  const size_t target = (size_t)env_int("FFTCONV_CUDA_HOST_RING_BLOCK_MB", 16) << 20;
-  const size_t rows_per_block = std::min(batch, std::max<size_t>(1, target / std::max<size_t>(1, row_bytes)));
+  const size_t target = (size_t)env_int("FFTCONV_CUDA_HOST_RING_BLOCK_MB", 32) << 20;
+  int max_workers = env_int("FFTCONV_CUDA_HOST_RING_THREADS", kRing);
+  max_workers = std::max(1, std::min(max_workers, kRing));
+  const unsigned hw = std::thread::hardware_concurrency();
+  if (hw) max_workers = std::min<int>(max_workers, (int)std::max(1u, hw / 2));
+  size_t rows_per_block = std::min(batch, std::max<size_t>(1, target / std::max<size_t>(1, row_bytes)));
+  // at least two blocks per worker, so that one worker's copies overlap its neighbours' transfers
+  while (rows_per_block > 1 && (batch + rows_per_block - 1) / rows_per_block < (size_t)(2 * max_workers) &&
+         rows_per_block * row_bytes > (size_t)(2 << 20))
+    rows_per_block = (rows_per_block + 1) / 2;
   const size_t n_blocks = (batch + rows_per_block - 1) / rows_per_block;
-  for (int s = 0; s < kPipe; ++s) {
-    if (int r = grow(&c.stage_in[s], &c.cap_in[s], rows_per_block * n * sizeof(T))) return r;
-    if (int r = grow(&c.stage_out[s], &c.cap_out[s], rows_per_block * out_len * sizeof(T))) return r;
-    if (c.ring_cap_in[s] < rows_per_block * n * sizeof(T)) {
-      cudaFreeHost(c.ring_in[s]);
-      c.ring_in[s] = nullptr;
-      c.ring_cap_in[s] = 0;
-      CU_TRY(cudaHostAlloc(&c.ring_in[s], rows_per_block * n * sizeof(T), cudaHostAllocPortable));
-      c.ring_cap_in[s] = rows_per_block * n * sizeof(T);
-    }
-    if (c.ring_cap_out[s] < rows_per_block * out_len * sizeof(T)) {
-      cudaFreeHost(c.ring_out[s]);
-      c.ring_out[s] = nullptr;
-      c.ring_cap_out[s] = 0;
-      CU_TRY(cudaHostAlloc(&c.ring_out[s], rows_per_block * out_len * sizeof(T), cudaHostAllocPortable));
-      c.ring_cap_out[s] = rows_per_block * out_len * sizeof(T);
-    }
+  const int workers = (int)std::min<size_t>((size_t)max_workers, n_blocks);
+  for (int s = 0; s < workers; ++s) {
+    RingSlot &r = c.ring[s];
+    if (!r.st) CU_TRY(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
+    if (int e = grow(&r.din, &r.cap_din, rows_per_block * n * sizeof(T))) return e;
+    if (int e = grow(&r.dout, &r.cap_dout, rows_per_block * out_len * sizeof(T))) return e;
+    if (int e = ring_alloc<T>(&r.hin, &r.cap_hin, rows_per_block * n * sizeof(T))) return e;
+    if (int e = ring_alloc<T>(&r.hout, &r.cap_hout, rows_per_block * out_len * sizeof(T))) return e;
   }
-  int status[kPipe] = {0, 0, 0};
-  std::string msgs[kPipe];
+  int status[kRing] = {0};
+  std::string msgs[kRing];
   const Filter *parent_filter = tl_filter; // thread_local call context: hand it to the workers
   const EnvOpts parent_env = tl_env;
   auto worker = [&](int s) {
@@ -1312,33 +1326,39 @@ int run_host_ring(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, size_
       tl_filter = parent_filter;
       tl_env = parent_env;
       CU_TRY(cudaSetDevice(c.device));
-      T *din = static_cast<T *>(c.stage_in[s]), *dout = static_cast<T *>(c.stage_out[s]);
-      T *hin = static_cast<T *>(c.ring_in[s]), *hout = static_cast<T *>(c.ring_out[s]);
-      for (size_t b = (size_t)s; b < n_blocks; b += kPipe) {
+      RingSlot &r = c.ring[s];
+      T *din = static_cast<T *>(r.din), *dout = static_cast<T *>(r.dout);
+      T *hin = static_cast<T *>(r.hin), *hout = static_cast<T *>(r.hout);
+      for (size_t b = (size_t)s; b < n_blocks; b += (size_t)workers) {
         const size_t r0 = b * rows_per_block, rows = std::min(rows_per_block, batch - r0);
         if (a_stride == n) std::memcpy(hin, a + r0 * n, rows * n * sizeof(T));
         else
-          for (size_t r = 0; r < rows; ++r) std::memcpy(hin + r * n, a + (r0 + r) * a_stride, n * sizeof(T));
-        CU_TRY(cudaMemcpyAsync(din, hin, rows * n * sizeof(T), cudaMemcpyHostToDevice, c.pipe[s]));
+          for (size_t i = 0; i < rows; ++i) std::memcpy(hin + i * n, a + (r0 + i) * a_stride, n * sizeof(T));
+        CU_TRY(cudaMemcpyAsync(din, hin, rows * n * sizeof(T), cudaMemcpyHostToDevice, r.st));
         {
           std::lock_guard<std::mutex> lock(c.mu);
-          if (int r = block_device<T>(c, c.pipe[s], op, s, rows_per_block, din, rows, n, k, klen, dout, out_len, mode)) return r;
+          if (int e = block_device<T>(c, r.st, op, &r.dtmp, &r.cap_dtmp, rows_per_block, din, rows, n, k, klen, dout,
+                                      out_len, mode))
+            return e;
         }
-        CU_TRY(cudaMemcpyAsync(hout, dout, rows * out_len * sizeof(T), cudaMemcpyDeviceToHost, c.pipe[s]));
-        CU_TRY(cudaStreamSynchronize(c.pipe[s]));
+        CU_TRY(cudaMemcpyAsync(hout, dout, rows * out_len * sizeof(T), cudaMemcpyDeviceToHost, r.st));
+        CU_TRY(cudaStreamSynchronize(r.st));
         if (out_stride == out_len) std::memcpy(out + r0 * out_len, hout, rows * out_len * sizeof(T));
         else
-          for (size_t r = 0; r < rows; ++r) std::memcpy(out + (r0 + r) * out_stride, hout + r * out_len, out_len * sizeof(T));
+          for (size_t i = 0; i < rows; ++i) std::memcpy(out + (r0 + i) * out_stride, hout + i * out_len, out_len * sizeof(T));
       }
       return 0;
     };
     status[s] = body();
     if (status[s]) msgs[s] = g_err; // g_err is thread_local: carry the message back
+    tl_filter = nullptr;
+    tl_env = EnvOpts();
   };
-  std::thread th[kPipe];
-  const int workers = (int)std::min<size_t>(kPipe, n_blocks);
+  std::thread th[kRing];
   for (int s = 1; s < workers; ++s) th[s] = std::thread(worker, s);
   worker(0);
+  tl_filter = parent_filter; // worker(0) ran on the calling thread
+  tl_env = parent_env;
   for (int s = 1; s < workers; ++s) th[s].join();
   for (int s = 0; s < workers; ++s)
     if (status[s]) return fail(status[s], msgs[s]);
@@ -1363,12 +1383,20 @@ template <typename T>
 int run_host_tiny(DeviceCtx &c, const T *a, size_t batch, size_t n, size_t a_stride, const T *k, size_t klen, T *out,
                   size_t out_len, size_t out_stride, int mode) {
   if (!c.tiny_host) {
-    CU_TRY(cudaHostAlloc(&c.tiny_host, kTinyBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    CU_TRY(cudaHostAlloc(&c.tiny_host, kTinyBytes + 64, cudaHostAllocMapped | cudaHostAllocPortable));
     CU_TRY(cudaHostGetDevicePointer(&c.tiny_dev, c.tiny_host, 0));
     CU_TRY(cudaStreamCreateWithFlags(&c.tiny_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaMalloc((void **)&c.tiny_counter, sizeof(unsigned)));
+    CU_TRY(cudaMemset(c.tiny_counter, 0, sizeof(unsigned)));
+    std::memset(static_cast<char *>(c.tiny_host) + kTinyBytes, 0, 64);
     c.tiny_bytes = kTinyBytes;
   }
   T *h = static_cast<T *>(c.tiny_host), *d = static_cast<T *>(c.tiny_dev);
+  // completion flag: the last 64 bytes of the mapped buffer.  The kernel's last CTA writes the
+  // call's epoch there after a system-wide fence; polling it costs less than a stream synchronise.
+  volatile unsigned *flag_h = reinterpret_cast<volatile unsigned *>(static_cast<char *>(c.tiny_host) + kTinyBytes);
+  unsigned *flag_d = reinterpret_cast<unsigned *>(static_cast<char *>(c.tiny_dev) + kTinyBytes);
+  const unsigned epoch = ++c.tiny_epoch ? c.tiny_epoch : ++c.tiny_epoch; // never 0
   for (size_t r = 0; r < batch; ++r) std::memcpy(h + r * n, a + r * a_stride, n * sizeof(T));
   const size_t out_off = batch * n, taps_off = out_off + batch * out_len;
   fc::direct::SmallArgs<T> p{};
@@ -1389,10 +1417,22 @@ int run_host_tiny(DeviceCtx &c, const T *a, size_t batch, size_t n, size_t a_str
     p.taps = d + taps_off;
   }
   const int tiles = (int)((out_len + 255) / 256);
-  fc::direct::direct_tiny_kernel<T><<<(unsigned)(batch * tiles), 256, 0, c.tiny_stream>>>(p, tiles);
+  fc::direct::direct_tiny_kernel<T><<<(unsigned)(batch * tiles), 256, 0, c.tiny_stream>>>(p, tiles, c.tiny_counter, flag_d, epoch);
   CU_TRY(cudaGetLastError());
   ++g_launches;
-  CU_TRY(cudaStreamSynchronize(c.tiny_stream));
+  if (env_int("FFTCONV_CUDA_TINY_SYNC", 0)) {
+    CU_TRY(cudaStreamSynchronize(c.tiny_stream));
+  } else {
+    // spin on the flag; every 4096 polls ask the stream, so that a failed launch cannot hang the caller
+    for (unsigned spins = 1; *flag_h != epoch; ++spins) {
+      if ((spins & 4095u) == 0) {
+        const cudaError_t q = cudaStreamQuery(c.tiny_stream);
+        if (q == cudaSuccess) break; // finished: the flag is visible after the stream drained
+        if (q != cudaErrorNotReady) return fail(FFTCONV_CUDA_ERR_CUDA, std::string("tiny kernel: ") + cudaGetErrorString(q));
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
   for (size_t r = 0; r < batch; ++r) std::memcpy(out + r * out_stride, h + out_off + r * out_len, out_len * sizeof(T));
   return 0;
 }
@@ -1554,7 +1594,7 @@ int fill_synthetic_entry(T *dst, size_t n, unsigned long long seed, unsigned lon
 }
 
 template <typename T> int oa_layout_for(const DeviceCtx &c, size_t N, size_t klen) {
-  if (const int e = oa2048_engine_for<T>(N, klen)) return e == 2 ? fc::generic::LAYOUT_W2 : fc::generic::LAYOUT_N2048;
+  if (oa2048_engine_for<T>(N, klen)) return fc::generic::LAYOUT_N2048;
   return fast_ok<T>(c, N, klen) ? fc::generic::LAYOUT_FAST : fc::generic::LAYOUT_DIF;
 }
 

@@ -96,33 +96,90 @@ template <int S, typename D> FC_HD void rot90(D &r, D &i) {
   else       { r = muls2(i, (Sc)-1); i = t; }
 }
 
+// 4-point DFT of (y0, w1 y1, w2 y2, w3 y3) with the constant twiddles folded into the butterflies
+// (Linzer-Feig): w_i = c_i (1 + j t_i) with t_i = tan(arg w_i), so that
+//   p_i = y_i (1 + j t_i)                       2 FMA
+//   s0, d0 = y0 +- c2 p2                        4 FMA
+//   s1', d1' = p1 +- (c3 / c1) p3               4 FMA      (s1 = c1 s1', d1 = c1 d1')
+//   X0, X2 = s0 +- c1 s1'   X1, X3 = d0 -+ j c1 d1'   8 FMA
+// 22 fused multiply-adds instead of 3 complex multiplications + 16 additions = 28 instructions.
+// The t_i are given for the FORWARD transform (S < 0); the inverse conjugates them.  |t|, |c3/c1|
+// <= tan(3 pi / 8) = 2.414 for every twiddle set used here, so nothing is amplified.
+template <int S, typename D, typename Sc>
+FC_HD void bfly4_tw(D &r0, D &i0, D &r1, D &i1, D &r2, D &i2, D &r3, D &i3, Sc c1, Sc t1f, Sc c2, Sc t2f, Sc t3f,
+                    Sc rho /* c3 / c1 */) {
+  const Sc t1 = S < 0 ? t1f : -t1f, t2 = S < 0 ? t2f : -t2f, t3 = S < 0 ? t3f : -t3f;
+  const D p2r = fmas2(i2, -t2, r2), p2i = fmas2(r2, t2, i2);
+  const D s0r = fmas2(p2r, c2, r0), s0i = fmas2(p2i, c2, i0);
+  const D d0r = fmas2(p2r, -c2, r0), d0i = fmas2(p2i, -c2, i0);
+  const D p1r = fmas2(i1, -t1, r1), p1i = fmas2(r1, t1, i1);
+  const D p3r = fmas2(i3, -t3, r3), p3i = fmas2(r3, t3, i3);
+  const D s1r = fmas2(p3r, rho, p1r), s1i = fmas2(p3i, rho, p1i);
+  const D d1r = fmas2(p3r, -rho, p1r), d1i = fmas2(p3i, -rho, p1i);
+  r0 = fmas2(s1r, c1, s0r); i0 = fmas2(s1i, c1, s0i);
+  r2 = fmas2(s1r, -c1, s0r); i2 = fmas2(s1i, -c1, s0i);
+  if (S < 0) { // X1 = d0 - j c1 d1', X3 = d0 + j c1 d1'
+    r1 = fmas2(d1i, c1, d0r); i1 = fmas2(d1r, -c1, d0i);
+    r3 = fmas2(d1i, -c1, d0r); i3 = fmas2(d1r, c1, d0i);
+  } else {
+    r1 = fmas2(d1i, -c1, d0r); i1 = fmas2(d1r, c1, d0i);
+    r3 = fmas2(d1i, c1, d0r); i3 = fmas2(d1r, -c1, d0i);
+  }
+}
+// the same for the twiddle set (W8, W4, W8^3) = (c8 (1 - j), -j, c8 (-1 - j)) (forward): only
+// additions until the last level -- 20 instructions
+template <int S, typename D, typename Sc>
+FC_HD void bfly4_w8(D &r0, D &i0, D &r1, D &i1, D &r2, D &i2, D &r3, D &i3, Sc c8) {
+  // w2 y2 = -+ j y2
+  D s0r, s0i, d0r, d0i, p1r, p1i, p3r, p3i;
+  if (S < 0) {
+    s0r = add2(r0, i2); s0i = sub2(i0, r2); d0r = sub2(r0, i2); d0i = add2(i0, r2);
+    p1r = add2(r1, i1); p1i = sub2(i1, r1);   // y1 (1 - j)
+    p3r = sub2(r3, i3); p3i = add2(i3, r3);   // y3 (1 + j);  w3 y3 = -c8 p3
+  } else {
+    s0r = sub2(r0, i2); s0i = add2(i0, r2); d0r = add2(r0, i2); d0i = sub2(i0, r2);
+    p1r = sub2(r1, i1); p1i = add2(i1, r1);   // y1 (1 + j)
+    p3r = add2(r3, i3); p3i = sub2(i3, r3);   // y3 (1 - j);  w3 y3 = -c8 p3
+  }
+  const D s1r = sub2(p1r, p3r), s1i = sub2(p1i, p3i); // s1 = c8 s1'
+  const D d1r = add2(p1r, p3r), d1i = add2(p1i, p3i);
+  r0 = fmas2(s1r, c8, s0r); i0 = fmas2(s1i, c8, s0i);
+  r2 = fmas2(s1r, -c8, s0r); i2 = fmas2(s1i, -c8, s0i);
+  if (S < 0) {
+    r1 = fmas2(d1i, c8, d0r); i1 = fmas2(d1r, -c8, d0i);
+    r3 = fmas2(d1i, -c8, d0r); i3 = fmas2(d1r, c8, d0i);
+  } else {
+    r1 = fmas2(d1i, -c8, d0r); i1 = fmas2(d1r, c8, d0i);
+    r3 = fmas2(d1i, c8, d0r); i3 = fmas2(d1r, -c8, d0i);
+  }
+}
+
 // 16-point DFT of v.re/im[0..15], natural order in, natural order out.
 //   m = m0 + 4 m1, k = k1 + 4 k0:
 //   X[k1 + 4 k0] = sum_m0 W4^{m0 k0} W16^{m0 k1} sum_m1 x[m0 + 4 m1] W4^{m1 k1}
+// 144 instructions: the twiddles W16^{m0 k1} between the two levels never appear as complex
+// multiplications, they ride in the fused multiply-adds of the second level (bfly4_tw / bfly4_w8).
 template <int S, typename D> FC_HD void dft16(RegsT<D> &v) {
   using Sc = scalar_of_t<D>;
   constexpr Sc kC8 = Consts<Sc>::c8, kC16 = Consts<Sc>::c16, kS16 = Consts<Sc>::s16;
+  constexpr Sc kT16 = kS16 / kC16;     // tan(pi / 8)
+  constexpr Sc kT316 = kC16 / kS16;    // tan(3 pi / 8)
   // step A: 4-point DFTs over m1 for each m0; result A[m0][k1] stays in slot m0 + 4 k1
 #pragma unroll
   for (int m0 = 0; m0 < 4; ++m0)
     bfly4<S>(v.re[m0], v.im[m0], v.re[m0 + 4], v.im[m0 + 4], v.re[m0 + 8], v.im[m0 + 8],
              v.re[m0 + 12], v.im[m0 + 12]);
-  // step B: twiddles W16^{m0 k1} on slot m0 + 4 k1   (imag sign follows S)
-  const Sc s = (S < 0) ? (Sc)-1 : (Sc)1;
-  cmul2(v.re[1 + 4], v.im[1 + 4], kC16, s * kS16);    // e = 1
-  cmul2(v.re[2 + 4], v.im[2 + 4], kC8, s * kC8);      // e = 2
-  cmul2(v.re[3 + 4], v.im[3 + 4], kS16, s * kC16);    // e = 3
-  cmul2(v.re[1 + 8], v.im[1 + 8], kC8, s * kC8);      // e = 2
-  rot90<S>(v.re[2 + 8], v.im[2 + 8]);                 // e = 4
-  cmul2(v.re[3 + 8], v.im[3 + 8], -kC8, s * kC8);     // e = 6
-  cmul2(v.re[1 + 12], v.im[1 + 12], kS16, s * kC16);  // e = 3
-  cmul2(v.re[2 + 12], v.im[2 + 12], -kC8, s * kC8);   // e = 6
-  cmul2(v.re[3 + 12], v.im[3 + 12], -kC16, -s * kS16); // e = 9
-  // step C: 4-point DFTs over m0 for each k1; X[k1 + 4 k0] lands in slot 4 k1 + k0
-#pragma unroll
-  for (int k1 = 0; k1 < 4; ++k1)
-    bfly4<S>(v.re[4 * k1], v.im[4 * k1], v.re[4 * k1 + 1], v.im[4 * k1 + 1], v.re[4 * k1 + 2],
-             v.im[4 * k1 + 2], v.re[4 * k1 + 3], v.im[4 * k1 + 3]);
+  // steps B + C: 4-point DFTs over m0 for each k1 with the twiddles W16^{m0 k1} (forward: e^{-j pi m0 k1 / 8})
+  // folded in; X[k1 + 4 k0] lands in slot 4 k1 + k0
+  bfly4<S>(v.re[0], v.im[0], v.re[1], v.im[1], v.re[2], v.im[2], v.re[3], v.im[3]);
+  // k1 = 1: w = (W16, W16^2, W16^3) = (c16 (1 - j t16), c8 (1 - j), s16 (1 - j t316))
+  bfly4_tw<S>(v.re[4], v.im[4], v.re[5], v.im[5], v.re[6], v.im[6], v.re[7], v.im[7],
+              kC16, -kT16, kC8, (Sc)-1, -kT316, kS16 / kC16);
+  // k1 = 2: w = (W16^2, W16^4, W16^6) = (c8 (1 - j), -j, c8 (-1 - j))
+  bfly4_w8<S>(v.re[8], v.im[8], v.re[9], v.im[9], v.re[10], v.im[10], v.re[11], v.im[11], kC8);
+  // k1 = 3: w = (W16^3, W16^6, W16^9) = (s16 (1 - j t316), -c8 (1 + j), -c16 (1 - j t16))
+  bfly4_tw<S>(v.re[12], v.im[12], v.re[13], v.im[13], v.re[14], v.im[14], v.re[15], v.im[15],
+              kS16, -kT316, -kC8, (Sc)1, -kT16, -kC16 / kS16);
 }
 // slot that holds output k of dft16 (k = k1 + 4 k0 sits in slot 4 k1 + k0)
 FC_HD constexpr int slot16(int k) { return 4 * (k & 3) + (k >> 2); }
@@ -130,20 +187,31 @@ FC_HD constexpr int slot16(int k) { return 4 * (k & 3) + (k >> 2); }
 // 8-point DFT on slots base..base+7, natural in, output k in slot base + slot8(k).
 //   m = m0 + 2 m1, k = k1 + 4 k0:
 //   X[k1 + 4 k0] = sum_m0 W2^{m0 k0} W8^{m0 k1} sum_m1 x[m0 + 2 m1] W4^{m1 k1}
+// 52 instructions: the W8 twiddles ride in the fused multiply-adds of the last level.
 template <int S, typename D> FC_HD void dft8(D *re, D *im) {
   using Sc = scalar_of_t<D>;
   constexpr Sc kC8 = Consts<Sc>::c8;
   bfly4<S>(re[0], im[0], re[2], im[2], re[4], im[4], re[6], im[6]); // m0 = 0: A[0][k1] in slot 2 k1
   bfly4<S>(re[1], im[1], re[3], im[3], re[5], im[5], re[7], im[7]); // m0 = 1: A[1][k1] in slot 2 k1 + 1
-  const Sc s = (S < 0) ? (Sc)-1 : (Sc)1;
-  cmul2(re[3], im[3], kC8, s * kC8);    // W8^1
-  rot90<S>(re[5], im[5]);               // W8^2
-  cmul2(re[7], im[7], -kC8, s * kC8);   // W8^3
-#pragma unroll
-  for (int k1 = 0; k1 < 4; ++k1) {      // X[k1] -> slot 2 k1, X[k1 + 4] -> slot 2 k1 + 1
-    const D ar = re[2 * k1], ai = im[2 * k1], br = re[2 * k1 + 1], bi = im[2 * k1 + 1];
-    re[2 * k1] = add2(ar, br); im[2 * k1] = add2(ai, bi);
-    re[2 * k1 + 1] = sub2(ar, br); im[2 * k1 + 1] = sub2(ai, bi);
+  // X[k1] = A0[k1] + W8^{k1} A1[k1] -> slot 2 k1,  X[k1 + 4] = A0[k1] - W8^{k1} A1[k1] -> slot 2 k1 + 1
+  { // k1 = 0
+    const D ar = re[0], ai = im[0], br = re[1], bi = im[1];
+    re[0] = add2(ar, br); im[0] = add2(ai, bi); re[1] = sub2(ar, br); im[1] = sub2(ai, bi);
+  }
+  { // k1 = 1: W8 = c8 (1 -+ j): u = b (1 -+ j), X = a +- c8 u
+    const D ar = re[2], ai = im[2], br = re[3], bi = im[3];
+    const D ur = S < 0 ? add2(br, bi) : sub2(br, bi), ui = S < 0 ? sub2(bi, br) : add2(bi, br);
+    re[2] = fmas2(ur, kC8, ar); im[2] = fmas2(ui, kC8, ai); re[3] = fmas2(ur, -kC8, ar); im[3] = fmas2(ui, -kC8, ai);
+  }
+  { // k1 = 2: W8^2 = -+ j
+    const D ar = re[4], ai = im[4], br = re[5], bi = im[5];
+    if (S < 0) { re[4] = add2(ar, bi); im[4] = sub2(ai, br); re[5] = sub2(ar, bi); im[5] = add2(ai, br); }
+    else       { re[4] = sub2(ar, bi); im[4] = add2(ai, br); re[5] = add2(ar, bi); im[5] = sub2(ai, br); }
+  }
+  { // k1 = 3: W8^3 = -c8 (1 +- j): u = b (1 +- j), X = a -+ c8 u
+    const D ar = re[6], ai = im[6], br = re[7], bi = im[7];
+    const D ur = S < 0 ? sub2(br, bi) : add2(br, bi), ui = S < 0 ? add2(bi, br) : sub2(bi, br);
+    re[6] = fmas2(ur, -kC8, ar); im[6] = fmas2(ui, -kC8, ai); re[7] = fmas2(ur, kC8, ar); im[7] = fmas2(ui, kC8, ai);
   }
 }
 FC_HD constexpr int slot8(int k) { return 2 * (k & 3) + (k >> 2); }

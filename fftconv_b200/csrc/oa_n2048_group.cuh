@@ -6,14 +6,22 @@
 // every block pos = 0, step, 2 step, ... add y = ifft(fft(pad(a[pos:pos+len])) H)/N
 // into out at pos (Full) or pos - K/2 (Same), clipped to out.size().
 //
-// Here nothing is zeroed and nothing is accumulated in global memory: a "stream"
-// (one row, or one chunk of consecutive segments of a row) is walked in order by
-// one lane of a 128-thread group; the K-1 sample tail of segment s stays in
-// shared memory and is added to the head of segment s+1 before that sample is
-// stored, so every output sample is written exactly once, with at most two
-// addends -> deterministic, no atomics.  A stream that starts in the middle of
-// a row first runs its predecessor segment with stores disabled ("warm-up") to
-// obtain the incoming tail.
+// Here nothing is zeroed and nothing is accumulated in global memory.  A "stream" is one row (or,
+// when there are fewer rows than lanes, one of a few "virtual rows" a row is cut into); NL streams
+// form a quad that one 128-thread group walks in lockstep, block after block.  Inside a walk the
+// K-1 sample tail of block s stays in shared memory and is added to the head of block s+1 before
+// that sample is stored, so every output sample is written exactly once, with at most two addends
+// -> deterministic, no atomics.
+//
+// Work is divided among the groups of the grid in equal numbers of BLOCKS, not rows: a group's
+// slice may begin in the middle of a row.  It then starts K-1 samples early and does not store the
+// first K-1 outputs of its first block -- they lack the contributions of the samples before the
+// block and belong to the previous slice, which in turn drops its last tail.  (Round 1 instead
+// replayed the predecessor block with stores off: one whole extra block per slice, 12 % of the
+// work when a slice is only 8 blocks long, e.g. config 2 sharded over 8 GPUs.)  Because a start
+// in mid-row costs K-1 samples, slice boundaries do not fall on a regular grid; the host walks the
+// same recurrence once per (batch, n, K, grid) and keeps the table of slice starts on the device
+// (oa_n2048_tables.h: plan_slices -- part of the plan cache).
 //
 // Global memory is touched in two ways:
 //   * fast path (all four lanes hold a full interior segment): the segment is
@@ -35,6 +43,12 @@ namespace n2048 {
 
 // S = scalar type (float: four streams per quad, double: two).  The word "quad" is kept for
 // the set of NL streams that one group transforms together.
+struct SlotStart {      // the slice of one group
+  long long quad;       // quad index; >= n_quads: nothing to do
+  long long u;          // first sample (local to the quad's streams) whose output the slice owns
+  long long budget;     // blocks in the slice
+};
+
 template <typename S> struct OaParamsT {
   static constexpr int NL = DataTraits<typename DataOf<S>::D>::NL;
   const S *in;
@@ -47,22 +61,23 @@ template <typename S> struct OaParamsT {
   int klen;             // K
   int step;             // N - (K - 1)
   int pad;              // 0 (Full) or K / 2 (Same)
-  long long segs;       // segments per row = ceil(n / step)
-  long long chunks;     // streams per row
-  long long segs_per_chunk;
-  long long n_streams;  // batch * chunks
+  long long vrows;      // virtual rows per row (1 unless batch < NL)
+  long long vlen;       // samples per virtual row (the last of a row may be shorter)
+  long long n_streams;  // batch * vrows
   long long n_quads;    // ceil(n_streams / NL)
-  long long total_work; // n_quads * segs_per_chunk
+  long long n_slots;    // slices = groups of the grid
+  const SlotStart *slots; // n_slots entries (device memory for the kernel)
   const CPairT<S> *tw1, *tw2, *hs; // global tables (see oa_n2048_core.cuh)
 };
 using OaParams = OaParamsT<float>;
 
 template <typename S> struct LaneT {
-  const S *in;
-  S *out;
-  long long seg0;
-  long long cnt;
+  const S *in;          // the ROW's first sample
+  S *out;               // the row's first output
+  long long a0;         // first sample of the stream inside its row
+  long long len;        // samples of the stream
   bool active;
+  bool row_end;         // the stream ends where the row ends: its last block also owns the final tail
 };
 using Lane = LaneT<float>;
 
@@ -71,57 +86,59 @@ template <typename S> FC_HD void make_lanes(const OaParamsT<S> &p, long long qua
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const long long sid = quad * NL + l;
-    if (l >= NL) { // unused slots of a two-lane (float64) quad
-      ln[l].active = false;
-      ln[l].seg0 = ln[l].cnt = 0;
-      ln[l].in = p.in;
-      ln[l].out = p.out;
-      continue;
-    }
-    ln[l].active = sid < p.n_streams;
-    const long long row = ln[l].active ? sid / p.chunks : 0;
-    const long long chunk = ln[l].active ? sid - row * p.chunks : 0;
-    ln[l].seg0 = chunk * p.segs_per_chunk;
-    const long long rem = p.segs - ln[l].seg0;
-    ln[l].cnt = rem < p.segs_per_chunk ? rem : p.segs_per_chunk;
+    ln[l].active = l < NL && sid < p.n_streams;
+    const long long row = ln[l].active ? sid / p.vrows : 0;
+    const long long v = ln[l].active ? sid - row * p.vrows : 0;
+    ln[l].a0 = v * p.vlen;
+    long long len = p.n - ln[l].a0;
+    if (len > p.vlen) len = p.vlen;
+    if (len <= 0) { len = 0; ln[l].active = false; }
+    ln[l].len = ln[l].active ? len : 0;
+    ln[l].row_end = ln[l].a0 + len >= p.n;
     ln[l].in = p.in + row * p.in_stride;
     ln[l].out = p.out + row * p.out_stride;
   }
 }
-
-// does any lane of this quad have a predecessor segment at chunk-local index j?
-template <typename S> FC_HD bool needs_warmup(const LaneT<S> (&ln)[4], long long j) {
+// samples the quad's longest stream has, and whether any of its streams starts in mid-row
+template <typename S> FC_HD long long quad_len(const LaneT<S> (&ln)[4]) {
+  long long m = 0;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) m = (ln[l].active && ln[l].len > m) ? ln[l].len : m;
+  return m;
+}
+template <typename S> FC_HD bool quad_has_prev(const LaneT<S> (&ln)[4]) {
   bool w = false;
 #pragma unroll
-  for (int l = 0; l < 4; ++l) w = w || (ln[l].active && j < ln[l].cnt && ln[l].seg0 + j > 0);
+  for (int l = 0; l < 4; ++l) w = w || (ln[l].active && ln[l].a0 > 0);
   return w;
 }
 
 // ---- slow path: direct global access -------------------------------------------
-// Load x[t + 128 m] of the four lanes' segments (chunk-local index j, may be -1
-// for a warm-up) into the packed registers, zero padded.
+// Load x[t + 128 m] of the block that starts at local sample u (may be negative: the K-1 samples
+// before a stream that begins a row are zeros) of the four lanes into the packed registers.
 //   lane 0 -> re, half A    lane 1 -> im, half A
 //   lane 2 -> re, half B    lane 3 -> im, half B
 template <typename D, typename S>
-FC_HD void io_load(int t, RegsT<D> &v, const OaParamsT<S> &p, const LaneT<S> (&ln)[4], long long j) {
+FC_HD void io_load(int t, RegsT<D> &v, const OaParamsT<S> &p, const LaneT<S> (&ln)[4], long long u) {
   constexpr int NL = DataTraits<D>::NL;
   S x[NL][kPts];
 #pragma unroll
   for (int l = 0; l < NL; ++l) {
-    const long long seg = ln[l].seg0 + j;
-    const bool on = ln[l].active && seg >= 0 && j < ln[l].cnt;
-    const long long pos = seg * p.step;
-    long long len = on ? p.n - pos : 0;
-    if (len > p.step) len = p.step;
+    const bool on = ln[l].active && u < ln[l].len;
+    const long long pos = ln[l].a0 + u;   // row coordinate of x[0]
+    // valid block-local indices: [lo, hi)
+    long long lo = on ? -pos : (long long)kN, hi = on ? p.n - pos : 0;
+    if (lo < 0) lo = 0;
+    if (hi > p.step) hi = p.step;
     const S *src = ln[l].in + (on ? pos : 0);
-    const int ilen = (int)len;
+    const int ilo = (int)lo, ihi = (int)hi;
 #pragma unroll
     for (int m = 0; m < kPts; ++m) {
       const int i = t + 128 * m;
 #if defined(__CUDA_ARCH__)
-      x[l][m] = (i < ilen) ? __ldg(src + i) : (S)0;
+      x[l][m] = (i >= ilo && i < ihi) ? __ldg(src + i) : (S)0;
 #else
-      x[l][m] = (i < ilen) ? src[i] : (S)0;
+      x[l][m] = (i >= ilo && i < ihi) ? src[i] : (S)0;
 #endif
     }
   }
@@ -134,26 +151,33 @@ FC_HD void io_load(int t, RegsT<D> &v, const OaParamsT<S> &p, const LaneT<S> (&l
   }
 }
 
+// Which y[i] of the block at local start u a lane owns: [lo, hi).  The first block of a slice that
+// starts in mid-row (skip) leaves its first K-1 outputs to the previous slice; a stream's last block
+// stops at the stream's end, plus the final K-1 tail where that is the row's end.
+template <typename S>
+FC_HD void owned_range(const OaParamsT<S> &p, const LaneT<S> &ln, long long u, bool skip, int &lo, int &hi) {
+  const bool on = ln.active && u < ln.len;
+  lo = skip ? p.klen - 1 : 0;
+  long long h = p.step;
+  if (u + p.step >= ln.len) {
+    h = ln.len - u + (ln.row_end ? p.klen - 1 : 0);
+    if (h > kN) h = kN;
+  }
+  hi = on ? (int)h : 0;
+}
+
 // v holds y[t + 128 m] in slot slot16(m).  Adds the incoming tail, saves the
-// outgoing tail, stores the samples this segment owns.
+// outgoing tail, stores the samples this block owns.
 template <typename D, typename S>
-FC_HD void io_store(int t, const RegsT<D> &v, const OaParamsT<S> &p, const LaneT<S> (&ln)[4], long long j,
-                    const PtT<D> *tail_prev, PtT<D> *tail_next, bool add_tail, bool warm) {
+FC_HD void io_store(int t, const RegsT<D> &v, const OaParamsT<S> &p, const LaneT<S> (&ln)[4], long long u,
+                    const PtT<D> *tail_prev, PtT<D> *tail_next, bool add_tail, bool skip) {
   constexpr int NL = DataTraits<D>::NL;
-  int limit[NL];
+  int lo[NL], hi[NL];
   long long obase[NL]; // output index of y[0]
 #pragma unroll
   for (int l = 0; l < NL; ++l) {
-    const long long seg = ln[l].seg0 + j;
-    const bool on = !warm && ln[l].active && j < ln[l].cnt;
-    const long long pos = seg * p.step;
-    long long lim = p.step;
-    if (seg == p.segs - 1) { // the row's final segment also owns its tail
-      lim = p.out_len + p.pad - pos;
-      if (lim > kN) lim = kN;
-    }
-    limit[l] = on ? (int)lim : 0;
-    obase[l] = pos - p.pad;
+    owned_range(p, ln[l], u, skip, lo[l], hi[l]);
+    obase[l] = ln[l].a0 + u - p.pad;
   }
   const int tail_len = p.klen - 1;
 #pragma unroll
@@ -173,7 +197,7 @@ FC_HD void io_store(int t, const RegsT<D> &v, const OaParamsT<S> &p, const LaneT
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const long long o = obase[l] + i;
-      if (i < limit[l] && o >= 0) ln[l].out[o] = y[l];
+      if (i >= lo[l] && i < hi[l] && o >= 0 && o < p.out_len) ln[l].out[o] = y[l];
     }
   }
 }
@@ -242,7 +266,7 @@ FC_HD void fast_load(int t, RegsT<D> &v, const S *in, int ls, const int (&shift)
 // b[l] points at y[t] of lane l (entries l >= NL are ignored)
 template <bool WIDE = false, typename D, typename S>
 FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const ThreadMasks &k, const PtT<D> *tail_prev,
-                         PtT<D> *tail_next, bool add_tail, bool stage, int step) {
+                         PtT<D> *tail_next, bool add_tail, bool skip_head, int step) {
   constexpr int NL = DataTraits<D>::NL;
 #pragma unroll
   for (int m = 0; m < kPts; ++m) {
@@ -258,9 +282,11 @@ FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const Threa
       }
     }
     const bool in_tail = (m >= pad_first_slot<WIDE>()) && ((k.in_zero >> m) & 1u); // i >= step
+    // the first block of a slice that starts in mid-row: y[i], i < K - 1, belongs to the previous slice
+    const bool head = skip_head && m < tail_in_slots<WIDE>() && ((k.tail_add >> m) & 1u);
     if (in_tail) {
       put(tail_next, i - step, yr, yi);
-    } else if (stage) {
+    } else if (!head) {
       S y[NL];
       DataTraits<D>::unpack(yr, yi, y);
 #pragma unroll
@@ -272,45 +298,49 @@ FC_HD void fast_store_to(int t, const RegsT<D> &v, S *const (&b)[4], const Threa
 // ---- uniform (per group) control flow ---------------------------------------------
 struct IterDesc {
   long long quad;
-  long long j;    // chunk-local segment index (jfirst - 1 for a warm-up)
-  bool warm;
-  bool first;     // first iteration of a quad visit: no incoming tail
+  long long u;    // local sample at which the block's input starts (negative: zeros before a row)
+  bool skip;      // first block of a slice that starts in mid-row: its first K-1 outputs are not stored
+  bool first;     // first block of a walk: no incoming tail
 };
 
-// Enumerates the iterations of the work slice [w0, w1): for every quad visit an
-// optional warm-up iteration, then the visit's segments in order.
+// Enumerates the blocks of one slice: `budget` blocks from (quad, ua) on, quad after quad.  The host
+// runs the same recurrence to find where every slice starts (oa_n2048_tables.h, plan_slices).
 struct WorkIter {
-  long long w, w1;
-  long long quad, j, jend, jfirst;
-  bool in_visit;
+  long long quad, ua, u, qlen;
+  int budget;
+  bool new_walk;
 
-  FC_HD void init(long long w0_, long long w1_) {
-    w = w0_;
-    w1 = w1_;
-    in_visit = false;
-    quad = j = jend = jfirst = 0;
+  FC_HD void init(long long quad0, long long ua0, int budget_) {
+    quad = quad0;
+    ua = ua0;
+    u = qlen = 0;
+    budget = budget_;
+    new_walk = true;
   }
   // returns false when the slice is exhausted; `ln` is refreshed on a new quad
   template <typename S> FC_HD bool next(const OaParamsT<S> &p, LaneT<S> (&ln)[4], IterDesc &d) {
-    if (!in_visit) {
-      if (w >= w1) return false;
-      quad = w / p.segs_per_chunk;
-      jfirst = w - quad * p.segs_per_chunk;
-      jend = jfirst + (w1 - w);
-      if (jend > p.segs_per_chunk) jend = p.segs_per_chunk;
+    if (budget <= 0 || quad >= p.n_quads) return false;
+    if (new_walk) {
       make_lanes(p, quad, ln);
-      w += jend - jfirst;
-      j = needs_warmup(ln, jfirst) ? jfirst - 1 : jfirst;
-      in_visit = true;
+      qlen = quad_len(ln);
+      const bool overlap = ua > 0 || quad_has_prev(ln);
+      u = overlap ? ua - (p.klen - 1) : 0;
       d.first = true;
+      d.skip = overlap;
+      new_walk = false;
     } else {
       d.first = false;
+      d.skip = false;
     }
     d.quad = quad;
-    d.j = j;
-    d.warm = j < jfirst;
-    ++j;
-    if (j >= jend) in_visit = false;
+    d.u = u;
+    u += p.step;
+    --budget;
+    if (u >= qlen) { // the quad's streams are exhausted: the slice goes on with the next quad
+      ++quad;
+      ua = 0;
+      new_walk = true;
+    }
     return true;
   }
 };
@@ -327,7 +357,7 @@ FC_HD int tail_pts(int klen) { return ((klen - 1) + 7) & ~7; }
 
 template <typename S> struct PacketT { // one iteration of one group, one lane per warp leader
   int valid;           // 0: the slice is exhausted
-  int warm;
+  int skip;            // the first K-1 outputs of this block are not stored (IterDesc::skip)
   int first;           // no incoming tail
   int in_fast[4];      // per lane; the quad takes the fast path when all lanes are set
   int out_fast[4];     //   (slots >= NL of a two-lane quad are preset to 1)
@@ -337,7 +367,7 @@ template <typename S> struct PacketT { // one iteration of one group, one lane p
   const S *in_src[4];
   S *out_dst[4];
   LaneT<S> ln[4];      // slow path only
-  long long j;
+  long long u;
 };
 using Packet = PacketT<float>;
 
@@ -374,7 +404,7 @@ template <typename S = float> inline size_t smem_bytes(int groups, int klen, boo
 // lane 0 also writes the fields shared by the quad.
 template <typename S>
 FC_HD void fill_packet_lane(const OaParamsT<S> &p, SchedSlotT<S> &slot, PacketT<S> *pk, int lane) {
-  constexpr int NL = OaParamsT<S>::NL, A = 16 / (int)sizeof(S);
+  constexpr int NL = OaParamsT<S>::NL;
   IterDesc d;
   if (!slot.it.next(p, slot.ln, d)) {
     if (lane == 0) pk->valid = 0;
@@ -389,12 +419,11 @@ FC_HD void fill_packet_lane(const OaParamsT<S> &p, SchedSlotT<S> &slot, PacketT<
     return;
   }
   const LaneT<S> ln = slot.ln[lane];
-  const long long seg = ln.seg0 + d.j;
-  const bool on = ln.active && seg >= 0 && d.j < ln.cnt;
-  const long long pos = seg * p.step;
-  // input: a full segment whose 16-byte aligned span stays inside the tensor
+  const bool on = ln.active && d.u < ln.len;
+  const long long pos = ln.a0 + d.u;
+  // input: a full block inside the row whose 16-byte aligned span stays inside the tensor
   const S *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
-  const bool full = on && (p.n - pos >= p.step);
+  const bool full = on && pos >= 0 && p.n - pos >= p.step;
   const S *a = ln.in + (full ? pos : 0);
   const int ish = align_shift(a);
   const int bytes = ((ish + p.step) * (int)sizeof(S) + 15) & ~15;
@@ -402,20 +431,21 @@ FC_HD void fill_packet_lane(const OaParamsT<S> &p, SchedSlotT<S> &slot, PacketT<
   pk->in_src[lane] = a - ish;
   pk->in_bytes[lane] = bytes;
   pk->in_fast[lane] = full && (a - ish + bytes / (int)sizeof(S) <= tensor_end);
-  (void)A;
-  // output: an interior segment owns exactly y[0..step), all of it inside the row
+  // output: the block owns exactly y[lo .. step) with lo = 0 or K - 1, all of it inside the row
+  int lo, hi;
+  owned_range(p, ln, d.u, d.skip, lo, hi);
   const long long o0 = pos - p.pad;
-  const bool interior = on && seg < p.segs - 1 && o0 >= 0;
-  S *dst = ln.out + (interior ? o0 : 0);
+  const bool whole = on && hi == p.step && o0 + lo >= 0 && o0 + p.step <= p.out_len;
+  S *dst = ln.out + (whole ? o0 : 0);
   pk->out_dst[lane] = dst;
   pk->out_shift[lane] = align_shift(dst);
-  pk->out_fast[lane] = interior && !d.warm;
+  pk->out_fast[lane] = whole;
   pk->ln[lane] = ln;
   if (lane == 0) {
     pk->valid = 1;
-    pk->warm = d.warm;
+    pk->skip = d.skip;
     pk->first = d.first;
-    pk->j = d.j;
+    pk->u = d.u;
   }
 }
 FC_HD bool all4(const int (&f)[4]) { return (f[0] & f[1] & f[2] & f[3]) != 0; }

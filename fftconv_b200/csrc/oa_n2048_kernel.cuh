@@ -1,8 +1,9 @@
 // oa_n2048_kernel.cuh -- the sm_100a overlap-add kernel for float32, FFT size 2048.
 //
 // Persistent grid: one CTA per SM, G groups of 128 threads per CTA (G = 4: 16
-// warps per SM, 128 registers per thread).  Every group owns an equal,
-// contiguous slice of the (stream-quad, segment) work list.
+// warps per SM, 128 registers per thread).  Every group owns a slice of `budget`
+// consecutive blocks of the (stream-quad, block) work list; where its slice
+// starts comes from the plan's table (oa_n2048_tables.h: plan_slices).
 //
 // Shared memory is the scarce resource (the 32 KB exchange buffer per group is
 // irreducible), so the global <-> shared staging areas ALIAS the exchange
@@ -130,16 +131,14 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
   for (int i = threadIdx.x; i < 128; i += blockDim.x) tw2[i] = p.tw2[i];
 
   const long long slot = (long long)blockIdx.x * G + g;
-  const long long n_slots = (long long)gridDim.x * G;
-  const long long w0 = p.total_work / n_slots * slot + min(p.total_work % n_slots, slot);
-  const long long w1 = w0 + p.total_work / n_slots + (slot < p.total_work % n_slots ? 1 : 0);
+  const SlotStart start = slot < p.n_slots ? p.slots[slot] : SlotStart{p.n_quads, 0, 0};
 
   // the four warp leaders of a group are its scheduler: leader w describes lane w
   const bool leader = (t & 31) == 0;
   const int my_lane = t >> 5;
   SchedSlot &sslot = reinterpret_cast<SchedSlot *>(base + L.sched)[my_lane];
   if (leader) {
-    sslot.it.init(w0, w1);
+    sslot.it.init(start.quad, start.u, (int)start.budget);
     fill_packet_lane(p, sslot, PK(0), my_lane); // iteration 0
     fill_packet_lane(p, sslot, PK(1), my_lane); // iteration 1
   }
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
 
   while (PK(ci)->valid) {
     const Packet *cur = PK(ci);
-    const bool warm = cur->warm != 0;
+    const bool skip = cur->skip != 0;
     const bool add_tail = cur->first == 0;
     const bool in_fast = all4(cur->in_fast), out_fast = all4(cur->out_fast);
     Regs v;
@@ -170,7 +169,7 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
       fast_load<WIDE>(t, v, stage, LS, sh, masks.in_zero);
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
-      io_load(t, v, p, ln, cur->j);
+      io_load(t, v, p, ln, cur->u);
     }
     phase0_compute<RECOMP, RECOMP>(t, v, tw1);
     dev::bar_sync(bar_id); // every thread has read its inputs out of the staging area
@@ -196,13 +195,13 @@ __global__ void __launch_bounds__(128 * G, 1) oa_n2048_kernel(const __grid_const
     if (t == 0) issue_loads(PK(ni), stage, LS, mbar);
     phase4_compute(v);
     pt *tail_prev = tails + (parity ^ 1) * tpts, *tail_next = tails + parity * tpts;
-    if (out_fast || warm) {
+    if (out_fast) {
       // coalesced element stores straight from registers (full 128-byte lines per warp instruction)
       S *const dst[4] = {cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t, cur->out_dst[3] + t};
-      fast_store_to<WIDE>(t, v, dst, masks, tail_prev, tail_next, add_tail, out_fast, p.step);
+      fast_store_to<WIDE>(t, v, dst, masks, tail_prev, tail_next, add_tail, skip, p.step);
     } else {
       Lane ln[4] = {cur->ln[0], cur->ln[1], cur->ln[2], cur->ln[3]};
-      io_store(t, v, p, ln, cur->j, tail_prev, tail_next, add_tail, warm);
+      io_store(t, v, p, ln, cur->u, tail_prev, tail_next, add_tail, skip);
     }
     // describe the iteration after next, one lane per warp leader (no warp is later
     // than the others, and the copies requested above are still in flight)

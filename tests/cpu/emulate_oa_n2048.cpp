@@ -4,7 +4,9 @@
 // with the barriers replaced by loop boundaries and the bulk (TMA) copies by
 // memcpy.  Checked against direct convolution in double.
 //
-// usage: emulate_oa_n2048 batch n K mode(0 full,1 same) chunks n_slots [misalign [recomp [f64]]]
+// usage: emulate_oa_n2048 batch n K mode(0 full,1 same) unused n_slots [misalign [recomp [f64]]]
+//   n_slots:  groups the work is sliced over (the kernel: 4 per SM); the slice starts come from
+//             plan_slices exactly as in the library
 //   misalign: shifts the input/output base pointers by that many elements (0..3 float, 0..1 double)
 //   recomp:   1 (default) = twiddles k = 3, 5..7, 9..15 formed as products in registers
 //   f64:      1 = the float64 instantiation (two streams per group); its error bound is 1e-13
@@ -52,13 +54,13 @@ template <typename D> struct HostGroup {
       for (int l = 0; l < NL; ++l) std::memcpy(stage + l * L.lane_stride, q->in_src[l], q->in_bytes[l]);
   }
 
-  template <bool RECOMP, bool WIDE> void run(long long w0, long long w1) {
+  template <bool RECOMP, bool WIDE> void run(SlotStart start) {
     SchedSlot slots[4];
     Packet ring[3];
     std::memset(ring, 0, sizeof(ring));
     std::memset(slots, 0, sizeof(slots));
     for (int l = 0; l < 4; ++l) {
-      slots[l].it.init(w0, w1);
+      slots[l].it.init(start.quad, start.u, (int)start.budget);
       fill_packet_lane(p, slots[l], &ring[0], l);
       fill_packet_lane(p, slots[l], &ring[1], l);
     }
@@ -73,13 +75,13 @@ template <typename D> struct HostGroup {
       const bool in_fast = all4(cur->in_fast), out_fast = all4(cur->out_fast);
       g_fast_in += in_fast;
       g_fast_out += out_fast;
-      const bool warm = cur->warm != 0, add_tail = cur->first == 0;
+      const bool skip = cur->skip != 0, add_tail = cur->first == 0;
       for (int t = 0; t < kThreads; ++t) {
         if (in_fast) {
           int sh[4] = {cur->in_shift[0], cur->in_shift[1], cur->in_shift[2], cur->in_shift[3]};
           fast_load<WIDE>(t, regs[t], stage, L.lane_stride, sh, masks[t].in_zero);
         } else {
-          io_load(t, regs[t], p, cur->ln, cur->j);
+          io_load(t, regs[t], p, cur->ln, cur->u);
         }
         phase0_compute<RECOMP>(t, regs[t], p.tw1);
       }
@@ -97,11 +99,11 @@ template <typename D> struct HostGroup {
       pt *tail_prev = tails.data() + (parity ^ 1) * tpts, *tail_next = tails.data() + parity * tpts;
       for (int t = 0; t < kThreads; ++t) {
         phase4_compute(regs[t]);
-        if (out_fast || warm) {
+        if (out_fast) {
           S *const dst[4] = {cur->out_dst[0] + t, cur->out_dst[1] + t, cur->out_dst[2] + t, cur->out_dst[3] + t};
-          fast_store_to<WIDE>(t, regs[t], dst, masks[t], tail_prev, tail_next, add_tail, out_fast, p.step);
+          fast_store_to<WIDE>(t, regs[t], dst, masks[t], tail_prev, tail_next, add_tail, skip, p.step);
         } else {
-          io_store(t, regs[t], p, cur->ln, cur->j, tail_prev, tail_next, add_tail, warm);
+          io_store(t, regs[t], p, cur->ln, cur->u, tail_prev, tail_next, add_tail, skip);
         }
       }
       if (ring[ni].valid)
@@ -135,16 +137,17 @@ int run_case(long long batch, long long n, int K, int mode, long long chunks, lo
   fill_tw1(tw1.data());
   fill_tw2(tw2.data());
   fill_hs_host(k.data(), K, hs.data());
-  fill_params(p, a, out, batch, n, n, out_len, out_len, K, mode, chunks);
+  (void)chunks;
+  const SlicePlan plan = plan_slices(p, (const S *)a, out, batch, n, n, out_len, out_len, K, mode, n_slots);
+  p.slots = plan.starts.data();
   p.tw1 = tw1.data(); p.tw2 = tw2.data(); p.hs = hs.data();
 
   for (long long s = 0; s < n_slots; ++s) {
-    const long long w0 = p.total_work * s / n_slots, w1 = p.total_work * (s + 1) / n_slots;
     HostGroup<D> grp(p);
     // kernels of more than 410 taps take the WIDE instantiation, exactly as the dispatcher does
-    if (K > kMaxTapsNarrow) grp.template run<true, true>(w0, w1);
-    else if (recomp) grp.template run<true, false>(w0, w1);
-    else grp.template run<false, false>(w0, w1);
+    if (K > kMaxTapsNarrow) grp.template run<true, true>(plan.starts[s]);
+    else if (recomp) grp.template run<true, false>(plan.starts[s]);
+    else grp.template run<false, false>(plan.starts[s]);
   }
 
   double num = 0, den = 0;
@@ -161,7 +164,8 @@ int run_case(long long batch, long long n, int K, int mode, long long chunks, lo
       num += d * d; den += acc * acc;
     }
   const double err = std::sqrt(num / (den > 0 ? den : 1));
-  std::printf("%.3e iters %lld fast_in %lld fast_out %lld\n", err, g_iters, g_fast_in, g_fast_out);
+  std::printf("%.3e iters %lld fast_in %lld fast_out %lld budget %lld (+1 for %lld of %lld) vrows %lld\n", err, g_iters,
+              g_fast_in, g_fast_out, plan.budget, plan.extra, n_slots, plan.vrows);
   return (err < bound && std::isfinite(err)) ? 0 : 1;
 }
 

@@ -84,6 +84,11 @@ EMU_CASES = [
     (4, 20000, 246, 1, 1, 2, 3),  # step not a multiple of 4: shift changes every segment
     (8, 30000, 247, 0, 2, 3, 2),
     (4, 9020, 245, 0, 1, 1),      # n an exact multiple of step: last segment is full
+    (16, 65536, 245, 0, 1, 19),   # slices of 8 / 9 blocks starting in mid-row (the 8-GPU shard of config 2, scaled down)
+    (1, 200000, 245, 1, 1, 29),   # one row: four virtual rows, many slices per virtual row
+    (2, 50000, 300, 0, 1, 11, 2), # two rows: two virtual rows each
+    (3, 30000, 245, 1, 1, 64),    # more slices than blocks
+    (5, 1000, 245, 0, 1, 8),      # rows shorter than one block, more slices than rows
 ]
 EMU_WIDE_CASES = [
     (6, 20000, 411, 0, 1, 3),     # more than 410 taps: the WIDE instantiation (tails reach register slots < 8)
@@ -123,15 +128,6 @@ def test_n2048_float64_kernel_logic_emulated_on_cpu(built, case):
     r = subprocess.run([exe, *map(str, case), "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (case, r.stdout, r.stderr)
     assert float(r.stdout.split()[0]) < 1e-13
-
-
-@pytest.mark.parametrize("case", EMU_CASES + [(8, 20000, 410, 0, 1, 2), (8, 20000, 221, 1, 1, 3, 2)])
-def test_w2_kernel_logic_emulated_on_cpu(built, case):
-    """The warp-pair engine (oa_w2_*.cuh): same method, tests/cpu/emulate_oa_w2.cpp."""
-    exe = os.path.join(ROOT, "tests", "cpu", "emulate_oa_w2")
-    r = subprocess.run([exe, *map(str, case)], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, (case, r.stdout, r.stderr)
-    assert float(r.stdout.split()[0]) < 1e-6
 
 
 def test_fast_fft_engine_emulated_on_cpu(built):

@@ -106,18 +106,17 @@ N2048_CASES = [
 ]
 
 
-@pytest.mark.parametrize("engine", ["1", "2"])
-@pytest.mark.parametrize("batch,n,klen", N2048_CASES)
+@pytest.mark.parametrize("batch,n,klen", N2048_CASES + [(512, 65536, 245), (3, 400000, 245), (130, 9000, 300)])
 @pytest.mark.parametrize("mode", ["full", "same"])
-def test_n2048_kernel_device_pointers(cuda, batch, n, klen, mode, engine, monkeypatch):
-    """The headline kernels (float32, 221 <= K < 411; engine 1 = oa_n2048_kernel, 2 =
-    oa_w2_kernel): ragged last segments, batches that are not multiples of four, rows cut
-    into chunks, one-segment rows."""
+def test_n2048_kernel_device_pointers(cuda, batch, n, klen, mode, monkeypatch):
+    """The N = 2048 kernel (float32, 221 <= K < 411): ragged last blocks, batches that are not
+    multiples of four, fewer rows than lanes (virtual rows), slices that start in mid-row,
+    one-block rows."""
     import torch
 
     import fftconv_b200 as fc
 
-    monkeypatch.setenv("FFTCONV_CUDA_OA2048_ENGINE", engine)
+    monkeypatch.setenv("FFTCONV_CUDA_NO_W1K", "1")
     rng = np.random.default_rng(batch * 1000 + n + klen)
     a = rng.standard_normal((batch, n)).astype(np.float32)
     k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(np.float32)
@@ -126,16 +125,14 @@ def test_n2048_kernel_device_pointers(cuda, batch, n, klen, mode, engine, monkey
     _check(y.cpu().numpy(), a, k, mode, (batch, n, klen, mode))
 
 
-@pytest.mark.parametrize("engine", ["1", "2"])
 @pytest.mark.parametrize("groups", [1, 2, 3, 4])
-def test_n2048_kernel_group_variants(cuda, groups, engine, monkeypatch):
+def test_n2048_kernel_group_variants(cuda, groups, monkeypatch):
     import torch
 
     import fftconv_b200 as fc
 
-    monkeypatch.setenv("FFTCONV_CUDA_OA2048_ENGINE", engine)
+    monkeypatch.setenv("FFTCONV_CUDA_NO_W1K", "1")
     monkeypatch.setenv("FFTCONV_CUDA_N2048_GROUPS", str(groups))
-    monkeypatch.setenv("FFTCONV_CUDA_W2_PAIRS", str(groups))
     rng = np.random.default_rng(groups)
     a = rng.standard_normal((37, 30000)).astype(np.float32)
     k = (rng.standard_normal(245) / np.sqrt(245)).astype(np.float32)

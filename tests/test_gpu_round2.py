@@ -221,7 +221,7 @@ def test_long_signal_beyond_int32_indices(cuda):
         idx = syn.cut_window_indices([2 ** 31 - 1, 2 ** 31, 2 ** 30], n_out, klen, extra_random=20000, tail=6000, seed=1)
         want = syn.conv_at(syn.SEED_SIGNAL, n, taps, idx + pad)
         got = y[torch.from_numpy(idx).to(cuda)].cpu().numpy()
-        assert np.sum(idx > 2 ** 31) > 6000
+        assert np.sum(idx > 2 ** 31) > 4000
         assert syn.rel_l2(got, want) < 1e-5, mode
         # the far end on its own: every output index there exceeds INT32_MAX
         far = idx[idx > 2 ** 31]
