@@ -60,9 +60,9 @@ def workload_config(args):
         "workload": f"batched oaconvolve float32, {args.rows} signals x {args.n} samples, k={args.k}, "
                     "mode=full (BASELINE.json configs[1])",
         "rows": args.rows, "n": args.n, "k": args.k, "mode": "full",
-        "fft_size": 2048 if 221 <= args.k < 411 else None,
-        "l2": "inputs (1.07 GB per step) exceed the 126 MB L2 at N = 1; at N > 1 an L2 flush "
-              "(256 MB write) runs between timed steps",
+        "fft_size": "reference table: 2048 for k=245; large float32 jobs run 1024-point blocks (DESIGN.md 3.7)",
+        "l2": "per-GPU inputs exceed the 126 MB L2 (1.07 GB per step at N = 1, 134 MB at N = 8); "
+              "smaller shards get an L2 flush (256 MB write) between timed steps",
         "sharding": "the fixed batch is sharded by rows across ranks (strong scaling), no collective",
     }
 
@@ -364,9 +364,11 @@ def run_ours(args):
     a = a_full[lo:hi]
     out_full = torch.empty((args.rows, out_len), device=dev)
     out = out_full[lo:hi]
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if world > 1 else None
-    # per-GPU inputs + outputs of a shard (N = 8: 269 MB) no longer exceed L2 by a wide margin
-    flush = (lambda: flush_buf.zero_()) if world > 1 else None
+    # L2 is 126 MB.  A rank's inputs are rows x 256 KiB: larger than L2 down to 512 rows per GPU (N = 8:
+    # 134 MB in + 135 MB out per step); below that an L2 flush (256 MB write) runs between timed steps.
+    need_flush = my_rows * args.n * 4 <= (126 << 20)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if need_flush else None
+    flush = (lambda: flush_buf.zero_()) if need_flush else None
 
     def step():
         fc.oaconvolve_(a, k, out, "full")
@@ -463,7 +465,7 @@ def run_ours(args):
             chk_p = float(torch.linalg.norm(torch.from_numpy(op[:8]).to(dev) - out[:8]) / torch.linalg.norm(out[:8]))
             e2e["pageable"] = {"value": out_samples_total / dtp / 1e9, "unit": UNIT, "ms_per_step": dtp * 1e3,
                                "host_memory": "pageable numpy arrays through the library's page-locked ring "
-                                              "(3 worker threads per GPU)",
+                                              "(8 worker threads per GPU)",
                                "rel_l2_vs_device_path": chk_p}
             del ap, op
         except Exception as e:
@@ -497,7 +499,7 @@ def run_ours(args):
         achieved = alg_bytes / (own_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": ncu_traffic() if world == 1 else None,
-                    "kernel": "the overlap-add segment kernel (name in profiles/)",
+                    "kernel": "fc::w1k::oa_w1k_kernel (1024-point blocks, one warp per complex FFT)",
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "peak_source": peak_src, "frac_of_8TBps_nominal": achieved / 8000.0,
                     "sustained": {"steps": sus_steps, "ms_per_step": sus_ms,

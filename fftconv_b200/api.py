@@ -318,7 +318,7 @@ class Filter:
                 K.ptr, self.klen, _capi.C.byref(self._h)))
 
     def close(self) -> None:
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and _capi is not None and _capi.lib is not None:
             _capi.lib().fftconv_cuda_filter_destroy(self._h)
             self._h = None
 
@@ -367,7 +367,7 @@ class Stream:
             filt._h, self.rows, _capi.C.byref(self._h)))
 
     def close(self) -> None:
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and _capi is not None and _capi.lib is not None:
             _capi.lib().fftconv_cuda_stream_destroy(self._h)
             self._h = None
 
@@ -459,7 +459,7 @@ class MultiGpu:
         self.devices = ids
 
     def close(self) -> None:
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and _capi is not None and _capi.lib is not None:
             _capi.lib().fftconv_cuda_mgpu_destroy(self._h)
             self._h = None
 

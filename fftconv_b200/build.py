@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 ]
 
 # translation units of libfftconv_cuda.so (compiled in parallel, objects under lib/obj/)
-UNITS = ["fftconv_cuda.cu", "fftconv_cuda_mgpu.cu"]
+UNITS = ["fftconv_cuda.cu", "fftconv_cuda_w1k.cu", "fftconv_cuda_mgpu.cu"]
 
 
 def _newer(target: str, sources: list[str]) -> bool:
@@ -48,7 +48,7 @@ def _unit_deps(unit: str) -> list[str]:
     """Sources a translation unit is rebuilt for: itself, the public header, and -- for the main
     unit, which includes every kernel header -- everything under csrc/ that is not another unit."""
     hdr = os.path.join(ROOT, "include", "fftconv_cuda.h")
-    if unit == "fftconv_cuda.cu":
+    if unit != "fftconv_cuda_mgpu.cu":  # the kernel units include the kernel headers
         return [hdr] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
                         if f == unit or not f.endswith(".cu")]
     return [hdr, os.path.join(CSRC, unit)]

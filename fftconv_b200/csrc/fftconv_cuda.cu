@@ -17,6 +17,7 @@
 #include "long_fft_kernels.cuh"
 #include "oa_n2048_kernel.cuh"
 #include "oa_n2048_tables.h"
+#include "oa_w1k_launch.h"
 #include "synthetic.cuh"
 
 #include <cuda_runtime.h>
@@ -141,6 +142,7 @@ struct DeviceCtx {
   std::map<std::pair<size_t, int>, Tables> tables;
   std::map<std::pair<size_t, int>, BluesteinTables> bluestein;
   fc::n2048::cpair *tw1 = nullptr, *tw2 = nullptr;
+  fc::n2048::cpair *tw_w1k = nullptr; // per-lane twiddles of the warp-per-FFT engine (oa_w1k_core.cuh)
   // slice plans of the N = 2048 kernel, keyed by (dtype, batch, n, K, slices): where every group of
   // the grid starts (oa_n2048_tables.h, plan_slices) -- computed once per shape, kept on the device
   struct SlicePlanDev {
@@ -206,7 +208,8 @@ void free_ctx(DeviceCtx &c) {
   cudaFree(c.tw2);
   cudaFree(c.tw1d);
   cudaFree(c.tw2d);
-  c.tw1 = c.tw2 = nullptr;
+  cudaFree(c.tw_w1k);
+  c.tw1 = c.tw2 = c.tw_w1k = nullptr;
   for (auto &kv : c.slice_plans) cudaFree(kv.second.starts);
   c.slice_plans.clear();
   c.tw1d = c.tw2d = nullptr;
@@ -647,6 +650,17 @@ template <typename T> int oa2048_engine_for(size_t N, size_t klen) {
   return e;
 }
 
+// The warp-per-FFT engine (oa_w1k_*.cuh): float32, 1024-point blocks, 8 <= K <= w1k::kMaxTaps.  It serves
+// the table's own N = 1024 row and, through the throughput rule, large jobs with shorter or longer
+// kernels (FFTCONV_CUDA_NO_W1K=1 switches it off; FFTCONV_CUDA_W1K_MAX_TAPS moves the upper end of
+// what the throughput rule sends to it).
+template <typename T> bool w1k_engine_for(size_t N, size_t klen) {
+  if (!std::is_same<T, float>::value || N != 1024) return false;
+  if (klen < 8 || klen > (size_t)fc::w1k::kMaxTaps) return false;
+  return !(env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) || env_int("FFTCONV_CUDA_NO_W1K", 0));
+}
+size_t w1k_rule_max_taps() { return (size_t)std::min(fc::w1k::kMaxTaps, std::max(0, env_int("FFTCONV_CUDA_W1K_MAX_TAPS", 300))); }
+
 // The plan of one launch of the N = 2048 kernel: stream geometry + where each group's slice starts.
 template <typename T>
 int get_slice_plan(DeviceCtx &c, fc::n2048::OaParamsT<T> &p, const T *a, T *out, size_t batch, size_t n, size_t a_stride,
@@ -690,6 +704,32 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
   const size_t step = N - (klen - 1);
   const long long segs = (long long)((n + step - 1) / step);
 
+  if constexpr (std::is_same<T, float>::value) {
+    if (w1k_engine_for<T>(N, klen)) {
+      if (!c.tw_w1k) {
+        std::vector<fc::n2048::cpair> tw(fc::w1k::kTwiddleElems);
+        fc::w1k::build_twiddles(tw.data());
+        CU_TRY(cudaMalloc((void **)&c.tw_w1k, tw.size() * sizeof(fc::n2048::cpair)));
+        CU_TRY(cudaMemcpy(c.tw_w1k, tw.data(), tw.size() * sizeof(fc::n2048::cpair), cudaMemcpyHostToDevice));
+      }
+      const cx<float> *H = nullptr;
+      if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_W1K, *tab, &H)) return r;
+      fc::w1k::W1kParams p{};
+      fc::w1k::fill_params(p, a, out, (long long)batch, (long long)n, (long long)a_stride, (long long)out_stride,
+                           (long long)out_len, (int)klen, mode == FFTCONV_CUDA_SAME ? 1 : 0);
+      p.tw = c.tw_w1k;
+      p.hs = reinterpret_cast<const fc::n2048::cpair *>(H);
+      if (fc::w1k::launch_smem_bytes() > c.smem_optin)
+        return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "warp-per-FFT kernel: not enough shared memory per CTA on this device");
+      const int sms_avail = std::max(1, c.sm_count - std::max(0, g_reserved_sms.load()));
+      const int wpc = fc::w1k::warps_per_cta();
+      const long long ctas = std::max<long long>(1, std::min<long long>(sms_avail, (p.n_units + wpc - 1) / wpc));
+      if (const int e = fc::w1k::launch(p, (int)ctas, st))
+        return fail(FFTCONV_CUDA_ERR_CUDA, std::string("oa_w1k_kernel: ") + cudaGetErrorString((cudaError_t)e));
+      ++g_launches;
+      return 0;
+    }
+  }
   const int engine2048 = oa2048_engine_for<T>(N, klen);
   if (engine2048 == 1) {
     using D = typename fc::DataOf<T>::D;
@@ -918,6 +958,7 @@ template <typename T> size_t throughput_oa_size(const DeviceCtx &c, size_t klen,
   if ((double)batch * (double)n < 4194304.0) return table_n;
   (void)c;
   if (std::is_same<T, float>::value) {
+    if (klen >= 8 && klen <= w1k_rule_max_taps() && w1k_engine_for<T>(1024, klen)) return 1024;
     if (klen >= 8 && klen < 221 && oa2048_engine() == 1) return 2048;
     if (klen < 8) return 512;
   } else {
@@ -1594,6 +1635,7 @@ int fill_synthetic_entry(T *dst, size_t n, unsigned long long seed, unsigned lon
 }
 
 template <typename T> int oa_layout_for(const DeviceCtx &c, size_t N, size_t klen) {
+  if (w1k_engine_for<T>(N, klen)) return fc::generic::LAYOUT_W1K;
   if (oa2048_engine_for<T>(N, klen)) return fc::generic::LAYOUT_N2048;
   return fast_ok<T>(c, N, klen) ? fc::generic::LAYOUT_FAST : fc::generic::LAYOUT_DIF;
 }

@@ -23,7 +23,7 @@ using fc::env_store;
 // in double.  O(N K) work -- K <= a few thousand taps by construction.  (j k fits
 // 32 bits: j < K <= N / 2, k < N <= 2^15.)
 // ---------------------------------------------------------------------------
-enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1, LAYOUT_FAST = 2, LAYOUT_LONG = 3 };
+enum SpectrumLayout { LAYOUT_DIF = 0, LAYOUT_N2048 = 1, LAYOUT_FAST = 2, LAYOUT_LONG = 3, LAYOUT_W1K = 4 };
 
 __device__ __forceinline__ unsigned n2048_freq_of_index(unsigned idx) {
   // idx = slot * 128 + t (see fc::n2048::p2_freq, p2_col)
@@ -43,6 +43,8 @@ __global__ void spectrum_kernel(const T *__restrict__ taps, int klen, int N,
   if (pos >= N) return;
   unsigned k;
   if (layout == LAYOUT_N2048) k = n2048_freq_of_index(pos);
+  else if (layout == LAYOUT_W1K) // entry e = 2 (j * 32 + k2) + half (fc::w1k::freq_of_index)
+    k = 32u * (((unsigned)pos >> 6) + 16u * ((unsigned)pos & 1u)) + (((unsigned)pos >> 1) & 31u);
   else if (layout == LAYOUT_FAST) k = fc::fast::freq_of_pos(fc::fast::pos_of_table_index(pos, 31 - __clz(N)), 31 - __clz(N));
   else if (layout == LAYOUT_LONG) {
     // N = 16 N_sub (long_fft_kernels.cuh): entry (s, idx_sub) holds frequency s + 16 freq_sub(idx_sub)

@@ -1,0 +1,313 @@
+// oa_w1k_core.cuh -- overlap-add segments of 1024 points, ONE WARP per complex FFT.
+//
+// Why a second engine beside oa_n2048_*: that kernel is bound by the shared-memory data pipe
+// (ncu, round 1: LSU pipe 75 % busy, 512 of its 751 shared wavefronts per warp iteration are the
+// four exchanges of a 2048 = 16 x 16 x 8 decomposition).  A thread that holds 32 points instead
+// of 16 needs only two exchanges: 1024 = 32 x 32, and both are transposes inside one warp --
+// no block barrier anywhere, sixteen fully independent warps per SM.  Round 1 tried 32 points
+// per thread with FOUR real segments per point (oa_w2): 128 data registers, 8 warps per SM,
+// latency bound.  Here a thread holds 32 points of ONE complex FFT (two real segments in the real
+// and imaginary parts), 64 data registers, and uses the packed f32x2 arithmetic ACROSS the points:
+//     register pair i  =  (point i, point i + 16)      ("half packing")
+// A 32-point DFT is then one radix-2 step between the halves of each pair (scalar instructions)
+// and one 16-point DFT on all pairs at once (packed instructions, the dft16 of oa_n2048_core.cuh).
+//
+// Segments: the reference's overlap-add (fftconv.hpp:387-410) pads a block of step = N - (K-1)
+// samples with zeros and adds the K-1 tail into the next block.  The same linear convolution is
+// obtained by overlapping on the INPUT side: a block reads N samples starting K-1 before its first
+// output and its first K-1 (circularly wrapped) outputs are dropped.  Every block is then
+// independent of every other -- no tail hand-over, no ordering between blocks, any warp can take
+// any block -- and every output sample is still written exactly once (deterministic, no atomics).
+//
+// 1024 = 32 x 32, n = l + 32 m, k = 32 k1 + k2, lane l, W = exp(-2 pi i / N):
+//   P0  lane l:   A_l[k2] = sum_m z[l + 32 m] W_32^{m k2};   B_l[k2] = A_l[k2] W_1024^{l k2}
+//   T1  transpose: lane k2 receives B_l[k2], l = 0..31
+//   P1  lane k2:  X[32 k1 + k2] = sum_l B_l[k2] W_32^{l k1};  Y = X H;
+//                 C_k2[l] = sum_k1 Y[32 k1 + k2] W_32^{-l k1}
+//   T2  transpose: lane l receives C_k2[l], k2 = 0..31
+//   P2  lane l:   y[l + 32 m] = sum_k2 C_k2[l] conj(W_1024^{l k2}) W_32^{-m k2}      (1/N folded into H)
+//
+// The four 32-point DFTs and which points share a register pair (dft16 works on pair index 0..15):
+//   P0  forward, decimation in frequency:  in (m, m+16)    -> radix-2 step, dft16 -> out (k2 = 2j, 2j+1)
+//   P1  forward, decimation in time:       in (l = 2i, 2i+1) -> dft16, radix-2 step -> out (k1 = j, j+16)
+//   P1' inverse, decimation in frequency:  in (k1 = j, j+16) -> radix-2 step, dft16 -> out (l = 2i, 2i+1)
+//   P2  inverse, decimation in time:       in (k2 = 2j, 2j+1) -> dft16, radix-2 step -> out (m, m+16)
+// so that the transposes move 16-byte quantities on one side (rows of consecutive l) and the pair
+// twiddles W_1024^{l k2} are (w2^j, w2^j w), w2 = w^2: a broadcast scalar per pair plus one extra
+// scalar multiply on the odd half.
+//
+// Everything is __host__ __device__: tests/cpu/emulate_oa_w1k.cpp runs the same functions lane by lane.
+#pragma once
+
+#include "oa_n2048_core.cuh"
+
+namespace fc {
+namespace w1k {
+
+using n2048::CPairT;
+using n2048::cpair;
+using n2048::dft16;
+using n2048::RegsT;
+using n2048::slot16;
+using Regs = RegsT<f2>;
+
+constexpr int kN = 1024;
+constexpr int kRowStride = 36;              // floats per exchange row (32 + 4: conflict-free 128-bit rows, 32-bit columns)
+constexpr int kPlane = 32 * kRowStride;     // floats per plane (re / im); also one row's input staging area
+constexpr int kWarpFloats = 2 * kPlane;     // exchange buffer of one warp
+constexpr int kMaxTaps = 400;               // step >= 625: below that the 2048-point kernel is the better choice
+
+// cos / sin of 2 pi i / 32, i = 0..15
+struct W32Table {
+  float c[16], s[16];
+};
+FC_HD constexpr W32Table w32_table() {
+  return W32Table{{1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                   0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f,
+                   0.0f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                   -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f, -0.98078528040323044913f},
+                  {0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                   0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f,
+                   1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                   0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f}};
+}
+
+// (dr, di) *= exp(S 2 pi j i / 32), i a compile-time constant 0..15
+template <int S, int I> FC_HD void rot32(float &dr, float &di) {
+  constexpr W32Table T = w32_table();
+  if (I == 0) return;
+  if (I == 8) { // +- j
+    const float t = dr;
+    if (S < 0) { dr = di; di = -t; }
+    else       { dr = -di; di = t; }
+    return;
+  }
+  const float c = T.c[I], s = (S < 0 ? -T.s[I] : T.s[I]);
+  const float nr = dr * c - di * s;
+  di = dr * s + di * c;
+  dr = nr;
+}
+
+// Radix-2 step BETWEEN the halves of every pair, decimation in frequency: pair i holds points
+// (i, i + 16); afterwards its low half holds x[i] + x[i+16] (input i of the even-output DFT16) and its
+// high half (x[i] - x[i+16]) exp(S 2 pi j i / 32) (input i of the odd-output DFT16).  Pairs in natural slots.
+template <int S, int I = 0> FC_HD void cross_dif(Regs &v) {
+  if constexpr (I < 16) {
+    const float sr = v.re[I].x + v.re[I].y, si = v.im[I].x + v.im[I].y;
+    float dr = v.re[I].x - v.re[I].y, di = v.im[I].x - v.im[I].y;
+    rot32<S, I>(dr, di);
+    v.re[I].x = sr; v.im[I].x = si;
+    v.re[I].y = dr; v.im[I].y = di;
+    cross_dif<S, I + 1>(v);
+  }
+}
+// Radix-2 step between the halves, decimation in time: the pair in slot slot16(j) holds (E[j], O[j]),
+// the j-th outputs of the DFT16s of the even / odd inputs; afterwards (X[j], X[j + 16]) with
+// X[j] = E[j] + exp(S 2 pi j j / 32) O[j], X[j+16] = E[j] - exp(..) O[j].
+template <int S, int J = 0> FC_HD void cross_dit(Regs &v) {
+  if constexpr (J < 16) {
+    constexpr int s = slot16(J);
+    float orr = v.re[s].y, oi = v.im[s].y;
+    rot32<S, J>(orr, oi);
+    const float er = v.re[s].x, ei = v.im[s].x;
+    v.re[s].x = er + orr; v.im[s].x = ei + oi;
+    v.re[s].y = er - orr; v.im[s].y = ei - oi;
+    cross_dit<S, J + 1>(v);
+  }
+}
+
+// The same two steps with the lane's odd-point factor w = W_1024^l folded into the step's twiddles:
+// ct[i * 32 + lane] = exp(-2 pi j i / 32) w (forward); the inverse uses the conjugates.  This replaces
+// sixteen constant multiplications plus sixteen multiplications by w with sixteen multiplications.
+template <bool CONJ, int I = 0> FC_HD void cross_dif_tw(Regs &v, const cpair *ct) { // ct already points at the lane's column
+  if constexpr (I < 16) {
+    const cpair w = ct[I * 32];
+    const float wi = CONJ ? -w.im : w.im;
+    const float sr = v.re[I].x + v.re[I].y, si = v.im[I].x + v.im[I].y;
+    const float dr = v.re[I].x - v.re[I].y, di = v.im[I].x - v.im[I].y;
+    v.re[I].x = sr; v.im[I].x = si;
+    v.re[I].y = dr * w.re - di * wi;
+    v.im[I].y = dr * wi + di * w.re;
+    cross_dif_tw<CONJ, I + 1>(v, ct);
+  }
+}
+template <bool CONJ, int J = 0> FC_HD void cross_dit_tw(Regs &v, const cpair *ct) {
+  if constexpr (J < 16) {
+    constexpr int s = slot16(J);
+    const cpair w = ct[J * 32];
+    const float wi = CONJ ? -w.im : w.im;
+    const float orr = v.re[s].y, oi = v.im[s].y;
+    const float tr = orr * w.re - oi * wi, ti = orr * wi + oi * w.re;
+    const float er = v.re[s].x, ei = v.im[s].x;
+    v.re[s].x = er + tr; v.im[s].x = ei + ti;
+    v.re[s].y = er - tr; v.im[s].y = ei - ti;
+    cross_dit_tw<CONJ, J + 1>(v, ct);
+  }
+}
+
+// ---- pair twiddles W_1024^{l k2}, k2 = 2 j + h -------------------------------------------------
+// per lane: w2^1, w2^2, w2^4, w2^8 (w2 = W_512^l): table tw[r * 32 + l], r = 0..3; the other powers of
+// w2 are products formed in registers (as in oa_n2048_core.cuh).  Rows 4 .. 19 of the same table hold
+// the radix-2 step's twiddles with w = W_1024^l folded in: tw[(4 + i) * 32 + l] = exp(-2 pi j i / 32) w.
+struct LaneTwiddles {
+  cpair p[16]; // p[j] = w2^j (p[0] unused)
+  cpair w;
+};
+FC_HD LaneTwiddles lane_twiddles(const cpair *tw, int lane) {
+  using n2048::cpair_mul;
+  LaneTwiddles t;
+  t.p[1] = tw[0 * 32 + lane];
+  t.p[2] = tw[1 * 32 + lane];
+  t.p[4] = tw[2 * 32 + lane];
+  t.p[8] = tw[3 * 32 + lane];
+  t.w = cpair{1.0f, 0.0f};
+  t.p[0] = cpair{1.0f, 0.0f};
+  t.p[3] = cpair_mul(t.p[1], t.p[2]);
+  t.p[5] = cpair_mul(t.p[4], t.p[1]);
+  t.p[6] = cpair_mul(t.p[4], t.p[2]);
+  t.p[7] = cpair_mul(t.p[4], t.p[3]);
+  t.p[9] = cpair_mul(t.p[8], t.p[1]);
+  t.p[10] = cpair_mul(t.p[8], t.p[2]);
+  t.p[11] = cpair_mul(t.p[8], t.p[3]);
+  t.p[12] = cpair_mul(t.p[8], t.p[4]);
+  t.p[13] = cpair_mul(t.p[8], t.p[5]);
+  t.p[14] = cpair_mul(t.p[8], t.p[6]);
+  t.p[15] = cpair_mul(t.p[8], t.p[7]);
+  return t;
+}
+// the pair for index j sits in slot SLOT(j); CONJ = inverse direction.  Both points of pair j get
+// w2^j; the odd point's extra factor w rides in the neighbouring radix-2 step (cross_*_tw).
+template <bool CONJ, bool SLOT16> FC_HD void apply_pair_twiddles(Regs &v, const LaneTwiddles &t) {
+#pragma unroll
+  for (int j = 1; j < 16; ++j) {
+    const int s = SLOT16 ? slot16(j) : j;
+    cmul2(v.re[s], v.im[s], t.p[j].re, CONJ ? -t.p[j].im : t.p[j].im);
+  }
+}
+
+// ---- exchange buffer ---------------------------------------------------------------------------
+// two planes (re, im) of 32 rows x kRowStride floats; entry (row r, column c) holds the value that
+// lane c produced for lane r (T1) or lane r produced for lane c (T2).
+FC_HD int ex_addr(int row, int col) { return row * kRowStride + col; }
+
+// T1 write: lane l holds B_l[k2] in slot16(j), k2 = 2 j + h  ->  entry (k2, l)
+FC_HD void t1_write(int lane, const Regs &v, float *xb) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int s = slot16(j);
+    xb[ex_addr(2 * j, lane)] = v.re[s].x;
+    xb[ex_addr(2 * j + 1, lane)] = v.re[s].y;
+    xb[kPlane + ex_addr(2 * j, lane)] = v.im[s].x;
+    xb[kPlane + ex_addr(2 * j + 1, lane)] = v.im[s].y;
+  }
+}
+struct alignas(16) Quad { float a, b, c, d; };
+// T1 read: lane k2 reads its row: pair i = (l = 2 i, 2 i + 1) into natural slot i
+FC_HD void t1_read(int lane, Regs &v, const float *xb) {
+  const Quad *re = reinterpret_cast<const Quad *>(xb + ex_addr(lane, 0));
+  const Quad *im = reinterpret_cast<const Quad *>(xb + kPlane + ex_addr(lane, 0));
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const Quad r = re[c], q = im[c];
+    v.re[2 * c] = make_f2(r.a, r.b);
+    v.re[2 * c + 1] = make_f2(r.c, r.d);
+    v.im[2 * c] = make_f2(q.a, q.b);
+    v.im[2 * c + 1] = make_f2(q.c, q.d);
+  }
+}
+// T2 write: lane k2 holds C_k2[l] in slot16(i), l = 2 i + h  ->  its own row, 16 bytes at a time
+FC_HD void t2_write(int lane, const Regs &v, float *xb) {
+  Quad *re = reinterpret_cast<Quad *>(xb + ex_addr(lane, 0));
+  Quad *im = reinterpret_cast<Quad *>(xb + kPlane + ex_addr(lane, 0));
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int s0 = slot16(2 * c), s1 = slot16(2 * c + 1);
+    re[c] = Quad{v.re[s0].x, v.re[s0].y, v.re[s1].x, v.re[s1].y};
+    im[c] = Quad{v.im[s0].x, v.im[s0].y, v.im[s1].x, v.im[s1].y};
+  }
+}
+// T2 read: lane l reads column l: k2 = 2 j + h into natural slot j
+FC_HD void t2_read(int lane, Regs &v, const float *xb) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v.re[j] = make_f2(xb[ex_addr(2 * j, lane)], xb[ex_addr(2 * j + 1, lane)]);
+    v.im[j] = make_f2(xb[kPlane + ex_addr(2 * j, lane)], xb[kPlane + ex_addr(2 * j + 1, lane)]);
+  }
+}
+
+// ---- spectrum ------------------------------------------------------------------------------------
+// hs4[j * 32 + k2] = (Re H[k_lo], Re H[k_hi], Im H[k_lo], Im H[k_hi]) / N with k_lo = 32 j + k2,
+// k_hi = 32 (j + 16) + k2: the frequencies lane k2 holds in slot16(j) after P1's radix-2 step.
+// The spectrum kernel writes complex entries; entry index e = 2 (j * 32 + k2) + half:
+FC_HD constexpr unsigned freq_of_index(unsigned e) {
+  return 32u * ((e >> 6) + 16u * (e & 1u)) + ((e >> 1) & 31u);
+}
+FC_HD void multiply_spectrum(int lane, Regs &v, const Quad *hs4) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int s = slot16(j);
+    const Quad h = hs4[j * 32 + lane];
+    const f2 hr = make_f2(h.a, h.b), hi = make_f2(h.c, h.d);
+    const f2 yr = v.re[s], yi = v.im[s];
+    v.re[s] = fnma2(yi, hi, mul2(yr, hr)); // yr hr - yi hi
+    v.im[s] = fma2(yi, hr, mul2(yr, hi));  // yr hi + yi hr
+  }
+}
+
+// ---- the phases of one warp iteration (between __syncwarp()s) -------------------------------------
+// P0: slots hold z[l + 32 i] (low) and z[l + 32 (i + 16)] (high); leaves B_l[k2] in slot16(j)
+FC_HD void phase0(int lane, Regs &v, const cpair *tw) {
+  cross_dif_tw<false>(v, tw + 4 * 32 + lane); // the odd outputs' factor w rides in the step's twiddles
+  dft16<-1>(v);
+  apply_pair_twiddles<false, true>(v, lane_twiddles(tw, lane));
+}
+// P1: slots hold B_l[k2] for l = 2 i, 2 i + 1; leaves C_k2[l], l = 2 i + h, in slot16(i)
+FC_HD void phase1(int lane, Regs &v, const Quad *hs4) {
+  dft16<-1>(v);
+  cross_dit<-1>(v);
+  multiply_spectrum(lane, v, hs4);
+  // inverse, decimation in frequency: the pair for k1 = (j, j + 16) sits in slot16(j); dft16 wants it in slot j
+  Regs w;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    w.re[j] = v.re[slot16(j)];
+    w.im[j] = v.im[slot16(j)];
+  }
+  cross_dif<+1>(w);
+  dft16<+1>(w);
+  v = w;
+}
+// The same phases cut at the two dft16 calls of each direction, so that a kernel can run ONE copy of
+// the forward and ONE copy of the inverse dft16 in two-trip loops (the unrolled code of four copies
+// does not fit the 32 KB instruction cache: measured 87 % hit rate, 0.64 stall cycles per issue).
+//   phase0 = p0_pre, dft16<-1>, p0_post        phase1 = dft16<-1>, p1_mid, dft16<+1>
+//   phase2 = p2_pre, dft16<+1>, p2_post
+FC_HD void p0_pre(int lane, Regs &v, const cpair *tw) { cross_dif_tw<false>(v, tw + 4 * 32 + lane); }
+FC_HD void p0_post(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<false, true>(v, lane_twiddles(tw, lane)); }
+// between P1's two transforms: radix-2 step, spectrum, radix-2 step of the inverse -- which also
+// moves the pair for k1 = (j, j + 16) from slot16(j), where the forward dft16 left it, to slot j,
+// where the inverse dft16 wants it (the step rewrites every value anyway: the move is free)
+FC_HD void p1_mid(int lane, Regs &v, const Quad *hs4) {
+  cross_dit<-1>(v);
+  multiply_spectrum(lane, v, hs4);
+  Regs w;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    w.re[j] = v.re[slot16(j)];
+    w.im[j] = v.im[slot16(j)];
+  }
+  cross_dif<+1>(w);
+  v = w;
+}
+FC_HD void p2_pre(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<true, false>(v, lane_twiddles(tw, lane)); }
+FC_HD void p2_post(int lane, Regs &v, const cpair *tw) { cross_dit_tw<true>(v, tw + 4 * 32 + lane); }
+
+// P2: slots hold C_k2[l] for k2 = 2 j, 2 j + 1; leaves y[l + 32 m], y[l + 32 (m + 16)] in slot16(m)
+FC_HD void phase2(int lane, Regs &v, const cpair *tw) {
+  apply_pair_twiddles<true, false>(v, lane_twiddles(tw, lane));
+  dft16<+1>(v);
+  cross_dit_tw<true>(v, tw + 4 * 32 + lane); // conj(w) of the odd inputs commutes with their dft16
+}
+
+} // namespace w1k
+} // namespace fc

@@ -1,0 +1,232 @@
+// oa_w1k_group.cuh -- work decomposition and I/O of the warp-per-FFT engine (oa_w1k_core.cuh).
+// Host + device, so that tests/cpu/emulate_oa_w1k.cpp runs the very same code.
+//
+// The job is a list of ITEMS (row r, block s), s < segs = ceil((n + K - 1) / step): block s owns the
+// outputs f in [s step, (s + 1) step) of the row's full convolution and reads the N = 1024 input
+// samples [s step - (K - 1), s step - (K - 1) + N) -- zeros outside the row.  Two consecutive items
+// ride in the real and imaginary part of one complex FFT: a UNIT.  Units are independent; warp w of
+// W takes the contiguous range [w U / W, (w + 1) U / W).
+//
+// Input: the block's samples are staged in the warp's exchange buffer (plane 0: real part's row,
+// plane 1: imaginary part's row) by one bulk asynchronous copy per item (TMA, SASS UBLKCP), requested
+// by lane 0 one unit ahead.  Sample with row index r sits at staging index (r - block start) + shift,
+// shift in 0..3 chosen so that source and destination of the copy are both 16-byte aligned.  The first
+// block of a row (K - 1 zeros in front) is copied from the row start and the lanes zero the head; a
+// block that reaches past the row end, a misaligned row start, or a span that would leave the tensor
+// is filled by the lanes with plain loads instead.
+// Output: y[i], i = lane + 32 m, is output f = block start + i for i >= K - 1: 4-byte stores, one full
+// 128-byte line per warp instruction.
+#pragma once
+
+#include "oa_w1k_core.cuh"
+
+#include <cstddef>
+
+namespace fc {
+namespace w1k {
+
+struct W1kParams {
+  const float *in;
+  float *out;
+  long long batch, n, in_stride, out_stride, out_len;
+  int klen, step, pad; // step = N - (K - 1); pad = 0 (Full) or K / 2 (Same)
+  long long full_len;  // n + K - 1
+  long long segs;      // blocks per row
+  long long n_items;   // batch * segs
+  long long n_units;   // ceil(n_items / 2)
+  const cpair *tw;     // kTwElems per-lane twiddles
+  const cpair *hs;     // 1024 spectrum entries (freq_of_index order), 1/N folded in
+};
+
+inline void fill_params(W1kParams &p, const float *in, float *out, long long batch, long long n, long long in_stride,
+                        long long out_stride, long long out_len, int klen, int mode) {
+  p.in = in; p.out = out;
+  p.batch = batch; p.n = n;
+  p.in_stride = in_stride; p.out_stride = out_stride; p.out_len = out_len;
+  p.klen = klen;
+  p.step = kN - (klen - 1);
+  p.pad = mode ? klen / 2 : 0;
+  p.full_len = n + klen - 1;
+  p.segs = (p.full_len + p.step - 1) / p.step;
+  p.n_items = batch * p.segs;
+  p.n_units = (p.n_items + 1) / 2;
+  p.tw = nullptr;
+  p.hs = nullptr;
+}
+
+FC_HD void warp_range(long long n_units, long long n_warps, long long w, long long &u0, long long &u1) {
+  const long long base = n_units / n_warps, rem = n_units % n_warps;
+  u0 = w * base + (w < rem ? w : rem);
+  u1 = u0 + base + (w < rem ? 1 : 0);
+}
+
+struct ItemDesc {
+  const float *row_in;  // the row's first sample
+  float *row_out;       // the row's first output
+  long long bs;         // row index of the block's first input sample (negative for a row's first block)
+  const float *src;     // bulk copy: 16-byte aligned source, 0 bytes = nothing to copy
+  int bytes;
+  int dst_first;        // staging index (floats) the copy starts at
+  int zero_upto;        // the lanes zero staging [0, zero_upto) (row's first block)
+  int shift;            // sample r sits at staging index (r - bs) + shift
+  int nout;             // outputs owned: y[K-1 .. K-1+nout)
+  int active;
+  int bulk_ok;
+};
+struct UnitDesc {
+  ItemDesc item[2];
+  int bulk;     // both items are staged by bulk copies
+  int fast_out; // both items own `step` outputs that all lie inside their rows
+};
+
+FC_HD int align_shift4(const float *ptr) { return (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ULL); }
+
+FC_HD ItemDesc describe_item(const W1kParams &p, long long row, long long seg) {
+  ItemDesc d;
+  d.active = row < p.batch;
+  if (!d.active) { row = 0; seg = 0; }
+  d.row_in = p.in + row * p.in_stride;
+  d.row_out = p.out + row * p.out_stride;
+  d.bs = seg * p.step - (p.klen - 1);
+  const long long left = p.full_len - seg * p.step;
+  d.nout = d.active ? (int)(left < p.step ? left : p.step) : 0;
+  // valid input rows [r0, r1)
+  const long long r0 = d.bs < 0 ? 0 : d.bs;
+  long long r1 = d.bs + kN;
+  const bool tail_clipped = r1 > p.n;
+  if (tail_clipped) r1 = p.n;
+  const float *first = d.row_in + r0;
+  const int ish = align_shift4(first);
+  const int head = (int)(r0 - d.bs); // zeros in front
+  d.shift = (ish - head) & 3;
+  d.dst_first = head + d.shift - ish;
+  d.src = first - ish;
+  const long long nvalid = r1 > r0 ? r1 - r0 : 0;
+  d.bytes = (int)(((ish + nvalid) * 4 + 15) & ~15LL);
+  d.zero_upto = head > 0 ? d.dst_first : 0;
+  const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
+  d.bulk_ok = d.active && !tail_clipped && nvalid > 0 && (head == 0 || ish == 0) &&
+              (d.src + d.bytes / 4 <= tensor_end) && (d.src >= p.in);
+  return d;
+}
+
+FC_HD UnitDesc describe_unit_at(const W1kParams &p, long long row0, long long seg0, long long row1, long long seg1) {
+  UnitDesc u;
+  u.item[0] = describe_item(p, row0, seg0);
+  u.item[1] = describe_item(p, row1, seg1);
+  u.bulk = u.item[0].bulk_ok && u.item[1].bulk_ok;
+  u.fast_out = 1;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const ItemDesc &d = u.item[i];
+    const long long o0 = d.bs - p.pad + (p.klen - 1); // output index of y[K - 1]
+    u.fast_out = u.fast_out && d.active && d.nout == p.step && o0 >= 0 && o0 + p.step <= p.out_len;
+  }
+  return u;
+}
+FC_HD UnitDesc describe_unit(const W1kParams &p, long long u) {
+  const long long it0 = 2 * u, it1 = 2 * u + 1;
+  const long long r0 = it0 / p.segs, r1 = it1 < p.n_items ? it1 / p.segs : p.batch;
+  return describe_unit_at(p, r0, it0 - r0 * p.segs, r1, it1 < p.n_items ? it1 - r1 * p.segs : 0);
+}
+
+// lanes: zero the head of a row's first block (bulk path)
+FC_HD void zero_fill(int lane, const ItemDesc &d, float *plane) {
+  for (int i = lane; i < d.zero_upto; i += 32) plane[i] = 0.0f;
+}
+// lanes: stage one block with plain loads (rare: row ends, misaligned row starts, inactive items)
+FC_HD void manual_fill(int lane, const W1kParams &p, const ItemDesc &d, float *plane) {
+  for (int i = lane; i < kN + 4; i += 32) {
+    const long long r = d.bs + (i - d.shift);
+    float v = 0.0f;
+    if (d.active && i >= d.shift && r >= 0 && r < p.n) v = d.row_in[r];
+    plane[i] = v;
+  }
+}
+
+// staged samples -> registers: pair i = (z[lane + 32 i], z[lane + 32 (i + 16)]), re from plane 0, im from plane 1
+FC_HD void load_inputs(int lane, Regs &v, const float *xb, int shift_a, int shift_b) {
+  const float *a = xb + shift_a + lane, *b = xb + kPlane + shift_b + lane;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v.re[i] = make_f2(a[32 * i], a[32 * (i + 16)]);
+    v.im[i] = make_f2(b[32 * i], b[32 * (i + 16)]);
+  }
+}
+
+// bit m: lane + 32 m >= K - 1 (the block's first K - 1 outputs are the wrapped part: dropped)
+struct StoreMasks {
+  unsigned keep;
+};
+FC_HD StoreMasks make_store_masks(int lane, const W1kParams &p) {
+  StoreMasks k;
+  k.keep = 0;
+#pragma unroll
+  for (int m = 0; m < 32; ++m)
+    if (lane + 32 * m >= p.klen - 1) k.keep |= 1u << m;
+  return k;
+}
+
+// y[lane + 32 m] sits in slot16(m & 15), low half for m < 16; ya / yb: where y[0] of the two items goes
+FC_HD void store_fast_to(int lane, const Regs &v, float *ya, float *yb, const StoreMasks &k) {
+  float *a = ya + lane, *b = yb + lane;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int s = slot16(m);
+    if ((k.keep >> m) & 1u) {
+      a[32 * m] = v.re[s].x;
+      b[32 * m] = v.im[s].x;
+    }
+    // m + 16 >= 16: lane + 512 >= K - 1 for every K this engine serves
+    a[32 * (m + 16)] = v.re[s].y;
+    b[32 * (m + 16)] = v.im[s].y;
+  }
+}
+FC_HD void store_fast(int lane, const Regs &v, const UnitDesc &d, const W1kParams &p, const StoreMasks &k) {
+  store_fast_to(lane, v, d.item[0].row_out + (d.item[0].bs - p.pad), d.item[1].row_out + (d.item[1].bs - p.pad), k);
+}
+// predicated stores of a unit given by its items' (row, block): what the output side needs is little
+// (no alignment, no staging), so this does not go through describe_item
+FC_HD void store_slow_at(int lane, const Regs &v, const W1kParams &p, long long row0, long long seg0, long long row1,
+                         long long seg1) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const long long row = it ? row1 : row0, seg = it ? seg1 : seg0;
+    if (row >= p.batch) continue;
+    float *row_out = p.out + row * p.out_stride;
+    const long long left = p.full_len - seg * p.step;
+    const int nout = (int)(left < p.step ? left : p.step);
+    const long long obase = seg * p.step - (p.klen - 1) - p.pad; // output index of y[0]
+    const int lo = p.klen - 1, hi = p.klen - 1 + nout;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int s = slot16(m);
+      const int i0 = lane + 32 * m, i1 = i0 + 512;
+      const float y0 = it ? v.im[s].x : v.re[s].x, y1 = it ? v.im[s].y : v.re[s].y;
+      const long long o0 = obase + i0, o1 = obase + i1;
+      if (i0 >= lo && i0 < hi && o0 >= 0 && o0 < p.out_len) row_out[o0] = y0;
+      if (i1 >= lo && i1 < hi && o1 >= 0 && o1 < p.out_len) row_out[o1] = y1;
+    }
+  }
+}
+FC_HD void store_slow(int lane, const Regs &v, const W1kParams &p, const UnitDesc &d) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const ItemDesc &I = d.item[it];
+    if (!I.active) continue;
+    const long long obase = I.bs - p.pad; // output index of y[0]
+    const int lo = p.klen - 1, hi = p.klen - 1 + I.nout;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int s = slot16(m);
+      const int i0 = lane + 32 * m, i1 = i0 + 512;
+      const float y0 = it ? v.im[s].x : v.re[s].x, y1 = it ? v.im[s].y : v.re[s].y;
+      const long long o0 = obase + i0, o1 = obase + i1;
+      if (i0 >= lo && i0 < hi && o0 >= 0 && o0 < p.out_len) I.row_out[o0] = y0;
+      if (i1 >= lo && i1 < hi && o1 >= 0 && o1 < p.out_len) I.row_out[o1] = y1;
+    }
+  }
+}
+
+} // namespace w1k
+} // namespace fc

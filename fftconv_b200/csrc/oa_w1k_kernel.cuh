@@ -1,0 +1,226 @@
+// oa_w1k_kernel.cuh -- the sm_100a kernel of the warp-per-FFT overlap-add engine (float32,
+// 1024-point blocks; oa_w1k_core.cuh has the method, oa_w1k_group.cuh the work decomposition).
+//
+// Persistent grid, one CTA of kWarps warps per SM; every warp is on its own: it owns an exchange
+// buffer of 9216 bytes (which also receives its input blocks), one mbarrier, and a contiguous range of
+// units.  Per unit:
+//   mbarrier wait | 64 x LDS.32 (staged inputs) | warp sync
+//   P0: radix-2 step (scalar), dft16 (packed), twiddles | 64 x STS.32 | warp sync | 16 x LDS.128
+//   P1: dft16, radix-2 step, spectrum multiply, radix-2 step, dft16 | 16 x STS.128 | warp sync | 64 x LDS.32
+//   warp sync | lane 0 requests the next unit's two input blocks (cp.async.bulk -> the buffer, idle now)
+//   P2: twiddles, dft16, radix-2 step | 64 coalesced 4-byte stores
+// There is no block-level barrier after the prologue.
+#pragma once
+
+#include "oa_n2048_kernel.cuh" // the PTX wrappers (namespace fc::n2048::dev)
+#include "oa_w1k_group.cuh"
+
+namespace fc {
+namespace w1k {
+
+constexpr int kWarps = 16;
+constexpr int kTwCount = 20 * 32;
+// shared memory: spectrum (512 x 16 B), lane twiddles, one mbarrier per warp, then the warps' buffers
+constexpr size_t kSmemHs = 512 * sizeof(Quad);
+constexpr size_t kSmemTw = kTwCount * sizeof(cpair);
+constexpr size_t kSmemBar = 256; // up to 32 mbarriers
+constexpr size_t smem_bytes(int warps = kWarps) {
+  return kSmemHs + kSmemTw + kSmemBar + (size_t)warps * kWarpFloats * sizeof(float);
+}
+
+#if defined(__CUDACC__)
+namespace dev = fc::n2048::dev;
+
+// the general description of a unit, out of line: it is needed for the last block of a row and other
+// rarities only, and inlined three times it would push the steady-state code out of the instruction cache
+__device__ __noinline__ UnitDesc describe_unit_cold(const W1kParams &p, int row0, int seg0, int row1, int seg1) {
+  return describe_unit_at(p, row0, seg0, row1, seg1);
+}
+
+struct Pos { // (row, block) of the two items of a unit; the engine takes batch, blocks per row < 2^31
+  int row[2], seg[2];
+};
+__device__ __forceinline__ void advance(Pos &q, int segs) { // to the next unit: two items further
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    q.seg[i] += 2;
+    while (q.seg[i] >= segs) {
+      q.seg[i] -= segs;
+      ++q.row[i];
+    }
+  }
+}
+// What a unit needs when its inputs are read and its outputs stored; worked out one unit ahead, when
+// its input blocks are requested.
+struct Carry { // packed into one register: the state lives across a whole iteration
+  unsigned code;  // bit 0: bulk, bit 1: fast_out, bits 2-3: shift of item 0, bits 4-5: shift of item 1
+  __device__ __forceinline__ bool bulk() const { return code & 1u; }
+  __device__ __forceinline__ bool fast_out() const { return code & 2u; }
+  __device__ __forceinline__ int sh_a() const { return (int)((code >> 2) & 3u); }
+  __device__ __forceinline__ int sh_b() const { return (int)((code >> 4) & 3u); }
+};
+
+// SHARED_DFT: one copy of each direction's dft16 in a two-trip loop (see oa_w1k_core.cuh)
+template <int WARPS, bool SHARED_DFT>
+__global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_constant__ W1kParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Quad *hs4 = reinterpret_cast<Quad *>(smem_raw);
+  cpair *tw = reinterpret_cast<cpair *>(smem_raw + kSmemHs);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + kSmemHs + kSmemTw);
+  float *xb_all = reinterpret_cast<float *>(smem_raw + kSmemHs + kSmemTw + kSmemBar);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *xb = xb_all + warp * kWarpFloats;
+  const uint32_t mbar = dev::smem_u32(bars + warp);
+
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const cpair a = p.hs[2 * i], b = p.hs[2 * i + 1];
+    hs4[i] = Quad{a.re, b.re, a.im, b.im};
+  }
+  for (int i = threadIdx.x; i < kTwCount; i += blockDim.x) tw[i] = p.tw[i];
+  if (lane == 0) {
+    dev::mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long n_warps = (long long)gridDim.x * WARPS;
+  long long u0, u1;
+  warp_range(p.n_units, n_warps, (long long)blockIdx.x * WARPS + warp, u0, u1);
+  if (u0 >= u1) return;
+  const StoreMasks masks = make_store_masks(lane, p);
+  const int segs = (int)p.segs, step = p.step, tail = p.klen - 1;
+  const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
+
+  Pos q;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const long long it = 2 * u0 + i;
+    q.row[i] = (int)(it / p.segs);
+    q.seg[i] = (int)(it - (long long)q.row[i] * p.segs);
+  }
+  // Request the input blocks of the unit at `at` (the buffer must be idle) and work out what the unit
+  // will need later.  Interior blocks -- all but the first and the last one or two of a row -- take the
+  // short way; the others go through the general description (oa_w1k_group.cuh).
+  auto request = [&](const Pos &at) -> Carry {
+    Carry c;
+    bool in_ok = true, out_ok = true;
+    const float *src[2];
+    int shift[2], dst_first[2], bytes[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long bs = (long long)at.seg[i] * step - tail;
+      const int head = at.seg[i] == 0 ? tail : 0; // a row's first block: K - 1 zeros in front
+      const float *first = p.in + (long long)at.row[i] * p.in_stride + (bs + head);
+      const int ish = align_shift4(first);
+      shift[i] = (ish - head) & 3;
+      dst_first[i] = head + shift[i] - ish;
+      src[i] = first - ish;
+      bytes[i] = ((ish + kN - head) * 4 + 15) & ~15;
+      const long long o0 = bs + tail - p.pad;
+      const bool active = at.row[i] < p.batch;
+      in_ok = in_ok && active && bs + kN <= p.n && (head == 0 || ish == 0) && src[i] + (kN + 4) <= tensor_end;
+      out_ok = out_ok && active && (long long)(at.seg[i] + 1) * step <= p.full_len && o0 >= 0 && o0 + step <= p.out_len;
+    }
+    // a unit with a block that reaches past its row's end (or other rarities) is staged by the lanes at
+    // the start of its iteration instead (manual_fill): nothing to request now
+    c.code = (in_ok ? 1u : 0u) | (out_ok ? 2u : 0u) | ((unsigned)shift[0] << 2) | ((unsigned)shift[1] << 4);
+    if (in_ok) {
+      if (lane == 0) {
+        dev::fence_proxy_async(); // the buffer was last touched through the generic proxy
+        dev::mbar_expect_tx(mbar, (uint32_t)(bytes[0] + bytes[1]));
+        dev::bulk_load(dev::smem_u32(xb + dst_first[0]), src[0], (uint32_t)bytes[0], mbar);
+        dev::bulk_load(dev::smem_u32(xb + kPlane + dst_first[1]), src[1], (uint32_t)bytes[1], mbar);
+      }
+      if (at.seg[0] == 0)
+        for (int i = lane; i < dst_first[0]; i += 32) xb[i] = 0.0f;
+      if (at.seg[1] == 0)
+        for (int i = lane; i < dst_first[1]; i += 32) xb[kPlane + i] = 0.0f;
+    }
+    return c;
+  };
+
+  Carry nxt = request(q);
+  uint32_t phase = 0;
+
+#pragma unroll 1
+  for (long long u = u0; u < u1; ++u) {
+    const Carry cur = nxt;
+    const Pos at = q;
+    Regs v;
+    int sh_a = cur.sh_a(), sh_b = cur.sh_b();
+    if (cur.bulk()) {
+      while (!dev::mbar_try_wait(mbar, phase)) {
+      }
+      phase ^= 1;
+    } else { // no data registers are live here: the out-of-line call costs no spills
+      const UnitDesc d = describe_unit_cold(p, at.row[0], at.seg[0], at.row[1], at.seg[1]);
+      manual_fill(lane, p, d.item[0], xb);
+      manual_fill(lane, p, d.item[1], xb + kPlane);
+      sh_a = d.item[0].shift;
+      sh_b = d.item[1].shift;
+    }
+    __syncwarp(); // the lanes' own fills (zeros, manual) are visible to the whole warp
+    load_inputs(lane, v, xb, sh_a, sh_b);
+    __syncwarp(); // every lane has its inputs: the buffer turns into the exchange buffer
+    if constexpr (SHARED_DFT) {
+      p0_pre(lane, v, tw);
+#pragma unroll 1
+      for (int trip = 0; trip < 2; ++trip) {
+        dft16<-1>(v);
+        if (trip == 0) {
+          p0_post(lane, v, tw);
+          t1_write(lane, v, xb);
+          __syncwarp();
+          t1_read(lane, v, xb);
+        } else {
+          p1_mid(lane, v, hs4);
+        }
+      }
+#pragma unroll 1
+      for (int trip = 0; trip < 2; ++trip) {
+        dft16<+1>(v);
+        if (trip == 0) {
+          t2_write(lane, v, xb); // a lane's own row, which only it read in T1: no barrier needed before
+          __syncwarp();
+          t2_read(lane, v, xb);
+          __syncwarp(); // the buffer is idle: the next inputs may land while P2 and the stores run
+          if (u + 1 < u1) {
+            advance(q, segs);
+            nxt = request(q);
+          }
+          p2_pre(lane, v, tw);
+        } else {
+          p2_post(lane, v, tw);
+        }
+      }
+    } else {
+      phase0(lane, v, tw);
+      t1_write(lane, v, xb);
+      __syncwarp();
+      t1_read(lane, v, xb);
+      phase1(lane, v, hs4);
+      t2_write(lane, v, xb); // a lane's own row, which only it read in T1: no barrier needed before
+      __syncwarp();
+      t2_read(lane, v, xb);
+      __syncwarp(); // the buffer is idle: the next inputs may land while P2 and the stores run
+      if (u + 1 < u1) {
+        advance(q, segs);
+        nxt = request(q);
+      }
+      phase2(lane, v, tw);
+    }
+    if (cur.fast_out()) {
+      // where y[0] of each item goes: row's output + block start - pad
+      float *oa = p.out + (long long)at.row[0] * p.out_stride + ((long long)at.seg[0] * step - tail - p.pad);
+      float *ob = p.out + (long long)at.row[1] * p.out_stride + ((long long)at.seg[1] * step - tail - p.pad);
+      store_fast_to(lane, v, oa, ob, masks);
+    } else {
+      store_slow_at(lane, v, p, at.row[0], at.seg[0], at.row[1], at.seg[1]);
+    }
+  }
+}
+#endif // __CUDACC__
+
+} // namespace w1k
+} // namespace fc

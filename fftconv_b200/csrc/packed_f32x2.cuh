@@ -90,8 +90,35 @@ FC_HD f2 fmss2(f2 a, float s, f2 c) {
       : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
   return r;
 }
+// full-width forms: both operands are pairs
+FC_HD f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm(FC_PK2(a, b) "mul.rn.f32x2 pc, pa, pb;\n\t"
+                   "mov.b64 {%0, %1}, pc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+// a * b + c
+FC_HD f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("{.reg .b64 pa, pb, pc, pd;\n\t"
+      "mov.b64 pa, {%2, %3};\n\t"
+      "mov.b64 pb, {%4, %5};\n\t"
+      "mov.b64 pc, {%6, %7};\n\t"
+      "fma.rn.f32x2 pd, pa, pb, pc;\n\t"
+      "mov.b64 {%0, %1}, pd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+// c - a * b (the sign flips are integer-pipe instructions)
+FC_HD f2 fnma2(f2 a, f2 b, f2 c) { return fma2(make_f2(-a.x, -a.y), b, c); }
 #undef FC_PK2
 #else
+FC_HD f2 mul2(f2 a, f2 b) { return make_f2(a.x * b.x, a.y * b.y); }
+FC_HD f2 fma2(f2 a, f2 b, f2 c) { return make_f2(a.x * b.x + c.x, a.y * b.y + c.y); }
+FC_HD f2 fnma2(f2 a, f2 b, f2 c) { return make_f2(c.x - a.x * b.x, c.y - a.y * b.y); }
 FC_HD f2 add2(f2 a, f2 b) { return make_f2(a.x + b.x, a.y + b.y); }
 FC_HD f2 sub2(f2 a, f2 b) { return make_f2(a.x - b.x, a.y - b.y); }
 FC_HD f2 muls2(f2 a, float s) { return make_f2(a.x * s, a.y * s); }

@@ -126,7 +126,8 @@ int main() {
       near<float>(got, direct(row, k, ConvMode::Full), 100.0);
     }
   }
-  { // filter handle: same samples as the plain call, taps transformed once
+  { // filter handle: the plain call's samples (to rounding: a handle is planned for large jobs and may
+    // use a different block size than a small plain call), taps transformed once
     const size_t batch = 3, n = 5000;
     auto a = randn<float>(batch * n, 19), k = randn<float>(245, 20);
     std::vector<float> want(batch * (n + 244)), got(batch * (n + 244));
@@ -135,7 +136,7 @@ int main() {
     fftconv::Filter<float> f{std::span<const float>(k)};
     f.oaconvolve_batched<ConvMode::Full>(std::span<const float>(a), n, std::span<float>(got));
     EXPECT(f.size() == 245);
-    for (size_t i = 0; i < got.size(); ++i) EXPECT(got[i] == want[i]);
+    for (size_t i = 0; i < got.size(); ++i) EXPECT(std::abs(got[i] - want[i]) < 1e-4);
   }
   { // Hilbert known-answer vector, double and float, abs 1e-6
     const std::array<double, 10> inp = {-0.999984, -0.736924, 0.511211, -0.0826997, 0.0655345,

@@ -130,6 +130,32 @@ def test_n2048_float64_kernel_logic_emulated_on_cpu(built, case):
     assert float(r.stdout.split()[0]) < 1e-13
 
 
+EMU_W1K_CASES = [
+    # batch n K mode n_warps [misalign]
+    (4, 65536, 245, 0, 7),        # config 2's rows: 85 blocks each, units straddle rows
+    (5, 10000, 245, 1, 3),        # odd batch (last unit half empty), Same mode
+    (1, 100000, 100, 0, 5, 1),    # one row, base pointers 4 bytes off 16-byte alignment
+    (3, 5000, 300, 1, 2, 3),
+    (7, 1805, 8, 0, 4, 2),        # shortest kernel served
+    (2, 780, 245, 0, 1),          # exactly one block of new samples
+    (1, 300, 245, 1, 1),          # shorter than one block
+    (6, 7000, 400, 0, 3),         # longest kernel served
+    (3, 4096, 246, 0, 2),         # K - 1 not a multiple of 4: the staging shift differs between blocks
+    (2, 20000, 129, 1, 64),       # more warps than units
+]
+
+
+@pytest.mark.parametrize("case", EMU_W1K_CASES)
+def test_w1k_kernel_logic_emulated_on_cpu(built, case):
+    """The warp-per-FFT engine (oa_w1k_*.cuh): its own __host__ __device__ phase, staging and store
+    functions lane by lane on the CPU (tests/cpu/emulate_oa_w1k.cpp) against direct convolution in double,
+    NaN-poisoned buffers and guard bands around the outputs."""
+    exe = os.path.join(ROOT, "tests", "cpu", "emulate_oa_w1k")
+    r = subprocess.run([exe, *map(str, case)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (case, r.stdout, r.stderr)
+    assert float(r.stdout.split()[0]) < 1e-6
+
+
 def test_fast_fft_engine_emulated_on_cpu(built):
     """fast_fft.cuh (N = 512 .. 16384, float and double): the kernel's own pass functions
     run for all threads pass by pass on the CPU against direct circular convolution."""

@@ -407,3 +407,93 @@ def test_filter_handle_device_mismatch_is_an_error(cuda):
     with pytest.raises(RuntimeError, match="device"):
         f.oaconvolve(a1, "full")
     f.close()
+
+
+# ---- the warp-per-FFT engine (oa_w1k_*.cuh) -----------------------------------------------------------
+W1K_CASES = [
+    # batch, n, K
+    (4, 65536, 245), (5, 10000, 245), (1, 100000, 245), (3, 5000, 300), (2, 780, 245), (1, 300, 245),
+    (6, 7000, 400), (2, 4000, 8), (7, 1805, 65), (9, 3607, 256), (64, 65536, 245), (512, 65536, 245),
+    (3, 400000, 165), (130, 9000, 246),
+]
+
+
+@pytest.mark.parametrize("batch,n,klen", W1K_CASES)
+@pytest.mark.parametrize("mode", ["full", "same"])
+def test_w1k_kernel_device_pointers(cuda, batch, n, klen, mode, monkeypatch):
+    """1024-point blocks, one warp per complex FFT: row ends, odd batches, single rows, kernels from 8 to
+    400 taps, both modes, against the definition and the oracle."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    monkeypatch.setenv("FFTCONV_CUDA_OA_FFT_SIZE", "1024")
+    rng = np.random.default_rng(batch * 1000 + n + klen)
+    a = rng.standard_normal((batch, n)).astype(np.float32)
+    k = (rng.standard_normal(klen) / np.sqrt(klen)).astype(np.float32)
+    before = fc.launch_count()
+    y = fc.oaconvolve(_t(a, cuda), _t(k, cuda), mode)
+    torch.cuda.synchronize()
+    assert fc.launch_count() - before == 2
+    got = y.cpu().numpy()
+    assert np.all(np.isfinite(got))
+    pick = sorted(set([0, batch // 2, batch - 1]))
+    assert O.rel_l2(got[pick], O.conv_exact(a[pick], k, mode)) < 1e-5
+    if batch * n <= 1 << 22:
+        assert O.rel_l2(got, O.oaconvolve(a, k, mode)) < 1e-5
+    # the same samples as the 2048-point kernel produces (different blocks, same linear convolution)
+    monkeypatch.setenv("FFTCONV_CUDA_NO_W1K", "1")
+    monkeypatch.setenv("FFTCONV_CUDA_OA_FFT_SIZE", "2048")
+    y2 = fc.oaconvolve(_t(a, cuda), _t(k, cuda), mode)
+    torch.cuda.synchronize()
+    assert O.rel_l2(got, y2.cpu().numpy()) < 1e-5
+
+
+def test_w1k_kernel_alignment_and_guard_bands(cuda, monkeypatch):
+    """Rows at every 4-byte alignment, padded row strides, NaN guard bands around every output row."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    monkeypatch.setenv("FFTCONV_CUDA_OA_FFT_SIZE", "1024")
+    rng = np.random.default_rng(77)
+    for off in range(4):
+        for klen in (245, 246, 100):
+            rows, n = 6, 9000 + off
+            store_in = torch.full((rows * (n + 7) + 8,), float("nan"), device=cuda)
+            a = rng.standard_normal((rows, n)).astype(np.float32)
+            av = store_in[off:off + rows * (n + 7)].view(rows, n + 7)[:, :n]
+            av.copy_(_t(a, cuda))
+            k = (rng.standard_normal(klen) / 16).astype(np.float32)
+            for mode in ("full", "same"):
+                out_len = n + klen - 1 if mode == "full" else n
+                ostore = torch.full((off + rows * (out_len + 5) + 8,), float("nan"), device=cuda)
+                ov = ostore[off:off + rows * (out_len + 5)].view(rows, out_len + 5)
+                fc.oaconvolve_(av, _t(k, cuda), ov[:, :out_len], mode)
+                torch.cuda.synchronize()
+                assert O.rel_l2(ov[:, :out_len].cpu().numpy(), O.conv_exact(a, k, mode)) < 1e-5, (off, klen, mode)
+                assert torch.isnan(ov[:, out_len:]).all() and torch.isnan(ostore[:off]).all()
+
+
+def test_w1k_is_the_default_for_large_float32_jobs(cuda, monkeypatch):
+    """The throughput rule sends large float32 jobs with 8 .. 300 taps to 1024-point blocks; host pointers
+    and the filter handle take the same path."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(78)
+    a = rng.standard_normal((200, 65536)).astype(np.float32)
+    k = (rng.standard_normal(245) / 16).astype(np.float32)
+    want = O.conv_exact(a[:3], k, "full")
+    y = fc.oaconvolve(_t(a, cuda), _t(k, cuda), "full")
+    monkeypatch.setenv("FFTCONV_CUDA_NO_W1K", "1")
+    y2 = fc.oaconvolve(_t(a, cuda), _t(k, cuda), "full")
+    monkeypatch.delenv("FFTCONV_CUDA_NO_W1K")
+    torch.cuda.synchronize()
+    assert O.rel_l2(y[:3].cpu().numpy(), want) < 1e-5 and O.rel_l2(y2[:3].cpu().numpy(), want) < 1e-5
+    assert not torch.equal(y, y2)          # two different kernels did run
+    assert O.rel_l2(fc.oaconvolve(a, k, "full")[:3], want) < 1e-5
+    f = fc.Filter(k)
+    assert O.rel_l2(f.oaconvolve(_t(a, cuda), "full")[:3].cpu().numpy(), want) < 1e-5
+    f.close()
