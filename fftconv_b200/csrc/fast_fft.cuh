@@ -20,6 +20,7 @@
 // makes every pass bank-conflict free for 8- and 16-byte elements.
 #pragma once
 
+#include "oa_n2048_core.cuh" // the fused-multiply-add forms of the 8- and 16-point DFTs (dft8, dft16)
 #include "packed_f32x2.cuh"
 
 #if defined(__CUDACC__)
@@ -131,58 +132,30 @@ template <int S, typename D> FCF_HD void dft4(cx<D> *v) {
   v[2] = s0 - s1;
   v[3] = sub_rot<S>(d0, d1);
 }
+// 8- and 16-point DFTs: the fused-multiply-add forms of oa_n2048_core.cuh (52 and 144 instructions;
+// the constant twiddles ride in the butterflies), wrapped to natural order in, natural order out --
+// the permutations are register renamings.
 template <int S, typename D> FCF_HD void dft8(cx<D> *v) {
-  using T = scalar_t<D>;
-  // m = m0 + 2 m1, k = k1 + 4 k0
-  cx<D> e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
-  dft4<S>(e);
-  dft4<S>(o);
-  const T h = (T)0.70710678118654752440084436210485L;
-  const T s = S < 0 ? (T)-1 : (T)1;
-  o[1] = cmul(o[1], cx<T>{h, s * h});
-  o[3] = cmul(o[3], cx<T>{-h, s * h});
+  D re[8], im[8];
 #pragma unroll
-  for (int k1 = 0; k1 < 4; ++k1) {
-    if (k1 == 2) { // W8^2 = -+j
-      v[k1] = add_rot<S>(e[k1], o[k1]);
-      v[k1 + 4] = sub_rot<S>(e[k1], o[k1]);
-    } else {
-      v[k1] = e[k1] + o[k1];
-      v[k1 + 4] = e[k1] - o[k1];
-    }
+  for (int i = 0; i < 8; ++i) {
+    re[i] = v[i].x;
+    im[i] = v[i].y;
   }
+  n2048::dft8<S>(re, im);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = cx<D>{re[n2048::slot8(k)], im[n2048::slot8(k)]};
 }
 template <int S, typename D> FCF_HD void dft16(cx<D> *v) {
-  using T = scalar_t<D>;
-  // m = m0 + 4 m1, k = k1 + 4 k0
-  const T c8 = (T)0.70710678118654752440084436210485L;
-  const T c16 = (T)0.92387953251128675612818318939679L;
-  const T s16 = (T)0.38268343236508977172845998403040L;
-  const T s = S < 0 ? (T)-1 : (T)1;
-  cx<D> a[4][4]; // a[m0][k1]
+  n2048::RegsT<D> r;
 #pragma unroll
-  for (int m0 = 0; m0 < 4; ++m0) {
-    cx<D> t[4] = {v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]};
-    dft4<S>(t);
-#pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1) a[m0][k1] = t[k1];
+  for (int i = 0; i < 16; ++i) {
+    r.re[i] = v[i].x;
+    r.im[i] = v[i].y;
   }
-  a[1][1] = cmul(a[1][1], cx<T>{c16, s * s16});
-  a[2][1] = cmul(a[2][1], cx<T>{c8, s * c8});
-  a[3][1] = cmul(a[3][1], cx<T>{s16, s * c16});
-  a[1][2] = cmul(a[1][2], cx<T>{c8, s * c8});
-  a[2][2] = rot90<S>(a[2][2]);
-  a[3][2] = cmul(a[3][2], cx<T>{-c8, s * c8});
-  a[1][3] = cmul(a[1][3], cx<T>{s16, s * c16});
-  a[2][3] = cmul(a[2][3], cx<T>{-c8, s * c8});
-  a[3][3] = cmul(a[3][3], cx<T>{-c16, -s * s16});
+  n2048::dft16<S>(r);
 #pragma unroll
-  for (int k1 = 0; k1 < 4; ++k1) {
-    cx<D> t[4] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1]};
-    dft4<S>(t);
-#pragma unroll
-    for (int k0 = 0; k0 < 4; ++k0) v[k1 + 4 * k0] = t[k0];
-  }
+  for (int k = 0; k < 16; ++k) v[k] = cx<D>{r.re[n2048::slot16(k)], r.im[n2048::slot16(k)]};
 }
 template <int S, int LOGR, typename D> FCF_HD void dft_small(cx<D> *v) {
   if (LOGR == 1) dft2<S>(v);

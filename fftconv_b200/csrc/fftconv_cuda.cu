@@ -1271,6 +1271,10 @@ int run_host_pinned(DeviceCtx &c, Op op, const T *a, size_t batch, size_t n, siz
   const size_t target = (size_t)env_int("FFTCONV_CUDA_HOST_BLOCK_MB", 32) << 20;
   size_t rows_per_block = std::max<size_t>(1, target / std::max<size_t>(1, row_bytes));
   rows_per_block = std::min(rows_per_block, batch);
+  // a medium batch (a 512-row shard is four 32 MB blocks) would barely pipeline: aim for >= 12 blocks, but
+  // not below 4 MB, where the per-copy overhead shows
+  while (rows_per_block > 1 && batch / rows_per_block < 12 && rows_per_block * row_bytes > (size_t)(4 << 20))
+    rows_per_block = (rows_per_block + 1) / 2;
   // Block schedule: full blocks in the middle, blocks of 1/8, 1/4, 1/2 of that at both ends -- the
   // first upload and the last download are the only copies nothing else overlaps with.
   std::vector<size_t> blocks;

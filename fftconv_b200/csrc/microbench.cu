@@ -4,7 +4,9 @@
 // copy bandwidth.  Run on the GPU box: fftconv_b200/lib/microbench
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
+#include <vector>
 #include <cstdlib>
 #include <vector>
 
@@ -132,7 +134,70 @@ template <typename F> float time_ms(F &&launch, int reps = 5) {
   return best;
 }
 
+// ---- host-call latency floor (BASELINE config 1 through host pointers) --------------------------------
+__global__ void k_flag(volatile unsigned *flag, unsigned epoch) {
+  __threadfence_system();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *flag = epoch;
+}
+__global__ void k_touch(const float *in, float *out, int n, volatile unsigned *flag, unsigned epoch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * 2.0f;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *flag = epoch; // (not a completion protocol: a latency probe)
+}
+template <class F> static double host_us(F &&f, int reps) {
+  for (int i = 0; i < 200; ++i) f();
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < reps; ++i) f();
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
+static void host_latency_floor() {
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  void *hm = nullptr, *dm = nullptr;
+  CK(cudaHostAlloc(&hm, 1 << 20, cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer(&dm, hm, 0));
+  volatile unsigned *flag_h = (volatile unsigned *)hm;
+  unsigned *flag_d = (unsigned *)dm;
+  float *in_d = (float *)dm + 1024, *out_d = (float *)dm + 1024 + 8192;
+  std::vector<float> pageable(4352, 1.0f);
+  unsigned epoch = 0;
+  const double t_attr = host_us([&] {
+    cudaPointerAttributes a;
+    cudaPointerGetAttributes(&a, pageable.data());
+  }, 20000);
+  const double t_sync = host_us([&] {
+    k_flag<<<1, 32, 0, st>>>(flag_d, ++epoch);
+    cudaStreamSynchronize(st);
+  }, 5000);
+  const double t_poll = host_us([&] {
+    k_flag<<<1, 32, 0, st>>>(flag_d, ++epoch);
+    while (*flag_h != epoch) {
+    }
+  }, 5000);
+  const double t_touch = host_us([&] {
+    k_touch<<<18, 256, 0, st>>>(in_d, out_d, 4416, flag_d, ++epoch);
+    while (*flag_h != epoch) {
+    }
+  }, 5000);
+  float *dd;
+  CK(cudaMalloc((void **)&dd, 1 << 20));
+  std::vector<float> back(4416);
+  const double t_copy = host_us([&] {
+    cudaMemcpyAsync(dd, pageable.data(), 4352 * 4, cudaMemcpyHostToDevice, st);
+    k_flag<<<1, 32, 0, st>>>(flag_d, ++epoch);
+    cudaMemcpyAsync(back.data(), dd, 4416 * 4, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+  }, 3000);
+  std::printf("host-call latency floor (us): cudaPointerGetAttributes(pageable) %.2f | empty kernel + "
+              "cudaStreamSynchronize %.2f | empty kernel + poll of a mapped flag %.2f | 18-CTA kernel reading 17 KB / "
+              "writing 17 KB of mapped host memory + poll %.2f | cudaMemcpyAsync H2D 17 KB + kernel + D2H 17 KB + sync %.2f\n",
+              t_attr, t_sync, t_poll, t_touch, t_copy);
+}
+
 int main() {
+  host_latency_floor();
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;

@@ -139,6 +139,13 @@ FC_HD void cmul2(double &re, double &im, double wr, double wi) {
   re = nre;
 }
 
+// ... and for a plain float (the register-blocked engine's two-rows-per-FFT instantiation)
+FC_HD float add2(float a, float b) { return a + b; }
+FC_HD float sub2(float a, float b) { return a - b; }
+FC_HD float muls2(float a, float s) { return a * s; }
+FC_HD float fmas2(float a, float s, float c) { return a * s + c; }
+FC_HD float fmss2(float a, float s, float c) { return a * s - c; }
+
 // Data-type traits of the overlap-add engines: scalar type and how many real streams ("lanes")
 // ride in one complex value -- f2: lane 0 = re half A, 1 = im half A, 2 = re half B, 3 = im half B;
 // double: lane 0 = re, lane 1 = im.
@@ -164,6 +171,10 @@ template <> struct DataTraits<double> {
   static FC_HD void unpack(double re, double im, double (&y)[2]) {
     y[0] = re; y[1] = im;
   }
+};
+template <> struct DataTraits<float> { // scalar float: one transform per thread, two real streams (re, im)
+  using S = float;
+  static constexpr int NL = 2;
 };
 template <typename S> struct DataOf;            // scalar type -> data type of the engine
 template <> struct DataOf<float> { using D = f2; };

@@ -501,9 +501,9 @@ def test_dlpack_inputs(cuda):
 
 @pytest.mark.parametrize("dt,klen", [(np.float32, 245), (np.float32, 65), (np.float64, 165), (np.float32, 7)])
 def test_filter_handle_reuses_the_spectrum(cuda, dt, klen):
-    """a filter handle gives the same samples as the plain call and launches no
-    spectrum kernel (a handle always uses the large-job segment size, a small plain call the
-    reference's table, so bit-equality holds only where the two coincide)."""
+    """a filter handle gives the same samples as the plain call (to rounding: a handle
+    always uses the large-job block size, a small plain call the reference's table) and launches no
+    spectrum kernel."""
     import torch
 
     import fftconv_b200 as fc
@@ -520,8 +520,6 @@ def test_filter_handle_reuses_the_spectrum(cuda, dt, klen):
         got = f.oaconvolve(ta, mode)
         torch.cuda.synchronize()
         assert fc.launch_count() - before == 1            # the overlap-add kernel alone
-        if dt == np.float64:                              # same segment size and kernel either way: bit for bit
-            assert torch.equal(got, want)
         assert O.rel_l2(got.cpu().numpy(), want.cpu().numpy()) < H.TOL[np.dtype(dt)]
         _check(got.cpu().numpy(), a, k, mode, ("filter", klen, mode))
     # host arrays go through the same handle
