@@ -30,7 +30,7 @@ SYMBOLS = [
                  "stream_flush", "envelope_batched", "rf_envelope_batched",
                  "oa_tail", "fill_synthetic",
                  "mgpu_oaconvolve_batched", "mgpu_hilbert_batched", "mgpu_oaconvolve_long",
-                 "mgpu_oaconvolve_long_host")
+                 "mgpu_oaconvolve_long_host", "fft_c2c", "fft_r2c", "fft_c2r")
 ] + ["fftconv_cuda_filter_destroy", "fftconv_cuda_stream_destroy"]
 
 
@@ -74,6 +74,11 @@ def lib():
         f.restype, f.argtypes = i, [vp, vp, sz, vp, vp]
         f = getattr(L, f"fftconv_cuda_fill_synthetic_{sfx}")
         f.restype, f.argtypes = i, [vp, sz, C.c_ulonglong, C.c_ulonglong, C.c_double, vp]
+        f = getattr(L, f"fftconv_cuda_fft_c2c_{sfx}")
+        f.restype, f.argtypes = i, [vp, vp, sz, sz, i, vp]
+        for name in ("r2c", "c2r"):
+            f = getattr(L, f"fftconv_cuda_fft_{name}_{sfx}")
+            f.restype, f.argtypes = i, [vp, vp, sz, sz, vp]
         f = getattr(L, f"fftconv_cuda_mgpu_oaconvolve_batched_{sfx}")
         f.restype, f.argtypes = i, [vp, vp, sz, sz, sz, vp, sz, vp, sz, sz, i]
         f = getattr(L, f"fftconv_cuda_mgpu_hilbert_batched_{sfx}")

@@ -286,6 +286,96 @@ def rf_envelope(a, k, *, log_compress: bool = False, ref: float = 1.0, dynamic_r
     return out
 
 
+# ---- general 1-D FFT surface (fftconv_cuda_fft_*) ------------------------
+_CPLX = {"complex64": ("f32", "float32"), "complex128": ("f64", "float64")}
+_REAL = {"float32": ("f32", "complex64"), "float64": ("f64", "complex128")}
+
+
+def _fft_call(name: str, x, out, n: int, batch: int, sign=None) -> None:
+    """x / out: contiguous numpy arrays or CUDA torch tensors (both of one kind)."""
+    if _is_tensor(x):
+        if not (x.is_cuda and out.is_cuda):
+            raise RuntimeError("fft: torch tensors must be CUDA tensors (host data: numpy arrays)")
+        xin = torch.view_as_real(x) if x.is_complex() else x
+        xout = torch.view_as_real(out) if out.is_complex() else out
+        sfx = "f32" if xin.dtype == torch.float32 else "f64"
+        fn = getattr(_capi.lib(), f"fftconv_cuda_fft_{name}_{sfx}")
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            args = (xin.data_ptr(), xout.data_ptr(), n, batch) + ((sign,) if sign is not None else ()) + (st,)
+            _capi.check(fn(*args))
+        return
+    sfx = "f32" if x.dtype in (np.float32, np.complex64) else "f64"
+    fn = getattr(_capi.lib(), f"fftconv_cuda_fft_{name}_{sfx}")
+    args = (x.ctypes.data, out.ctypes.data, n, batch) + ((sign,) if sign is not None else ()) + (None,)
+    _capi.check(fn(*args))
+
+
+def _rows(x, name):
+    if _is_tensor(x):
+        if x.dim() not in (1, 2):
+            raise RuntimeError(f"{name}: 1-D or 2-D input expected")
+        return x.contiguous()
+    x = np.ascontiguousarray(x)
+    if x.ndim not in (1, 2):
+        raise RuntimeError(f"{name}: 1-D or 2-D input expected")
+    return x
+
+
+def _new(x, shape, dtype_name):
+    if _is_tensor(x):
+        return torch.empty(shape, dtype=getattr(torch, dtype_name), device=x.device)
+    return np.empty(shape, dtype=dtype_name)
+
+
+def _dtype_name(x) -> str:
+    return str(x.dtype).replace("torch.", "") if _is_tensor(x) else x.dtype.name
+
+
+def fft(x, *, inverse: bool = False):
+    """Complex transform along the last axis of a 1-D or 2-D complex64 / complex128 array (any length):
+    numpy.fft.fft; with inverse=True FFTW's BACKWARD transform, i.e. numpy.fft.ifft(x) * n
+    (the reference's fftw::Plan<T>::dft_1d + execute, include/fftconv/fftw.hpp:152-155)."""
+    x = _rows(x, "fft")
+    dn = _dtype_name(x)
+    if dn not in _CPLX:
+        raise TypeError(f"fft: complex64 or complex128 expected, got {dn}")
+    out = _new(x, tuple(x.shape), dn)
+    if x.shape[-1] == 0:
+        raise RuntimeError("fft: empty transform")
+    _fft_call("c2c", x, out, x.shape[-1], 1 if len(x.shape) == 1 else x.shape[0], +1 if inverse else -1)
+    return out
+
+
+def rfft(x):
+    """numpy.fft.rfft along the last axis of a real float32 / float64 array: n // 2 + 1 points per row
+    (fftw::Plan<T>::dft_r2c_1d, include/fftconv/fftw.hpp:174-177)."""
+    x = _rows(x, "rfft")
+    dn = _dtype_name(x)
+    if dn not in _REAL:
+        raise TypeError(f"rfft: float32 or float64 expected, got {dn}")
+    n = x.shape[-1]
+    if n == 0:
+        raise RuntimeError("rfft: empty transform")
+    out = _new(x, tuple(x.shape[:-1]) + (n // 2 + 1,), _REAL[dn][1])
+    _fft_call("r2c", x, out, n, 1 if len(x.shape) == 1 else x.shape[0])
+    return out
+
+
+def irfft(x, n: int):
+    """FFTW's c2r transform (unnormalised: numpy.fft.irfft(x, n) * n) of rows of n // 2 + 1 complex points
+    (fftw::Plan<T>::dft_c2r_1d, include/fftconv/fftw.hpp:191-194)."""
+    x = _rows(x, "irfft")
+    dn = _dtype_name(x)
+    if dn not in _CPLX:
+        raise TypeError(f"irfft: complex64 or complex128 expected, got {dn}")
+    if n <= 0 or x.shape[-1] != n // 2 + 1:
+        raise RuntimeError("irfft: rows must hold n // 2 + 1 points")
+    out = _new(x, tuple(x.shape[:-1]) + (n,), _CPLX[dn][1])
+    _fft_call("c2r", x, out, n, 1 if len(x.shape) == 1 else x.shape[0])
+    return out
+
+
 def optimal_fft_size(klen: int) -> int:
     """Segment FFT size for `klen` taps (include/fftconv/fftconv.hpp:53-66)."""
     return int(_capi.lib().fftconv_cuda_optimal_fft_size(int(klen)))

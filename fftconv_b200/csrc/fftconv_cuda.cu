@@ -13,6 +13,7 @@
 
 #include "direct_kernels.cuh"
 #include "fast_kernels.cuh"
+#include "fft_global.cuh"
 #include "generic_kernels.cuh"
 #include "long_fft_kernels.cuh"
 #include "oa_n2048_kernel.cuh"
@@ -150,6 +151,14 @@ struct DeviceCtx {
     long long vrows = 1, vlen = 0, n_streams = 0, n_quads = 0;
   };
   std::map<std::array<long long, 5>, SlicePlanDev> slice_plans;
+  // general FFT surface (fft_global.cuh): twiddle tables per (length, dtype); chirp-z plans per (n, dtype)
+  struct ChirpPlan {
+    size_t M = 0;
+    void *chirp = nullptr; // cx[n]  exp(-pi i j^2 / n)
+    void *Bf = nullptr;    // cx[M]  FFT_M of the wrapped conjugate chirp
+  };
+  std::map<std::pair<size_t, int>, void *> gfft_w;
+  std::map<std::pair<size_t, int>, ChirpPlan> gfft_chirp;
   fc::n2048::CPairT<double> *tw1d = nullptr, *tw2d = nullptr; // the float64 instantiation's tables
   std::map<cudaStream_t, StreamWs> ws;
   cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr};
@@ -212,6 +221,13 @@ void free_ctx(DeviceCtx &c) {
   c.tw1 = c.tw2 = c.tw_w1k = nullptr;
   for (auto &kv : c.slice_plans) cudaFree(kv.second.starts);
   c.slice_plans.clear();
+  for (auto &kv : c.gfft_w) cudaFree(kv.second);
+  c.gfft_w.clear();
+  for (auto &kv : c.gfft_chirp) {
+    cudaFree(kv.second.chirp);
+    cudaFree(kv.second.Bf);
+  }
+  c.gfft_chirp.clear();
   c.tw1d = c.tw2d = nullptr;
   for (auto &kv : c.ws) free_ws(kv.second);
   c.ws.clear();
@@ -1134,6 +1150,216 @@ int conv_device(DeviceCtx &c, cudaStream_t st, Op op, const T *a, size_t batch, 
   return oa_device<T>(c, st, a, batch, n, a_stride, k, klen, out, out_len, out_stride, mode, N);
 }
 
+
+// ---- general FFT surface (fft_global.cuh) ---------------------------------------
+// Batched complex transforms of any length through global memory, FFTW conventions.  Used by the
+// fftconv_cuda_fft_* entry points and by Hilbert envelopes of lines beyond the on-chip / split kernels.
+using fc::gfft::cxg;
+inline unsigned gblocks(long long total) { return (unsigned)((total + 255) / 256); }
+
+template <typename T> int gfft_twiddles(DeviceCtx &c, size_t m, const cxg<T> **out) {
+  auto key = std::make_pair(m, dtype_id<T>());
+  auto it = c.gfft_w.find(key);
+  if (it == c.gfft_w.end()) {
+    std::vector<cxg<T>> w(m);
+    for (size_t k = 0; k < m; ++k) {
+      const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)m;
+      w[k].x = (T)cosl(a);
+      w[k].y = (T)(-sinl(a));
+    }
+    void *d = nullptr;
+    CU_TRY(cudaMalloc(&d, m * sizeof(cxg<T>)));
+    CU_TRY(cudaMemcpy(d, w.data(), m * sizeof(cxg<T>), cudaMemcpyHostToDevice));
+    it = c.gfft_w.emplace(key, d).first;
+  }
+  *out = static_cast<const cxg<T> *>(it->second);
+  return 0;
+}
+
+// rows x m complex points, m a power of two; in, out, tmp distinct (in is not modified)
+template <typename T>
+int gfft_pow2(DeviceCtx &c, cudaStream_t st, const cxg<T> *in, cxg<T> *out, cxg<T> *tmp, size_t m, size_t rows, int sign) {
+  if (m == 1) {
+    CU_TRY(cudaMemcpyAsync(out, in, rows * sizeof(cxg<T>), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  const cxg<T> *W = nullptr;
+  if (int r = gfft_twiddles<T>(c, m, &W)) return r;
+  const int l2 = ilog2(m);
+  const int passes = l2 / 2 + (l2 & 1);
+  const cxg<T> *src = in;
+  size_t ns = 1;
+  for (int p = 1; p <= passes; ++p) {
+    cxg<T> *dst = ((passes - p) % 2 == 0) ? out : tmp;
+    const bool radix2 = (l2 & 1) && p == passes; // the odd factor of two goes last
+    if (radix2) {
+      fc::gfft::stockham_pass<T, 2><<<gblocks((long long)(rows * m / 2)), 256, 0, st>>>(src, dst, W, (long long)m, (long long)ns, sign, (long long)rows);
+      ns *= 2;
+    } else {
+      fc::gfft::stockham_pass<T, 4><<<gblocks((long long)(rows * m / 4)), 256, 0, st>>>(src, dst, W, (long long)m, (long long)ns, sign, (long long)rows);
+      ns *= 4;
+    }
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+    src = dst;
+  }
+  return 0;
+}
+
+template <typename T> int gfft_chirp_plan(DeviceCtx &c, cudaStream_t st, size_t n, DeviceCtx::ChirpPlan **out) {
+  auto key = std::make_pair(n, dtype_id<T>());
+  auto it = c.gfft_chirp.find(key);
+  if (it == c.gfft_chirp.end()) {
+    size_t M = 1;
+    while (M < 2 * n - 1) M *= 2;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    std::vector<cxg<T>> chirp(n), b(M);
+    for (size_t i = 0; i < M; ++i) b[i] = {(T)0, (T)0};
+    for (size_t j = 0; j < n; ++j) {
+      const unsigned long long j2 = (unsigned long long)((unsigned __int128)j * j % (2ULL * n)); // angle reduced exactly
+      const long double a = pi * (long double)j2 / (long double)n;
+      chirp[j] = {(T)cosl(a), (T)(-sinl(a))};
+      const cxg<T> cj = {chirp[j].x, -chirp[j].y};
+      b[j] = cj;
+      if (j) b[M - j] = cj;
+    }
+    DeviceCtx::ChirpPlan pl;
+    pl.M = M;
+    void *braw = nullptr, *tmp = nullptr;
+    CU_TRY(cudaMalloc(&pl.chirp, n * sizeof(cxg<T>)));
+    CU_TRY(cudaMalloc(&pl.Bf, M * sizeof(cxg<T>)));
+    CU_TRY(cudaMalloc(&braw, M * sizeof(cxg<T>)));
+    CU_TRY(cudaMalloc(&tmp, M * sizeof(cxg<T>)));
+    CU_TRY(cudaMemcpy(pl.chirp, chirp.data(), n * sizeof(cxg<T>), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(braw, b.data(), M * sizeof(cxg<T>), cudaMemcpyHostToDevice));
+    const int r = gfft_pow2<T>(c, st, static_cast<const cxg<T> *>(braw), static_cast<cxg<T> *>(pl.Bf), static_cast<cxg<T> *>(tmp), M, 1, -1);
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(braw);
+    cudaFree(tmp);
+    if (r) return r;
+    it = c.gfft_chirp.emplace(key, pl).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+// work-buffer elements (complex) a transform of `rows` rows of n points needs beside in and out
+template <typename T> size_t gfft_work_elems(size_t n, size_t rows) {
+  if ((n & (n - 1)) == 0) return rows * n;
+  size_t M = 1;
+  while (M < 2 * n - 1) M *= 2;
+  return 3 * rows * M;
+}
+// rows x n complex points, any n; in and out distinct; `work`: gfft_work_elems elements
+template <typename T>
+int gfft_any(DeviceCtx &c, cudaStream_t st, const cxg<T> *in, cxg<T> *out, cxg<T> *work, size_t n, size_t rows, int sign) {
+  if ((n & (n - 1)) == 0) return gfft_pow2<T>(c, st, in, out, work, n, rows, sign);
+  DeviceCtx::ChirpPlan *pl = nullptr;
+  if (int r = gfft_chirp_plan<T>(c, st, n, &pl)) return r;
+  const size_t M = pl->M;
+  cxg<T> *a = work, *A = work + rows * M, *t = work + 2 * rows * M;
+  const cxg<T> *chirp = static_cast<const cxg<T> *>(pl->chirp);
+  const int cj = sign > 0 ? 1 : 0; // backward = conj o forward o conj
+  fc::gfft::chirp_in<T><<<gblocks((long long)(rows * M)), 256, 0, st>>>(in, (long long)n, (long long)rows, chirp, a, (long long)M, cj);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  if (int r = gfft_pow2<T>(c, st, a, A, t, M, rows, -1)) return r;
+  fc::gfft::pointwise_mul<T><<<gblocks((long long)(rows * M)), 256, 0, st>>>(A, static_cast<const cxg<T> *>(pl->Bf), (long long)M, (long long)rows);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  if (int r = gfft_pow2<T>(c, st, A, a, t, M, rows, +1)) return r;
+  fc::gfft::chirp_out<T><<<gblocks((long long)(rows * n)), 256, 0, st>>>(a, (long long)M, (long long)n, (long long)rows, chirp, out, (T)(1.0 / (double)M), cj);
+  CU_TRY(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+// Hilbert envelope of lines of any length (device pointers): pairs of rows as real / imaginary part
+template <typename T>
+int hilbert_general_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size_t n, size_t x_stride, T *env,
+                           size_t env_stride) {
+  const size_t pairs_total = (batch + 1) / 2;
+  const size_t per_pair = 2 * n + gfft_work_elems<T>(n, 1); // Z, H, work
+  const size_t budget = ((size_t)env_int("FFTCONV_CUDA_SCRATCH_MB", 512) << 20) / sizeof(cxg<T>);
+  const size_t pairs_per = std::max<size_t>(1, std::min(pairs_total, budget / per_pair));
+  StreamWs &ws = c.ws[st];
+  const size_t need = pairs_per * per_pair * sizeof(cxg<T>);
+  if (ws.scratch_bytes < need) CU_TRY(cudaStreamSynchronize(st));
+  if (int r = grow(&ws.scratch, &ws.scratch_bytes, need)) return r;
+  cxg<T> *Z = static_cast<cxg<T> *>(ws.scratch), *Hh = Z + pairs_per * n, *work = Hh + pairs_per * n;
+  const fc::EnvEpilogue<T> epi = current_epilogue<T>(n);
+  for (size_t p0 = 0; p0 < pairs_total; p0 += pairs_per) {
+    const size_t np = std::min(pairs_per, pairs_total - p0);
+    const size_t r0 = 2 * p0, rows = std::min(batch - r0, 2 * np);
+    fc::gfft::real_to_complex<T><<<gblocks((long long)(np * n)), 256, 0, st>>>(x + r0 * x_stride, (long long)x_stride, (long long)n, (long long)rows, Hh, (long long)n, 1);
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+    if (int r = gfft_any<T>(c, st, Hh, Z, work, n, np, -1)) return r;
+    fc::gfft::hilbert_multiplier<T><<<gblocks((long long)(np * n)), 256, 0, st>>>(Z, (long long)n, (long long)np);
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+    if (int r = gfft_any<T>(c, st, Z, Hh, work, n, np, +1)) return r;
+    fc::gfft::envelope_from_pairs<T><<<gblocks((long long)(rows * n)), 256, 0, st>>>(
+        x + r0 * x_stride, (long long)x_stride, (long long)n, (long long)rows, Hh, env + r0 * env_stride, (long long)env_stride,
+        (long long)(epi.plain ? 1 : epi.dec), epi.plain ? 0 : epi.log, epi.a, epi.b);
+    CU_TRY(cudaGetLastError());
+    ++g_launches;
+  }
+  return 0;
+}
+
+// fftconv_cuda_fft_*: batched 1-D transforms with FFTW's conventions (unnormalised; sign -1 forward, +1 backward;
+// r2c writes n / 2 + 1 points per row, c2r reads as many and ignores the imaginary parts of DC and Nyquist).
+// kind 0: c2c, 1: r2c, 2: c2r.  Device pointers; rows contiguous.  c.mu held by the caller.
+template <typename T>
+int fft_device(DeviceCtx &c, cudaStream_t st, int kind, const void *in, void *out, size_t n, size_t batch, int sign) {
+  const size_t half = n / 2 + 1;
+  // complex elements per row beside the caller's arrays: work + (r2c / c2r, or in-place c2c: two staging rows)
+  const bool staged = kind != 0 || in == out;
+  const size_t per_row = gfft_work_elems<T>(n, 1) + (kind != 0 ? 2 * n : (staged ? n : 0));
+  const size_t budget = ((size_t)env_int("FFTCONV_CUDA_SCRATCH_MB", 512) << 20) / sizeof(cxg<T>);
+  const size_t rows_per = std::max<size_t>(1, std::min(batch, budget / std::max<size_t>(1, per_row)));
+  StreamWs &ws = c.ws[st];
+  const size_t need = std::max<size_t>(16, rows_per * per_row * sizeof(cxg<T>));
+  if (ws.scratch_bytes < need) CU_TRY(cudaStreamSynchronize(st));
+  if (int r = grow(&ws.scratch, &ws.scratch_bytes, need)) return r;
+  cxg<T> *work = static_cast<cxg<T> *>(ws.scratch);
+  cxg<T> *za = work + rows_per * gfft_work_elems<T>(n, 1), *zb = za + rows_per * n;
+  for (size_t r0 = 0; r0 < batch; r0 += rows_per) {
+    const size_t rows = std::min(rows_per, batch - r0);
+    if (kind == 0) {
+      const cxg<T> *src = static_cast<const cxg<T> *>(in) + r0 * n;
+      cxg<T> *dst = static_cast<cxg<T> *>(out) + r0 * n;
+      if (staged) {
+        CU_TRY(cudaMemcpyAsync(za, src, rows * n * sizeof(cxg<T>), cudaMemcpyDeviceToDevice, st));
+        src = za;
+      }
+      if (int r = gfft_any<T>(c, st, src, dst, work, n, rows, sign)) return r;
+    } else if (kind == 1) {
+      fc::gfft::real_to_complex<T><<<gblocks((long long)(rows * n)), 256, 0, st>>>(
+          static_cast<const T *>(in) + r0 * n, (long long)n, (long long)n, (long long)rows, za, (long long)n, 0);
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+      if (int r = gfft_any<T>(c, st, za, zb, work, n, rows, -1)) return r;
+      fc::gfft::complex_take<T><<<gblocks((long long)(rows * half)), 256, 0, st>>>(
+          zb, (long long)n, (long long)rows, static_cast<cxg<T> *>(out) + r0 * half, (long long)half);
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+    } else {
+      fc::gfft::hermitian_expand<T><<<gblocks((long long)(rows * n)), 256, 0, st>>>(
+          static_cast<const cxg<T> *>(in) + r0 * half, (long long)n, (long long)rows, za);
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+      if (int r = gfft_any<T>(c, st, za, zb, work, n, rows, +1)) return r;
+      fc::gfft::complex_real_part<T><<<gblocks((long long)(rows * n)), 256, 0, st>>>(zb, (long long)n, (long long)rows,
+                                                                                    static_cast<T *>(out) + r0 * n);
+      CU_TRY(cudaGetLastError());
+      ++g_launches;
+    }
+  }
+  return 0;
+}
+
 template <typename T>
 int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size_t n,
                    size_t x_stride, T *env, size_t env_stride) {
@@ -1143,10 +1369,8 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
     const size_t smem_b = M * sizeof(cx<T>);
     if (smem_b > c.smem_optin) {
       // the chirp filter's two convolutions as split FFTs of M = 16 N_sub points through global scratch
-      if (!long_ok<T>(c, M))
-        return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
-                                                     " needs a chirp-z FFT of " + std::to_string(M) +
-                                                     " points, beyond the split (16 x 16384) FFT");
+      if (!long_ok<T>(c, M)) // beyond the split (16 x 16384) FFT: the general transform through global memory
+        return hilbert_general_device<T>(c, st, x, batch, n, x_stride, env, env_stride);
       BluesteinTables *btl = nullptr;
       if (int r = get_bluestein<T>(c, n, &btl, true)) return r;
       return long_device<T>(c, st, x, batch, n, x_stride, env, env_out_len(n), env_stride, 0, M,
@@ -1198,9 +1422,8 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
                           static_cast<const cx<T> *>(tbig->Glong), true);
   }
   const size_t smem = n * sizeof(cx<T>);
-  if (smem > c.smem_optin)
-    return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "hilbert: length " + std::to_string(n) +
-                                                 " exceeds the single-CTA and the split (16 x 16384) FFT");
+  if (smem > c.smem_optin) // beyond the single-CTA and the split (16 x 16384) FFT
+    return hilbert_general_device<T>(c, st, x, batch, n, x_stride, env, env_stride);
   Tables *tab = nullptr;
   if (int r = get_tables<T>(c, n, &tab)) return r;
   const bool use_fast = fast_ok<T>(c, n, 0);
@@ -1638,6 +1861,44 @@ int fill_synthetic_entry(T *dst, size_t n, unsigned long long seed, unsigned lon
   return 0;
 }
 
+// the general FFT surface: the reference's FFTW wrappers dft_1d / dft_r2c_1d /
+// dft_c2r_1d and their batched forms (/root/reference/include/fftconv/fftw.hpp:152-195, :396-423)
+template <typename T> int fft_entry(int kind, const void *in, void *out, size_t n, size_t batch, int sign, void *stream) {
+  if (batch == 0) return 0;
+  if (!in || !out) return fail(FFTCONV_CUDA_ERR_ARG, "fft: null pointer");
+  if (n == 0) return fail(FFTCONV_CUDA_ERR_ARG, "fft: empty transform");
+  if (kind == 0 && sign != -1 && sign != 1) return fail(FFTCONV_CUDA_ERR_ARG, "fft: sign must be -1 (forward) or +1 (backward)");
+  if (n > ((size_t)1 << 30)) return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "fft: transforms beyond 2^30 points are not covered");
+  DeviceCtx *c = nullptr;
+  if (int r = get_ctx(&c)) return r;
+  const size_t half = n / 2 + 1;
+  const size_t in_bytes = batch * (kind == 1 ? n * sizeof(T) : (kind == 2 ? half : n) * sizeof(cxg<T>));
+  const size_t out_bytes = batch * (kind == 2 ? n * sizeof(T) : (kind == 1 ? half : n) * sizeof(cxg<T>));
+  const bool dev_in = ptr_kind(in) == PTR_DEVICE, dev_out = ptr_kind(out) == PTR_DEVICE;
+  if (dev_in != dev_out) return fail(FFTCONV_CUDA_ERR_ARG, "fft: input and output must both be host or both be device pointers");
+  if (dev_in) {
+    std::lock_guard<std::mutex> lock(c->mu);
+    return fft_device<T>(*c, static_cast<cudaStream_t>(stream), kind, in, out, n, batch, sign);
+  }
+  // host pointers: upload, transform, download (the slow lane: no pipelining)
+  void *din = nullptr, *dout = nullptr;
+  auto body = [&]() -> int {
+    CU_TRY(cudaMalloc(&din, in_bytes));
+    CU_TRY(cudaMalloc(&dout, out_bytes));
+    CU_TRY(cudaMemcpy(din, in, in_bytes, cudaMemcpyHostToDevice));
+    {
+      std::lock_guard<std::mutex> lock(c->mu);
+      if (int r = fft_device<T>(*c, nullptr, kind, din, dout, n, batch, sign)) return r;
+    }
+    CU_TRY(cudaMemcpy(out, dout, out_bytes, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  const int r = body();
+  cudaFree(din);
+  cudaFree(dout);
+  return r;
+}
+
 template <typename T> int oa_layout_for(const DeviceCtx &c, size_t N, size_t klen) {
   if (w1k_engine_for<T>(N, klen)) return fc::generic::LAYOUT_W1K;
   if (oa2048_engine_for<T>(N, klen)) return fc::generic::LAYOUT_N2048;
@@ -1830,6 +2091,19 @@ int fftconv_cuda_release_stream(void *stream) {
   c->ws.erase(it);
   return 0;
 }
+
+#define FFTCONV_FFT_API(SFX, T)                                                                              \
+  int fftconv_cuda_fft_c2c_##SFX(const T *in, T *out, size_t n, size_t batch, int sign, void *stream) {      \
+    return fft_entry<T>(0, in, out, n, batch, sign, stream);                                                 \
+  }                                                                                                          \
+  int fftconv_cuda_fft_r2c_##SFX(const T *in, T *out, size_t n, size_t batch, void *stream) {                \
+    return fft_entry<T>(1, in, out, n, batch, -1, stream);                                                   \
+  }                                                                                                          \
+  int fftconv_cuda_fft_c2r_##SFX(const T *in, T *out, size_t n, size_t batch, void *stream) {                \
+    return fft_entry<T>(2, in, out, n, batch, +1, stream);                                                   \
+  }
+FFTCONV_FFT_API(f32, float)
+FFTCONV_FFT_API(f64, double)
 
 #define FFTCONV_API(SFX, T)                                                                      \
   int fftconv_cuda_oaconvolve_##SFX(const T *a, size_t n, const T *k, size_t klen, T *out,       \
