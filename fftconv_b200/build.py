@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 ]
 
 # translation units of libfftconv_cuda.so (compiled in parallel, objects under lib/obj/)
-UNITS = ["fftconv_cuda.cu", "fftconv_cuda_w1k.cu", "fftconv_cuda_mgpu.cu"]
+UNITS = ["fftconv_cuda.cu", "fftconv_cuda_w1k.cu", "fftconv_cuda_hr2c.cu", "fftconv_cuda_mgpu.cu"]
 
 
 def _newer(target: str, sources: list[str]) -> bool:
@@ -45,13 +45,25 @@ def _sources() -> list[str]:
 
 
 def _unit_deps(unit: str) -> list[str]:
-    """Sources a translation unit is rebuilt for: itself, the public header, and -- for the main
-    unit, which includes every kernel header -- everything under csrc/ that is not another unit."""
+    """Sources a translation unit is rebuilt for: itself, the public header, and the transitive
+    closure of its `#include "..."` lines under csrc/."""
+    import re
+
     hdr = os.path.join(ROOT, "include", "fftconv_cuda.h")
-    if unit != "fftconv_cuda_mgpu.cu":  # the kernel units include the kernel headers
-        return [hdr] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
-                        if f == unit or not f.endswith(".cu")]
-    return [hdr, os.path.join(CSRC, unit)]
+    seen, todo = set(), [unit]
+    while todo:
+        f = todo.pop()
+        if f in seen:
+            continue
+        seen.add(f)
+        path = os.path.join(CSRC, f)
+        if not os.path.exists(path):
+            continue
+        with open(path) as fh:
+            for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', fh.read(), flags=re.M):
+                if os.path.exists(os.path.join(CSRC, inc)):
+                    todo.append(inc)
+    return [hdr] + [os.path.join(CSRC, f) for f in sorted(seen)]
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:

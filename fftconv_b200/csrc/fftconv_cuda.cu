@@ -18,6 +18,7 @@
 #include "long_fft_kernels.cuh"
 #include "oa_n2048_kernel.cuh"
 #include "oa_n2048_tables.h"
+#include "hilbert_r2c_launch.h"
 #include "oa_w1k_launch.h"
 #include "synthetic.cuh"
 
@@ -157,6 +158,7 @@ struct DeviceCtx {
     void *chirp = nullptr; // cx[n]  exp(-pi i j^2 / n)
     void *Bf = nullptr;    // cx[M]  FFT_M of the wrapped conjugate chirp
   };
+  void *hr2c_tables = nullptr; // the real-input Hilbert engine's twiddle / mirror tables (hilbert_r2c_*.cuh)
   std::map<std::pair<size_t, int>, void *> gfft_w;
   std::map<std::pair<size_t, int>, ChirpPlan> gfft_chirp;
   fc::n2048::CPairT<double> *tw1d = nullptr, *tw2d = nullptr; // the float64 instantiation's tables
@@ -221,6 +223,8 @@ void free_ctx(DeviceCtx &c) {
   c.tw1 = c.tw2 = c.tw_w1k = nullptr;
   for (auto &kv : c.slice_plans) cudaFree(kv.second.starts);
   c.slice_plans.clear();
+  cudaFree(c.hr2c_tables);
+  c.hr2c_tables = nullptr;
   for (auto &kv : c.gfft_w) cudaFree(kv.second);
   c.gfft_w.clear();
   for (auto &kv : c.gfft_chirp) {
@@ -1399,6 +1403,29 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
     CU_TRY(cudaGetLastError());
     ++g_launches;
     return 0;
+  }
+  if constexpr (std::is_same<T, float>::value) {
+    // 8192-sample float32 lines (BASELINE config 4): the real-input engine -- one 4096-point complex FFT per
+    // line, 128 threads per line, four independent lines per SM (hilbert_r2c_core.cuh).  Needs 16-byte aligned
+    // rows, the plain epilogue, and enough lines to give every group a few; FFTCONV_CUDA_NO_HR2C=1 switches it off.
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(env)) & 15) == 0 &&
+                           (x_stride & 3) == 0 && (env_stride & 3) == 0;
+    if (n == fc::hr2c::kLineSamples && aligned16 && current_epilogue<T>(n).plain && batch >= 64 &&
+        fc::hr2c::table_bytes() + 4 * 2 * 4352 * sizeof(float) <= c.smem_optin && !env_int("FFTCONV_CUDA_NO_HR2C", 0) &&
+        !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0)) {
+      if (!c.hr2c_tables) {
+        std::vector<unsigned char> host(fc::hr2c::table_bytes());
+        fc::hr2c::build_tables(host.data());
+        CU_TRY(cudaMalloc(&c.hr2c_tables, host.size()));
+        CU_TRY(cudaMemcpy(c.hr2c_tables, host.data(), host.size(), cudaMemcpyHostToDevice));
+      }
+      const long long ctas = std::max<long long>(1, std::min<long long>(c.sm_count, ((long long)batch + 3) / 4));
+      if (const int e = fc::hr2c::launch(x, env, (long long)batch, (long long)x_stride, (long long)env_stride,
+                                         c.hr2c_tables, (int)ctas, st))
+        return fail(FFTCONV_CUDA_ERR_CUDA, std::string("hilbert_r2c_kernel: ") + cudaGetErrorString((cudaError_t)e));
+      ++g_launches;
+      return 0;
+    }
   }
   if (!fast_ok<T>(c, n, 0) && long_ok<T>(c, n)) {
     Tables *tbig = nullptr;

@@ -592,3 +592,52 @@ def test_hilbert_lines_beyond_the_split_fft(cuda, dt, n):
     # envelope post-processing rides the same path
     dec = fc.envelope(torch.from_numpy(x[:1]).to(cuda), decimate=4)
     assert _crel(dec.cpu().numpy(), want[:1, ::4]) < H.TOL[np.dtype(dt)]
+
+
+# ---- the real-input Hilbert engine (hilbert_r2c_*.cuh): 8192-sample float32 lines ---------------------
+@pytest.mark.parametrize("rows", [64, 67, 592, 1000, 2371])
+def test_hilbert_r2c_engine_matches_oracle(cuda, rows, monkeypatch):
+    """BASELINE config 4's line length on the real-input engine (one 4096-point complex FFT per line,
+    mirror pass in registers) against scipy's float64 Hilbert transform and against the register-blocked
+    engine it replaces; rows not a multiple of the groups per launch; NaN guard rows around the output."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(rows)
+    x = rng.standard_normal((rows, 8192)).astype(np.float32)
+    x[1] += 3.0                                   # a line with a DC offset (DC and Nyquist bins are zeroed)
+    x[2, :] = 0.0
+    x[2, 4097] = 1.0                              # an impulse
+    xt = torch.from_numpy(x).to(cuda)
+    out = torch.full((rows + 2, 8192), float("nan"), device=cuda)
+    before = fc.launch_count()
+    fc.hilbert_(xt, out[1:-1])
+    torch.cuda.synchronize()
+    assert fc.launch_count() - before == 1
+    got = out.cpu().numpy()
+    assert np.isnan(got[0]).all() and np.isnan(got[-1]).all()
+    want = O.hilbert_exact(x)
+    assert O.rel_l2(got[1:-1], want) < 1e-5
+    assert np.abs(got[1:-1] - want).max() < 2e-5 * np.abs(want).max()
+    monkeypatch.setenv("FFTCONV_CUDA_NO_HR2C", "1")
+    old = fc.hilbert(xt).cpu().numpy()
+    assert O.rel_l2(got[1:-1], old) < 1e-6
+
+
+def test_hilbert_r2c_engine_needs_aligned_rows(cuda):
+    """Rows that are not 16-byte aligned, strided rows and small batches take the other kernels; same answer."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((70, 8192 + 8)).astype(np.float32)
+    want = O.hilbert_exact(x[:, 1:8193])
+    xt = torch.from_numpy(x).to(cuda)
+    got = fc.hilbert(xt[:, 1:8193])               # misaligned rows, stride 8200
+    assert O.rel_l2(got.cpu().numpy(), want) < 1e-5
+    got4 = torch.empty((70, 8192), device=cuda)
+    fc.hilbert_(xt[:, 4:8196], got4)              # aligned, strided: the r2c engine with a row stride
+    assert O.rel_l2(got4.cpu().numpy(), O.hilbert_exact(x[:, 4:8196])) < 1e-5
+    assert O.rel_l2(fc.hilbert(x[:5, :8192].copy()), O.hilbert_exact(x[:5, :8192])) < 1e-5   # small host batch
