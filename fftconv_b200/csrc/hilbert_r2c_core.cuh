@@ -27,7 +27,7 @@
 // Index algebra.  m = 256 a + 16 b + c, k = k0 + 16 k1 + 256 k2, W = exp(-2 pi j / 4096):
 //   W^{mk} = W16^{a k0} . W^{(16 b + c) k0} . W16^{b k1} . W256^{c k1} . W16^{c k2}
 //   P1 (thread t: b = t >> 3, c = 2 (t & 7) + h):  DFT16 over a -> k0, times W^{(16 b + c) k0}
-//   P2 (thread u: k0 = u >> 3, c = 2 (u & 7) + h): DFT16 over b -> k1, times W256^{c k1}
+//   P2 (thread u: k0 = p2_k0(u), c = 2 (u & 7) + h): DFT16 over b -> k1, times W256^{c k1}
 //   P3 (thread s: (k0, k1) and its mirror partner): DFT16 over c -> k2
 // h = 0 / 1 is the low / high half of the packed registers.  The inverse runs the same passes
 // backwards (P3', P2', P1') with conjugated twiddles applied BEFORE each butterfly; 1 / M rides in
@@ -73,8 +73,17 @@ struct alignas(16) Quad {
 // ---- which butterflies a thread runs ---------------------------------------------------------------
 // P1 / P1': thread t, digits (b, c) = (t >> 3, 2 (t & 7) + h)
 FC_HD int p1_base(int t) { return beta(t >> 3) + 2 * (t & 7); }
-// P2 / P2': thread u, digits (k0, c) = (u >> 3, 2 (u & 7) + h)
-FC_HD int p2_base(int u) { return alpha(u >> 3) + 2 * (u & 7); }
+// P2 / P2': thread u, digits (k0, c) = (p2_k0(u), 2 (u & 7) + h).  Warp w owns a set of k0 that is closed under
+// the mirror map k0 -> 16 - k0: {2w+1, 2w+2, 15-2w, 14-2w} (w < 3), {7, 8, 9, 0} -- exactly the blocks its
+// threads read in P3, where a thread holds a butterfly and its mirror partner.  The exchanges P2 -> P3 and
+// P3' -> P2' therefore stay inside a warp and need __syncwarp() only; neighbours in a half-warp have k0 of
+// opposite parity (blocks 16 words apart mod 32: conflict-free 64-bit accesses).
+FC_HD int p2_k0(int u) {
+  const int w = u >> 5, q = (u >> 3) & 3;
+  if (w < 3) return q < 2 ? 2 * w + 1 + q : 16 - (2 * w + 1 + (q - 2));
+  return q == 3 ? 0 : 7 + q;
+}
+FC_HD int p2_base(int u) { return alpha(p2_k0(u)) + 2 * (u & 7); }
 // P3 / P3': thread s holds butterfly A = (k0, k1) in the low halves and its mirror partner B in the
 // high halves: bins M - (k0 + 16 k1 + 256 k2) = k0' + 16 k1' + 256 (15 - k2).
 //   s < 112:        A = (1 + (s >> 4), s & 15)   B = (16 - k0, 15 - k1)
@@ -139,18 +148,16 @@ template <bool CONJ, bool SLOT16> FC_HD void apply_powers(Regs &v, const Quad *t
     const int s = SLOT16 ? slot16(j) : j;
     twp_apply<CONJ>(v.re[s], v.im[s], w);
   };
-  use(1, w1); use(2, w2); use(4, w4); use(8, w8);
-  const TwP w3 = twp_mul(w1, w2); use(3, w3);
-  const TwP w5 = twp_mul(w4, w1); use(5, w5);
-  const TwP w6 = twp_mul(w4, w2); use(6, w6);
-  const TwP w7 = twp_mul(w4, w3); use(7, w7);
-  use(9, twp_mul(w8, w1));
-  use(10, twp_mul(w8, w2));
-  use(11, twp_mul(w8, w3));
-  use(12, twp_mul(w8, w4));
-  use(13, twp_mul(w8, w5));
-  use(14, twp_mul(w8, w6));
-  use(15, twp_mul(w8, w7));
+  // order: every power is used -- and its product with w^8 formed and used -- as soon as it exists, so that
+  // at most five twiddles are alive beside the data
+  use(1, w1); use(9, twp_mul(w8, w1));
+  use(2, w2); use(10, twp_mul(w8, w2));
+  const TwP w3 = twp_mul(w1, w2); use(3, w3); use(11, twp_mul(w8, w3));
+  const TwP w5 = twp_mul(w4, w1); use(5, w5); use(13, twp_mul(w8, w5));
+  const TwP w6 = twp_mul(w4, w2); use(6, w6); use(14, twp_mul(w8, w6));
+  const TwP w7 = twp_mul(w4, w3); use(7, w7); use(15, twp_mul(w8, w7));
+  use(4, w4); use(12, twp_mul(w8, w4));
+  use(8, w8);
 }
 // tables (hilbert_r2c_tables.h):
 //   tw1[p * 128 + t] = W4096^{r 2^p},  r = 16 (t >> 3) + 2 (t & 7) + h      (thread t of P1 / P1')
@@ -229,18 +236,27 @@ FC_HD void p3_store(const Regs &v, float *planes, int base_a, int base_b) {
 // After P3 slot16(k2) holds Z[k] (low half: butterfly A, high half: B).  G[k] = C conj(Z[M - k]) + j S Z[k];
 // for the partner bin k' = M - k: cos -> -C, sin -> S.  Results go to NATURAL slots (k2 for A, 15 - k2 for
 // B's bin M - k), which is where the inverse dft16 wants its inputs.
-FC_HD void mirror(Regs &v, const Pair *cs /* this thread's 16 (C, S) */) {
+FC_HD void mirror(Regs &v, const Pair *cs /* this thread's column of the (C, S) table */) {
   Regs w;
+  // slots k2 and 15 - k2 together: the four points they hold are consumed and the four results produced in
+  // one step, so nothing but the data itself is alive (taken one k2 at a time half of the inputs stay alive
+  // for eight steps beside the results: spills)
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) {
-    const int sa = slot16(k2), sb = slot16(15 - k2);
-    const float C = cs[k2 * kMirStride].x, S = cs[k2 * kMirStride].y;
-    const float zxr = v.re[sa].x, zxi = v.im[sa].x; // Z[k]
-    const float zyr = v.re[sb].y, zyi = v.im[sb].y; // Z[M - k]
-    w.re[k2].x = C * zyr - S * zxi;
-    w.im[k2].x = S * zxr - C * zyi;
-    w.re[15 - k2].y = -C * zxr - S * zyi;
-    w.im[15 - k2].y = C * zxi + S * zyr;
+  for (int k2 = 0; k2 < 8; ++k2) {
+    const int j2 = 15 - k2, sa = slot16(k2), sb = slot16(j2);
+    const float C = cs[k2 * kMirStride].x, S = cs[k2 * kMirStride].y;   // bin k of A, slot k2
+    const float D = cs[j2 * kMirStride].x, T = cs[j2 * kMirStride].y;   // bin of A, slot 15 - k2
+    const float axr = v.re[sa].x, axi = v.im[sa].x, ayr = v.re[sa].y, ayi = v.im[sa].y;
+    const float bxr = v.re[sb].x, bxi = v.im[sb].x, byr = v.re[sb].y, byi = v.im[sb].y;
+    // A's bin in slot k2 pairs with B's bin in slot 15 - k2 (by), A's bin in slot 15 - k2 with B's in slot k2 (ay)
+    w.re[k2].x = C * byr - S * axi;
+    w.im[k2].x = S * axr - C * byi;
+    w.re[j2].y = -C * axr - S * byi;
+    w.im[j2].y = C * axi + S * byr;
+    w.re[j2].x = D * ayr - T * bxi;
+    w.im[j2].x = T * bxr - D * ayi;
+    w.re[k2].y = -D * bxr - T * ayi;
+    w.im[k2].y = D * bxi + T * ayr;
   }
   v = w;
 }

@@ -75,22 +75,26 @@ int main(int argc, char **argv) {
       dft16<-1>(regs[t]);
       fwd_a_pre(regs[t], planes.data(), maps[t]);
     }
-    for (int t = 0; t < kThreads; ++t) {
-      fwd_a_post(regs[t], planes.data(), maps[t]);
-      dft16<-1>(regs[t]);
-      fwd_b_pre(regs[t], planes.data(), maps[t]);
-    }
-    for (int t = 0; t < kThreads; ++t) {
-      fwd_b_post(regs[t], planes.data(), maps[t]);
-      dft16<-1>(regs[t]);
-      fwd_c(t, regs[t], maps[t], mir.data());
-      dft16<+1>(regs[t]);
-      inv_a_pre(regs[t], planes.data(), maps[t]);
-    }
-    for (int t = 0; t < kThreads; ++t) {
-      inv_a_post(regs[t], planes.data(), maps[t]);
-      dft16<+1>(regs[t]);
-      inv_b_pre(regs[t], planes.data(), maps[t]);
+    // between the two group barriers a warp only synchronises with itself (__syncwarp): run warp after warp,
+    // so that a warp that needed another warp's P2 output would read stale data and fail the comparison
+    for (int w = 0; w < kThreads / 32; ++w) {
+      for (int t = 32 * w; t < 32 * w + 32; ++t) {
+        fwd_a_post(regs[t], planes.data(), maps[t]);
+        dft16<-1>(regs[t]);
+        fwd_b_pre(regs[t], planes.data(), maps[t]);
+      }
+      for (int t = 32 * w; t < 32 * w + 32; ++t) {
+        fwd_b_post(regs[t], planes.data(), maps[t]);
+        dft16<-1>(regs[t]);
+        fwd_c(t, regs[t], maps[t], mir.data());
+        dft16<+1>(regs[t]);
+        inv_a_pre(regs[t], planes.data(), maps[t]);
+      }
+      for (int t = 32 * w; t < 32 * w + 32; ++t) {
+        inv_a_post(regs[t], planes.data(), maps[t]);
+        dft16<+1>(regs[t]);
+        inv_b_pre(regs[t], planes.data(), maps[t]);
+      }
     }
     std::vector<float> h(kRow, NAN);
     for (int t = 0; t < kThreads; ++t) {
