@@ -6,6 +6,9 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace fc {
 namespace hr2c {
 
@@ -18,17 +21,25 @@ void build_tables(void *host_buf) {
   fill_tables(tw1, tw2, mir);
 }
 
-int launch(const float *in, float *out, long long batch, long long in_stride, long long out_stride,
-           const void *tables, int sms, void *stream) {
+template <int GROUPS>
+static int launch_variant(const HrParams &p, long long batch, int sms, void *stream) {
   static bool configured[64] = {false}; // per device: the opt-in to > 48 KB of dynamic shared memory
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
+  auto kern = hilbert_r2c_kernel<GROUPS>;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(hilbert_r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(GROUPS));
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
+  const long long ctas = std::max<long long>(1, std::min<long long>(sms, (batch + GROUPS - 1) / GROUPS));
+  kern<<<(unsigned)ctas, GROUPS * kThreads, smem_bytes(GROUPS), static_cast<cudaStream_t>(stream)>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int launch(const float *in, float *out, long long batch, long long in_stride, long long out_stride,
+           const void *tables, int sms, void *stream) {
   HrParams p;
   p.in = in;
   p.out = out;
@@ -38,8 +49,12 @@ int launch(const float *in, float *out, long long batch, long long in_stride, lo
   p.tw1 = static_cast<const Quad *>(tables);
   p.tw2 = p.tw1 + kTw1Quads;
   p.mir = reinterpret_cast<const Pair *>(p.tw2 + kTw2Quads);
-  hilbert_r2c_kernel<<<(unsigned)sms, kGroups * kThreads, smem_bytes(), static_cast<cudaStream_t>(stream)>>>(p);
-  return (int)cudaGetLastError();
+  // FFTCONV_CUDA_HR2C_GROUPS=3 / 5: lines in flight per SM (A/B measurements; 4 = 128 registers per thread)
+  const char *g = std::getenv("FFTCONV_CUDA_HR2C_GROUPS");
+  const int groups = g ? std::atoi(g) : kGroups;
+  if (groups == 3) return launch_variant<3>(p, batch, sms, stream);
+  if (groups == 5) return launch_variant<5>(p, batch, sms, stream);
+  return launch_variant<kGroups>(p, batch, sms, stream);
 }
 
 } // namespace hr2c

@@ -26,7 +26,7 @@ struct HrParams {
 
 constexpr size_t kSmemTables = (kTw1Quads + kTw2Quads) * sizeof(Quad) + kMirPairs * sizeof(Pair);
 constexpr size_t kSmemTablesPadded = (kSmemTables + 15) & ~size_t(15);
-constexpr size_t smem_bytes() { return kSmemTablesPadded + (size_t)kGroups * kGroupWords * sizeof(float); }
+constexpr size_t smem_bytes(int groups = kGroups) { return kSmemTablesPadded + (size_t)groups * kGroupWords * sizeof(float); }
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ void group_barrier(int id) {
@@ -102,7 +102,8 @@ __device__ __forceinline__ void prefetch_line_l2(const float *x) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "r"(kRow * 4) : "memory");
 }
 
-__global__ void __launch_bounds__(kGroups *kThreads, 1) hilbert_r2c_kernel(const __grid_constant__ HrParams p) {
+template <int GROUPS>
+__global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const __grid_constant__ HrParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Quad *tw1 = reinterpret_cast<Quad *>(smem_raw);
   Quad *tw2 = tw1 + kTw1Quads;
@@ -122,10 +123,10 @@ __global__ void __launch_bounds__(kGroups *kThreads, 1) hilbert_r2c_kernel(const
   // with the other butterfly's point
   asm volatile("" : "+r"(m.base3a), "+r"(m.base3b));
   const int bar = g + 1;
-  const long long n_groups = (long long)gridDim.x * kGroups;
+  const long long n_groups = (long long)gridDim.x * GROUPS;
 
 #pragma unroll 1
-  for (long long line = (long long)blockIdx.x * kGroups + g; line < p.batch; line += n_groups) {
+  for (long long line = (long long)blockIdx.x * GROUPS + g; line < p.batch; line += n_groups) {
     const float *x = p.in + line * p.in_stride;
     if (t == 0 && line + n_groups < p.batch) prefetch_line_l2(x + n_groups * p.in_stride);
     // Nothing but addresses lives across a trip boundary: every trip starts with a load (global or shared)

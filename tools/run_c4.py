@@ -30,8 +30,14 @@ def timed(n):
 
 
 res = {}
-for name, env in (("r2c", "0"), ("register_blocked", "1")):
+variants = [("r2c", "0", None), ("register_blocked", "1", None)]
+if len(sys.argv) > 2:
+    variants += [(f"r2c_groups{g}", "0", g) for g in sys.argv[2].split(",")]
+for name, env, groups in variants:
     os.environ["FFTCONV_CUDA_NO_HR2C"] = env
+    os.environ.pop("FFTCONV_CUDA_HR2C_GROUPS", None)
+    if groups:
+        os.environ["FFTCONV_CUDA_HR2C_GROUPS"] = groups
     ms = timed(steps)
     ms_long = timed(3000)
     ref = np.abs(__import__("scipy.signal").signal.hilbert(x[:4].cpu().numpy().astype(np.float64), axis=-1))
