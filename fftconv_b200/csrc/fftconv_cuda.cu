@@ -1407,10 +1407,12 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
   if constexpr (std::is_same<T, float>::value) {
     // 8192-sample float32 lines (BASELINE config 4): the real-input engine -- one 4096-point complex FFT per
     // line, 128 threads per line, four independent lines per SM (hilbert_r2c_core.cuh).  Needs 16-byte aligned
-    // rows, the plain epilogue, and enough lines to give every group a few; FFTCONV_CUDA_NO_HR2C=1 switches it off.
-    const bool aligned16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(env)) & 15) == 0 &&
-                           (x_stride & 3) == 0 && (env_stride & 3) == 0;
-    if (n == fc::hr2c::kLineSamples && aligned16 && current_epilogue<T>(n).plain && batch >= 64 &&
+    // input rows (and output rows, for the plain epilogue) and enough lines to give every group a few;
+    // FFTCONV_CUDA_NO_HR2C=1 switches it off.
+    const fc::EnvEpilogue<T> epi = current_epilogue<T>(n);
+    const bool in16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_stride & 3) == 0;
+    const bool out16 = (reinterpret_cast<uintptr_t>(env) & 15) == 0 && (env_stride & 3) == 0;
+    if (n == fc::hr2c::kLineSamples && in16 && (out16 || !epi.plain) && batch >= 64 &&
         fc::hr2c::table_bytes() + 4 * 2 * 4352 * sizeof(float) <= c.smem_optin && !env_int("FFTCONV_CUDA_NO_HR2C", 0) &&
         !env_int("FFTCONV_CUDA_FORCE_GENERIC", 0)) {
       if (!c.hr2c_tables) {
@@ -1420,8 +1422,9 @@ int hilbert_device(DeviceCtx &c, cudaStream_t st, const T *x, size_t batch, size
         CU_TRY(cudaMemcpy(c.hr2c_tables, host.data(), host.size(), cudaMemcpyHostToDevice));
       }
       const long long ctas = std::max<long long>(1, std::min<long long>(c.sm_count, ((long long)batch + 3) / 4));
+      const fc::hr2c::Epilogue he{epi.plain, epi.log, epi.dec, epi.magic, (float)epi.a, (float)epi.b};
       if (const int e = fc::hr2c::launch(x, env, (long long)batch, (long long)x_stride, (long long)env_stride,
-                                         c.hr2c_tables, (int)ctas, st))
+                                         c.hr2c_tables, he, (int)ctas, st))
         return fail(FFTCONV_CUDA_ERR_CUDA, std::string("hilbert_r2c_kernel: ") + cudaGetErrorString((cudaError_t)e));
       ++g_launches;
       return 0;

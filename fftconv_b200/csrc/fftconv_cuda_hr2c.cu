@@ -21,13 +21,13 @@ void build_tables(void *host_buf) {
   fill_tables(tw1, tw2, mir);
 }
 
-template <int GROUPS>
+template <int GROUPS, bool PLAIN>
 static int launch_variant(const HrParams &p, long long batch, int sms, void *stream) {
   static bool configured[64] = {false}; // per device: the opt-in to > 48 KB of dynamic shared memory
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
-  auto kern = hilbert_r2c_kernel<GROUPS>;
+  auto kern = hilbert_r2c_kernel<GROUPS, PLAIN>;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(GROUPS));
     if (e != cudaSuccess) return (int)e;
@@ -39,7 +39,7 @@ static int launch_variant(const HrParams &p, long long batch, int sms, void *str
 }
 
 int launch(const float *in, float *out, long long batch, long long in_stride, long long out_stride,
-           const void *tables, int sms, void *stream) {
+           const void *tables, const Epilogue &epi, int sms, void *stream) {
   HrParams p;
   p.in = in;
   p.out = out;
@@ -50,11 +50,13 @@ int launch(const float *in, float *out, long long batch, long long in_stride, lo
   p.tw2 = p.tw1 + kTw1Quads;
   p.mir = reinterpret_cast<const Pair *>(p.tw2 + kTw2Quads);
   // FFTCONV_CUDA_HR2C_GROUPS=3 / 5: lines in flight per SM (A/B measurements; 4 = 128 registers per thread)
+  p.epi = EnvEpilogue<float>{epi.plain, epi.log, epi.dec, epi.magic, epi.a, epi.b};
+  if (!epi.plain) return launch_variant<kGroups, false>(p, batch, sms, stream);
   const char *g = std::getenv("FFTCONV_CUDA_HR2C_GROUPS");
   const int groups = g ? std::atoi(g) : kGroups;
-  if (groups == 3) return launch_variant<3>(p, batch, sms, stream);
-  if (groups == 5) return launch_variant<5>(p, batch, sms, stream);
-  return launch_variant<kGroups>(p, batch, sms, stream);
+  if (groups == 3) return launch_variant<3, true>(p, batch, sms, stream);
+  if (groups == 5) return launch_variant<5, true>(p, batch, sms, stream);
+  return launch_variant<kGroups, true>(p, batch, sms, stream);
 }
 
 } // namespace hr2c

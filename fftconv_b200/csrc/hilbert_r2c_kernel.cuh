@@ -11,6 +11,7 @@
 // straight-line middle section (P3, mirror, P3').
 #pragma once
 
+#include "envelope_epilogue.cuh"
 #include "hilbert_r2c_core.cuh"
 
 namespace fc {
@@ -22,6 +23,7 @@ struct HrParams {
   long long batch, in_stride, out_stride;
   const Quad *tw1, *tw2; // kTw1Quads, kTw2Quads
   const Pair *mir;       // kMirPairs
+  EnvEpilogue<float> epi; // envelope post-processing in the store (envelope_epilogue.cuh); plain = the bare envelope
 };
 
 constexpr size_t kSmemTables = (kTw1Quads + kTw2Quads) * sizeof(Quad) + kMirPairs * sizeof(Pair);
@@ -72,7 +74,9 @@ __device__ __forceinline__ float sqrt_approx(float x) { // MUFU.SQRT
 
 // slot16(a) of v holds g[256 a + 2 t + h] = h[2m] + j h[2m+1]: env = sqrt(x^2 + h^2), four samples per store.
 // The line is read again (from L2) in batches of four 128-bit loads, two batches in flight.
-__device__ __forceinline__ void envelope_store(int t, const Regs &v, const float *x, float *out) {
+template <bool PLAIN>
+__device__ __forceinline__ void envelope_store(int t, const Regs &v, const float *x, float *out,
+                                               const EnvEpilogue<float> &epi) {
   const float4 *xi = reinterpret_cast<const float4 *>(x) + t;
   float4 *eo = reinterpret_cast<float4 *>(out) + t;
   float4 q[2][4];
@@ -93,7 +97,15 @@ __device__ __forceinline__ void envelope_store(int t, const Regs &v, const float
       e.y = sqrt_approx(fmaf(xv.y, xv.y, v.im[s].x * v.im[s].x));
       e.z = sqrt_approx(fmaf(xv.z, xv.z, v.re[s].y * v.re[s].y));
       e.w = sqrt_approx(fmaf(xv.w, xv.w, v.im[s].y * v.im[s].y));
-      eo[128 * (4 * b + i)] = e;
+      if (PLAIN) {
+        eo[128 * (4 * b + i)] = e;
+      } else { // decimation / log compression: sample by sample
+        const long long i0 = 4LL * (128 * (4 * b + i) + t);
+        env_store<false>(epi, out, i0, e.x);
+        env_store<false>(epi, out, i0 + 1, e.y);
+        env_store<false>(epi, out, i0 + 2, e.z);
+        env_store<false>(epi, out, i0 + 3, e.w);
+      }
     }
   }
 }
@@ -102,7 +114,7 @@ __device__ __forceinline__ void prefetch_line_l2(const float *x) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "r"(kRow * 4) : "memory");
 }
 
-template <int GROUPS>
+template <int GROUPS, bool PLAIN>
 __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const __grid_constant__ HrParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Quad *tw1 = reinterpret_cast<Quad *>(smem_raw);
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const 
         inv_b_pre(v, planes, m);
         group_barrier(bar);
       } else {
-        envelope_store(t, v, x, p.out + line * p.out_stride);
+        envelope_store<PLAIN>(t, v, x, p.out + line * p.out_stride, p.epi);
       }
     }
   }

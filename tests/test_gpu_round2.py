@@ -641,3 +641,35 @@ def test_hilbert_r2c_engine_needs_aligned_rows(cuda):
     fc.hilbert_(xt[:, 4:8196], got4)              # aligned, strided: the r2c engine with a row stride
     assert O.rel_l2(got4.cpu().numpy(), O.hilbert_exact(x[:, 4:8196])) < 1e-5
     assert O.rel_l2(fc.hilbert(x[:5, :8192].copy()), O.hilbert_exact(x[:5, :8192])) < 1e-5   # small host batch
+
+
+@pytest.mark.parametrize("dec,log", [(4, True), (3, False), (1, True)])
+def test_hilbert_r2c_engine_envelope_epilogue(cuda, dec, log, monkeypatch):
+    """Decimation / log compression in the store of the real-input engine (fftconv_cuda_envelope_*,
+    SURVEY.md 8f-3) on 8192-sample lines, against the oracle restatement and the register-blocked kernel;
+    and the rf_envelope chain (band-pass, envelope) on the same lines."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(100 + dec)
+    rows = 130
+    x = (rng.standard_normal((rows, 8192)) * np.exp(rng.uniform(-4, 1, (rows, 1)))).astype(np.float32)
+    kw = dict(log_compress=log, ref=1.5, dynamic_range_db=50.0, decimate=dec)
+    xt = torch.from_numpy(x).to(cuda)
+    got = fc.envelope(xt, **kw).cpu().numpy()
+    pick = [0, 1, 63, 64, 129]
+    want = O.envelope(x[pick], **kw)
+    assert got.shape == (rows, (8192 + dec - 1) // dec)
+    if log:
+        assert got.min() >= 0.0 and got.max() <= 1.0
+        assert np.linalg.norm(got[pick].astype(np.float64) - want) / np.sqrt(want.size) < 4e-5
+    else:
+        assert O.rel_l2(got[pick], want) < 1e-5
+    k = (rng.standard_normal(65) / 8).astype(np.float32)
+    chain = fc.rf_envelope(xt, torch.from_numpy(k).to(cuda), **kw).cpu().numpy()
+    monkeypatch.setenv("FFTCONV_CUDA_NO_HR2C", "1")
+    old = fc.envelope(xt, **kw).cpu().numpy()
+    old_chain = fc.rf_envelope(xt, torch.from_numpy(k).to(cuda), **kw).cpu().numpy()
+    assert np.abs(got - old).max() < (2e-4 if log else 1e-5 * np.abs(old).max())
+    assert np.abs(chain - old_chain).max() < (2e-4 if log else 1e-5 * np.abs(old_chain).max())
