@@ -7,8 +7,8 @@
 //   16 x LDG.128 (the line, coalesced) | P1 | 32 x STS.64 | bar | 32 x LDS.64 | P2 | 32 x STS.64 | bar |
 //   64 x LDS.32 | P3 | mirror pass in registers | P3' | 64 x STS.32 | bar | 32 x LDS.64 | P2' |
 //   32 x STS.64 | bar | 32 x LDS.64 | P1' | 16 x LDG.128 (the line again, from L2) | sqrt | 16 x STG.128
-// Each direction's dft16 exists twice: once in a two-trip loop (P1 / P2, P2' / P1') and once in the
-// straight-line middle section (P3, mirror, P3').
+// All six passes are straight-line code (2.6 k instructions; the instruction cache holds it: hit rate in
+// profiles/).
 #pragma once
 
 #include "envelope_epilogue.cuh"
@@ -74,23 +74,30 @@ __device__ __forceinline__ float sqrt_approx(float x) { // MUFU.SQRT
 
 // slot16(a) of v holds g[256 a + 2 t + h] = h[2m] + j h[2m+1]: env = sqrt(x^2 + h^2), four samples per store.
 // The line is read again (from L2) in batches of four 128-bit loads, two batches in flight.
+// While the envelope is stored the registers of v free up, four slots per batch: the NEXT line's samples are
+// requested into them (nq, consumed by the next iteration's first pass), so that no load latency is exposed at
+// the top of the line loop.
 template <bool PLAIN>
 __device__ __forceinline__ void envelope_store(int t, const Regs &v, const float *x, float *out,
-                                               const EnvEpilogue<float> &epi) {
+                                               const EnvEpilogue<float> &epi, float4 (&nq)[16], const float *x_next) {
+  const float4 *xn = reinterpret_cast<const float4 *>(x_next) + t;
   const float4 *xi = reinterpret_cast<const float4 *>(x) + t;
   float4 *eo = reinterpret_cast<float4 *>(out) + t;
-  float4 q[2][4];
+  // batches of two slots: two batches of the second read in flight (16 registers), and the next line's
+  // samples take over the registers of the slots just consumed
+  constexpr int B = 2;
+  float4 q[2][B];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) q[0][i] = __ldg(xi + 128 * i);
+  for (int i = 0; i < B; ++i) q[0][i] = __ldg(xi + 128 * i);
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    if (b < 3) {
+  for (int b = 0; b < 16 / B; ++b) {
+    if (b + 1 < 16 / B) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) q[(b + 1) & 1][i] = __ldg(xi + 128 * (4 * (b + 1) + i));
+      for (int i = 0; i < B; ++i) q[(b + 1) & 1][i] = __ldg(xi + 128 * (B * (b + 1) + i));
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int s = slot16(4 * b + i);
+    for (int i = 0; i < B; ++i) {
+      const int a = B * b + i, s = slot16(a);
       const float4 xv = q[b & 1][i];
       float4 e;
       e.x = sqrt_approx(fmaf(xv.x, xv.x, v.re[s].x * v.re[s].x));
@@ -98,15 +105,33 @@ __device__ __forceinline__ void envelope_store(int t, const Regs &v, const float
       e.z = sqrt_approx(fmaf(xv.z, xv.z, v.re[s].y * v.re[s].y));
       e.w = sqrt_approx(fmaf(xv.w, xv.w, v.im[s].y * v.im[s].y));
       if (PLAIN) {
-        eo[128 * (4 * b + i)] = e;
+        eo[128 * a] = e;
       } else { // decimation / log compression: sample by sample
-        const long long i0 = 4LL * (128 * (4 * b + i) + t);
+        const long long i0 = 4LL * (128 * a + t);
         env_store<false>(epi, out, i0, e.x);
         env_store<false>(epi, out, i0 + 1, e.y);
         env_store<false>(epi, out, i0 + 2, e.z);
         env_store<false>(epi, out, i0 + 3, e.w);
       }
     }
+    // unconditional (the caller passes the current line again when there is no next one): a conditional
+    // assignment would keep the old nq alive through the whole iteration -- 64 more registers
+#pragma unroll
+    for (int i = 0; i < B; ++i) nq[B * b + i] = xn[128 * (B * b + i)];
+  }
+}
+// the first line of a group: all sixteen loads at once
+__device__ __forceinline__ void load_quads(int t, float4 (&nq)[16], const float *x) {
+  const float4 *q = reinterpret_cast<const float4 *>(x) + t;
+#pragma unroll
+  for (int a = 0; a < 16; ++a) nq[a] = q[128 * a];
+}
+// P1 input: slot a = points m = 256 a + 2 t and + 1 (low / high halves)
+__device__ __forceinline__ void quads_to_regs(const float4 (&nq)[16], Regs &v) {
+#pragma unroll
+  for (int a = 0; a < 16; ++a) {
+    v.re[a] = make_f2(nq[a].x, nq[a].z);
+    v.im[a] = make_f2(nq[a].y, nq[a].w);
   }
 }
 // ask for the group's next line to be brought into L2 while the current one is transformed
@@ -137,33 +162,32 @@ __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const 
   const int bar = g + 1;
   const long long n_groups = (long long)gridDim.x * GROUPS;
 
+  float4 nq[16]; // the samples of the line about to be transformed
+  {
+    const long long first = (long long)blockIdx.x * GROUPS + g;
+    if (first < p.batch) load_quads(t, nq, p.in + first * p.in_stride);
+  }
 #pragma unroll 1
   for (long long line = (long long)blockIdx.x * GROUPS + g; line < p.batch; line += n_groups) {
     const float *x = p.in + line * p.in_stride;
-    if (t == 0 && line + n_groups < p.batch) prefetch_line_l2(x + n_groups * p.in_stride);
-    // Nothing but addresses lives across a trip boundary: every trip starts with a load (global or shared)
-    // and ends with a store.  (With the 32 points carried in registers around three-trip loops the compiler
-    // re-paired them with ~1000 MOVs per line.)
-#pragma unroll 1
-    for (int trip = 0; trip < 2; ++trip) { // P1, P2
+    const float *x_next = line + n_groups < p.batch ? x + n_groups * p.in_stride : nullptr;
+    if (t == 0 && x_next) prefetch_line_l2(x_next);
+    // Straight-line code, six inlined dft16: with the passes in two- or three-trip loops the compiler either
+    // re-paired the 32 points with ~1000 MOVs per line (points carried in registers around the loop) or kept the
+    // next line's 64 prefetched registers alive through whole trips (anything assigned in one branch of a trip).
+    { // P1: straight-line, so that nq is dead before anything else needs its registers
       Regs v;
-      Packed q;
-      if (trip == 0) {
-        load_line(t, v, x);
-        pack_regs(v, q);
-      } else {
-        fwd_a_post(v, planes, m);
-        pack_regs(v, q);
-      }
-      unpack_regs(q, v);
+      quads_to_regs(nq, v);
       dft16<-1>(v);
-      if (trip == 0) {
-        fwd_a_pre(v, planes, m);
-        group_barrier(bar);
-      } else {
-        fwd_b_pre(v, planes, m);
-        __syncwarp(); // P2 -> P3 stays inside the warp (p2_k0)
-      }
+      fwd_a_pre(v, planes, m);
+      group_barrier(bar);
+    }
+    { // P2
+      Regs v;
+      fwd_a_post(v, planes, m);
+      dft16<-1>(v);
+      fwd_b_pre(v, planes, m);
+      __syncwarp(); // P2 -> P3 stays inside the warp (p2_k0)
     }
     { // P3, the mirror pass, P3': no exchange in between
       Regs v;
@@ -182,25 +206,18 @@ __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const 
       inv_a_pre(v, planes, m);
       __syncwarp(); // P3' -> P2' stays inside the warp
     }
-#pragma unroll 1
-    for (int trip = 0; trip < 2; ++trip) { // P2', P1'
+    { // P2'
       Regs v;
-      Packed q;
-      if (trip == 0) {
-        inv_a_post(v, planes, m);
-        pack_regs(v, q);
-      } else {
-        inv_b_post(v, planes, m);
-        pack_regs(v, q);
-      }
-      unpack_regs(q, v);
+      inv_a_post(v, planes, m);
       dft16<+1>(v);
-      if (trip == 0) {
-        inv_b_pre(v, planes, m);
-        group_barrier(bar);
-      } else {
-        envelope_store<PLAIN>(t, v, x, p.out + line * p.out_stride, p.epi);
-      }
+      inv_b_pre(v, planes, m);
+      group_barrier(bar);
+    }
+    { // P1', envelope; the next line's samples are requested as registers free up
+      Regs v;
+      inv_b_post(v, planes, m);
+      dft16<+1>(v);
+      envelope_store<PLAIN>(t, v, x, p.out + line * p.out_stride, p.epi, nq, x_next ? x_next : x);
     }
   }
 }
