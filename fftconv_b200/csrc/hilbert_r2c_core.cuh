@@ -221,14 +221,17 @@ FC_HD void p3_fetch(Regs &v, const float *planes, int base_a, int base_b) {
     v.im[c] = make_f2(planes[kPlane + base_a + c], planes[kPlane + base_b + c]);
   }
 }
+// 64-bit stores of two neighbouring points of ONE butterfly (base_a, base_b are even): the halves have to be
+// re-paired in registers (MOVs, on the idle integer pipe), but 32-bit stores from a warp whose 32 butterflies
+// all sit at even words would hit only half of the banks (two-way conflict: 128 wavefronts instead of 64)
 FC_HD void p3_store(const Regs &v, float *planes, int base_a, int base_b) {
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int s = slot16(c);
-    planes[base_a + c] = v.re[s].x;
-    planes[base_b + c] = v.re[s].y;
-    planes[kPlane + base_a + c] = v.im[s].x;
-    planes[kPlane + base_b + c] = v.im[s].y;
+  for (int c = 0; c < 16; c += 2) {
+    const int s0 = slot16(c), s1 = slot16(c + 1);
+    *reinterpret_cast<Pair *>(planes + base_a + c) = Pair{v.re[s0].x, v.re[s1].x};
+    *reinterpret_cast<Pair *>(planes + base_b + c) = Pair{v.re[s0].y, v.re[s1].y};
+    *reinterpret_cast<Pair *>(planes + kPlane + base_a + c) = Pair{v.im[s0].x, v.im[s1].x};
+    *reinterpret_cast<Pair *>(planes + kPlane + base_b + c) = Pair{v.im[s0].y, v.im[s1].y};
   }
 }
 

@@ -156,6 +156,17 @@ def test_w1k_kernel_logic_emulated_on_cpu(built, case):
     assert float(r.stdout.split()[0]) < 1e-6
 
 
+def test_hilbert_r2c_engine_emulated_on_cpu(built):
+    """The real-input Hilbert engine (hilbert_r2c_core.cuh): its own __host__ __device__ pass functions for all
+    128 threads of a line, barrier interval by barrier interval (warp after warp where the kernel only has
+    __syncwarp), on NaN-poisoned planes, against a float64 Hilbert transform from the definition; also that the
+    plane layout has no collisions and that the third pass's thread map owns every butterfly exactly once."""
+    exe = os.path.join(ROOT, "tests", "cpu", "emulate_hilbert_r2c")
+    r = subprocess.run([exe, "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL PASSED" in r.stdout, r.stdout + r.stderr
+    assert float(r.stdout.split()[0]) < 1e-6
+
+
 def test_fast_fft_engine_emulated_on_cpu(built):
     """fast_fft.cuh (N = 512 .. 16384, float and double): the kernel's own pass functions
     run for all threads pass by pass on the CPU against direct circular convolution."""
