@@ -153,9 +153,18 @@ struct LaneTwiddles {
   cpair p[16]; // p[j] = w2^j (p[0] unused)
   cpair w;
 };
-FC_HD LaneTwiddles lane_twiddles(const cpair *tw, int lane) {
+// FULL: all fifteen powers come from the table (rows 20 .. 34: tw[(19 + j) * 32 + l] = w2^j) -- 15 shared loads
+// instead of 4 loads and 44 scalar multiply-adds; which is better depends on which pipe has room (A/B switch).
+template <bool FULL = false> FC_HD LaneTwiddles lane_twiddles(const cpair *tw, int lane) {
   using n2048::cpair_mul;
   LaneTwiddles t;
+  if (FULL) {
+    t.w = cpair{1.0f, 0.0f};
+    t.p[0] = cpair{1.0f, 0.0f};
+#pragma unroll
+    for (int j = 1; j < 16; ++j) t.p[j] = tw[(19 + j) * 32 + lane];
+    return t;
+  }
   t.p[1] = tw[0 * 32 + lane];
   t.p[2] = tw[1 * 32 + lane];
   t.p[4] = tw[2 * 32 + lane];
@@ -283,7 +292,7 @@ FC_HD void phase1(int lane, Regs &v, const Quad *hs4) {
 //   phase0 = p0_pre, dft16<-1>, p0_post        phase1 = dft16<-1>, p1_mid, dft16<+1>
 //   phase2 = p2_pre, dft16<+1>, p2_post
 FC_HD void p0_pre(int lane, Regs &v, const cpair *tw) { cross_dif_tw<false>(v, tw + 4 * 32 + lane); }
-FC_HD void p0_post(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<false, true>(v, lane_twiddles(tw, lane)); }
+template <bool FULL = false> FC_HD void p0_post(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<false, true>(v, lane_twiddles<FULL>(tw, lane)); }
 // between P1's two transforms: radix-2 step, spectrum, radix-2 step of the inverse -- which also
 // moves the pair for k1 = (j, j + 16) from slot16(j), where the forward dft16 left it, to slot j,
 // where the inverse dft16 wants it (the step rewrites every value anyway: the move is free)
@@ -299,7 +308,7 @@ FC_HD void p1_mid(int lane, Regs &v, const Quad *hs4) {
   cross_dif<+1>(w);
   v = w;
 }
-FC_HD void p2_pre(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<true, false>(v, lane_twiddles(tw, lane)); }
+template <bool FULL = false> FC_HD void p2_pre(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<true, false>(v, lane_twiddles<FULL>(tw, lane)); }
 FC_HD void p2_post(int lane, Regs &v, const cpair *tw) { cross_dit_tw<true>(v, tw + 4 * 32 + lane); }
 
 // P2: slots hold C_k2[l] for k2 = 2 j, 2 j + 1; leaves y[l + 32 m], y[l + 32 (m + 16)] in slot16(m)

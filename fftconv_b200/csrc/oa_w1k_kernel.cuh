@@ -19,7 +19,7 @@ namespace fc {
 namespace w1k {
 
 constexpr int kWarps = 16;
-constexpr int kTwCount = 20 * 32;
+constexpr int kTwCount = 35 * 32;
 // shared memory: spectrum (512 x 16 B), lane twiddles, one mbarrier per warp, then the warps' buffers
 constexpr size_t kSmemHs = 512 * sizeof(Quad);
 constexpr size_t kSmemTw = kTwCount * sizeof(cpair);
@@ -61,7 +61,7 @@ struct Carry { // packed into one register: the state lives across a whole itera
 };
 
 // SHARED_DFT: one copy of each direction's dft16 in a two-trip loop (see oa_w1k_core.cuh)
-template <int WARPS, bool SHARED_DFT>
+template <int WARPS, bool SHARED_DFT, bool FULL_TW = false>
 __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_constant__ W1kParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Quad *hs4 = reinterpret_cast<Quad *>(smem_raw);
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
       for (int trip = 0; trip < 2; ++trip) {
         dft16<-1>(v);
         if (trip == 0) {
-          p0_post(lane, v, tw);
+          p0_post<FULL_TW>(lane, v, tw);
           t1_write(lane, v, xb);
           __syncwarp();
           t1_read(lane, v, xb);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
             advance(q, segs);
             nxt = request(q);
           }
-          p2_pre(lane, v, tw);
+          p2_pre<FULL_TW>(lane, v, tw);
         } else {
           p2_post(lane, v, tw);
         }
