@@ -1,6 +1,8 @@
 """Randomized differential run of hilbert / envelope on a GPU box (not collected by pytest): any
 length up to 131072 (float32) / 65536 (float64), powers of two and not, decimation and log
-compression, host or device pointers; reference = scipy.signal.hilbert in float64.
+compression, host or device pointers; reference = scipy.signal.hilbert in float64.  Round 2: one case in
+seven is a batch of 64 .. 700 float32 lines of 8192 samples (the real-input engine, hilbert_r2c_*.cuh) and one
+in twenty a line of up to 2^20 samples (the general FFT path, fft_global.cuh).
 `SEED=3 FUZZ_SECONDS=50 python tests/fuzz_gpu_hilbert.py`.  Round 1: 3 478 cases, 0 failures."""
 import os, sys, json, time
 import numpy as np, torch
@@ -16,6 +18,11 @@ while time.time() - t0 < float(os.environ.get("FUZZ_SECONDS", "45")):
     nmax = 131072 if dt == np.float32 else 65536
     n = int(rng.choice([rng.integers(1, 64), rng.integers(64, 9000), 2 ** int(rng.integers(1, 17)), rng.integers(9000, nmax)]))
     batch = int(rng.integers(1, 8)) if n < 20000 else int(rng.integers(1, 3))
+    u = rng.random()
+    if u < 0.15:
+        dt, n, batch = np.float32, 8192, int(rng.integers(64, 700))
+    elif u < 0.20:
+        n, batch = int(rng.integers(nmax, 1 << 20)), 1
     dec = int(rng.choice([1, 1, 2, 3, 5, 16])); log = bool(rng.random() < 0.5)
     x = (rng.standard_normal((batch, n)) * np.exp(rng.uniform(-3, 1, (batch, 1)))).astype(dt)
     env = np.abs(signal.hilbert(x.astype(np.float64), axis=-1))[:, ::dec]
