@@ -21,13 +21,13 @@ void build_tables(void *host_buf) {
   fill_tables(tw1, tw2, mir);
 }
 
-template <int GROUPS, bool PLAIN>
+template <int GROUPS, int EPI>
 static int launch_variant(const HrParams &p, long long batch, int sms, void *stream) {
   static bool configured[64] = {false}; // per device: the opt-in to > 48 KB of dynamic shared memory
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
-  auto kern = hilbert_r2c_kernel<GROUPS, PLAIN>;
+  auto kern = hilbert_r2c_kernel<GROUPS, EPI>;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(GROUPS));
     if (e != cudaSuccess) return (int)e;
@@ -51,12 +51,17 @@ int launch(const float *in, float *out, long long batch, long long in_stride, lo
   p.mir = reinterpret_cast<const Pair *>(p.tw2 + kTw2Quads);
   // FFTCONV_CUDA_HR2C_GROUPS=3 / 5: lines in flight per SM (A/B measurements; 4 = 128 registers per thread)
   p.epi = EnvEpilogue<float>{epi.plain, epi.log, epi.dec, epi.magic, epi.a, epi.b};
-  if (!epi.plain) return launch_variant<kGroups, false>(p, batch, sms, stream);
+  if (!epi.plain && epi.dec % 4 == 0) { // only the first of a thread's four samples can survive
+    p.epi.dec = epi.dec / 4;
+    p.epi.magic = p.epi.dec > 1 ? (unsigned)(4294967296ULL / (unsigned)p.epi.dec) + 1u : 0u; // exact for j < 2048
+    return launch_variant<kGroups, 2>(p, batch, sms, stream);
+  }
+  if (!epi.plain) return launch_variant<kGroups, 1>(p, batch, sms, stream);
   const char *g = std::getenv("FFTCONV_CUDA_HR2C_GROUPS");
   const int groups = g ? std::atoi(g) : kGroups;
-  if (groups == 3) return launch_variant<3, true>(p, batch, sms, stream);
-  if (groups == 5) return launch_variant<5, true>(p, batch, sms, stream);
-  return launch_variant<kGroups, true>(p, batch, sms, stream);
+  if (groups == 3) return launch_variant<3, 0>(p, batch, sms, stream);
+  if (groups == 5) return launch_variant<5, 0>(p, batch, sms, stream);
+  return launch_variant<kGroups, 0>(p, batch, sms, stream);
 }
 
 } // namespace hr2c

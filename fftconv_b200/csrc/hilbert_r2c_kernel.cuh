@@ -77,7 +77,9 @@ __device__ __forceinline__ float sqrt_approx(float x) { // MUFU.SQRT
 // While the envelope is stored the registers of v free up, four slots per batch: the NEXT line's samples are
 // requested into them (nq, consumed by the next iteration's first pass), so that no load latency is exposed at
 // the top of the line loop.
-template <bool PLAIN>
+// EPI: 0 = plain envelope, 1 = decimation / log compression sample by sample, 2 = decimation by a multiple of
+// four: only the first sample of a thread's four can survive (epi.dec = decimation / 4, epi.magic for it)
+template <int EPI>
 __device__ __forceinline__ void envelope_store(int t, const Regs &v, const float *x, float *out,
                                                const EnvEpilogue<float> &epi, float4 (&nq)[16], const float *x_next) {
   const float4 *xn = reinterpret_cast<const float4 *>(x_next) + t;
@@ -99,12 +101,26 @@ __device__ __forceinline__ void envelope_store(int t, const Regs &v, const float
     for (int i = 0; i < B; ++i) {
       const int a = B * b + i, s = slot16(a);
       const float4 xv = q[b & 1][i];
+      if (EPI == 2) {
+        const unsigned j = (unsigned)(128 * a + t);
+        const unsigned qd = epi.dec > 1 ? __umulhi(j, epi.magic) : j;
+        if (qd * (unsigned)epi.dec == j) {
+          float y = sqrt_approx(fmaf(xv.x, xv.x, v.re[s].x * v.re[s].x));
+          if (epi.log) {
+            y = epi.a * env_log2(y) + epi.b; // env = 0 -> -inf -> 0
+            y = y < 0.0f ? 0.0f : (y > 1.0f ? 1.0f : y);
+            if (!(y == y)) y = 0.0f;
+          }
+          out[qd] = y;
+        }
+        continue;
+      }
       float4 e;
       e.x = sqrt_approx(fmaf(xv.x, xv.x, v.re[s].x * v.re[s].x));
       e.y = sqrt_approx(fmaf(xv.y, xv.y, v.im[s].x * v.im[s].x));
       e.z = sqrt_approx(fmaf(xv.z, xv.z, v.re[s].y * v.re[s].y));
       e.w = sqrt_approx(fmaf(xv.w, xv.w, v.im[s].y * v.im[s].y));
-      if (PLAIN) {
+      if (EPI == 0) {
         eo[128 * a] = e;
       } else { // decimation / log compression: sample by sample
         const long long i0 = 4LL * (128 * a + t);
@@ -139,7 +155,7 @@ __device__ __forceinline__ void prefetch_line_l2(const float *x) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "r"(kRow * 4) : "memory");
 }
 
-template <int GROUPS, bool PLAIN>
+template <int GROUPS, int EPI>
 __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const __grid_constant__ HrParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Quad *tw1 = reinterpret_cast<Quad *>(smem_raw);
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const 
       Regs v;
       inv_b_post(v, planes, m);
       dft16<+1>(v);
-      envelope_store<PLAIN>(t, v, x, p.out + line * p.out_stride, p.epi, nq, x_next ? x_next : x);
+      envelope_store<EPI>(t, v, x, p.out + line * p.out_stride, p.epi, nq, x_next ? x_next : x);
     }
   }
 }

@@ -643,7 +643,7 @@ def test_hilbert_r2c_engine_needs_aligned_rows(cuda):
     assert O.rel_l2(fc.hilbert(x[:5, :8192].copy()), O.hilbert_exact(x[:5, :8192])) < 1e-5   # small host batch
 
 
-@pytest.mark.parametrize("dec,log", [(4, True), (3, False), (1, True)])
+@pytest.mark.parametrize("dec,log", [(4, True), (8, False), (12, True), (3, False), (1, True)])
 def test_hilbert_r2c_engine_envelope_epilogue(cuda, dec, log, monkeypatch):
     """Decimation / log compression in the store of the real-input engine (fftconv_cuda_envelope_*,
     SURVEY.md 8f-3) on 8192-sample lines, against the oracle restatement and the register-blocked kernel;
