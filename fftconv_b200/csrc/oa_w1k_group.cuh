@@ -81,6 +81,51 @@ struct UnitDesc {
 
 FC_HD int align_shift4(const float *ptr) { return (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ULL); }
 
+// What the kernel needs to stage one block by a bulk copy and to store its outputs, worked out one unit ahead
+// (the kernel and tests/cpu/emulate_oa_w1k.cpp both use this).  Besides interior blocks this covers
+//   * a row's first block: copied from the row start, the lanes zero the K - 1 samples in front (head_zero);
+//   * a block that reaches past the row's end (every row's last block; on short rows -- 8192-sample A-lines --
+//     one block in eleven): the copy stops at the row's end (rounded up to 16 bytes: it may bring up to three
+//     floats of whatever follows the row) and the lanes zero the staging area from `zero_from` on AFTER the
+//     copy has landed.
+// Still staged by the lanes with plain loads (manual_fill): misaligned first blocks, copies that would leave the
+// tensor (the last row's end when it is not a multiple of 16 bytes), inactive items.
+struct ItemReq {
+  const float *src; // 16-byte aligned
+  int bytes;        // multiple of 16
+  int dst_first;    // staging index the copy starts at (multiple of 4)
+  int shift;        // sample r sits at staging index (r - block start) + shift
+  int head_zero;    // the lanes zero staging [0, head_zero) at request time
+  int zero_from;    // the lanes zero staging [zero_from, kN + 4) after the copy has landed (kN + 4: nothing)
+  bool in_ok, out_ok;
+};
+FC_HD ItemReq item_request(const W1kParams &p, int row, int seg, const float *tensor_end) {
+  ItemReq r;
+  const int tail = p.klen - 1;
+  const long long bs = (long long)seg * p.step - tail;
+  const int head = seg == 0 ? tail : 0; // a row's first block: K - 1 zeros in front
+  const float *first = p.in + (long long)row * p.in_stride + (bs + head);
+  const int ish = align_shift4(first);
+  r.shift = (ish - head) & 3;
+  r.dst_first = head + r.shift - ish;
+  r.src = first - ish;
+  const long long avail = p.n - (bs + head); // samples of the row from `first` on (>= 1 for every block)
+  const int want = kN - head;
+  const int nval = avail < want ? (int)avail : want;
+  r.bytes = ((ish + nval) * 4 + 15) & ~15;
+  r.head_zero = head > 0 ? r.dst_first : 0;
+  r.zero_from = nval < want ? head + r.shift + nval : kN + 4;
+  const bool active = row < p.batch;
+  r.in_ok = active && (head == 0 || ish == 0) && r.src + r.bytes / 4 <= tensor_end && r.src >= p.in;
+  const long long o0 = bs + tail - p.pad; // output index of the block's first kept sample
+  r.out_ok = active && (long long)(seg + 1) * p.step <= p.full_len && o0 >= 0 && o0 + p.step <= p.out_len;
+  return r;
+}
+// lanes: zeros behind a block that was clipped at its row's end (after the bulk copy has landed)
+FC_HD void zero_tail(int lane, int zero_from, float *plane) {
+  for (int i = zero_from + lane; i < kN + 4; i += 32) plane[i] = 0.0f;
+}
+
 FC_HD ItemDesc describe_item(const W1kParams &p, long long row, long long seg) {
   ItemDesc d;
   d.active = row < p.batch;
@@ -180,6 +225,37 @@ FC_HD void store_fast_to(int lane, const Regs &v, float *ya, float *yb, const St
     // m + 16 >= 16: lane + 512 >= K - 1 for every K this engine serves
     a[32 * (m + 16)] = v.re[s].y;
     b[32 * (m + 16)] = v.im[s].y;
+  }
+}
+// one item of a unit (IT = 0: real parts, 1: imaginary parts); y: where y[0] of the item goes
+template <int IT> FC_HD void store_item_fast(int lane, const Regs &v, float *y, const StoreMasks &k) {
+  float *a = y + lane;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int s = slot16(m);
+    if ((k.keep >> m) & 1u) a[32 * m] = IT ? v.im[s].x : v.re[s].x;
+    a[32 * (m + 16)] = IT ? v.im[s].y : v.re[s].y; // lane + 512 >= K - 1 for every K this engine serves
+  }
+}
+// predicated stores of one item given by its (row, block): row ends, Same-mode edges
+template <int IT> FC_HD void store_item_slow(int lane, const Regs &v, const W1kParams &p, long long row, long long seg) {
+  if (row >= p.batch) return;
+  float *row_out = p.out + row * p.out_stride;
+  const long long left = p.full_len - seg * p.step;
+  const int nout = (int)(left < p.step ? left : p.step);
+  const long long obase = seg * p.step - (p.klen - 1) - p.pad; // output index of y[0]
+  // y[i] is stored iff K - 1 <= i < K - 1 + nout and 0 <= obase + i < out_len: one 32-bit range [lo, hi)
+  long long lo = p.klen - 1, hi = p.klen - 1 + nout;
+  if (-obase > lo) lo = -obase;
+  if (p.out_len - obase < hi) hi = p.out_len - obase;
+  const int ilo = (int)lo, ihi = (int)(hi > lo ? hi : lo);
+  float *a = row_out + obase + lane;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int s = slot16(m);
+    const int i0 = lane + 32 * m, i1 = i0 + 512;
+    if (i0 >= ilo && i0 < ihi) a[32 * m] = IT ? v.im[s].x : v.re[s].x;
+    if (i1 >= ilo && i1 < ihi) a[32 * (m + 16)] = IT ? v.im[s].y : v.re[s].y;
   }
 }
 FC_HD void store_fast(int lane, const Regs &v, const UnitDesc &d, const W1kParams &p, const StoreMasks &k) {

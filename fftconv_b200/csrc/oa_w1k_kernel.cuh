@@ -53,11 +53,13 @@ __device__ __forceinline__ void advance(Pos &q, int segs) { // to the next unit:
 // What a unit needs when its inputs are read and its outputs stored; worked out one unit ahead, when
 // its input blocks are requested.
 struct Carry { // packed into one register: the state lives across a whole iteration
-  unsigned code;  // bit 0: bulk, bit 1: fast_out, bits 2-3: shift of item 0, bits 4-5: shift of item 1
+  // bit 0: bulk, bits 1-2: fast_out of item 0 / 1, bits 3-4 / 5-6: shifts, bits 7-17 / 18-28: zero_from of item 0 / 1
+  unsigned code;
   __device__ __forceinline__ bool bulk() const { return code & 1u; }
-  __device__ __forceinline__ bool fast_out() const { return code & 2u; }
-  __device__ __forceinline__ int sh_a() const { return (int)((code >> 2) & 3u); }
-  __device__ __forceinline__ int sh_b() const { return (int)((code >> 4) & 3u); }
+  __device__ __forceinline__ bool fast_out(int i) const { return (code >> (1 + i)) & 1u; }
+  __device__ __forceinline__ int sh_a() const { return (int)((code >> 3) & 3u); }
+  __device__ __forceinline__ int sh_b() const { return (int)((code >> 5) & 3u); }
+  __device__ __forceinline__ int zero_from(int i) const { return (int)((code >> (7 + 11 * i)) & 2047u); }
 };
 
 // SHARED_DFT: one copy of each direction's dft16 in a two-trip loop (see oa_w1k_core.cuh)
@@ -99,43 +101,26 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
     q.row[i] = (int)(it / p.segs);
     q.seg[i] = (int)(it - (long long)q.row[i] * p.segs);
   }
-  // Request the input blocks of the unit at `at` (the buffer must be idle) and work out what the unit
-  // will need later.  Interior blocks -- all but the first and the last one or two of a row -- take the
-  // short way; the others go through the general description (oa_w1k_group.cuh).
+  // Request the input blocks of the unit at `at` (the buffer must be idle) and work out what the unit will need
+  // later (oa_w1k_group.cuh: item_request).
   auto request = [&](const Pos &at) -> Carry {
     Carry c;
-    bool in_ok = true, out_ok = true;
-    const float *src[2];
-    int shift[2], dst_first[2], bytes[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const long long bs = (long long)at.seg[i] * step - tail;
-      const int head = at.seg[i] == 0 ? tail : 0; // a row's first block: K - 1 zeros in front
-      const float *first = p.in + (long long)at.row[i] * p.in_stride + (bs + head);
-      const int ish = align_shift4(first);
-      shift[i] = (ish - head) & 3;
-      dst_first[i] = head + shift[i] - ish;
-      src[i] = first - ish;
-      bytes[i] = ((ish + kN - head) * 4 + 15) & ~15;
-      const long long o0 = bs + tail - p.pad;
-      const bool active = at.row[i] < p.batch;
-      in_ok = in_ok && active && bs + kN <= p.n && (head == 0 || ish == 0) && src[i] + (kN + 4) <= tensor_end;
-      out_ok = out_ok && active && (long long)(at.seg[i] + 1) * step <= p.full_len && o0 >= 0 && o0 + step <= p.out_len;
-    }
-    // a unit with a block that reaches past its row's end (or other rarities) is staged by the lanes at
-    // the start of its iteration instead (manual_fill): nothing to request now
-    c.code = (in_ok ? 1u : 0u) | (out_ok ? 2u : 0u) | ((unsigned)shift[0] << 2) | ((unsigned)shift[1] << 4);
+    const ItemReq r0 = item_request(p, at.row[0], at.seg[0], tensor_end);
+    const ItemReq r1 = item_request(p, at.row[1], at.seg[1], tensor_end);
+    const bool in_ok = r0.in_ok && r1.in_ok;
+    // a unit with a block that cannot be copied in bulk (misaligned row starts, the tensor's end, the odd last
+    // item) is staged by the lanes at the start of its iteration instead (manual_fill): nothing to request now
+    c.code = (in_ok ? 1u : 0u) | (r0.out_ok ? 2u : 0u) | (r1.out_ok ? 4u : 0u) | ((unsigned)r0.shift << 3) |
+             ((unsigned)r1.shift << 5) | ((unsigned)r0.zero_from << 7) | ((unsigned)r1.zero_from << 18);
     if (in_ok) {
       if (lane == 0) {
         dev::fence_proxy_async(); // the buffer was last touched through the generic proxy
-        dev::mbar_expect_tx(mbar, (uint32_t)(bytes[0] + bytes[1]));
-        dev::bulk_load(dev::smem_u32(xb + dst_first[0]), src[0], (uint32_t)bytes[0], mbar);
-        dev::bulk_load(dev::smem_u32(xb + kPlane + dst_first[1]), src[1], (uint32_t)bytes[1], mbar);
+        dev::mbar_expect_tx(mbar, (uint32_t)(r0.bytes + r1.bytes));
+        dev::bulk_load(dev::smem_u32(xb + r0.dst_first), r0.src, (uint32_t)r0.bytes, mbar);
+        dev::bulk_load(dev::smem_u32(xb + kPlane + r1.dst_first), r1.src, (uint32_t)r1.bytes, mbar);
       }
-      if (at.seg[0] == 0)
-        for (int i = lane; i < dst_first[0]; i += 32) xb[i] = 0.0f;
-      if (at.seg[1] == 0)
-        for (int i = lane; i < dst_first[1]; i += 32) xb[kPlane + i] = 0.0f;
+      for (int i = lane; i < r0.head_zero; i += 32) xb[i] = 0.0f;
+      for (int i = lane; i < r1.head_zero; i += 32) xb[kPlane + i] = 0.0f;
     }
     return c;
   };
@@ -153,6 +138,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
       while (!dev::mbar_try_wait(mbar, phase)) {
       }
       phase ^= 1;
+      // blocks clipped at their row's end: zeros behind the copied samples
+      zero_tail(lane, cur.zero_from(0), xb);
+      zero_tail(lane, cur.zero_from(1), xb + kPlane);
     } else { // no data registers are live here: the out-of-line call costs no spills
       const UnitDesc d = describe_unit_cold(p, at.row[0], at.seg[0], at.row[1], at.seg[1]);
       manual_fill(lane, p, d.item[0], xb);
@@ -210,14 +198,15 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
       }
       phase2(lane, v, tw);
     }
-    if (cur.fast_out()) {
-      // where y[0] of each item goes: row's output + block start - pad
-      float *oa = p.out + (long long)at.row[0] * p.out_stride + ((long long)at.seg[0] * step - tail - p.pad);
-      float *ob = p.out + (long long)at.row[1] * p.out_stride + ((long long)at.seg[1] * step - tail - p.pad);
-      store_fast_to(lane, v, oa, ob, masks);
-    } else {
-      store_slow_at(lane, v, p, at.row[0], at.seg[0], at.row[1], at.seg[1]);
-    }
+    // where y[0] of each item goes: row's output + block start - pad
+    if (cur.fast_out(0))
+      store_item_fast<0>(lane, v, p.out + (long long)at.row[0] * p.out_stride + ((long long)at.seg[0] * step - tail - p.pad), masks);
+    else
+      store_item_slow<0>(lane, v, p, at.row[0], at.seg[0]);
+    if (cur.fast_out(1))
+      store_item_fast<1>(lane, v, p.out + (long long)at.row[1] * p.out_stride + ((long long)at.seg[1] * step - tail - p.pad), masks);
+    else
+      store_item_slow<1>(lane, v, p, at.row[1], at.seg[1]);
   }
 }
 #endif // __CUDACC__

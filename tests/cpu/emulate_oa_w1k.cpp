@@ -25,18 +25,31 @@ static void run_warp(const W1kParams &p, long long u0, long long u1, const cpair
     ++g_units;
     const UnitDesc d = describe_unit(p, u);
     for (auto &v : xb) v = NAN;                       // nothing left over may be consumed
-    if (d.bulk) {                                      // what lane 0 asks the TMA for + the lanes' zero fill
+    // the kernel's own request logic (item_request): bulk copies where it says so, lanes otherwise
+    const long long it0 = 2 * u, it1 = 2 * u + 1;
+    const int row0 = (int)(it0 / p.segs), seg0 = (int)(it0 - (long long)row0 * p.segs);
+    const int row1 = it1 < p.n_items ? (int)(it1 / p.segs) : (int)p.batch;
+    const int seg1 = it1 < p.n_items ? (int)(it1 - (long long)row1 * p.segs) : 0;
+    const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
+    const ItemReq rq[2] = {item_request(p, row0, seg0, tensor_end), item_request(p, row1, seg1, tensor_end)};
+    const bool bulk = rq[0].in_ok && rq[1].in_ok;
+    int shift[2] = {d.item[0].shift, d.item[1].shift};
+    if (bulk) {                                        // what lane 0 asks the TMA for + the lanes' fills
       ++g_bulk;
       for (int it = 0; it < 2; ++it) {
-        const ItemDesc &I = d.item[it];
-        if (I.bytes) std::memcpy(xb.data() + it * kPlane + I.dst_first, I.src, I.bytes);
-        for (int lane = 0; lane < 32; ++lane) zero_fill(lane, I, xb.data() + it * kPlane);
+        float *plane = xb.data() + it * kPlane;
+        if ((reinterpret_cast<unsigned long long>(rq[it].src) & 15ULL) || (rq[it].bytes & 15) || (rq[it].dst_first & 3) ||
+            rq[it].src < p.in || rq[it].src + rq[it].bytes / 4 > tensor_end) { std::printf("bad bulk request\n"); std::exit(1); }
+        for (int i = 0; i < rq[it].head_zero; ++i) plane[i] = 0.0f;          // at request time
+        std::memcpy(plane + rq[it].dst_first, rq[it].src, rq[it].bytes);   // the copy lands
+        for (int lane = 0; lane < 32; ++lane) zero_tail(lane, rq[it].zero_from, plane);
+        shift[it] = rq[it].shift;
       }
     } else {
       for (int it = 0; it < 2; ++it)
         for (int lane = 0; lane < 32; ++lane) manual_fill(lane, p, d.item[it], xb.data() + it * kPlane);
     }
-    for (int lane = 0; lane < 32; ++lane) load_inputs(lane, regs[lane], xb.data(), d.item[0].shift, d.item[1].shift);
+    for (int lane = 0; lane < 32; ++lane) load_inputs(lane, regs[lane], xb.data(), shift[0], shift[1]);
     for (auto &v : xb) v = NAN;
     // odd units run the phases as the kernel's two-trip loops cut them, even units the fused forms
     const bool split = (u & 1) != 0;
@@ -57,13 +70,13 @@ static void run_warp(const W1kParams &p, long long u0, long long u1, const cpair
       if (split) { p2_pre(lane, regs[lane], tw); dft16<+1>(regs[lane]); p2_post(lane, regs[lane], tw); }
       else phase2(lane, regs[lane], tw);
       const StoreMasks m = make_store_masks(lane, p);
-      if (d.fast_out) store_fast(lane, regs[lane], d, p, m);
-      else if (split) store_slow(lane, regs[lane], p, d);
-      else {
-        const long long it0 = 2 * u, it1 = 2 * u + 1;
-        const long long r0 = it0 / p.segs, r1 = it1 < p.n_items ? it1 / p.segs : p.batch;
-        store_slow_at(lane, regs[lane], p, r0, it0 - r0 * p.segs, r1, it1 < p.n_items ? it1 - r1 * p.segs : 0);
-      }
+      if (split) { // the kernel's per-item paths
+        if (rq[0].out_ok) store_item_fast<0>(lane, regs[lane], p.out + (long long)row0 * p.out_stride + ((long long)seg0 * p.step - (p.klen - 1) - p.pad), m);
+        else store_item_slow<0>(lane, regs[lane], p, row0, seg0);
+        if (rq[1].out_ok) store_item_fast<1>(lane, regs[lane], p.out + (long long)row1 * p.out_stride + ((long long)seg1 * p.step - (p.klen - 1) - p.pad), m);
+        else store_item_slow<1>(lane, regs[lane], p, row1, seg1);
+      } else if (d.fast_out) store_fast(lane, regs[lane], d, p, m);
+      else store_slow_at(lane, regs[lane], p, row0, seg0, row1, seg1);
     }
     g_fast_out += d.fast_out;
   }

@@ -142,6 +142,11 @@ EMU_W1K_CASES = [
     (6, 7000, 400, 0, 3),         # longest kernel served
     (3, 4096, 246, 0, 2),         # K - 1 not a multiple of 4: the staging shift differs between blocks
     (2, 20000, 129, 1, 64),       # more warps than units
+    (64, 8192, 245, 1, 9),        # short rows (A-lines): every row's last block is clipped, all staged in bulk
+    (33, 8192, 245, 0, 9),
+    (40, 2048, 65, 1, 5),
+    (9, 4099, 245, 0, 4),         # rows whose ends are not 16-byte aligned
+    (9, 4101, 245, 1, 4, 2),
 ]
 
 
