@@ -732,13 +732,31 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
         CU_TRY(cudaMalloc((void **)&c.tw_w1k, tw.size() * sizeof(fc::n2048::cpair)));
         CU_TRY(cudaMemcpy(c.tw_w1k, tw.data(), tw.size() * sizeof(fc::n2048::cpair), cudaMemcpyHostToDevice));
       }
+      // The spectrum: resident in a filter handle, else transformed by the kernel itself (one warp per CTA runs the
+      // forward half of a unit on the taps: no separate spectrum kernel, no launch gap).  FFTCONV_CUDA_W1K_SPECTRUM_KERNEL=1
+      // restores the separate kernel (double-precision DFT of the taps) for A/B measurements.
       const cx<float> *H = nullptr;
-      if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_W1K, *tab, &H)) return r;
+      const float *taps_dev = nullptr;
+      const bool handle = tl_filter && tl_filter->dtype == dtype_id<float>() && tl_filter->N == N &&
+                          tl_filter->layout == fc::generic::LAYOUT_W1K && tl_filter->klen == klen &&
+                          tl_filter->device == c.device && tl_filter->taps == (const void *)k;
+      if (handle || env_int("FFTCONV_CUDA_W1K_SPECTRUM_KERNEL", 0)) {
+        if (int r = prepare_spectrum<float>(c, st, k, klen, N, fc::generic::LAYOUT_W1K, *tab, &H)) return r;
+      } else {
+        taps_dev = k;
+        if (!is_device_ptr(k)) {
+          StreamWs &ws = c.ws[st];
+          if (int r = grow(&ws.taps, &ws.taps_bytes, klen * sizeof(float))) return r;
+          CU_TRY(cudaMemcpyAsync(ws.taps, k, klen * sizeof(float), cudaMemcpyHostToDevice, st));
+          taps_dev = static_cast<const float *>(ws.taps);
+        }
+      }
       fc::w1k::W1kParams p{};
       fc::w1k::fill_params(p, a, out, (long long)batch, (long long)n, (long long)a_stride, (long long)out_stride,
                            (long long)out_len, (int)klen, mode == FFTCONV_CUDA_SAME ? 1 : 0);
       p.tw = c.tw_w1k;
       p.hs = reinterpret_cast<const fc::n2048::cpair *>(H);
+      p.taps = taps_dev;
       if (fc::w1k::launch_smem_bytes() > c.smem_optin)
         return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "warp-per-FFT kernel: not enough shared memory per CTA on this device");
       const int sms_avail = std::max(1, c.sm_count - std::max(0, g_reserved_sms.load()));

@@ -35,7 +35,8 @@ struct W1kParams {
   long long n_items;   // batch * segs
   long long n_units;   // ceil(n_items / 2)
   const cpair *tw;     // kTwElems per-lane twiddles
-  const cpair *hs;     // 1024 spectrum entries (freq_of_index order), 1/N folded in
+  const cpair *hs;     // 1024 spectrum entries (freq_of_index order), 1/N folded in; or nullptr:
+  const float *taps;   // ... the kernel transforms the taps itself (klen device floats), see spectrum_by_warp
 };
 
 inline void fill_params(W1kParams &p, const float *in, float *out, long long batch, long long n, long long in_stride,
@@ -52,6 +53,7 @@ inline void fill_params(W1kParams &p, const float *in, float *out, long long bat
   p.n_units = (p.n_items + 1) / 2;
   p.tw = nullptr;
   p.hs = nullptr;
+  p.taps = nullptr;
 }
 
 FC_HD void warp_range(long long n_units, long long n_warps, long long w, long long &u0, long long &u1) {
@@ -301,6 +303,31 @@ FC_HD void store_slow(int lane, const Regs &v, const W1kParams &p, const UnitDes
       if (i0 >= lo && i0 < hi && o0 >= 0 && o0 < p.out_len) I.row_out[o0] = y0;
       if (i1 >= lo && i1 < hi && o1 >= 0 && o1 < p.out_len) I.row_out[o1] = y1;
     }
+  }
+}
+
+// ---- the kernel spectrum by the engine's own forward transform ----------------------------------------------
+// The reference transforms the (zero-padded) taps in every call (fftconv.hpp:391-392).  Here one warp of every
+// CTA does it with the forward half of a unit -- the taps as the real part of a block, P0, T1, P1's dft16 and
+// radix-2 step -- which leaves lane k2 with exactly the frequencies, in exactly the registers, in which
+// multiply_spectrum consumes them: hs4[j * 32 + k2] = (re lo, re hi, im lo, im hi) / N.  No separate spectrum
+// kernel, no launch gap in front of the segment kernel (measured: 11 us of a 90 us step at 512 rows per GPU).
+// stage: lanes fill the warp's buffer with the taps (plane 0) and zeros
+FC_HD void spectrum_stage(int lane, const float *taps, int klen, float *xb) {
+  for (int i = lane; i < kN + 4; i += 32) {
+    xb[i] = i < klen ? taps[i] : 0.0f;
+    xb[kPlane + i] = 0.0f;
+  }
+}
+// after load_inputs, phase0, t1_write / t1_read: finish the forward transform and emit the lane's 16 entries
+FC_HD void spectrum_finish(int lane, Regs &v, Quad *hs4) {
+  dft16<-1>(v);
+  cross_dit<-1>(v);
+  constexpr float inv_n = 1.0f / (float)kN;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int s = slot16(j);
+    hs4[j * 32 + lane] = Quad{v.re[s].x * inv_n, v.re[s].y * inv_n, v.im[s].x * inv_n, v.im[s].y * inv_n};
   }
 }
 

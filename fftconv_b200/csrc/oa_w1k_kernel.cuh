@@ -75,9 +75,11 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
   float *xb = xb_all + warp * kWarpFloats;
   const uint32_t mbar = dev::smem_u32(bars + warp);
 
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-    const cpair a = p.hs[2 * i], b = p.hs[2 * i + 1];
-    hs4[i] = Quad{a.re, b.re, a.im, b.im};
+  if (p.hs) { // a filter handle: the spectrum is resident
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+      const cpair a = p.hs[2 * i], b = p.hs[2 * i + 1];
+      hs4[i] = Quad{a.re, b.re, a.im, b.im};
+    }
   }
   for (int i = threadIdx.x; i < kTwCount; i += blockDim.x) tw[i] = p.tw[i];
   if (lane == 0) {
@@ -85,6 +87,21 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (!p.hs) { // transform the taps: the forward half of a unit, by one warp (oa_w1k_group.cuh: spectrum_*)
+    if (warp == 0) {
+      spectrum_stage(lane, p.taps, p.klen, xb);
+      __syncwarp();
+      Regs v;
+      load_inputs(lane, v, xb, 0, 0);
+      __syncwarp();
+      phase0(lane, v, tw);
+      t1_write(lane, v, xb);
+      __syncwarp();
+      t1_read(lane, v, xb);
+      spectrum_finish(lane, v, hs4);
+    }
+    __syncthreads();
+  }
 
   const long long n_warps = (long long)gridDim.x * WARPS;
   long long u0, u1;

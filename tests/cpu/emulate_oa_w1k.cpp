@@ -105,6 +105,23 @@ int main(int argc, char **argv) {
   fill_tw(tw.data());
   fill_hs_host(k.data(), K, hs.data());
   pack_hs(hs.data(), hs4.data());
+  { // the kernel's own spectrum (one warp transforms the taps) against the long-double DFT above; then use it
+    std::vector<float> xb(kWarpFloats + 8, NAN);
+    std::vector<Regs> regs(32);
+    std::vector<Quad> own(512);
+    for (int lane = 0; lane < 32; ++lane) spectrum_stage(lane, k.data(), K, xb.data());
+    for (int lane = 0; lane < 32; ++lane) load_inputs(lane, regs[lane], xb.data(), 0, 0);
+    for (int lane = 0; lane < 32; ++lane) { phase0(lane, regs[lane], tw.data()); t1_write(lane, regs[lane], xb.data()); }
+    for (int lane = 0; lane < 32; ++lane) { t1_read(lane, regs[lane], xb.data()); spectrum_finish(lane, regs[lane], own.data()); }
+    double num = 0, den = 0;
+    for (int q = 0; q < 512; ++q) {
+      const float a[4] = {own[q].a, own[q].b, own[q].c, own[q].d}, b[4] = {hs4[q].a, hs4[q].b, hs4[q].c, hs4[q].d};
+      for (int i = 0; i < 4; ++i) { num += ((double)a[i] - b[i]) * ((double)a[i] - b[i]); den += (double)b[i] * b[i]; }
+    }
+    const double serr = std::sqrt(num / (den > 0 ? den : 1));
+    if (!(serr < 1e-6)) { std::printf("spectrum by the engine: rel l2 %.3e\n", serr); return 1; }
+    hs4 = own;
+  }
   W1kParams p{};
   fill_params(p, a, out, batch, n, n, out_len, out_len, K, mode);
   for (long long w = 0; w < n_warps; ++w) {

@@ -577,6 +577,8 @@ def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch)
         y = fc.oaconvolve(ta, tk, mode)
         if klen <= (16 if dt == np.float32 else 8):
             assert fc.launch_count() - before == 1     # direct time-domain kernel
+        elif dt == np.float32 and klen <= 300:
+            assert fc.launch_count() - before == 1     # the warp-per-FFT kernel transforms the taps itself
         elif klen <= (1024 if dt == np.float32 else 640):
             assert fc.launch_count() - before == 2     # spectrum + the N = 2048 kernel (wide form beyond 410 taps)
         monkeypatch.setenv("FFTCONV_CUDA_STRICT_TABLE", "1")

@@ -448,7 +448,7 @@ def test_w1k_kernel_device_pointers(cuda, batch, n, klen, mode, monkeypatch):
     before = fc.launch_count()
     y = fc.oaconvolve(_t(a, cuda), _t(k, cuda), mode)
     torch.cuda.synchronize()
-    assert fc.launch_count() - before == 2
+    assert fc.launch_count() - before == 1            # one launch: the kernel transforms the taps itself
     got = y.cpu().numpy()
     assert np.all(np.isfinite(got))
     pick = sorted(set([0, batch // 2, batch - 1]))
@@ -511,6 +511,35 @@ def test_w1k_is_the_default_for_large_float32_jobs(cuda, monkeypatch):
     f = fc.Filter(k)
     assert O.rel_l2(f.oaconvolve(_t(a, cuda), "full")[:3].cpu().numpy(), want) < 1e-5
     f.close()
+
+
+@pytest.mark.parametrize("klen", [17, 65, 245, 300])
+def test_w1k_spectrum_in_kernel_matches_spectrum_kernel(cuda, klen, monkeypatch):
+    """The warp-per-FFT kernel transforms the taps itself (one warp per CTA, the forward half of a unit, float32);
+    FFTCONV_CUDA_W1K_SPECTRUM_KERNEL=1 restores the separate spectrum kernel (DFT in double).  Same answer
+    to rounding, one launch instead of two, taps as host or device pointer."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(klen)
+    a = rng.standard_normal((128, 40000)).astype(np.float32)       # > 4 Mi samples: the throughput rule applies
+    k = (rng.standard_normal(klen) * np.exp(rng.uniform(-3, 3, klen))).astype(np.float32)   # taps of very different size
+    ta, tk = _t(a, cuda), _t(k, cuda)
+    before = fc.launch_count()
+    y = fc.oaconvolve(ta, tk, "full")
+    torch.cuda.synchronize()
+    assert fc.launch_count() - before == 1
+    y_host_taps = fc.oaconvolve(ta, k, "full")          # taps from host memory, signal on the device
+    monkeypatch.setenv("FFTCONV_CUDA_W1K_SPECTRUM_KERNEL", "1")
+    before = fc.launch_count()
+    y2 = fc.oaconvolve(ta, tk, "full")
+    torch.cuda.synchronize()
+    assert fc.launch_count() - before == 2
+    want = O.conv_exact(a[:4], k, "full")
+    assert O.rel_l2(y[:4].cpu().numpy(), want) < 2e-6 and O.rel_l2(y2[:4].cpu().numpy(), want) < 2e-6
+    assert O.rel_l2(y.cpu().numpy(), y2.cpu().numpy()) < 1e-6
+    assert torch.equal(y, y_host_taps)
 
 
 # ---- SURVEY.md 8f-4: the general 1-D FFT surface and Hilbert envelopes of any length -------------------
