@@ -757,6 +757,7 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
       p.tw = c.tw_w1k;
       p.hs = reinterpret_cast<const fc::n2048::cpair *>(H);
       p.taps = taps_dev;
+      p.cta_major = env_int("FFTCONV_CUDA_W1K_CTA_MAJOR", 0);
       if (fc::w1k::launch_smem_bytes() > c.smem_optin)
         return fail(FFTCONV_CUDA_ERR_UNSUPPORTED, "warp-per-FFT kernel: not enough shared memory per CTA on this device");
       const int sms_avail = std::max(1, c.sm_count - std::max(0, g_reserved_sms.load()));

@@ -37,6 +37,7 @@ struct W1kParams {
   const cpair *tw;     // kTwElems per-lane twiddles
   const cpair *hs;     // 1024 spectrum entries (freq_of_index order), 1/N folded in; or nullptr:
   const float *taps;   // ... the kernel transforms the taps itself (klen device floats), see spectrum_by_warp
+  int cta_major;       // A/B switch: deal unit ranges CTA by CTA (the first version) instead of warp-major
 };
 
 inline void fill_params(W1kParams &p, const float *in, float *out, long long batch, long long n, long long in_stride,
@@ -54,6 +55,7 @@ inline void fill_params(W1kParams &p, const float *in, float *out, long long bat
   p.tw = nullptr;
   p.hs = nullptr;
   p.taps = nullptr;
+  p.cta_major = 0;
 }
 
 FC_HD void warp_range(long long n_units, long long n_warps, long long w, long long &u0, long long &u1) {

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
   }
   __syncthreads();
   if (!p.hs) { // transform the taps: the forward half of a unit, by one warp (oa_w1k_group.cuh: spectrum_*)
-    if (warp == 0) {
+    if (warp == WARPS - 1) {
       spectrum_stage(lane, p.taps, p.klen, xb);
       __syncwarp();
       Regs v;
@@ -105,7 +105,11 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
 
   const long long n_warps = (long long)gridDim.x * WARPS;
   long long u0, u1;
-  warp_range(p.n_units, n_warps, (long long)blockIdx.x * WARPS + warp, u0, u1);
+  // Ranges are dealt out warp-major (range index = warp * CTAs + CTA): the n_units mod n_warps ranges that are one
+  // unit longer then sit in the first warps of EVERY CTA instead of filling the first CTAs -- the warps of an SM
+  // share its pipes, so what counts is units per SM (512 rows: 148 on the busiest SM instead of 160) -- and the
+  // last warp, which transformed the taps, is the last to get a longer range.
+  warp_range(p.n_units, n_warps, p.cta_major ? (long long)blockIdx.x * WARPS + warp : (long long)warp * gridDim.x + blockIdx.x, u0, u1);
   if (u0 >= u1) return;
   const StoreMasks masks = make_store_masks(lane, p);
   const int segs = (int)p.segs, step = p.step, tail = p.klen - 1;
