@@ -87,7 +87,13 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (!p.hs) { // transform the taps: the forward half of a unit, by one warp (oa_w1k_group.cuh: spectrum_*)
+  // The spectrum is needed for the first time in the middle of a warp's first unit.  The last warp transforms the
+  // taps (oa_w1k_group.cuh: spectrum_*) and ARRIVES at a named barrier; the other warps start their first unit at
+  // once -- its bulk copies are in flight while the taps are transformed -- and wait at that barrier just before
+  // their first spectrum multiply (a warp without units only arrives).
+  constexpr int kSpectrumBarrier = 1;
+  bool wait_spectrum = false;
+  if (!p.hs) {
     if (warp == WARPS - 1) {
       spectrum_stage(lane, p.taps, p.klen, xb);
       __syncwarp();
@@ -99,10 +105,12 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
       __syncwarp();
       t1_read(lane, v, xb);
       spectrum_finish(lane, v, hs4);
+      __syncwarp(); // its own first request reuses the buffer
+      asm volatile("bar.arrive %0, %1;" ::"n"(kSpectrumBarrier), "n"(32 * WARPS) : "memory");
+    } else {
+      wait_spectrum = true;
     }
-    __syncthreads();
   }
-
   const long long n_warps = (long long)gridDim.x * WARPS;
   long long u0, u1;
   // Ranges are dealt out warp-major (range index = warp * CTAs + CTA): the n_units mod n_warps ranges that are one
@@ -110,7 +118,10 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
   // share its pipes, so what counts is units per SM (512 rows: 148 on the busiest SM instead of 160) -- and the
   // last warp, which transformed the taps, is the last to get a longer range.
   warp_range(p.n_units, n_warps, p.cta_major ? (long long)blockIdx.x * WARPS + warp : (long long)warp * gridDim.x + blockIdx.x, u0, u1);
-  if (u0 >= u1) return;
+  if (u0 >= u1) {
+    if (wait_spectrum) asm volatile("bar.arrive %0, %1;" ::"n"(kSpectrumBarrier), "n"(32 * WARPS) : "memory");
+    return;
+  }
   const StoreMasks masks = make_store_masks(lane, p);
   const int segs = (int)p.segs, step = p.step, tail = p.klen - 1;
   const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
@@ -147,7 +158,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
   };
 
   Carry nxt = request(q);
-  uint32_t phase = 0;
+  uint32_t phase = wait_spectrum ? 2u : 0u; // bit 0: the mbarrier's phase parity; bit 1: the spectrum barrier is still ahead
 
 #pragma unroll 1
   for (long long u = u0; u < u1; ++u) {
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
     Regs v;
     int sh_a = cur.sh_a(), sh_b = cur.sh_b();
     if (cur.bulk()) {
-      while (!dev::mbar_try_wait(mbar, phase)) {
+      while (!dev::mbar_try_wait(mbar, phase & 1u)) {
       }
       phase ^= 1;
       // blocks clipped at their row's end: zeros behind the copied samples
@@ -183,6 +194,10 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
           __syncwarp();
           t1_read(lane, v, xb);
         } else {
+          if (phase & 2u) { // first unit only
+            asm volatile("bar.sync %0, %1;" ::"n"(kSpectrumBarrier), "n"(32 * WARPS) : "memory");
+            phase &= 1u;
+          }
           p1_mid(lane, v, hs4);
         }
       }
@@ -208,6 +223,10 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
       t1_write(lane, v, xb);
       __syncwarp();
       t1_read(lane, v, xb);
+      if (phase & 2u) {
+        asm volatile("bar.sync %0, %1;" ::"n"(kSpectrumBarrier), "n"(32 * WARPS) : "memory");
+        phase &= 1u;
+      }
       phase1(lane, v, hs4);
       t2_write(lane, v, xb); // a lane's own row, which only it read in T1: no barrier needed before
       __syncwarp();
