@@ -702,3 +702,21 @@ def test_hilbert_r2c_engine_envelope_epilogue(cuda, dec, log, monkeypatch):
     old_chain = fc.rf_envelope(xt, torch.from_numpy(k).to(cuda), **kw).cpu().numpy()
     assert np.abs(got - old).max() < (2e-4 if log else 1e-5 * np.abs(old).max())
     assert np.abs(chain - old_chain).max() < (2e-4 if log else 1e-5 * np.abs(old_chain).max())
+
+
+@pytest.mark.parametrize("rows,n", [(100, 8192), (700, 8192), (64, 4096), (600, 2048), (8, 1000), (4, 32768), (3, 300001)])
+def test_hilbert_in_place(cuda, rows, n):
+    """The reference's hilbert(x, env) works with env aliasing x (it reads x[i] right before it writes env[i],
+    hilbert.hpp:57-63).  Every Hilbert kernel here must too: each reads a sample for the magnitude before the
+    envelope is stored over it, and nothing reads a line after its envelope has been stored."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(rows + n)
+    x = rng.standard_normal((rows, n)).astype(np.float32)
+    xt = torch.from_numpy(x).to(cuda)
+    fc.hilbert_(xt, xt)
+    torch.cuda.synchronize()
+    pick = sorted(set([0, 1, rows // 2, rows - 1]))
+    assert O.rel_l2(xt[pick].cpu().numpy(), O.hilbert_exact(x[pick])) < 1e-5
