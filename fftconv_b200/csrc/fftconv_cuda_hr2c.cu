@@ -21,13 +21,13 @@ void build_tables(void *host_buf) {
   fill_tables(tw1, tw2, mir);
 }
 
-template <int GROUPS, int EPI>
+template <int GROUPS, int EPI, int ENVB = 2>
 static int launch_variant(const HrParams &p, long long batch, int sms, void *stream) {
   static bool configured[64] = {false}; // per device: the opt-in to > 48 KB of dynamic shared memory
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
-  auto kern = hilbert_r2c_kernel<GROUPS, EPI>;
+  auto kern = hilbert_r2c_kernel<GROUPS, EPI, ENVB>;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(GROUPS));
     if (e != cudaSuccess) return (int)e;

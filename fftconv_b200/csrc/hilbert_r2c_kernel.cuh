@@ -79,7 +79,7 @@ __device__ __forceinline__ float sqrt_approx(float x) { // MUFU.SQRT
 // the top of the line loop.
 // EPI: 0 = plain envelope, 1 = decimation / log compression sample by sample, 2 = decimation by a multiple of
 // four: only the first sample of a thread's four can survive (epi.dec = decimation / 4, epi.magic for it)
-template <int EPI>
+template <int EPI, int ENVB = 2>
 __device__ __forceinline__ void envelope_store(int t, const Regs &v, const float *x, float *out,
                                                const EnvEpilogue<float> &epi, float4 (&nq)[16], const float *x_next) {
   const float4 *xn = reinterpret_cast<const float4 *>(x_next) + t;
@@ -87,7 +87,7 @@ __device__ __forceinline__ void envelope_store(int t, const Regs &v, const float
   float4 *eo = reinterpret_cast<float4 *>(out) + t;
   // batches of two slots: two batches of the second read in flight (16 registers), and the next line's
   // samples take over the registers of the slots just consumed
-  constexpr int B = 2;
+  constexpr int B = ENVB;
   float4 q[2][B];
 #pragma unroll
   for (int i = 0; i < B; ++i) q[0][i] = __ldg(xi + 128 * i);
@@ -155,7 +155,7 @@ __device__ __forceinline__ void prefetch_line_l2(const float *x) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "r"(kRow * 4) : "memory");
 }
 
-template <int GROUPS, int EPI>
+template <int GROUPS, int EPI, int ENVB = 2>
 __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const __grid_constant__ HrParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Quad *tw1 = reinterpret_cast<Quad *>(smem_raw);
@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const 
   // of two neighbouring points of ONE butterfly into a 64-bit load and then needs ~200 MOVs to pair each of them
   // with the other butterfly's point
   asm volatile("" : "+r"(m.base3a), "+r"(m.base3b));
+  // (measured with the second read of the line in batches of 1, 2 and 4 loads: no difference beyond the run-to-run
+  // drift of the clocks; 2 it is)
   const int bar = g + 1;
   const long long n_groups = (long long)gridDim.x * GROUPS;
 
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(GROUPS *kThreads, 1) hilbert_r2c_kernel(const 
       Regs v;
       inv_b_post(v, planes, m);
       dft16<+1>(v);
-      envelope_store<EPI>(t, v, x, p.out + line * p.out_stride, p.epi, nq, x_next ? x_next : x);
+      envelope_store<EPI, ENVB>(t, v, x, p.out + line * p.out_stride, p.epi, nq, x_next ? x_next : x);
     }
   }
 }
