@@ -9,10 +9,21 @@
 //   fftw::WisdomSetup           fftw.hpp:30-45  -> no-op: there is nothing to tune
 //   FFTW_ESTIMATE / MEASURE / PATIENT / EXHAUSTIVE: accepted as the PlannerFlag
 //   template argument of convolve_fftw / oaconvolve_fftw and ignored.
-// The c2c / r2r / many / guru wrappers of the reference are out of scope (SURVEY.md
-// section 2, row 2).
+// Round 2: fftw::Plan<T> is back for the 1-D transforms the
+// C ABI serves (fftconv_cuda_fft_*): dft_1d, dft_r2c_1d, dft_c2r_1d and their contiguous
+// batched ("many", rank 1, unit stride) forms, with execute() and the new-array execute
+// functions -- same names, argument order and conventions (unnormalised, FFTW_FORWARD = -1)
+// as the reference's wrapper (fftw.hpp:134-147, :158-160, :180-182, :197-199, :244-278,
+// :396-423).  A plan holds no tables: it records the shape and the pointers it was planned
+// with; the library caches twiddles per device.  Pointers may be host or device pointers.
+// 2-D / 3-D, r2r, strided "many" and guru plans stay out of scope.
 #pragma once
 
+#include "../fftconv_cuda.h"
+
+#include <cstddef>
+#include <stdexcept>
+#include <string>
 #include <type_traits>
 
 // planner flag values as published in the FFTW 3.3 manual
@@ -21,6 +32,10 @@
 #define FFTW_EXHAUSTIVE (1U << 3)
 #define FFTW_PATIENT (1U << 5)
 #define FFTW_ESTIMATE (1U << 6)
+#endif
+#ifndef FFTW_FORWARD
+#define FFTW_FORWARD (-1)
+#define FFTW_BACKWARD (+1)
 #endif
 
 namespace fftw {
@@ -37,6 +52,99 @@ struct WisdomSetup {
   explicit WisdomSetup(bool /*threadSafe*/) {}
   WisdomSetup(const WisdomSetup &) = delete;
   WisdomSetup &operator=(const WisdomSetup &) = delete;
+};
+
+// FFTW's complex type: T[2] = (re, im), fftw.hpp:50-75
+template <Floating T> using Complex = T[2];
+
+// fftw::Plan<T> (fftw.hpp:134-147): the 1-D kinds, contiguous batches
+template <Floating T> struct Plan {
+  enum class Kind { none, c2c, r2c, c2r };
+  Kind kind = Kind::none;
+  std::size_t n = 0, howmany = 1;
+  int sign = FFTW_FORWARD;
+  const void *in = nullptr;
+  void *out = nullptr;
+
+  Plan() = default;
+  Plan(const Plan &) = delete;
+  Plan(Plan &&) = default;
+  Plan &operator=(const Plan &) = delete;
+  Plan &operator=(Plan &&) = default;
+
+  // fftw.hpp:158-160, :180-182, :197-199 (flags are accepted and ignored: there is nothing to plan)
+  [[nodiscard]] static Plan dft_1d(int n, Complex<T> *in, Complex<T> *out, int sign, unsigned /*flags*/) {
+    return make(Kind::c2c, n, 1, in, out, sign);
+  }
+  [[nodiscard]] static Plan dft_r2c_1d(int n, T *in, Complex<T> *out, unsigned /*flags*/) {
+    return make(Kind::r2c, n, 1, in, out, FFTW_FORWARD);
+  }
+  [[nodiscard]] static Plan dft_c2r_1d(int n, Complex<T> *in, T *out, unsigned /*flags*/) {
+    return make(Kind::c2r, n, 1, in, out, FFTW_BACKWARD);
+  }
+  // fftw.hpp:244-278: rank 1, unit stride, rows back to back (idist / odist = the row length) -- the only
+  // "many" layout the batched kernels take; anything else throws
+  [[nodiscard]] static Plan many_dft(int rank, const int *n, int howmany, Complex<T> *in, const int *inembed,
+                                     int istride, int idist, Complex<T> *out, const int *onembed, int ostride,
+                                     int odist, int sign, unsigned /*flags*/) {
+    contiguous(rank, n, inembed, istride, idist, n[0], onembed, ostride, odist, n[0]);
+    return make(Kind::c2c, n[0], howmany, in, out, sign);
+  }
+  [[nodiscard]] static Plan many_dft_r2c(int rank, const int *n, int howmany, T *in, const int *inembed, int istride,
+                                         int idist, Complex<T> *out, const int *onembed, int ostride, int odist,
+                                         unsigned /*flags*/) {
+    contiguous(rank, n, inembed, istride, idist, n[0], onembed, ostride, odist, n[0] / 2 + 1);
+    return make(Kind::r2c, n[0], howmany, in, out, FFTW_FORWARD);
+  }
+  [[nodiscard]] static Plan many_dft_c2r(int rank, const int *n, int howmany, Complex<T> *in, const int *inembed,
+                                         int istride, int idist, T *out, const int *onembed, int ostride, int odist,
+                                         unsigned /*flags*/) {
+    contiguous(rank, n, inembed, istride, idist, n[0] / 2 + 1, onembed, ostride, odist, n[0]);
+    return make(Kind::c2r, n[0], howmany, in, out, FFTW_BACKWARD);
+  }
+
+  // fftw.hpp:396-423
+  void execute() const { run(in, out); }
+  void execute_dft(const Complex<T> *i, Complex<T> *o) const { expect(Kind::c2c); run(i, o); }
+  void execute_dft_r2c(const T *i, Complex<T> *o) const { expect(Kind::r2c); run(i, o); }
+  void execute_dft_c2r(const Complex<T> *i, T *o) const { expect(Kind::c2r); run(i, o); }
+
+private:
+  static Plan make(Kind k, int n, int howmany, const void *in, void *out, int sign) {
+    if (n <= 0 || howmany <= 0) throw std::invalid_argument("fftw::Plan: n and howmany must be positive");
+    Plan p;
+    p.kind = k;
+    p.n = (std::size_t)n;
+    p.howmany = (std::size_t)howmany;
+    p.sign = sign;
+    p.in = in;
+    p.out = out;
+    return p;
+  }
+  static void contiguous(int rank, const int *n, const int *inembed, int istride, int idist, int irow,
+                         const int *onembed, int ostride, int odist, int orow) {
+    if (rank != 1 || !n || istride != 1 || ostride != 1 || idist != irow || odist != orow ||
+        (inembed && inembed[0] != irow && inembed[0] != n[0]) || (onembed && onembed[0] != orow && onembed[0] != n[0]))
+      throw std::invalid_argument("fftw::Plan: only rank-1, unit-stride batches with rows back to back are supported");
+  }
+  void expect(Kind k) const {
+    if (kind != k) throw std::logic_error("fftw::Plan: executed with the arrays of another plan kind");
+  }
+  void run(const void *i, void *o) const {
+    int rc = FFTCONV_CUDA_ERR_ARG;
+    const T *ti = static_cast<const T *>(i);
+    T *to = static_cast<T *>(o);
+    if constexpr (std::is_same_v<T, float>) {
+      if (kind == Kind::c2c) rc = fftconv_cuda_fft_c2c_f32(ti, to, n, howmany, sign, nullptr);
+      if (kind == Kind::r2c) rc = fftconv_cuda_fft_r2c_f32(ti, to, n, howmany, nullptr);
+      if (kind == Kind::c2r) rc = fftconv_cuda_fft_c2r_f32(ti, to, n, howmany, nullptr);
+    } else {
+      if (kind == Kind::c2c) rc = fftconv_cuda_fft_c2c_f64(ti, to, n, howmany, sign, nullptr);
+      if (kind == Kind::r2c) rc = fftconv_cuda_fft_r2c_f64(ti, to, n, howmany, nullptr);
+      if (kind == Kind::c2r) rc = fftconv_cuda_fft_c2r_f64(ti, to, n, howmany, nullptr);
+    }
+    if (rc != 0) throw std::runtime_error(std::string("fftw::Plan: ") + fftconv_cuda_last_error());
+  }
 };
 
 } // namespace fftw

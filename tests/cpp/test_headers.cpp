@@ -73,8 +73,59 @@ template <class T, ConvMode Mode, class F> void test_oaconv(F f) {
   }
 }
 
+// fftw::Plan<T> (round 2): the reference's 1-D plan kinds over fftconv_cuda_fft_*
+template <typename T> void test_fftw_plans(double tol) {
+  using Cx = fftw::Complex<T>;
+  for (int n : {1, 2, 20, 64, 100, 243}) {
+    const int rows = 3;
+    auto re = randn<T>(n * rows, 7 * n), im = randn<T>(n * rows, 9 * n + 1);
+    std::vector<T> z(2 * n * rows), Z(2 * n * rows), back(2 * n * rows);
+    for (int i = 0; i < n * rows; ++i) { z[2 * i] = re[i]; z[2 * i + 1] = im[i]; }
+    auto fwd = fftw::Plan<T>::many_dft(1, &n, rows, reinterpret_cast<Cx *>(z.data()), nullptr, 1, n,
+                                       reinterpret_cast<Cx *>(Z.data()), nullptr, 1, n, FFTW_FORWARD, FFTW_ESTIMATE);
+    fwd.execute();
+    double worst = 0, scale = 0;
+    for (int r = 0; r < rows; ++r)
+      for (int k = 0; k < n; ++k) { // direct DFT in double
+        double sr = 0, si = 0;
+        for (int j = 0; j < n; ++j) {
+          const double a = -2.0 * M_PI * (double)((long long)j * k % n) / n, c = std::cos(a), s = std::sin(a);
+          sr += re[r * n + j] * c - im[r * n + j] * s;
+          si += re[r * n + j] * s + im[r * n + j] * c;
+        }
+        worst = std::max({worst, std::abs(sr - Z[2 * (r * n + k)]), std::abs(si - Z[2 * (r * n + k) + 1])});
+        scale = std::max({scale, std::abs(sr), std::abs(si)});
+      }
+    EXPECT(worst <= tol * std::max(scale, 1.0) * 8);
+    auto bwd = fftw::Plan<T>::dft_1d(n, reinterpret_cast<Cx *>(Z.data()), reinterpret_cast<Cx *>(back.data()), FFTW_BACKWARD,
+                                     FFTW_ESTIMATE);
+    bwd.execute(); // first row only; unnormalised: back = n z
+    for (int i = 0; i < 2 * n; ++i) EXPECT(std::abs(back[i] - n * z[i]) <= tol * n * 8 * std::max(scale, 1.0));
+    // r2c -> c2r round trip through the new-array execute functions
+    std::vector<T> half(2 * (n / 2 + 1)), rt(n);
+    auto r2c = fftw::Plan<T>::dft_r2c_1d(n, re.data(), reinterpret_cast<Cx *>(half.data()), FFTW_ESTIMATE);
+    auto c2r = fftw::Plan<T>::dft_c2r_1d(n, reinterpret_cast<Cx *>(half.data()), rt.data(), FFTW_ESTIMATE);
+    r2c.execute_dft_r2c(re.data() + n, reinterpret_cast<Cx *>(half.data())); // the second row, not the planned one
+    c2r.execute();
+    for (int i = 0; i < n; ++i) EXPECT(std::abs(rt[i] - n * re[n + i]) <= tol * n * 8 * std::max(scale, 1.0));
+    bool threw = false;
+    try { r2c.execute_dft(reinterpret_cast<Cx *>(z.data()), reinterpret_cast<Cx *>(Z.data())); } catch (const std::logic_error &) { threw = true; }
+    EXPECT(threw);
+  }
+  bool threw = false;
+  const int n = 16;
+  std::vector<T> a(64), b(64);
+  try {
+    (void)fftw::Plan<T>::many_dft(1, &n, 2, reinterpret_cast<Cx *>(a.data()), nullptr, 2, n, reinterpret_cast<Cx *>(b.data()),
+                                  nullptr, 1, n, FFTW_FORWARD, FFTW_ESTIMATE); // strided: not supported
+  } catch (const std::invalid_argument &) { threw = true; }
+  EXPECT(threw);
+}
+
 int main() {
   fftw::WisdomSetup wisdom(false);
+  test_fftw_plans<double>(1e-13);
+  test_fftw_plans<float>(1e-6);
   { // copy_to_padded_buffer
     const std::vector<int> src = {1, 2, 3};
     std::vector<int> dst(5, -1);
