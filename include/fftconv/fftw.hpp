@@ -22,9 +22,12 @@
 #include "../fftconv_cuda.h"
 
 #include <cstddef>
+#include <cstdlib>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 
 // planner flag values as published in the FFTW 3.3 manual
 #ifndef FFTW_ESTIMATE
@@ -145,6 +148,84 @@ private:
     }
     if (rc != 0) throw std::runtime_error(std::string("fftw::Plan: ") + fftconv_cuda_last_error());
   }
+};
+
+// ---- host buffers and the per-length engines built on Plan (fftw.hpp:77-104, :441-600) -----------------------
+// fftw_malloc's 64-byte aligned host arrays; the transforms copy them to the device and back
+// (fftconv_cuda_fft_* with host pointers), so code written against the reference's EngineDFT1D /
+// EngineR2C1D -- buffers `buf.in` / `buf.out`, forward(), backward(), the thread_local cache behind
+// get(n) -- runs unchanged.
+inline void *malloc(std::size_t bytes) {
+  void *p = std::aligned_alloc(64, (bytes + 63) / 64 * 64);
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+template <Floating T> T *alloc_real(std::size_t n) { return static_cast<T *>(fftw::malloc(n * sizeof(T))); }
+template <Floating T> Complex<T> *alloc_complex(std::size_t n) {
+  return static_cast<Complex<T> *>(fftw::malloc(n * sizeof(Complex<T>)));
+}
+template <Floating T> void free(void *p) { std::free(p); }
+
+template <typename T, bool InPlace = false> struct C2CBuffer {
+  using Cx = Complex<T>;
+  Cx *in, *out;
+  explicit C2CBuffer(std::size_t n) : in(alloc_complex<T>(n)), out(InPlace ? in : alloc_complex<T>(n)) {}
+  C2CBuffer(const C2CBuffer &) = delete;
+  C2CBuffer &operator=(const C2CBuffer &) = delete;
+  ~C2CBuffer() noexcept {
+    if (!InPlace) fftw::free<T>(out);
+    fftw::free<T>(in);
+  }
+};
+template <typename T> struct R2CBuffer {
+  using Cx = Complex<T>;
+  T *in;
+  Cx *out;
+  explicit R2CBuffer(std::size_t n) : in(alloc_real<T>(n)), out(alloc_complex<T>(n / 2 + 1)) {}
+  R2CBuffer(const R2CBuffer &) = delete;
+  R2CBuffer &operator=(const R2CBuffer &) = delete;
+  ~R2CBuffer() noexcept {
+    fftw::free<T>(in);
+    fftw::free<T>(out);
+  }
+};
+
+// one engine per transform length and thread, created on first use (fftw.hpp:443-461)
+template <typename Child> struct cache_mixin {
+  static Child &get(std::size_t n) {
+    thread_local std::unordered_map<std::size_t, std::unique_ptr<Child>> cache;
+    auto &slot = cache[n];
+    if (!slot) slot = std::make_unique<Child>(n);
+    return *slot;
+  }
+};
+
+template <Floating T, int PlannerFlag = FFTW_ESTIMATE, bool InPlace = false>
+struct EngineDFT1D : public cache_mixin<EngineDFT1D<T, PlannerFlag, InPlace>> {
+  using Cx = Complex<T>;
+  C2CBuffer<T, InPlace> buf;
+  Plan<T> plan_forward, plan_backward;
+  explicit EngineDFT1D(std::size_t n)
+      : buf(n), plan_forward(Plan<T>::dft_1d((int)n, buf.in, buf.out, FFTW_FORWARD, PlannerFlag)),
+        plan_backward(Plan<T>::dft_1d((int)n, buf.out, buf.in, FFTW_BACKWARD, PlannerFlag)) {}
+  void forward() { plan_forward.execute(); }
+  void forward(const Cx *in, Cx *out) const { plan_forward.execute_dft(in, out); }
+  void backward() { plan_backward.execute(); }
+  void backward(const Cx *in, Cx *out) const { plan_backward.execute_dft(in, out); }
+};
+
+template <Floating T, int PlannerFlag = FFTW_ESTIMATE>
+struct EngineR2C1D : public cache_mixin<EngineR2C1D<T, PlannerFlag>> {
+  using Cx = Complex<T>;
+  R2CBuffer<T> buf;
+  Plan<T> plan_forward, plan_backward;
+  explicit EngineR2C1D(std::size_t n)
+      : buf(n), plan_forward(Plan<T>::dft_r2c_1d((int)n, buf.in, buf.out, PlannerFlag)),
+        plan_backward(Plan<T>::dft_c2r_1d((int)n, buf.out, buf.in, PlannerFlag)) {}
+  void forward() { plan_forward.execute(); }
+  void forward(const T *in, Cx *out) const { plan_forward.execute_dft_r2c(in, out); }
+  void backward() { plan_backward.execute(); }
+  void backward(const Cx *in, T *out) const { plan_backward.execute_dft_c2r(in, out); }
 };
 
 } // namespace fftw

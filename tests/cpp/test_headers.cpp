@@ -12,6 +12,7 @@
 #include <fftconv/multi_gpu.hpp>
 
 #include <array>
+#include <cstdint>
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -111,6 +112,25 @@ template <typename T> void test_fftw_plans(double tol) {
     bool threw = false;
     try { r2c.execute_dft(reinterpret_cast<Cx *>(z.data()), reinterpret_cast<Cx *>(Z.data())); } catch (const std::logic_error &) { threw = true; }
     EXPECT(threw);
+  }
+  { // the engines of fftw.hpp:575-600 on their own aligned buffers: r2c, the reference's Hilbert multiplier, c2r
+    const std::size_t n = 10;
+    auto &eng = fftw::EngineR2C1D<T>::get(n);
+    EXPECT(&eng == &fftw::EngineR2C1D<T>::get(n));                       // cached per length and thread
+    EXPECT((reinterpret_cast<std::uintptr_t>(eng.buf.in) & 63) == 0);
+    const double x[10] = {-0.999984, -0.736924, 0.511211, -0.0826997, 0.0655345, -0.562082, -0.905911, 0.357729, 0.358593, 0.869386};
+    for (std::size_t i = 0; i < n; ++i) eng.buf.in[i] = (T)x[i];
+    eng.forward();
+    double dc = 0;
+    for (double v : x) dc += v;
+    EXPECT(std::abs(eng.buf.out[0][0] - dc) < 1e-5 && std::abs(eng.buf.out[0][1]) < 1e-5);
+    eng.backward();
+    for (std::size_t i = 0; i < n; ++i) EXPECT(std::abs(eng.buf.in[i] - n * x[i]) < 1e-4);
+    auto &c2c = fftw::EngineDFT1D<T>::get(8);
+    for (int i = 0; i < 8; ++i) { c2c.buf.in[i][0] = (T)(i == 1); c2c.buf.in[i][1] = 0; }
+    c2c.forward(); // a shifted impulse: exp(-2 pi j k / 8)
+    for (int k = 0; k < 8; ++k)
+      EXPECT(std::abs(c2c.buf.out[k][0] - std::cos(2 * M_PI * k / 8)) < 1e-6 && std::abs(c2c.buf.out[k][1] + std::sin(2 * M_PI * k / 8)) < 1e-6);
   }
   bool threw = false;
   const int n = 16;
