@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfftconv_cuda.so")
+# FFTCONV_B200_LIB: another build of the same library (A/B measurements of two builds on one box)
+LIB_PATH = os.environ.get("FFTCONV_B200_LIB") or os.path.join(_HERE, "lib", "libfftconv_cuda.so")
 
 FULL, SAME = 0, 1
 

@@ -41,6 +41,8 @@
 
 #include "oa_n2048_core.cuh"
 
+#include <cmath>
+
 namespace fc {
 namespace w1k {
 
@@ -137,8 +139,8 @@ template <bool CONJ, int J = 0> FC_HD void cross_dit_tw(Regs &v, const cpair *ct
     const cpair w = ct[J * 32];
     const float wi = CONJ ? -w.im : w.im;
     const float orr = v.re[s].y, oi = v.im[s].y;
-    const float tr = orr * w.re - oi * wi, ti = orr * wi + oi * w.re;
     const float er = v.re[s].x, ei = v.im[s].x;
+    const float tr = orr * w.re - oi * wi, ti = orr * wi + oi * w.re;
     v.re[s].x = er + tr; v.im[s].x = ei + ti;
     v.re[s].y = er - tr; v.im[s].y = ei - ti;
     cross_dit_tw<CONJ, J + 1>(v, ct);
@@ -245,21 +247,59 @@ FC_HD void t2_read(int lane, Regs &v, const float *xb) {
 }
 
 // ---- spectrum ------------------------------------------------------------------------------------
-// hs4[j * 32 + k2] = (Re H[k_lo], Re H[k_hi], Im H[k_lo], Im H[k_hi]) / N with k_lo = 32 j + k2,
-// k_hi = 32 (j + 16) + k2: the frequencies lane k2 holds in slot16(j) after P1's radix-2 step.
-// The spectrum kernel writes complex entries; entry index e = 2 (j * 32 + k2) + half:
+// Lane k2 holds, after P1's forward dft16, the pair (E[j], O[j]) in slot16(j): the j-th outputs of the DFT16s of
+// its even / odd inputs.  The reference's three steps -- last radix-2 step of the forward transform, multiply by
+// the spectrum, first radix-2 step of the inverse (fftconv.hpp:398-400: forward, multiply_cx, backward) --
+//   X_lo = E + w O, X_hi = E - w O            (w = exp(-2 pi i j / 32); frequencies k_lo = 32 j + k2, k_hi = k_lo + 512)
+//   Y_lo = X_lo H_lo, Y_hi = X_hi H_hi
+//   s = Y_lo + Y_hi,  d = (Y_lo - Y_hi) conj(w)
+// collapse into one 2 x 2 complex matrix per (j, k2), because w conj(w) = 1:
+//   s = E A + O B,   d = E C + O A,      A = H_lo + H_hi,  B = w (H_lo - H_hi),  C = conj(w) (H_lo - H_hi)
+// 16 fused multiply-adds per pair instead of 8 + 8 (two packed complex products) + 8.  Shared-memory form:
+// ab[j * 32 + k2] = (A.re, A.im, B.re, B.im), c()[j * 32 + k2] = C; 1 / N is folded in.  (Measured against
+// tabulating only A and C and forming B = w^2 C with four more instructions per pair -- a third less table
+// traffic -- : this form is 0.8 % faster, profiles/r02_w1k_session4_ab.jsonl.)
+// A spectrum given as complex entries (filter handles, tests) is indexed by e = 2 (j * 32 + k2) + half:
 FC_HD constexpr unsigned freq_of_index(unsigned e) {
   return 32u * ((e >> 6) + 16u * (e & 1u)) + ((e >> 1) & 31u);
 }
-FC_HD void multiply_spectrum(int lane, Regs &v, const Quad *hs4) {
+struct SpectrumTables { // one pointer: 512 entries ab, then 512 entries c
+  Quad *ab;
+  FC_HD cpair *c() const { return reinterpret_cast<cpair *>(ab + 512); }
+};
+// w = exp(-2 pi i j / 32): entry (4 + j) * 32 of the lane-twiddle table (oa_w1k_tables.h: fill_tw, lane 0)
+FC_HD void fold_spectrum_entry(cpair w, cpair h_lo, cpair h_hi, Quad &ab, cpair &c) {
+  const float wr = w.re, wi = w.im;
+  const float ar = h_lo.re + h_hi.re, ai = h_lo.im + h_hi.im;
+  const float dr = h_lo.re - h_hi.re, di = h_lo.im - h_hi.im;
+  ab = Quad{ar, ai, dr * wr - di * wi, dr * wi + di * wr};
+  c = cpair{dr * wr + di * wi, di * wr - dr * wi};
+}
+// one pair: (E, O) in -> (s, d) out
+FC_HD void spectrum_pair(int lane, int j, f2 inr, f2 ini, f2 &outr, f2 &outi, const SpectrumTables &h) {
+  const Quad ab = h.ab[j * 32 + lane];
+  const cpair c = h.c()[j * 32 + lane];
+  const float er = inr.x, ei = ini.x, orr = inr.y, oi = ini.y;
+  const float sr = fmaf(-oi, ab.d, fmaf(orr, ab.c, fmaf(-ei, ab.b, er * ab.a)));
+  const float si = fmaf(oi, ab.c, fmaf(orr, ab.d, fmaf(ei, ab.a, er * ab.b)));
+  const float dr = fmaf(-oi, ab.b, fmaf(orr, ab.a, fmaf(-ei, c.im, er * c.re)));
+  const float di = fmaf(oi, ab.a, fmaf(orr, ab.b, fmaf(ei, c.re, er * c.im)));
+  outr = make_f2(sr, dr);
+  outi = make_f2(si, di);
+}
+// v: (E, O) in slot16(j)  ->  (s, d) in slot j, where the inverse dft16 wants them.  slot16 is an involution
+// (a 4 x 4 transpose of the slot index), so the move happens in place: j and slot16(j) trade places.
+FC_HD void multiply_spectrum_fused(int lane, Regs &v, const SpectrumTables &h) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const int s = slot16(j);
-    const Quad h = hs4[j * 32 + lane];
-    const f2 hr = make_f2(h.a, h.b), hi = make_f2(h.c, h.d);
-    const f2 yr = v.re[s], yi = v.im[s];
-    v.re[s] = fnma2(yi, hi, mul2(yr, hr)); // yr hr - yi hi
-    v.im[s] = fma2(yi, hr, mul2(yr, hi));  // yr hi + yi hr
+    const int t = slot16(j);
+    if (t == j) {
+      spectrum_pair(lane, j, v.re[j], v.im[j], v.re[j], v.im[j], h);
+    } else if (j < t) {
+      const f2 ar = v.re[t], ai = v.im[t], br = v.re[j], bi = v.im[j]; // inputs of outputs j and t
+      spectrum_pair(lane, j, ar, ai, v.re[j], v.im[j], h);
+      spectrum_pair(lane, t, br, bi, v.re[t], v.im[t], h);
+    }
   }
 }
 
@@ -271,20 +311,10 @@ FC_HD void phase0(int lane, Regs &v, const cpair *tw) {
   apply_pair_twiddles<false, true>(v, lane_twiddles(tw, lane));
 }
 // P1: slots hold B_l[k2] for l = 2 i, 2 i + 1; leaves C_k2[l], l = 2 i + h, in slot16(i)
-FC_HD void phase1(int lane, Regs &v, const Quad *hs4) {
+FC_HD void phase1(int lane, Regs &v, const SpectrumTables &h) {
   dft16<-1>(v);
-  cross_dit<-1>(v);
-  multiply_spectrum(lane, v, hs4);
-  // inverse, decimation in frequency: the pair for k1 = (j, j + 16) sits in slot16(j); dft16 wants it in slot j
-  Regs w;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    w.re[j] = v.re[slot16(j)];
-    w.im[j] = v.im[slot16(j)];
-  }
-  cross_dif<+1>(w);
-  dft16<+1>(w);
-  v = w;
+  multiply_spectrum_fused(lane, v, h);
+  dft16<+1>(v);
 }
 // The same phases cut at the two dft16 calls of each direction, so that a kernel can run ONE copy of
 // the forward and ONE copy of the inverse dft16 in two-trip loops (the unrolled code of four copies
@@ -293,21 +323,8 @@ FC_HD void phase1(int lane, Regs &v, const Quad *hs4) {
 //   phase2 = p2_pre, dft16<+1>, p2_post
 FC_HD void p0_pre(int lane, Regs &v, const cpair *tw) { cross_dif_tw<false>(v, tw + 4 * 32 + lane); }
 template <bool FULL = false> FC_HD void p0_post(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<false, true>(v, lane_twiddles<FULL>(tw, lane)); }
-// between P1's two transforms: radix-2 step, spectrum, radix-2 step of the inverse -- which also
-// moves the pair for k1 = (j, j + 16) from slot16(j), where the forward dft16 left it, to slot j,
-// where the inverse dft16 wants it (the step rewrites every value anyway: the move is free)
-FC_HD void p1_mid(int lane, Regs &v, const Quad *hs4) {
-  cross_dit<-1>(v);
-  multiply_spectrum(lane, v, hs4);
-  Regs w;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    w.re[j] = v.re[slot16(j)];
-    w.im[j] = v.im[slot16(j)];
-  }
-  cross_dif<+1>(w);
-  v = w;
-}
+// between P1's two transforms: radix-2 step, spectrum, radix-2 step of the inverse in one (multiply_spectrum_fused)
+FC_HD void p1_mid(int lane, Regs &v, const SpectrumTables &h) { multiply_spectrum_fused(lane, v, h); }
 template <bool FULL = false> FC_HD void p2_pre(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<true, false>(v, lane_twiddles<FULL>(tw, lane)); }
 FC_HD void p2_post(int lane, Regs &v, const cpair *tw) { cross_dit_tw<true>(v, tw + 4 * 32 + lane); }
 

@@ -125,6 +125,18 @@ FC_HD ItemReq item_request(const W1kParams &p, int row, int seg, const float *te
   r.out_ok = active && (long long)(seg + 1) * p.step <= p.full_len && o0 >= 0 && o0 + p.step <= p.out_len;
   return r;
 }
+// Blocks 1 <= seg <= interior_seg_hi(p) of any row are INTERIOR: item_request gives them in_ok, out_ok, head_zero = 0,
+// zero_from = kN + 4, shift = the source's misalignment, dst_first = 0, bytes = 4 kN (+ 16 when misaligned).  Why:
+// the block reads row samples [bs, bs + kN) with bs = seg step - (K - 1) >= step - (K - 1) > 0 and
+// bs + kN + 3 <= n, so the copy -- rounded out to 16-byte boundaries, at most 3 floats either side -- stays inside
+// the row; its outputs are [seg step, (seg + 1) step) with (seg + 1) step = bs + kN <= n - 3 <= out_len + pad - 3.
+// (tests/cpu/emulate_oa_w1k.cpp checks the claim against item_request for every block of every case.)
+FC_HD int interior_seg_hi(const W1kParams &p) {
+  const long long hi = (p.n + (p.klen - 1) - kN - 3) / p.step; // floor for non-negative numerators; negative: none
+  if (p.n + (p.klen - 1) - kN - 3 < 0) return 0;
+  return (int)(hi < 0x7fffffff ? hi : 0x7fffffff);
+}
+
 // lanes: zeros behind a block that was clipped at its row's end (after the bulk copy has landed)
 FC_HD void zero_tail(int lane, int zero_from, float *plane) {
   for (int i = zero_from + lane; i < kN + 4; i += 32) plane[i] = 0.0f;
@@ -312,7 +324,7 @@ FC_HD void store_slow(int lane, const Regs &v, const W1kParams &p, const UnitDes
 // The reference transforms the (zero-padded) taps in every call (fftconv.hpp:391-392).  Here one warp of every
 // CTA does it with the forward half of a unit -- the taps as the real part of a block, P0, T1, P1's dft16 and
 // radix-2 step -- which leaves lane k2 with exactly the frequencies, in exactly the registers, in which
-// multiply_spectrum consumes them: hs4[j * 32 + k2] = (re lo, re hi, im lo, im hi) / N.  No separate spectrum
+// multiply_spectrum_fused consumes them (its tables follow from E and O directly).  No separate spectrum
 // kernel, no launch gap in front of the segment kernel (measured: 11 us of a 90 us step at 512 rows per GPU).
 // stage: lanes fill the warp's buffer with the taps (plane 0) and zeros
 FC_HD void spectrum_stage(int lane, const float *taps, int klen, float *xb) {
@@ -321,16 +333,25 @@ FC_HD void spectrum_stage(int lane, const float *taps, int klen, float *xb) {
     xb[kPlane + i] = 0.0f;
   }
 }
-// after load_inputs, phase0, t1_write / t1_read: finish the forward transform and emit the lane's 16 entries
-FC_HD void spectrum_finish(int lane, Regs &v, Quad *hs4) {
-  dft16<-1>(v);
-  cross_dit<-1>(v);
-  constexpr float inv_n = 1.0f / (float)kN;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int s = slot16(j);
-    hs4[j * 32 + lane] = Quad{v.re[s].x * inv_n, v.re[s].y * inv_n, v.im[s].x * inv_n, v.im[s].y * inv_n};
+// after load_inputs, phase0, t1_write / t1_read: the forward dft16 leaves (E[j], O[j]) of the taps' transform in
+// slot16(j), and the folded tables of multiply_spectrum_fused follow without the radix-2 step: with
+// H_lo, H_hi = (E +- w O) / N:  A = 2 E / N,  C = conj(w) (H_lo - H_hi) = 2 O / N,  B = w^2 C,  w^2 = exp(-2 pi i j / 16).
+template <int J = 0> FC_HD void spectrum_emit(int lane, const Regs &v, const SpectrumTables &h) {
+  if constexpr (J < 16) {
+    constexpr int s = slot16(J);
+    constexpr float sc = 2.0f / (float)kN;
+    const float ar = v.re[s].x * sc, ai = v.im[s].x * sc, cr = v.re[s].y * sc, ci = v.im[s].y * sc;
+    float br = cr, bi = ci;
+    rot32<-1, (2 * J) & 15>(br, bi);
+    if (J >= 8) { br = -br; bi = -bi; }
+    h.ab[J * 32 + lane] = Quad{ar, ai, br, bi};
+    h.c()[J * 32 + lane] = cpair{cr, ci};
+    spectrum_emit<J + 1>(lane, v, h);
   }
+}
+FC_HD void spectrum_finish(int lane, Regs &v, const SpectrumTables &h) {
+  dft16<-1>(v);
+  spectrum_emit(lane, v, h);
 }
 
 } // namespace w1k

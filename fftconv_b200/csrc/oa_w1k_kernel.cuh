@@ -20,8 +20,8 @@ namespace w1k {
 
 constexpr int kWarps = 16;
 constexpr int kTwCount = 35 * 32;
-// shared memory: spectrum (512 x 16 B), lane twiddles, one mbarrier per warp, then the warps' buffers
-constexpr size_t kSmemHs = 512 * sizeof(Quad);
+// shared memory: spectrum (512 x 24 B), lane twiddles, one mbarrier per warp, then the warps' buffers
+constexpr size_t kSmemHs = 512 * (sizeof(Quad) + sizeof(cpair)); // folded spectrum tables (oa_w1k_core.cuh)
 constexpr size_t kSmemTw = kTwCount * sizeof(cpair);
 constexpr size_t kSmemBar = 256; // up to 32 mbarriers
 constexpr size_t smem_bytes(int warps = kWarps) {
@@ -66,7 +66,7 @@ struct Carry { // packed into one register: the state lives across a whole itera
 template <int WARPS, bool SHARED_DFT, bool FULL_TW = false>
 __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_constant__ W1kParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Quad *hs4 = reinterpret_cast<Quad *>(smem_raw);
+  const SpectrumTables hs4{reinterpret_cast<Quad *>(smem_raw)};
   cpair *tw = reinterpret_cast<cpair *>(smem_raw + kSmemHs);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + kSmemHs + kSmemTw);
   float *xb_all = reinterpret_cast<float *>(smem_raw + kSmemHs + kSmemTw + kSmemBar);
@@ -77,8 +77,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
 
   if (p.hs) { // a filter handle: the spectrum is resident
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-      const cpair a = p.hs[2 * i], b = p.hs[2 * i + 1];
-      hs4[i] = Quad{a.re, b.re, a.im, b.im};
+      fold_spectrum_entry(p.tw[(4 + (i >> 5)) * 32], p.hs[2 * i], p.hs[2 * i + 1], hs4.ab[i], hs4.c()[i]);
     }
   }
   for (int i = threadIdx.x; i < kTwCount; i += blockDim.x) tw[i] = p.tw[i];
@@ -135,8 +134,28 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
   }
   // Request the input blocks of the unit at `at` (the buffer must be idle) and work out what the unit will need
   // later (oa_w1k_group.cuh: item_request).
+  // Interior blocks -- not a row's first, and ending at least three samples before the row's end, so that the
+  // 16-byte rounding of the copy stays inside the row -- need none of item_request's case analysis: the copy is
+  // kN samples (+ 16 bytes when the block start is not 16-byte aligned), nothing is zeroed, all `step` outputs lie
+  // inside the row (oa_w1k_group.cuh: interior_seg_hi has the argument).  83 of config 2's 85 blocks per row.
+  const int seg_hi = interior_seg_hi(p);
+  const int batch_i = (int)p.batch;
   auto request = [&](const Pos &at) -> Carry {
     Carry c;
+    if (at.seg[0] >= 1 && at.seg[0] <= seg_hi && at.seg[1] >= 1 && at.seg[1] <= seg_hi && at.row[1] < batch_i) {
+      const float *f0 = p.in + ((long long)at.row[0] * p.in_stride + ((long long)at.seg[0] * step - tail));
+      const float *f1 = p.in + ((long long)at.row[1] * p.in_stride + ((long long)at.seg[1] * step - tail));
+      const unsigned i0 = (unsigned)align_shift4(f0), i1 = (unsigned)align_shift4(f1);
+      c.code = 7u | (i0 << 3) | (i1 << 5) | ((unsigned)(kN + 4) << 7) | ((unsigned)(kN + 4) << 18);
+      if (lane == 0) {
+        const uint32_t b0 = 4u * kN + (i0 ? 16u : 0u), b1 = 4u * kN + (i1 ? 16u : 0u);
+        dev::fence_proxy_async(); // the buffer was last touched through the generic proxy
+        dev::mbar_expect_tx(mbar, b0 + b1);
+        dev::bulk_load(dev::smem_u32(xb), f0 - i0, b0, mbar);
+        dev::bulk_load(dev::smem_u32(xb + kPlane), f1 - i1, b1, mbar);
+      }
+      return c;
+    }
     const ItemReq r0 = item_request(p, at.row[0], at.seg[0], tensor_end);
     const ItemReq r1 = item_request(p, at.row[1], at.seg[1], tensor_end);
     const bool in_ok = r0.in_ok && r1.in_ok;

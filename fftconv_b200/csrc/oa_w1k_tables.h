@@ -35,9 +35,10 @@ inline void fill_hs_host(const float *taps, int klen, cpair *hs) {
     hs[e].im = (float)(im / 1024.0L);
   }
 }
-// the kernel's shared-memory form: (re lo, re hi, im lo, im hi) per pair
-inline void pack_hs(const cpair *hs, Quad *hs4) {
-  for (int q = 0; q < 512; ++q) hs4[q] = Quad{hs[2 * q].re, hs[2 * q + 1].re, hs[2 * q].im, hs[2 * q + 1].im};
+// the kernel's shared-memory form: the folded tables of multiply_spectrum_fused
+inline void pack_hs(const cpair *hs, Quad *ab, cpair *c) {
+  for (int q = 0; q < 512; ++q)
+    fold_spectrum_entry(n2048::unit_root<float>(32 * (q >> 5), 1024), hs[2 * q], hs[2 * q + 1], ab[q], c[q]);
 }
 
 } // namespace w1k

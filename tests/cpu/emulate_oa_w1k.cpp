@@ -16,9 +16,9 @@
 using namespace fc;
 using namespace fc::w1k;
 
-static long long g_units = 0, g_bulk = 0, g_fast_out = 0;
+static long long g_units = 0, g_bulk = 0, g_fast_out = 0, g_interior = 0;
 
-static void run_warp(const W1kParams &p, long long u0, long long u1, const cpair *tw, const Quad *hs4) {
+static void run_warp(const W1kParams &p, long long u0, long long u1, const cpair *tw, const SpectrumTables &hs4) {
   std::vector<float> xb(kWarpFloats + 8);
   std::vector<Regs> regs(32);
   for (long long u = u0; u < u1; ++u) {
@@ -33,6 +33,18 @@ static void run_warp(const W1kParams &p, long long u0, long long u1, const cpair
     const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
     const ItemReq rq[2] = {item_request(p, row0, seg0, tensor_end), item_request(p, row1, seg1, tensor_end)};
     const bool bulk = rq[0].in_ok && rq[1].in_ok;
+    { // the kernel's shortcut for interior blocks (interior_seg_hi) must agree with item_request
+      const int hi = interior_seg_hi(p), rows[2] = {row0, row1}, segs2[2] = {seg0, seg1};
+      for (int it = 0; it < 2; ++it) {
+        if (!(segs2[it] >= 1 && segs2[it] <= hi && rows[it] < p.batch)) continue;
+        const float *f = p.in + ((long long)rows[it] * p.in_stride + ((long long)segs2[it] * p.step - (p.klen - 1)));
+        const int ish = align_shift4(f);
+        const ItemReq &r = rq[it];
+        if (!(r.in_ok && r.out_ok && r.head_zero == 0 && r.zero_from == kN + 4 && r.shift == ish && r.dst_first == 0 &&
+              r.src == f - ish && r.bytes == 4 * kN + (ish ? 16 : 0))) { std::printf("interior shortcut disagrees\n"); std::exit(1); }
+        ++g_interior;
+      }
+    }
     int shift[2] = {d.item[0].shift, d.item[1].shift};
     if (bulk) {                                        // what lane 0 asks the TMA for + the lanes' fills
       ++g_bulk;
@@ -101,33 +113,34 @@ int main(int argc, char **argv) {
   for (auto &v : k) v = nd(rng);
 
   std::vector<cpair> tw(kTwElems), hs(1024);
-  std::vector<Quad> hs4(512);
+  std::vector<Quad> hab(768); // 512 entries ab, then 512 entries c (SpectrumTables)
+  cpair *hc = reinterpret_cast<cpair *>(hab.data() + 512);
   fill_tw(tw.data());
   fill_hs_host(k.data(), K, hs.data());
-  pack_hs(hs.data(), hs4.data());
+  pack_hs(hs.data(), hab.data(), hc);
   { // the kernel's own spectrum (one warp transforms the taps) against the long-double DFT above; then use it
     std::vector<float> xb(kWarpFloats + 8, NAN);
     std::vector<Regs> regs(32);
-    std::vector<Quad> own(512);
+    std::vector<Quad> own(768);
+    const SpectrumTables own_t{own.data()};
     for (int lane = 0; lane < 32; ++lane) spectrum_stage(lane, k.data(), K, xb.data());
     for (int lane = 0; lane < 32; ++lane) load_inputs(lane, regs[lane], xb.data(), 0, 0);
     for (int lane = 0; lane < 32; ++lane) { phase0(lane, regs[lane], tw.data()); t1_write(lane, regs[lane], xb.data()); }
-    for (int lane = 0; lane < 32; ++lane) { t1_read(lane, regs[lane], xb.data()); spectrum_finish(lane, regs[lane], own.data()); }
+    for (int lane = 0; lane < 32; ++lane) { t1_read(lane, regs[lane], xb.data()); spectrum_finish(lane, regs[lane], own_t); }
     double num = 0, den = 0;
-    for (int q = 0; q < 512; ++q) {
-      const float a[4] = {own[q].a, own[q].b, own[q].c, own[q].d}, b[4] = {hs4[q].a, hs4[q].b, hs4[q].c, hs4[q].d};
-      for (int i = 0; i < 4; ++i) { num += ((double)a[i] - b[i]) * ((double)a[i] - b[i]); den += (double)b[i] * b[i]; }
-    }
+    const float *a = reinterpret_cast<const float *>(own.data()), *b = reinterpret_cast<const float *>(hab.data());
+    for (int i = 0; i < 768 * 4; ++i) { num += ((double)a[i] - b[i]) * ((double)a[i] - b[i]); den += (double)b[i] * b[i]; }
     const double serr = std::sqrt(num / (den > 0 ? den : 1));
     if (!(serr < 1e-6)) { std::printf("spectrum by the engine: rel l2 %.3e\n", serr); return 1; }
-    hs4 = own;
+    if (K % 2) hab = own; // odd K: the engine's own tables; even K: the host's (both paths stay covered)
   }
+  const SpectrumTables hs4{hab.data()};
   W1kParams p{};
   fill_params(p, a, out, batch, n, n, out_len, out_len, K, mode);
   for (long long w = 0; w < n_warps; ++w) {
     long long u0, u1;
     warp_range(p.n_units, n_warps, w, u0, u1);
-    run_warp(p, u0, u1, tw.data(), hs4.data());
+    run_warp(p, u0, u1, tw.data(), hs4);
   }
   double num = 0, den = 0;
   const int pad = mode ? K / 2 : 0;
@@ -149,6 +162,6 @@ int main(int argc, char **argv) {
   for (float *q = out_store.data(); q < out; ++q) if (!std::isnan(*q)) ++bad;
   for (float *q = out + batch * out_len; q < out_store.data() + out_store.size(); ++q) if (!std::isnan(*q)) ++bad;
   const double err = std::sqrt(num / (den > 0 ? den : 1));
-  std::printf("%.3e units %lld bulk %lld fast_out %lld bad %lld\n", err, g_units, g_bulk, g_fast_out, bad);
+  std::printf("%.3e units %lld bulk %lld fast_out %lld interior %lld bad %lld\n", err, g_units, g_bulk, g_fast_out, g_interior, bad);
   return (err < 2e-6 && std::isfinite(err) && bad == 0) ? 0 : 1;
 }
