@@ -117,6 +117,7 @@ struct StreamWs {         // per stream: everything a call in flight on that str
   size_t part_bytes = 0;
   void *scratch = nullptr; // long-FFT intermediate (grow only): per stream, so that launches on
   size_t scratch_bytes = 0; // different streams (the host pipeline's three) never share it
+  unsigned *sched = nullptr; // two counters of the warp-per-FFT kernel's dynamic tail (oa_w1k_group.cuh), zero between launches
 };
 void free_ws(StreamWs &w) {
   cudaFree(w.taps);
@@ -124,6 +125,7 @@ void free_ws(StreamWs &w) {
   cudaFree(w.rf);
   cudaFree(w.part);
   cudaFree(w.scratch);
+  cudaFree(w.sched);
   w = StreamWs();
 }
 
@@ -763,6 +765,26 @@ int oa_device(DeviceCtx &c, cudaStream_t st, const T *a, size_t batch, size_t n,
       const int sms_avail = std::max(1, c.sm_count - std::max(0, g_reserved_sms.load()));
       const int wpc = fc::w1k::warps_per_cta();
       const long long ctas = std::max<long long>(1, std::min<long long>(sms_avail, (p.n_units + wpc - 1) / wpc));
+      // FFTCONV_CUDA_W1K_POOL_PCT=p (default 0: fixed ranges): the last p per cent of the units of a large job are
+      // handed out one at a time (W1kParams::sched); the counters live with the stream, whose launches follow each
+      // other.  Measured (profiles/r02_w1k_session4_ab.jsonl): the SMs' active cycles differ by 4 % under fixed
+      // ranges, yet p = 5 .. 50 changes nothing (+-0.3 %) -- the sustained rate is set by the 1 kW power cap, and
+      // an SM that idles at the end of a launch lends its power to the others.  Kept as an A/B switch.
+      const long long n_warps = ctas * wpc;
+      const int pool_pct = std::min(90, std::max(0, env_int("FFTCONV_CUDA_W1K_POOL_PCT", 0)));
+      if (pool_pct > 0 && p.n_units >= 16 * n_warps) {
+        StreamWs &ws = c.ws[st];
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (!ws.sched && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+          CU_TRY(cudaMalloc((void **)&ws.sched, 2 * sizeof(unsigned)));
+          CU_TRY(cudaMemset(ws.sched, 0, 2 * sizeof(unsigned)));
+        }
+        if (ws.sched) {
+          p.sched = ws.sched;
+          p.static_per_warp = std::max<long long>(1, p.n_units * (100 - pool_pct) / 100 / n_warps);
+          p.pool_first = p.static_per_warp * n_warps;
+        }
+      }
       if (const int e = fc::w1k::launch(p, (int)ctas, st))
         return fail(FFTCONV_CUDA_ERR_CUDA, std::string("oa_w1k_kernel: ") + cudaGetErrorString((cudaError_t)e));
       ++g_launches;

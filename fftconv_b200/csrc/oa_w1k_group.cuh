@@ -38,6 +38,12 @@ struct W1kParams {
   const cpair *hs;     // 1024 spectrum entries (freq_of_index order), 1/N folded in; or nullptr:
   const float *taps;   // ... the kernel transforms the taps itself (klen device floats), see spectrum_by_warp
   int cta_major;       // A/B switch: deal unit ranges CTA by CTA (the first version) instead of warp-major
+  // Dynamic tail (kernel only): warp w owns units [w S, (w + 1) S), S = static_per_warp, and then takes one unit at a
+  // time from the pool [pool_first, n_units) through an atomic counter, so that SMs that run a few per cent faster
+  // than others (measured: 934 k .. 972 k active cycles of 1 M) take more units.  sched[0]: next pool unit,
+  // sched[1]: warps that have finished; both return to zero at the end of every launch.  nullptr: fixed ranges.
+  unsigned *sched;
+  long long static_per_warp, pool_first;
 };
 
 inline void fill_params(W1kParams &p, const float *in, float *out, long long batch, long long n, long long in_stride,
@@ -56,6 +62,9 @@ inline void fill_params(W1kParams &p, const float *in, float *out, long long bat
   p.hs = nullptr;
   p.taps = nullptr;
   p.cta_major = 0;
+  p.sched = nullptr;
+  p.static_per_warp = 0;
+  p.pool_first = 0;
 }
 
 FC_HD void warp_range(long long n_units, long long n_warps, long long w, long long &u0, long long &u1) {
@@ -215,16 +224,15 @@ FC_HD void load_inputs(int lane, Regs &v, const float *xb, int shift_a, int shif
   }
 }
 
-// bit m: lane + 32 m >= K - 1 (the block's first K - 1 outputs are the wrapped part: dropped)
+// y[lane + 32 m] is kept iff lane + 32 m >= K - 1 (the block's first K - 1 outputs are the wrapped part: dropped),
+// i.e. iff 32 m >= keep_from with keep_from = K - 1 - lane: one register, one compare against an immediate per store.
+// (The first version kept a bit mask; the compiler turned it into nine loop-invariant registers -- and spills.)
 struct StoreMasks {
-  unsigned keep;
+  int keep_from;
 };
 FC_HD StoreMasks make_store_masks(int lane, const W1kParams &p) {
   StoreMasks k;
-  k.keep = 0;
-#pragma unroll
-  for (int m = 0; m < 32; ++m)
-    if (lane + 32 * m >= p.klen - 1) k.keep |= 1u << m;
+  k.keep_from = p.klen - 1 - lane;
   return k;
 }
 
@@ -234,7 +242,7 @@ FC_HD void store_fast_to(int lane, const Regs &v, float *ya, float *yb, const St
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
     const int s = slot16(m);
-    if ((k.keep >> m) & 1u) {
+    if (32 * m >= k.keep_from) {
       a[32 * m] = v.re[s].x;
       b[32 * m] = v.im[s].x;
     }
@@ -249,7 +257,7 @@ template <int IT> FC_HD void store_item_fast(int lane, const Regs &v, float *y, 
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
     const int s = slot16(m);
-    if ((k.keep >> m) & 1u) a[32 * m] = IT ? v.im[s].x : v.re[s].x;
+    if (32 * m >= k.keep_from) a[32 * m] = IT ? v.im[s].x : v.re[s].x;
     a[32 * (m + 16)] = IT ? v.im[s].y : v.re[s].y; // lane + 512 >= K - 1 for every K this engine serves
   }
 }

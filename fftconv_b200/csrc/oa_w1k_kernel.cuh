@@ -40,6 +40,17 @@ __device__ __noinline__ UnitDesc describe_unit_cold(const W1kParams &p, int row0
 struct Pos { // (row, block) of the two items of a unit; the engine takes batch, blocks per row < 2^31
   int row[2], seg[2];
 };
+// (row, block) of a unit's two items from its index: 64-bit divisions, out of line (pool units only)
+__device__ __noinline__ Pos position_of_unit_cold(long long u, long long segs) {
+  Pos q;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const long long it = 2 * u + i;
+    q.row[i] = (int)(it / segs);
+    q.seg[i] = (int)(it - (long long)q.row[i] * segs);
+  }
+  return q;
+}
 __device__ __forceinline__ void advance(Pos &q, int segs) { // to the next unit: two items further
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -116,12 +127,29 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
   // unit longer then sit in the first warps of EVERY CTA instead of filling the first CTAs -- the warps of an SM
   // share its pipes, so what counts is units per SM (512 rows: 148 on the busiest SM instead of 160) -- and the
   // last warp, which transformed the taps, is the last to get a longer range.
-  warp_range(p.n_units, n_warps, p.cta_major ? (long long)blockIdx.x * WARPS + warp : (long long)warp * gridDim.x + blockIdx.x, u0, u1);
+  const long long range_id = p.cta_major ? (long long)blockIdx.x * WARPS + warp : (long long)warp * gridDim.x + blockIdx.x;
+  const bool dynamic = p.sched != nullptr; // fixed ranges of static_per_warp units, then single units from the pool
+  if (dynamic) {
+    u0 = range_id * p.static_per_warp;
+    u1 = u0 + p.static_per_warp;
+  } else {
+    warp_range(p.n_units, n_warps, range_id, u0, u1);
+  }
+  // a warp's last act in a dynamic launch: count itself out; the last one of the grid rewinds the pool counter
+  // (atomicInc wraps the count of finished warps to zero by itself), so the next launch finds both at zero
+  auto sign_off = [&]() { // (nothing of the set-up above is kept alive for this)
+    if (p.sched != nullptr && (threadIdx.x & 31) == 0) {
+      const unsigned last = gridDim.x * WARPS - 1;
+      __threadfence();
+      if (atomicInc(p.sched + 1, last) == last) p.sched[0] = 0u;
+    }
+  };
   if (u0 >= u1) {
     if (wait_spectrum) asm volatile("bar.arrive %0, %1;" ::"n"(kSpectrumBarrier), "n"(32 * WARPS) : "memory");
+    sign_off();
     return;
   }
-  const StoreMasks masks = make_store_masks(lane, p);
+  StoreMasks masks = make_store_masks(lane, p);
   const int segs = (int)p.segs, step = p.step, tail = p.klen - 1;
   const float *tensor_end = p.in + (p.batch - 1) * p.in_stride + p.n;
 
@@ -179,11 +207,30 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
   Carry nxt = request(q);
   uint32_t phase = wait_spectrum ? 2u : 0u; // bit 0: the mbarrier's phase parity; bit 1: the spectrum barrier is still ahead
 
+  int static_left = (int)(u1 - u0) - 1;    // units of the fixed range after the current one
+  unsigned fetched = 0;                 // lane 0: the pool unit the counter handed out
 #pragma unroll 1
-  for (long long u = u0; u < u1; ++u) {
+  for (;;) {
+    // the unit after this one comes from the pool: ask for it now, the answer is needed half a unit from here
+    const bool from_pool = p.sched != nullptr && static_left == 0;
+    if (from_pool && lane == 0) fetched = atomicAdd(p.sched, 1u);
     const Carry cur = nxt;
     const Pos at = q;
     Regs v;
+    bool has_next = false;
+    // moves q to the unit after this one; false: there is none
+    auto next_unit = [&]() -> bool {
+      if (!from_pool) {
+        if (static_left <= 0) return false; // fixed ranges only, and this was the last unit
+        --static_left;
+        advance(q, segs);
+        return true;
+      }
+      const long long nu = p.pool_first + (long long)__shfl_sync(0xffffffffu, fetched, 0);
+      if (nu >= p.n_units) return false;
+      q = position_of_unit_cold(nu, p.segs);
+      return true;
+    };
     int sh_a = cur.sh_a(), sh_b = cur.sh_b();
     if (cur.bulk()) {
       while (!dev::mbar_try_wait(mbar, phase & 1u)) {
@@ -228,10 +275,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
           __syncwarp();
           t2_read(lane, v, xb);
           __syncwarp(); // the buffer is idle: the next inputs may land while P2 and the stores run
-          if (u + 1 < u1) {
-            advance(q, segs);
-            nxt = request(q);
-          }
+          has_next = next_unit();
+          if (has_next) nxt = request(q);
           p2_pre<FULL_TW>(lane, v, tw);
         } else {
           p2_post(lane, v, tw);
@@ -251,12 +296,11 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
       __syncwarp();
       t2_read(lane, v, xb);
       __syncwarp(); // the buffer is idle: the next inputs may land while P2 and the stores run
-      if (u + 1 < u1) {
-        advance(q, segs);
-        nxt = request(q);
-      }
+      has_next = next_unit();
+      if (has_next) nxt = request(q);
       phase2(lane, v, tw);
     }
+    asm volatile("" : "+r"(masks.keep_from)); // not loop-invariant as far as the compiler knows: no hoisted predicates
     // where y[0] of each item goes: row's output + block start - pad
     if (cur.fast_out(0))
       store_item_fast<0>(lane, v, p.out + (long long)at.row[0] * p.out_stride + ((long long)at.seg[0] * step - tail - p.pad), masks);
@@ -266,7 +310,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
       store_item_fast<1>(lane, v, p.out + (long long)at.row[1] * p.out_stride + ((long long)at.seg[1] * step - tail - p.pad), masks);
     else
       store_item_slow<1>(lane, v, p, at.row[1], at.seg[1]);
+    if (!has_next) break;
   }
+  sign_off();
 }
 #endif // __CUDACC__
 
