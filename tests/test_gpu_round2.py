@@ -542,6 +542,39 @@ def test_w1k_spectrum_in_kernel_matches_spectrum_kernel(cuda, klen, monkeypatch)
     assert torch.equal(y, y_host_taps)
 
 
+@pytest.mark.parametrize("pct", [15, 50, 90])
+def test_w1k_dynamic_tail_is_bit_identical_and_rewinds_its_counters(cuda, pct, monkeypatch):
+    """FFTCONV_CUDA_W1K_POOL_PCT=p: the last p per cent of a large job's units are handed out through an atomic
+    counter instead of fixed ranges (oa_w1k_group.cuh: W1kParams::sched).  Which warp takes a unit does not change
+    the unit's arithmetic, so the output is bit-identical to the fixed ranges -- on the first launch and on every
+    later one (the kernel's last warp rewinds both counters), on a second stream too, for a job whose rows end in
+    clipped blocks, in both modes."""
+    import torch
+
+    import fftconv_b200 as fc
+
+    rng = np.random.default_rng(pct)
+    a = rng.standard_normal((1200, 65536 - 24)).astype(np.float32)   # 50 units per warp: the dynamic rule applies
+    k = (rng.standard_normal(245) / 16).astype(np.float32)
+    ta, tk = _t(a, cuda), _t(k, cuda)
+    for mode in ("full", "same"):
+        want = fc.oaconvolve(ta, tk, mode)
+        torch.cuda.synchronize()
+        assert O.rel_l2(want[[0, 599, 1199]].cpu().numpy(), O.conv_exact(a[[0, 599, 1199]], k, mode)) < 1e-5
+        monkeypatch.setenv("FFTCONV_CUDA_W1K_POOL_PCT", str(pct))
+        for _ in range(3):
+            y = fc.oaconvolve(ta, tk, mode)
+            torch.cuda.synchronize()
+            assert torch.equal(y, want), (mode, pct)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                y = fc.oaconvolve(ta, tk, mode)
+        side.synchronize()
+        assert torch.equal(y, want), (mode, pct, "second stream")
+        monkeypatch.delenv("FFTCONV_CUDA_W1K_POOL_PCT")
+
+
 # ---- SURVEY.md 8f-4: the general 1-D FFT surface and Hilbert envelopes of any length -------------------
 def _crel(y, ref) -> float:
     y, ref = np.asarray(y).astype(np.complex128).ravel(), np.asarray(ref).astype(np.complex128).ravel()
