@@ -255,37 +255,39 @@ FC_HD void t2_read(int lane, Regs &v, const float *xb) {
 //   s = Y_lo + Y_hi,  d = (Y_lo - Y_hi) conj(w)
 // collapse into one 2 x 2 complex matrix per (j, k2), because w conj(w) = 1:
 //   s = E A + O B,   d = E C + O A,      A = H_lo + H_hi,  B = w (H_lo - H_hi),  C = conj(w) (H_lo - H_hi)
-// 16 fused multiply-adds per pair instead of 8 + 8 (two packed complex products) + 8.  Shared-memory form:
-// ab[j * 32 + k2] = (A.re, A.im, B.re, B.im), c()[j * 32 + k2] = C; 1 / N is folded in.  (Measured against
+// 16 fused multiply-adds per pair instead of 8 + 8 (two packed complex products) + 8; 1 / N is folded in.  (Measured against
 // tabulating only A and C and forming B = w^2 C with four more instructions per pair -- a third less table
 // traffic -- : this form is 0.8 % faster, profiles/r02_w1k_session4_ab.jsonl.)
 // A spectrum given as complex entries (filter handles, tests) is indexed by e = 2 (j * 32 + k2) + half:
 FC_HD constexpr unsigned freq_of_index(unsigned e) {
   return 32u * ((e >> 6) + 16u * (e & 1u)) + ((e >> 1) & 31u);
 }
-struct SpectrumTables { // one pointer: 512 entries ab, then 512 entries c
-  Quad *ab;
-  FC_HD cpair *c() const { return reinterpret_cast<cpair *>(ab + 512); }
+// In registers the pair (s, d) is one packed value per component, so the eight products per component pair up:
+//   (s.re, d.re) = E.re (A.re, C.re) - E.im (A.im, C.im) + O.re (B.re, A.re) - O.im (B.im, A.im)
+//   (s.im, d.im) = E.re (A.im, C.im) + E.im (A.re, C.re) + O.re (B.im, A.im) + O.im (B.re, A.re)
+// eight packed multiply-adds with a broadcast scalar instead of sixteen scalar ones; the table holds the four
+// constant pairs per (j, k2): q0 = (A.re, C.re, A.im, C.im), q1 = (B.re, A.re, B.im, A.im) -- 32 bytes.
+struct SpectrumTables { // one pointer: 512 entries q0, then 512 entries q1
+  Quad *q0;
+  FC_HD Quad *q1() const { return q0 + 512; }
 };
 // w = exp(-2 pi i j / 32): entry (4 + j) * 32 of the lane-twiddle table (oa_w1k_tables.h: fill_tw, lane 0)
-FC_HD void fold_spectrum_entry(cpair w, cpair h_lo, cpair h_hi, Quad &ab, cpair &c) {
+FC_HD void fold_spectrum_entry(cpair w, cpair h_lo, cpair h_hi, Quad &q0, Quad &q1) {
   const float wr = w.re, wi = w.im;
   const float ar = h_lo.re + h_hi.re, ai = h_lo.im + h_hi.im;
   const float dr = h_lo.re - h_hi.re, di = h_lo.im - h_hi.im;
-  ab = Quad{ar, ai, dr * wr - di * wi, dr * wi + di * wr};
-  c = cpair{dr * wr + di * wi, di * wr - dr * wi};
+  const float br = dr * wr - di * wi, bi = dr * wi + di * wr;   // B = w D
+  const float cr = dr * wr + di * wi, ci = di * wr - dr * wi;   // C = conj(w) D
+  q0 = Quad{ar, cr, ai, ci};
+  q1 = Quad{br, ar, bi, ai};
 }
 // one pair: (E, O) in -> (s, d) out
 FC_HD void spectrum_pair(int lane, int j, f2 inr, f2 ini, f2 &outr, f2 &outi, const SpectrumTables &h) {
-  const Quad ab = h.ab[j * 32 + lane];
-  const cpair c = h.c()[j * 32 + lane];
+  const Quad a = h.q0[j * 32 + lane], b = h.q1()[j * 32 + lane];
+  const f2 p0 = make_f2(a.a, a.b), p1 = make_f2(a.c, a.d), p2 = make_f2(b.a, b.b), p3 = make_f2(b.c, b.d);
   const float er = inr.x, ei = ini.x, orr = inr.y, oi = ini.y;
-  const float sr = fmaf(-oi, ab.d, fmaf(orr, ab.c, fmaf(-ei, ab.b, er * ab.a)));
-  const float si = fmaf(oi, ab.c, fmaf(orr, ab.d, fmaf(ei, ab.a, er * ab.b)));
-  const float dr = fmaf(-oi, ab.b, fmaf(orr, ab.a, fmaf(-ei, c.im, er * c.re)));
-  const float di = fmaf(oi, ab.a, fmaf(orr, ab.b, fmaf(ei, c.re, er * c.im)));
-  outr = make_f2(sr, dr);
-  outi = make_f2(si, di);
+  outr = fmas2(p0, er, fmas2(p1, -ei, fmas2(p2, orr, muls2(p3, -oi))));
+  outi = fmas2(p1, er, fmas2(p0, ei, fmas2(p3, orr, muls2(p2, oi))));
 }
 // v: (E, O) in slot16(j)  ->  (s, d) in slot j, where the inverse dft16 wants them.  slot16 is an involution
 // (a 4 x 4 transpose of the slot index), so the move happens in place: j and slot16(j) trade places.

@@ -352,8 +352,8 @@ template <int J = 0> FC_HD void spectrum_emit(int lane, const Regs &v, const Spe
     float br = cr, bi = ci;
     rot32<-1, (2 * J) & 15>(br, bi);
     if (J >= 8) { br = -br; bi = -bi; }
-    h.ab[J * 32 + lane] = Quad{ar, ai, br, bi};
-    h.c()[J * 32 + lane] = cpair{cr, ci};
+    h.q0[J * 32 + lane] = Quad{ar, cr, ai, ci};
+    h.q1()[J * 32 + lane] = Quad{br, ar, bi, ai};
     spectrum_emit<J + 1>(lane, v, h);
   }
 }

@@ -36,9 +36,9 @@ inline void fill_hs_host(const float *taps, int klen, cpair *hs) {
   }
 }
 // the kernel's shared-memory form: the folded tables of multiply_spectrum_fused
-inline void pack_hs(const cpair *hs, Quad *ab, cpair *c) {
+inline void pack_hs(const cpair *hs, Quad *q0, Quad *q1) {
   for (int q = 0; q < 512; ++q)
-    fold_spectrum_entry(n2048::unit_root<float>(32 * (q >> 5), 1024), hs[2 * q], hs[2 * q + 1], ab[q], c[q]);
+    fold_spectrum_entry(n2048::unit_root<float>(32 * (q >> 5), 1024), hs[2 * q], hs[2 * q + 1], q0[q], q1[q]);
 }
 
 } // namespace w1k

@@ -113,15 +113,15 @@ int main(int argc, char **argv) {
   for (auto &v : k) v = nd(rng);
 
   std::vector<cpair> tw(kTwElems), hs(1024);
-  std::vector<Quad> hab(768); // 512 entries ab, then 512 entries c (SpectrumTables)
-  cpair *hc = reinterpret_cast<cpair *>(hab.data() + 512);
+  std::vector<Quad> hab(1024); // 512 entries q0, then 512 entries q1 (SpectrumTables)
+  Quad *hc = hab.data() + 512;
   fill_tw(tw.data());
   fill_hs_host(k.data(), K, hs.data());
   pack_hs(hs.data(), hab.data(), hc);
   { // the kernel's own spectrum (one warp transforms the taps) against the long-double DFT above; then use it
     std::vector<float> xb(kWarpFloats + 8, NAN);
     std::vector<Regs> regs(32);
-    std::vector<Quad> own(768);
+    std::vector<Quad> own(1024);
     const SpectrumTables own_t{own.data()};
     for (int lane = 0; lane < 32; ++lane) spectrum_stage(lane, k.data(), K, xb.data());
     for (int lane = 0; lane < 32; ++lane) load_inputs(lane, regs[lane], xb.data(), 0, 0);
@@ -129,7 +129,7 @@ int main(int argc, char **argv) {
     for (int lane = 0; lane < 32; ++lane) { t1_read(lane, regs[lane], xb.data()); spectrum_finish(lane, regs[lane], own_t); }
     double num = 0, den = 0;
     const float *a = reinterpret_cast<const float *>(own.data()), *b = reinterpret_cast<const float *>(hab.data());
-    for (int i = 0; i < 768 * 4; ++i) { num += ((double)a[i] - b[i]) * ((double)a[i] - b[i]); den += (double)b[i] * b[i]; }
+    for (int i = 0; i < 1024 * 4; ++i) { num += ((double)a[i] - b[i]) * ((double)a[i] - b[i]); den += (double)b[i] * b[i]; }
     const double serr = std::sqrt(num / (den > 0 ? den : 1));
     if (!(serr < 1e-6)) { std::printf("spectrum by the engine: rel l2 %.3e\n", serr); return 1; }
     if (K % 2) hab = own; // odd K: the engine's own tables; even K: the host's (both paths stay covered)
