@@ -675,13 +675,14 @@ template <typename T> int oa2048_engine_for(size_t N, size_t klen) {
 // The warp-per-FFT engine (oa_w1k_*.cuh): float32, 1024-point blocks, 8 <= K <= w1k::kMaxTaps.  It serves
 // the table's own N = 1024 row and, through the throughput rule, large jobs with shorter or longer
 // kernels (FFTCONV_CUDA_NO_W1K=1 switches it off; FFTCONV_CUDA_W1K_MAX_TAPS moves the upper end of
-// what the throughput rule sends to it).
+// what the throughput rule sends to it: 360 taps, where the 2048-point kernel takes over -- measured on 4096 x 65536,
+// sustained: K = 340 0.592 against 0.615 ms, K = 360 0.606 / 0.622, K = 400 0.636 / 0.626; profiles/r02_w1k_tap_limit.jsonl).
 template <typename T> bool w1k_engine_for(size_t N, size_t klen) {
   if (!std::is_same<T, float>::value || N != 1024) return false;
   if (klen < 8 || klen > (size_t)fc::w1k::kMaxTaps) return false;
   return !(env_int("FFTCONV_CUDA_FORCE_GENERIC", 0) || env_int("FFTCONV_CUDA_NO_W1K", 0));
 }
-size_t w1k_rule_max_taps() { return (size_t)std::min(fc::w1k::kMaxTaps, std::max(0, env_int("FFTCONV_CUDA_W1K_MAX_TAPS", 300))); }
+size_t w1k_rule_max_taps() { return (size_t)std::min(fc::w1k::kMaxTaps, std::max(0, env_int("FFTCONV_CUDA_W1K_MAX_TAPS", 360))); }
 
 // The plan of one launch of the N = 2048 kernel: stream geometry + where each group's slice starts.
 template <typename T>

@@ -558,8 +558,8 @@ def test_streaming_overlap_add_across_calls(cuda, dt, klen, pieces):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("klen", [1, 3, 7, 8, 9, 16, 17, 20, 65, 165, 220, 221, 410, 411, 500, 560, 561, 640, 641, 768,
-                                  1024, 1025])
+@pytest.mark.parametrize("klen", [1, 3, 7, 8, 9, 16, 17, 20, 65, 165, 220, 221, 300, 360, 361, 410, 411, 500, 560, 561, 640,
+                                  641, 768, 1024, 1025])
 def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch):
     """Jobs of >= 4 Mi samples move short kernels off the reference's (CPU cost model) segment
     size onto the fastest kernel's; the samples are the same linear convolution either way."""
@@ -577,7 +577,7 @@ def test_large_jobs_use_the_throughput_segment_size(cuda, dt, klen, monkeypatch)
         y = fc.oaconvolve(ta, tk, mode)
         if klen <= (16 if dt == np.float32 else 8):
             assert fc.launch_count() - before == 1     # direct time-domain kernel
-        elif dt == np.float32 and klen <= 300:
+        elif dt == np.float32 and klen <= 360:
             assert fc.launch_count() - before == 1     # the warp-per-FFT kernel transforms the taps itself
         elif klen <= (1024 if dt == np.float32 else 640):
             assert fc.launch_count() - before == 2     # spectrum + the N = 2048 kernel (wide form beyond 410 taps)

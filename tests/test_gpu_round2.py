@@ -490,7 +490,7 @@ def test_w1k_kernel_alignment_and_guard_bands(cuda, monkeypatch):
 
 
 def test_w1k_is_the_default_for_large_float32_jobs(cuda, monkeypatch):
-    """The throughput rule sends large float32 jobs with 8 .. 300 taps to 1024-point blocks; host pointers
+    """The throughput rule sends large float32 jobs with 8 .. 360 taps to 1024-point blocks; host pointers
     and the filter handle take the same path."""
     import torch
 
