@@ -575,6 +575,21 @@ def test_w1k_dynamic_tail_is_bit_identical_and_rewinds_its_counters(cuda, pct, m
         monkeypatch.delenv("FFTCONV_CUDA_W1K_POOL_PCT")
 
 
+def test_w1k_on_a_cut_down_grid(cuda):
+    """tests/sanitize_w1k.py (written for compute-sanitizer, which this pool does not offer): the warp-per-FFT
+    kernel on 6 CTAs -- fixed ranges and the dynamic tail, each launched twice, a filter handle, Same mode, clipped
+    and misaligned rows -- against the float64 definition.  A grid of a few CTAs gives every warp long ranges and
+    the pool many rounds, the opposite of the full-size runs."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "sanitize_w1k.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "sanitize w1k done" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ---- SURVEY.md 8f-4: the general 1-D FFT surface and Hilbert envelopes of any length -------------------
 def _crel(y, ref) -> float:
     y, ref = np.asarray(y).astype(np.complex128).ravel(), np.asarray(ref).astype(np.complex128).ravel()
