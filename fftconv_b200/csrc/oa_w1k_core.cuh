@@ -121,34 +121,51 @@ template <int S, int J = 0> FC_HD void cross_dit(Regs &v) {
 // The same two steps with the lane's odd-point factor w = W_1024^l folded into the step's twiddles:
 // ct[i * 32 + lane] = exp(-2 pi j i / 32) w (forward); the inverse uses the conjugates.  This replaces
 // sixteen constant multiplications plus sixteen multiplications by w with sixteen multiplications.
-template <bool CONJ, int I = 0> FC_HD void cross_dif_tw(Regs &v, const cpair *ct) { // ct already points at the lane's column
+// Table rows come in pairs: rows 2 q and 2 q + 1 of a lane are one 16-byte entry (tw_index), so the sixteen
+// twiddles of a step are eight 128-bit loads.
+struct alignas(16) Quad { float a, b, c, d; };
+FC_HD constexpr int tw_index(int row, int lane) { return (((row >> 1) * 32 + lane) << 1) + (row & 1); }
+FC_HD Quad tw_pair(const cpair *tw, int even_row, int lane) { return *reinterpret_cast<const Quad *>(tw + tw_index(even_row, lane)); }
+constexpr int kTwRowCross = 4;   // rows 4 .. 19: exp(-2 pi j i / 32) W_1024^l, i = 0 .. 15
+constexpr int kTwRowPowers = 19; // rows 20 .. 34: W_512^{l j}, j = 1 .. 15 (row 19 + j); row 35 pads the last pair
+constexpr int kTwRows = 36;
+
+template <bool CONJ, int I> FC_HD void cross_dif_one(Regs &v, float wr, float wim) {
+  const float wi = CONJ ? -wim : wim;
+  const float sr = v.re[I].x + v.re[I].y, si = v.im[I].x + v.im[I].y;
+  const float dr = v.re[I].x - v.re[I].y, di = v.im[I].x - v.im[I].y;
+  v.re[I].x = sr; v.im[I].x = si;
+  v.re[I].y = dr * wr - di * wi;
+  v.im[I].y = dr * wi + di * wr;
+}
+template <bool CONJ, int I = 0> FC_HD void cross_dif_tw(Regs &v, const cpair *tw, int lane) {
   if constexpr (I < 16) {
-    const cpair w = ct[I * 32];
-    const float wi = CONJ ? -w.im : w.im;
-    const float sr = v.re[I].x + v.re[I].y, si = v.im[I].x + v.im[I].y;
-    const float dr = v.re[I].x - v.re[I].y, di = v.im[I].x - v.im[I].y;
-    v.re[I].x = sr; v.im[I].x = si;
-    v.re[I].y = dr * w.re - di * wi;
-    v.im[I].y = dr * wi + di * w.re;
-    cross_dif_tw<CONJ, I + 1>(v, ct);
+    const Quad w = tw_pair(tw, kTwRowCross + I, lane);
+    cross_dif_one<CONJ, I>(v, w.a, w.b);
+    cross_dif_one<CONJ, I + 1>(v, w.c, w.d);
+    cross_dif_tw<CONJ, I + 2>(v, tw, lane);
   }
 }
-template <bool CONJ, int J = 0> FC_HD void cross_dit_tw(Regs &v, const cpair *ct) {
+template <bool CONJ, int J> FC_HD void cross_dit_one(Regs &v, float wr, float wim) {
+  constexpr int s = slot16(J);
+  const float wi = CONJ ? -wim : wim;
+  const float orr = v.re[s].y, oi = v.im[s].y;
+  const float tr = orr * wr - oi * wi, ti = orr * wi + oi * wr;
+  const float er = v.re[s].x, ei = v.im[s].x;
+  v.re[s].x = er + tr; v.im[s].x = ei + ti;
+  v.re[s].y = er - tr; v.im[s].y = ei - ti;
+}
+template <bool CONJ, int J = 0> FC_HD void cross_dit_tw(Regs &v, const cpair *tw, int lane) {
   if constexpr (J < 16) {
-    constexpr int s = slot16(J);
-    const cpair w = ct[J * 32];
-    const float wi = CONJ ? -w.im : w.im;
-    const float orr = v.re[s].y, oi = v.im[s].y;
-    const float er = v.re[s].x, ei = v.im[s].x;
-    const float tr = orr * w.re - oi * wi, ti = orr * wi + oi * w.re;
-    v.re[s].x = er + tr; v.im[s].x = ei + ti;
-    v.re[s].y = er - tr; v.im[s].y = ei - ti;
-    cross_dit_tw<CONJ, J + 1>(v, ct);
+    const Quad w = tw_pair(tw, kTwRowCross + J, lane);
+    cross_dit_one<CONJ, J>(v, w.a, w.b);
+    cross_dit_one<CONJ, J + 1>(v, w.c, w.d);
+    cross_dit_tw<CONJ, J + 2>(v, tw, lane);
   }
 }
 
 // ---- pair twiddles W_1024^{l k2}, k2 = 2 j + h -------------------------------------------------
-// per lane: w2^1, w2^2, w2^4, w2^8 (w2 = W_512^l): table tw[r * 32 + l], r = 0..3; the other powers of
+// per lane: w2^1, w2^2, w2^4, w2^8 (w2 = W_512^l): table rows r = 0..3 (entry tw_index(r, l)); the other powers of
 // w2 are products formed in registers (as in oa_n2048_core.cuh).  Rows 4 .. 19 of the same table hold
 // the radix-2 step's twiddles with w = W_1024^l folded in: tw[(4 + i) * 32 + l] = exp(-2 pi j i / 32) w.
 struct LaneTwiddles {
@@ -164,13 +181,17 @@ template <bool FULL = false> FC_HD LaneTwiddles lane_twiddles(const cpair *tw, i
     t.w = cpair{1.0f, 0.0f};
     t.p[0] = cpair{1.0f, 0.0f};
 #pragma unroll
-    for (int j = 1; j < 16; ++j) t.p[j] = tw[(19 + j) * 32 + lane];
+    for (int j = 1; j < 16; j += 2) { // rows 19 + j and 20 + j: one 128-bit load
+      const Quad q = tw_pair(tw, kTwRowPowers + j, lane);
+      t.p[j] = cpair{q.a, q.b};
+      if (j + 1 < 16) t.p[j + 1] = cpair{q.c, q.d};
+    }
     return t;
   }
-  t.p[1] = tw[0 * 32 + lane];
-  t.p[2] = tw[1 * 32 + lane];
-  t.p[4] = tw[2 * 32 + lane];
-  t.p[8] = tw[3 * 32 + lane];
+  t.p[1] = tw[tw_index(0, lane)];
+  t.p[2] = tw[tw_index(1, lane)];
+  t.p[4] = tw[tw_index(2, lane)];
+  t.p[8] = tw[tw_index(3, lane)];
   t.w = cpair{1.0f, 0.0f};
   t.p[0] = cpair{1.0f, 0.0f};
   t.p[3] = cpair_mul(t.p[1], t.p[2]);
@@ -212,7 +233,6 @@ FC_HD void t1_write(int lane, const Regs &v, float *xb) {
     xb[kPlane + ex_addr(2 * j + 1, lane)] = v.im[s].y;
   }
 }
-struct alignas(16) Quad { float a, b, c, d; };
 // T1 read: lane k2 reads its row: pair i = (l = 2 i, 2 i + 1) into natural slot i
 FC_HD void t1_read(int lane, Regs &v, const float *xb) {
   const Quad *re = reinterpret_cast<const Quad *>(xb + ex_addr(lane, 0));
@@ -271,7 +291,7 @@ struct SpectrumTables { // one pointer: 512 entries q0, then 512 entries q1
   Quad *q0;
   FC_HD Quad *q1() const { return q0 + 512; }
 };
-// w = exp(-2 pi i j / 32): entry (4 + j) * 32 of the lane-twiddle table (oa_w1k_tables.h: fill_tw, lane 0)
+// w = exp(-2 pi i j / 32): row 4 + j of the lane-twiddle table at lane 0 (oa_w1k_tables.h: fill_tw)
 FC_HD void fold_spectrum_entry(cpair w, cpair h_lo, cpair h_hi, Quad &q0, Quad &q1) {
   const float wr = w.re, wi = w.im;
   const float ar = h_lo.re + h_hi.re, ai = h_lo.im + h_hi.im;
@@ -308,7 +328,7 @@ FC_HD void multiply_spectrum_fused(int lane, Regs &v, const SpectrumTables &h) {
 // ---- the phases of one warp iteration (between __syncwarp()s) -------------------------------------
 // P0: slots hold z[l + 32 i] (low) and z[l + 32 (i + 16)] (high); leaves B_l[k2] in slot16(j)
 FC_HD void phase0(int lane, Regs &v, const cpair *tw) {
-  cross_dif_tw<false>(v, tw + 4 * 32 + lane); // the odd outputs' factor w rides in the step's twiddles
+  cross_dif_tw<false>(v, tw, lane); // the odd outputs' factor w rides in the step's twiddles
   dft16<-1>(v);
   apply_pair_twiddles<false, true>(v, lane_twiddles(tw, lane));
 }
@@ -323,18 +343,18 @@ FC_HD void phase1(int lane, Regs &v, const SpectrumTables &h) {
 // does not fit the 32 KB instruction cache: measured 87 % hit rate, 0.64 stall cycles per issue).
 //   phase0 = p0_pre, dft16<-1>, p0_post        phase1 = dft16<-1>, p1_mid, dft16<+1>
 //   phase2 = p2_pre, dft16<+1>, p2_post
-FC_HD void p0_pre(int lane, Regs &v, const cpair *tw) { cross_dif_tw<false>(v, tw + 4 * 32 + lane); }
+FC_HD void p0_pre(int lane, Regs &v, const cpair *tw) { cross_dif_tw<false>(v, tw, lane); }
 template <bool FULL = false> FC_HD void p0_post(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<false, true>(v, lane_twiddles<FULL>(tw, lane)); }
 // between P1's two transforms: radix-2 step, spectrum, radix-2 step of the inverse in one (multiply_spectrum_fused)
 FC_HD void p1_mid(int lane, Regs &v, const SpectrumTables &h) { multiply_spectrum_fused(lane, v, h); }
 template <bool FULL = false> FC_HD void p2_pre(int lane, Regs &v, const cpair *tw) { apply_pair_twiddles<true, false>(v, lane_twiddles<FULL>(tw, lane)); }
-FC_HD void p2_post(int lane, Regs &v, const cpair *tw) { cross_dit_tw<true>(v, tw + 4 * 32 + lane); }
+FC_HD void p2_post(int lane, Regs &v, const cpair *tw) { cross_dit_tw<true>(v, tw, lane); }
 
 // P2: slots hold C_k2[l] for k2 = 2 j, 2 j + 1; leaves y[l + 32 m], y[l + 32 (m + 16)] in slot16(m)
 FC_HD void phase2(int lane, Regs &v, const cpair *tw) {
   apply_pair_twiddles<true, false>(v, lane_twiddles(tw, lane));
   dft16<+1>(v);
-  cross_dit_tw<true>(v, tw + 4 * 32 + lane); // conj(w) of the odd inputs commutes with their dft16
+  cross_dit_tw<true>(v, tw, lane); // conj(w) of the odd inputs commutes with their dft16
 }
 
 } // namespace w1k

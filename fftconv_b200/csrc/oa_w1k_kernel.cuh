@@ -19,7 +19,7 @@ namespace fc {
 namespace w1k {
 
 constexpr int kWarps = 16;
-constexpr int kTwCount = 35 * 32;
+constexpr int kTwCount = kTwRows * 32;
 // shared memory: spectrum (512 x 32 B), lane twiddles, one mbarrier per warp, then the warps' buffers
 constexpr size_t kSmemHs = 1024 * sizeof(Quad); // folded spectrum tables (oa_w1k_core.cuh)
 constexpr size_t kSmemTw = kTwCount * sizeof(cpair);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) oa_w1k_kernel(const __grid_cons
 
   if (p.hs) { // a filter handle: the spectrum is resident
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-      fold_spectrum_entry(p.tw[(4 + (i >> 5)) * 32], p.hs[2 * i], p.hs[2 * i + 1], hs4.q0[i], hs4.q1()[i]);
+      fold_spectrum_entry(p.tw[tw_index(kTwRowCross + (i >> 5), 0)], p.hs[2 * i], p.hs[2 * i + 1], hs4.q0[i], hs4.q1()[i]);
     }
   }
   for (int i = threadIdx.x; i < kTwCount; i += blockDim.x) tw[i] = p.tw[i];

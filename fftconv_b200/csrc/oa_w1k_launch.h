@@ -15,7 +15,7 @@ int warps_per_cta();
 int launch(const W1kParams &p, int sms, void *stream);
 // fills kTwElems entries (oa_w1k_tables.h: fill_tw)
 void build_twiddles(cpair *tw);
-constexpr int kTwiddleElems = 35 * 32;
+constexpr int kTwiddleElems = 36 * 32;
 
 } // namespace w1k
 } // namespace fc

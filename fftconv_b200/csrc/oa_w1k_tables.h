@@ -8,14 +8,16 @@
 namespace fc {
 namespace w1k {
 
-constexpr int kTwElems = 35 * 32;
-// tw[r * 32 + l]: r = 0..3: W_512^{l 2^r};  r = 4 + i: exp(-2 pi j i / 32) W_1024^l = W_1024^{32 i + l};
-// r = 19 + j, j = 1..15: W_512^{l j} (every power, for the kernel variant that does not recompute them)
+constexpr int kTwElems = kTwRows * 32;
+// row r of lane l sits at tw_index(r, l) (rows in pairs, 16 bytes per lane and pair).  r = 0..3: W_512^{l 2^r};
+// r = 4 + i: exp(-2 pi j i / 32) W_1024^l = W_1024^{32 i + l}; r = 19 + j, j = 1..15: W_512^{l j} (every power, for the
+// kernel variant that does not recompute them); r = 35: padding
 inline void fill_tw(cpair *tw) {
   for (int l = 0; l < 32; ++l) {
-    for (int r = 0; r < 4; ++r) tw[r * 32 + l] = n2048::unit_root<float>((long long)l << r, 512);
-    for (int i = 0; i < 16; ++i) tw[(4 + i) * 32 + l] = n2048::unit_root<float>(32 * i + l, 1024);
-    for (int j = 1; j < 16; ++j) tw[(19 + j) * 32 + l] = n2048::unit_root<float>((long long)l * j, 512);
+    for (int r = 0; r < 4; ++r) tw[tw_index(r, l)] = n2048::unit_root<float>((long long)l << r, 512);
+    for (int i = 0; i < 16; ++i) tw[tw_index(kTwRowCross + i, l)] = n2048::unit_root<float>(32 * i + l, 1024);
+    for (int j = 1; j < 16; ++j) tw[tw_index(kTwRowPowers + j, l)] = n2048::unit_root<float>((long long)l * j, 512);
+    tw[tw_index(35, l)] = cpair{1.0f, 0.0f};
   }
 }
 

@@ -112,7 +112,9 @@ int main(int argc, char **argv) {
   for (long long i = 0; i < batch * n; ++i) a[i] = nd(rng);
   for (auto &v : k) v = nd(rng);
 
-  std::vector<cpair> tw(kTwElems), hs(1024);
+  std::vector<Quad> tw_store(kTwElems / 2); // 16-byte aligned: the kernel reads pairs of rows as one Quad
+  struct { cpair *p; cpair *data() const { return p; } } tw{reinterpret_cast<cpair *>(tw_store.data())};
+  std::vector<cpair> hs(1024);
   std::vector<Quad> hab(1024); // 512 entries q0, then 512 entries q1 (SpectrumTables)
   Quad *hc = hab.data() + 512;
   fill_tw(tw.data());
